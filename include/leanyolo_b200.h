@@ -1,0 +1,159 @@
+/* leanyolo_b200 — C ABI of the B200-native YOLOv10 inference hot path.
+ *
+ * Drop-in boundary for jremillard/leanyolo's `get_model()` -> `model(x)` ->
+ * `model.decode_forward()` path.  The reference is pure Python/PyTorch and has no
+ * FFI of its own, so each entry point below names the reference Python call it
+ * replaces (paths relative to the reference root).  Plain pointers and sizes
+ * only: no torch types.  All pointers are DEVICE pointers unless named `h_*`.
+ * Every function is asynchronous on `stream` (a cudaStream_t passed as void*),
+ * performs no allocation, and returns 0 on success or a negative LY_E_* code;
+ * `ly_last_error()` gives the message.  INTEGRATION.md shows the ctypes binding.
+ *
+ * Layouts: activations NHWC `[B,H,W,Ctot]`, element = bf16 (LY_BF16) or fp32
+ * (LY_F32, the 1e-4 check mode); dense weights `[Cout_pad][kh][kw][Cin_pad]`,
+ * depthwise weights `[kh*kw][C_pad]`, biases fp32.  Channel counts of views are
+ * multiples of 16 (zero-padded weights make padded channels exact zeros).
+ */
+#ifndef LEANYOLO_B200_H
+#define LEANYOLO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LY_ABI_VERSION 1
+
+#if defined(LY_BUILD) && defined(__GNUC__)
+#define LY_API __attribute__((visibility("default")))
+#else
+#define LY_API
+#endif
+
+enum { LY_BF16 = 0, LY_F32 = 1 };
+
+enum {
+  LY_OK = 0,
+  LY_E_ARG = -1,      /* bad argument (shape, alignment, unsupported size) */
+  LY_E_CUDA = -2,     /* a CUDA runtime / driver call failed                */
+  LY_E_ARCH = -3,     /* device is not sm_100 (no CPU / other-arch fallback) */
+};
+
+/* op kinds of ly_op.kind */
+enum {
+  LY_OP_STEM = 1,     /* backbone.cv0: NCHW fp32 image -> NHWC, normalise + 3x3 s2 + SiLU   backbone.py:68, yolov10s.py:107-112 */
+  LY_OP_CONV = 2,     /* dense Conv+BN+SiLU k in {1,3}, s in {1,2} (implicit GEMM)         layers.py:51-88 */
+  LY_OP_DW = 3,       /* depthwise Conv+BN(+SiLU) k in {3,7}, s in {1,2}; RepVGGDW merged  layers.py:274-294,455 */
+  LY_OP_POOL = 4,     /* SPPF: three chained 5x5 max-pools written into the concat buffer  layers.py:210-217 */
+  LY_OP_UP = 5,       /* nearest x2 upsample into a concat slice                           layers.py:240, neck.py:116-120 */
+  LY_OP_ATTN = 6,     /* PSA attention core softmax(q^T k * scale) applied to v            layers.py:369-378 */
+  LY_OP_EXPORT = 7,   /* NHWC storage -> public NCHW fp32 (taps / sub-module outputs)      */
+  LY_OP_IMPORT = 8,   /* public NCHW fp32 -> NHWC storage (sub-module inputs)              */
+};
+
+/* conv implementation selector (ly_op.impl) */
+enum {
+  LY_IMPL_AUTO = 0,   /* bf16: tcgen05/TMEM/TMA implicit GEMM; f32: CUDA-core check kernel */
+  LY_IMPL_SIMT = 1,   /* force the CUDA-core tiled kernel (bring-up / bisecting only)      */
+};
+
+/* A channel slice [c0, c0+c) of an NHWC buffer whose pixel pitch is `ctot` elements. */
+typedef struct ly_view {
+  void* ptr;          /* base of the whole buffer (NULL = absent) */
+  int32_t H, W;
+  int32_t ctot;
+  int32_t c0, c;
+} ly_view;
+
+/* One kernel launch.  Unused fields are zero. */
+typedef struct ly_op {
+  int32_t kind;       /* LY_OP_*  */
+  int32_t dtype;      /* LY_BF16 | LY_F32: element type of src/dst/res and dense/dw weights */
+  int32_t B;          /* images in this launch */
+  int32_t k, stride;  /* filter size, stride */
+  int32_t act;        /* 1 = SiLU after bias, 0 = none */
+  int32_t impl;       /* LY_IMPL_* (CONV only) */
+  int32_t nh, kdp, hd;/* ATTN: heads, padded key dim, head (value) dim */
+  float scale;        /* ATTN: key_dim^-0.5 */
+  float sub[3], div[3]; /* STEM: x' = (x - sub) / div per input channel */
+  ly_view src, dst, res;  /* res: added after the activation (Bottleneck/CIB/PSA shortcuts) */
+  const void* w;      /* weights (dtype; STEM: fp32 [Cout_pad][27]) */
+  const float* bias;  /* [Cout_pad] fp32 */
+  float* nchw;        /* optional public NCHW fp32 tensor [B, nchw_ctot, Ho, Wo] (CONV/EXPORT dst, STEM/IMPORT src) */
+  int32_t nchw_ctot, nchw_c0, nchw_c;
+  int32_t ext_slot;   /* plan only: >=0 -> `nchw` is taken from ly_plan_run's ext[] table */
+} ly_op;
+
+/* ---- library ---------------------------------------------------------- */
+LY_API int32_t ly_abi_version(void);
+LY_API const char* ly_last_error(void);
+/* LY_OK iff the current device is compute capability 10.x; fills sm count.  */
+LY_API int32_t ly_device_check(int32_t* sm_count);
+/* number of kernels launched by this process through this library (bench `gpu_launches`) */
+LY_API int64_t ly_launch_count(void);
+
+/* ---- single ops ------------------------------------------------------- */
+/* Launch one op (any kind).  Replaces one `Conv.forward` / `nn.MaxPool2d` /
+ * `F.interpolate` / attention matmul+softmax call site of layers.py.          */
+LY_API int32_t ly_launch(const ly_op* op, void* stream);
+
+/* ---- whole-forward plan ---------------------------------------------- */
+/* Replaces `YOLOv10x.forward` (yolov10s.py:105-122): a pre-resolved op list
+ * (tensor maps encoded once) executed back to back on one stream.  `ext[]`
+ * carries the per-call external tensors (input image, NCHW outputs); `img0`
+ * offsets them by whole images so one plan built for a sub-batch can sweep a
+ * larger batch.                                                              */
+typedef struct ly_plan ly_plan;
+LY_API int32_t ly_plan_create(const ly_op* ops, int32_t n_ops, ly_plan** out);
+LY_API int32_t ly_plan_run(ly_plan* plan, float* const* ext, int32_t n_ext, int32_t img0, void* stream);
+LY_API int32_t ly_plan_num_launches(const ly_plan* plan);
+LY_API void ly_plan_destroy(ly_plan* plan);
+
+/* ---- decode tail ------------------------------------------------------ */
+/* `preds[l]` = level-l head tensor, NCHW fp32 `[B, 4*reg_max+nc, Hl, Wl]`
+ * (exactly what `model(x)` returns / caches in `_eval_branches`).            */
+typedef struct ly_levels {
+  const float* preds[4];
+  int32_t H[4], W[4], stride[4];
+  int32_t n_levels;
+  int32_t B, nc, reg_max;
+  /* direct != 0: legacy `[B, 4+nc, H, W]` direct-offset layout of
+   * decode_v10_predictions (postprocess.py:70-101), boxes clamped to
+   * [0,clamp_w] x [0,clamp_h] when clamp_w > 0 (its `img_size`). NMS path only. */
+  int32_t direct, clamp_h, clamp_w;
+} ly_levels;
+
+/* Bytes of scratch the decode entry points need for `lv` (same for both). */
+LY_API int64_t ly_decode_scratch_bytes(const ly_levels* lv, int32_t max_det);
+
+/* Replaces `decode_v10_official_topk` (postprocess.py:166-261): DFL expectation,
+ * anchor decode, sigmoid, two-stage top-k with the canonical tie rule (score
+ * desc, index asc).  out: `[B, k, 6]` fp32 rows [x1,y1,x2,y2,score,cls],
+ * k = min(max_det, A).  Optional out_anchor/out_cls `[B,k]` int32 (may be NULL). */
+LY_API int32_t ly_decode_topk(const ly_levels* lv, int32_t max_det, float* out, int32_t* out_anchor,
+                       int32_t* out_cls, void* scratch, int64_t scratch_bytes, void* stream);
+
+/* Replaces `decode_v10_predictions` DFL branch (postprocess.py:103-161) +
+ * `nms` (box_ops.py:49-78): per-anchor max-class candidate, `score > conf`,
+ * greedy IoU NMS (suppress iff IoU > iou_thresh), first max_det survivors.
+ * classwise=0: class-agnostic (what the reference code does); 1: only equal
+ * labels suppress each other (export.py:145-198).  out `[B, max_det, 6]` (rows
+ * past the count are zero), out_count `[B]`, out_anchor `[B,max_det]` (-1 pad). */
+LY_API int32_t ly_decode_nms(const ly_levels* lv, float conf_thresh, float iou_thresh, int32_t max_det,
+                      int32_t classwise, float* out, int32_t* out_count, int32_t* out_anchor,
+                      void* scratch, int64_t scratch_bytes, void* stream);
+
+/* Replaces `leanyolo.utils.box_ops.nms` on explicit inputs: boxes `[B,N,4]`
+ * xyxy fp32, scores `[B,N]`, labels `[B,N]` int32 (may be NULL when
+ * classwise=0), n_valid `[B]` int32 (may be NULL = N).  keep `[B,max_keep]`
+ * indices into the input order, score-descending; keep_count `[B]`.          */
+LY_API int64_t ly_nms_scratch_bytes(int32_t B, int32_t N);
+LY_API int32_t ly_nms(const float* boxes, const float* scores, const int32_t* labels, const int32_t* n_valid,
+               int32_t B, int32_t N, float iou_thresh, int32_t max_keep, int32_t classwise,
+               int32_t* keep, int32_t* keep_count, void* scratch, int64_t scratch_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LEANYOLO_B200_H */

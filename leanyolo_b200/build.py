@@ -1,0 +1,79 @@
+"""In-tree build of libleanyolo_b200.so (hand-written sm_100a kernels + C ABI).
+
+``python -m leanyolo_b200.build`` or ``__graft_entry__.build()``.  nvcc cross-compiles
+without a GPU; the resulting .so is git-ignored but travels with the repo snapshot.
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+import shutil
+import subprocess
+import sys
+from pathlib import Path
+
+PKG = Path(__file__).resolve().parent
+CSRC = PKG / "csrc"
+OUT_DIR = PKG / "_lib"
+LIB = OUT_DIR / "libleanyolo_b200.so"
+STAMP = OUT_DIR / "build.stamp"
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-lineinfo", "-std=c++17",
+    "-DLY_BUILD=1",
+    "-Xcompiler", "-fPIC,-O2,-fvisibility=hidden",
+    "-Xptxas", "-v",
+    "-cudart", "static",
+    "-shared",
+]
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found (set NVCC=/path/to/nvcc)")
+
+
+def _sources():
+    return sorted(CSRC.glob("*.cu"))
+
+
+def _fingerprint() -> str:
+    h = hashlib.sha256()
+    for f in sorted(list(CSRC.glob("*")) + [PKG.parent / "include" / "leanyolo_b200.h"]):
+        h.update(f.name.encode())
+        h.update(f.read_bytes())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
+def build(force: bool = False, verbose: bool = False) -> Path:
+    OUT_DIR.mkdir(exist_ok=True)
+    fp = _fingerprint()
+    if not force and LIB.exists() and STAMP.exists() and STAMP.read_text().strip() == fp:
+        return LIB
+    objs = []
+    for src in _sources():
+        obj = OUT_DIR / (src.stem + ".o")
+        cmd = [_nvcc(), *[f for f in NVCC_FLAGS if f != "-shared"], "-c", str(src), "-o", str(obj)]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if verbose or r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed for {src.name}")
+        (OUT_DIR / (src.stem + ".ptxas.log")).write_text(r.stderr)
+        objs.append(str(obj))
+    cmd = [_nvcc(), "-shared", "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a",
+           "-Xcompiler", "-fPIC", "-o", str(LIB), *objs]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("link failed")
+    STAMP.write_text(fp)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose=True))

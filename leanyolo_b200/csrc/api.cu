@@ -1,0 +1,165 @@
+// extern "C" boundary of libleanyolo_b200.so: error state, op dispatch, whole-forward plan.
+#include <stdarg.h>
+#include <string.h>
+#include <vector>
+#include "common.cuh"
+
+namespace ly {
+
+static thread_local char g_err[512] = "";
+std::atomic<long long> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+  }
+  return n;
+}
+
+static int32_t check_arch() {
+  static int ok = -1;
+  if (ok < 0) {
+    int dev = 0, major = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) {
+      set_error("no CUDA device available (leanyolo_b200 has no CPU fallback)");
+      return LY_E_CUDA;
+    }
+    ok = (major == 10) ? 1 : 0;
+    if (!ok) set_error("device compute capability %d.x is not sm_100 (this library is built for sm_100a only)", major);
+  }
+  if (!ok) return LY_E_ARCH;
+  return LY_OK;
+}
+
+static bool use_tc(const ly_op& op) { return op.dtype == LY_BF16 && op.impl != LY_IMPL_SIMT; }
+
+static int32_t dispatch(const ly_op& op, cudaStream_t s) {
+  switch (op.kind) {
+    case LY_OP_STEM: return launch_stem(op, s);
+    case LY_OP_CONV: {
+      if (!use_tc(op)) return launch_conv_simt(op, s);
+      ConvTcState* st = nullptr;
+      int32_t rc = conv_tc_prepare(op, &st);
+      if (rc != LY_OK) return rc;
+      rc = conv_tc_launch(st, nullptr, s);
+      conv_tc_free(st);
+      return rc;
+    }
+    case LY_OP_DW: return launch_dw(op, s);
+    case LY_OP_POOL: return launch_pool(op, s);
+    case LY_OP_UP: return launch_up(op, s);
+    case LY_OP_ATTN: return launch_attn(op, s);
+    case LY_OP_EXPORT: return launch_export(op, s);
+    case LY_OP_IMPORT: return launch_import(op, s);
+    default: set_error("unknown op kind %d", op.kind); return LY_E_ARG;
+  }
+}
+
+}  // namespace ly
+
+using namespace ly;
+
+struct ly_plan {
+  std::vector<ly_op> ops;
+  std::vector<ConvTcState*> tc;   // per op (nullptr when not a tensor-core conv)
+  ~ly_plan() {
+    for (auto* t : tc)
+      if (t) conv_tc_free(t);
+  }
+};
+
+extern "C" {
+
+int32_t ly_abi_version(void) { return LY_ABI_VERSION; }
+const char* ly_last_error(void) { return g_err; }
+int64_t ly_launch_count(void) { return g_launches.load(); }
+
+int32_t ly_device_check(int32_t* sms) {
+  int32_t rc = check_arch();
+  if (rc != LY_OK) return rc;
+  if (sms) *sms = sm_count();
+  return LY_OK;
+}
+
+int32_t ly_launch(const ly_op* op, void* stream) {
+  LY_CHECK_ARG(op != nullptr, "ly_launch: null op");
+  int32_t rc = check_arch();
+  if (rc != LY_OK) return rc;
+  return dispatch(*op, (cudaStream_t)stream);
+}
+
+int32_t ly_plan_create(const ly_op* ops, int32_t n_ops, ly_plan** out) {
+  LY_CHECK_ARG(ops && n_ops > 0 && out, "ly_plan_create: bad arguments");
+  int32_t rc = check_arch();
+  if (rc != LY_OK) return rc;
+  ly_plan* pl = new ly_plan();
+  pl->ops.assign(ops, ops + n_ops);
+  pl->tc.assign(n_ops, nullptr);
+  for (int i = 0; i < n_ops; ++i) {
+    const ly_op& op = pl->ops[i];
+    if (op.kind == LY_OP_CONV && use_tc(op)) {
+      ly_op tmp = op;
+      if (tmp.ext_slot >= 0 && !tmp.nchw) tmp.nchw = reinterpret_cast<float*>(16);  // placeholder: real pointer comes at run time
+      rc = conv_tc_prepare(tmp, &pl->tc[i]);
+      if (rc != LY_OK) {
+        char msg[400];
+        snprintf(msg, sizeof(msg), "%s", g_err);
+        set_error("plan op %d: %s", i, msg);
+        delete pl;
+        return rc;
+      }
+    }
+  }
+  *out = pl;
+  return LY_OK;
+}
+
+int32_t ly_plan_run(ly_plan* pl, float* const* ext, int32_t n_ext, int32_t img0, void* stream) {
+  LY_CHECK_ARG(pl != nullptr, "ly_plan_run: null plan");
+  cudaStream_t s = (cudaStream_t)stream;
+  for (size_t i = 0; i < pl->ops.size(); ++i) {
+    const ly_op& op = pl->ops[i];
+    float* nchw = op.nchw;
+    if (op.ext_slot >= 0) {
+      LY_CHECK_ARG(ext && op.ext_slot < n_ext && ext[op.ext_slot], "ly_plan_run: op %d needs ext[%d]", (int)i, op.ext_slot);
+      // offset by img0 whole images of the external NCHW tensor
+      long long per_img;
+      if (op.kind == LY_OP_STEM) per_img = 3LL * (2 * op.dst.H) * (2 * op.dst.W);
+      else if (op.kind == LY_OP_IMPORT) per_img = (long long)op.nchw_ctot * op.dst.H * op.dst.W;
+      else if (op.kind == LY_OP_EXPORT) per_img = (long long)op.nchw_ctot * op.src.H * op.src.W;
+      else per_img = (long long)op.nchw_ctot * (op.src.H / op.stride) * (op.src.W / op.stride);
+      nchw = ext[op.ext_slot] + (long long)img0 * per_img;
+    }
+    int32_t rc;
+    if (pl->tc[i]) {
+      rc = conv_tc_launch(pl->tc[i], op.ext_slot >= 0 ? nchw : nullptr, s);
+    } else {
+      ly_op tmp = op;
+      tmp.nchw = nchw;
+      rc = dispatch(tmp, s);
+    }
+    if (rc != LY_OK) {
+      char msg[400];
+      snprintf(msg, sizeof(msg), "%s", g_err);
+      set_error("plan op %d (kind %d): %s", (int)i, op.kind, msg);
+      return rc;
+    }
+  }
+  return LY_OK;
+}
+
+int32_t ly_plan_num_launches(const ly_plan* pl) { return pl ? (int32_t)pl->ops.size() : 0; }
+
+void ly_plan_destroy(ly_plan* pl) { delete pl; }
+
+}  // extern "C"

@@ -1,0 +1,119 @@
+// Shared helpers for the leanyolo_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <atomic>
+#include "../../include/leanyolo_b200.h"
+
+namespace ly {
+
+// ---- error plumbing ---------------------------------------------------------
+void set_error(const char* fmt, ...);
+extern std::atomic<long long> g_launches;
+
+#define LY_CHECK_ARG(cond, ...)                 \
+  do {                                          \
+    if (!(cond)) {                              \
+      ly::set_error(__VA_ARGS__);               \
+      return LY_E_ARG;                          \
+    }                                           \
+  } while (0)
+
+#define LY_CUDA(call)                                                                   \
+  do {                                                                                  \
+    cudaError_t e__ = (call);                                                           \
+    if (e__ != cudaSuccess) {                                                           \
+      ly::set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+      return LY_E_CUDA;                                                                 \
+    }                                                                                   \
+  } while (0)
+
+inline int32_t post_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("launch of %s failed: %s", what, cudaGetErrorString(e));
+    return LY_E_CUDA;
+  }
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return LY_OK;
+}
+
+// ---- per-op launchers (defined in the .cu files) ----------------------------
+int32_t launch_stem(const ly_op& op, cudaStream_t s);
+int32_t launch_conv_simt(const ly_op& op, cudaStream_t s);
+int32_t launch_dw(const ly_op& op, cudaStream_t s);
+int32_t launch_pool(const ly_op& op, cudaStream_t s);
+int32_t launch_up(const ly_op& op, cudaStream_t s);
+int32_t launch_attn(const ly_op& op, cudaStream_t s);
+int32_t launch_export(const ly_op& op, cudaStream_t s);
+int32_t launch_import(const ly_op& op, cudaStream_t s);
+
+// tcgen05 implicit-GEMM conv: tensor maps are encoded once (prepare) and reused.
+struct ConvTcState;
+int32_t conv_tc_prepare(const ly_op& op, ConvTcState** out);
+int32_t conv_tc_launch(const ConvTcState* st, float* nchw_override, cudaStream_t s);
+void conv_tc_free(ConvTcState* st);
+bool conv_tc_supported(const ly_op& op);
+
+int sm_count();
+
+// ---- device helpers ---------------------------------------------------------
+#ifdef __CUDACC__
+
+__device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+// check-mode SiLU: full-precision expf and IEEE division (1e-4 parity vs the fp32 oracle)
+__device__ __forceinline__ float silu_precise(float x) { return x / (1.0f + expf(-x)); }
+
+template <typename T> struct Elem;
+template <> struct Elem<float> {
+  static constexpr int kVec = 4;  // elements per 16-byte vector
+  __device__ static __forceinline__ float to_f(float v) { return v; }
+  __device__ static __forceinline__ float from_f(float v) { return v; }
+  __device__ static __forceinline__ float act(float v) { return silu_precise(v); }
+};
+template <> struct Elem<__nv_bfloat16> {
+  static constexpr int kVec = 8;
+  __device__ static __forceinline__ float to_f(__nv_bfloat16 v) { return __bfloat162float(v); }
+  __device__ static __forceinline__ __nv_bfloat16 from_f(float v) { return __float2bfloat16_rn(v); }
+  __device__ static __forceinline__ float act(float v) { return silu_f(v); }
+};
+
+// 16-byte vector of T <-> float[kVec]
+template <typename T>
+__device__ __forceinline__ void load_vec(const T* p, float* out);
+template <>
+__device__ __forceinline__ void load_vec<float>(const float* p, float* out) {
+  float4 v = *reinterpret_cast<const float4*>(p);
+  out[0] = v.x; out[1] = v.y; out[2] = v.z; out[3] = v.w;
+}
+template <>
+__device__ __forceinline__ void load_vec<__nv_bfloat16>(const __nv_bfloat16* p, float* out) {
+  uint4 v = *reinterpret_cast<const uint4*>(p);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 f = __bfloat1622float2(h[i]);
+    out[2 * i] = f.x;
+    out[2 * i + 1] = f.y;
+  }
+}
+template <typename T>
+__device__ __forceinline__ void store_vec(T* p, const float* in);
+template <>
+__device__ __forceinline__ void store_vec<float>(float* p, const float* in) {
+  *reinterpret_cast<float4*>(p) = make_float4(in[0], in[1], in[2], in[3]);
+}
+template <>
+__device__ __forceinline__ void store_vec<__nv_bfloat16>(__nv_bfloat16* p, const float* in) {
+  uint4 v;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(in[2 * i], in[2 * i + 1]);
+  *reinterpret_cast<uint4*>(p) = v;
+}
+
+#endif  // __CUDACC__
+
+}  // namespace ly

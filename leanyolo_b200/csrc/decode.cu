@@ -1,0 +1,524 @@
+// GPU-resident detection tail.
+//
+//  dfl_kernel    DFL softmax-expectation + anchor decode + sigmoid, one thread per anchor.
+//                (postprocess.py:217-235 / 103-131, utils/tal.py:10-46)  -- HBM-bound: reads
+//                (4*reg_max+nc)*4 B per anchor once, coalesced along the anchor axis.
+//  topk_kernel   two-stage top-k (postprocess.py:243-261), one CTA per image: 64-bit
+//                radix-select + bitonic sort in shared memory.  Keys are
+//                (score bits << 32 | ~index): all distinct, so the canonical tie rule
+//                (score desc, index asc) is exact and the result is deterministic.
+//  nms_kernel    greedy IoU NMS (box_ops.py:49-78), one CTA per image: candidate compaction,
+//                bitonic sort by (score desc, index asc), then chunks of 512 candidates:
+//                (A) suppression by the already-kept set, (B) 512x512 IoU bitmask,
+//                (C) warp-ballot sequential scan.  Stops at max_keep survivors -- identical
+//                to the reference's run-to-exhaustion + [:max_det] (later boxes never affect
+//                earlier decisions).  IoU uses the reference's exact fp32 operation order
+//                with explicitly rounded intrinsics (no FMA contraction) so keep-sets are
+//                bit-exact against the CPU oracle on identical inputs.
+#include "common.cuh"
+
+namespace ly {
+
+namespace {
+
+constexpr int TOPK_MAX = 1024;   // max_det supported by the per-CTA sort buffers
+constexpr int NMS_CH = 512;      // candidates per NMS chunk
+constexpr int NT = 1024;
+
+struct Levels {
+  const float* p[4];
+  int H[4], W[4], stride[4], off[4];  // off = first global anchor index of the level
+  int n, B, nc, reg_max, A, direct, clamp_h, clamp_w;
+};
+
+__device__ __forceinline__ float sigmoid_precise(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+__device__ __forceinline__ int level_of(const Levels& lv, int g) {
+  int l = 0;
+#pragma unroll
+  for (int i = 1; i < 4; ++i)
+    if (i < lv.n && g >= lv.off[i]) l = i;
+  return l;
+}
+
+// ------------------------------------------------------------------------------------ DFL
+__global__ void __launch_bounds__(256)
+dfl_kernel(Levels lv, float* __restrict__ boxes, float* __restrict__ best, int* __restrict__ label) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (g >= lv.A) return;
+  const int l = level_of(lv, g);
+  const int a = g - lv.off[l];
+  const int HW = lv.H[l] * lv.W[l];
+  const int y = a / lv.W[l], x = a - y * lv.W[l];
+  const float s = (float)lv.stride[l];
+  const int creg = lv.direct ? 4 : 4 * lv.reg_max;
+  const float* p = lv.p[l] + (long long)b * (creg + lv.nc) * HW + a;
+  float x1, y1, x2, y2;
+  if (lv.direct) {
+    // postprocess.py:70-92: sigmoid centre offsets on the integer grid, exp sizes
+    const float cx = (sigmoid_precise(p[0]) + (float)x) * s;
+    const float cy = (sigmoid_precise(p[(long long)HW]) + (float)y) * s;
+    const float bw = expf(p[2LL * HW]) * s, bh = expf(p[3LL * HW]) * s;
+    x1 = cx - bw / 2; y1 = cy - bh / 2; x2 = cx + bw / 2; y2 = cy + bh / 2;
+    if (lv.clamp_w > 0) {
+      x1 = fminf(fmaxf(x1, 0.f), (float)lv.clamp_w); x2 = fminf(fmaxf(x2, 0.f), (float)lv.clamp_w);
+      y1 = fminf(fmaxf(y1, 0.f), (float)lv.clamp_h); y2 = fminf(fmaxf(y2, 0.f), (float)lv.clamp_h);
+    }
+  } else {
+    float d[4];
+#pragma unroll
+    for (int side = 0; side < 4; ++side) {
+      const float* q = p + (long long)side * lv.reg_max * HW;
+      float mx = -INFINITY;
+      for (int i = 0; i < lv.reg_max; ++i) mx = fmaxf(mx, q[(long long)i * HW]);
+      float den = 0.f, num = 0.f;
+      for (int i = 0; i < lv.reg_max; ++i) {
+        const float e = expf(q[(long long)i * HW] - mx);
+        den += e;
+        num += e * (float)i;
+      }
+      d[side] = num / den;
+    }
+    const float ax = (float)x + 0.5f, ay = (float)y + 0.5f;
+    x1 = (ax - d[0]) * s; y1 = (ay - d[1]) * s; x2 = (ax + d[2]) * s; y2 = (ay + d[3]) * s;
+  }
+  const float* c = p + (long long)creg * HW;
+  float bs = -1.f;
+  int bl = 0;
+  for (int i = 0; i < lv.nc; ++i) {
+    const float v = sigmoid_precise(c[(long long)i * HW]);
+    if (v > bs) { bs = v; bl = i; }   // first maximum wins, like torch.max
+  }
+  const long long o = (long long)b * lv.A + g;
+  reinterpret_cast<float4*>(boxes)[o] = make_float4(x1, y1, x2, y2);
+  best[o] = bs;
+  label[o] = bl;
+}
+
+// ------------------------------------------------------------------- block-wide primitives
+__device__ __forceinline__ unsigned orderable(float f) {
+  const unsigned u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+// k-th largest of n DISTINCT 64-bit keys (k in [1,n]); key(i) may be called many times.
+template <typename KeyFn>
+__device__ unsigned long long block_kth_largest(KeyFn key, int n, int k, unsigned* hist, unsigned* bcast) {
+  unsigned long long prefix = 0, mask = 0;
+  for (int pass = 7; pass >= 0; --pass) {
+    const int shift = pass * 8;
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    for (int i0 = 0; i0 < n; i0 += blockDim.x) {
+      const int i = i0 + threadIdx.x;
+      unsigned digit = 0xFFFFFFFFu;  // sentinel: not a candidate
+      if (i < n) {
+        const unsigned long long kk = key(i);
+        if ((kk & mask) == prefix) digit = (unsigned)(kk >> shift) & 255u;
+      }
+      // warp-aggregated histogram: one shared atomic per distinct digit per warp
+      const unsigned peers = __match_any_sync(0xFFFFFFFFu, digit);
+      if (digit != 0xFFFFFFFFu && (__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&hist[digit], __popc(peers));
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int cum = 0, d = 255;
+      for (; d > 0; --d) {
+        if (cum + (int)hist[d] >= k) break;
+        cum += hist[d];
+      }
+      bcast[0] = d;
+      bcast[1] = k - cum;
+    }
+    __syncthreads();
+    prefix |= (unsigned long long)bcast[0] << shift;
+    mask |= 0xFFull << shift;
+    k = bcast[1];
+    __syncthreads();
+  }
+  return prefix;
+}
+
+// in-place bitonic sort, descending, n a power of two, buffer in shared or global memory
+__device__ void block_bitonic_desc(unsigned long long* a, int n) {
+  for (int size = 2; size <= n; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int t = threadIdx.x; t < (n >> 1); t += blockDim.x) {
+        const int lo = 2 * t - (t & (stride - 1));
+        const int hi = lo + stride;
+        const bool desc = (lo & size) == 0;
+        const unsigned long long x = a[lo], y = a[hi];
+        if ((x < y) == desc) { a[lo] = y; a[hi] = x; }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+__device__ __forceinline__ int next_pow2(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+// ----------------------------------------------------------------------------------- top-k
+__global__ void __launch_bounds__(NT)
+topk_kernel(Levels lv, int k, const float* __restrict__ boxes, const float* __restrict__ best, float* s2,
+            float* __restrict__ out, int* __restrict__ out_anchor, int* __restrict__ out_cls) {
+  __shared__ unsigned long long sortbuf[TOPK_MAX];
+  __shared__ int anchors[TOPK_MAX];
+  __shared__ unsigned hist[256];
+  __shared__ unsigned bcast[2];
+  __shared__ int cnt;
+  const int b = blockIdx.x;
+  const int A = lv.A, nc = lv.nc;
+  const int P = next_pow2(k);
+  const float* bestb = best + (long long)b * A;
+
+  // ---- stage 1: top-k anchors by best class score
+  auto key1 = [&](int i) -> unsigned long long {
+    return ((unsigned long long)orderable(bestb[i]) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)i);
+  };
+  unsigned long long thr = block_kth_largest(key1, A, k, hist, bcast);
+  if (threadIdx.x == 0) cnt = 0;
+  for (int i = threadIdx.x; i < P; i += blockDim.x) sortbuf[i] = 0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < A; i += blockDim.x) {
+    const unsigned long long kk = key1(i);
+    if (kk >= thr) sortbuf[atomicAdd(&cnt, 1)] = kk;
+  }
+  __syncthreads();
+  block_bitonic_desc(sortbuf, P);
+  for (int r = threadIdx.x; r < k; r += blockDim.x) anchors[r] = (int)(0xFFFFFFFFu - (unsigned)(sortbuf[r] & 0xFFFFFFFFull));
+  __syncthreads();
+
+  // ---- stage 2: scores of the k selected anchors x nc classes
+  float* s2b = s2 + (long long)b * k * nc;
+  const int creg = 4 * lv.reg_max;
+  for (int i = threadIdx.x; i < k * nc; i += blockDim.x) {
+    const int r = i / nc, c = i - r * nc;
+    const int g = anchors[r];
+    const int l = level_of(lv, g);
+    const int HW = lv.H[l] * lv.W[l];
+    s2b[i] = sigmoid_precise(lv.p[l][((long long)b * (creg + nc) + creg + c) * HW + (g - lv.off[l])]);
+  }
+  __syncthreads();
+  auto key2 = [&](int i) -> unsigned long long {
+    return ((unsigned long long)orderable(s2b[i]) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)i);
+  };
+  thr = block_kth_largest(key2, k * nc, k, hist, bcast);
+  if (threadIdx.x == 0) cnt = 0;
+  for (int i = threadIdx.x; i < P; i += blockDim.x) sortbuf[i] = 0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < k * nc; i += blockDim.x) {
+    const unsigned long long kk = key2(i);
+    if (kk >= thr) sortbuf[atomicAdd(&cnt, 1)] = kk;
+  }
+  __syncthreads();
+  block_bitonic_desc(sortbuf, P);
+
+  for (int r = threadIdx.x; r < k; r += blockDim.x) {
+    const int flat = (int)(0xFFFFFFFFu - (unsigned)(sortbuf[r] & 0xFFFFFFFFull));
+    const int rel = flat / nc, c = flat - rel * nc;
+    const int g = anchors[rel];
+    const float4 bx = reinterpret_cast<const float4*>(boxes)[(long long)b * A + g];
+    float* o = out + ((long long)b * k + r) * 6;
+    o[0] = bx.x; o[1] = bx.y; o[2] = bx.z; o[3] = bx.w;
+    o[4] = s2b[flat];
+    o[5] = (float)c;
+    if (out_anchor) out_anchor[(long long)b * k + r] = g;
+    if (out_cls) out_cls[(long long)b * k + r] = c;
+  }
+}
+
+// ------------------------------------------------------------------------------------- NMS
+// IoU > thr, evaluated exactly like box_ops.py:31-46 in fp32 (each op individually rounded)
+__device__ __forceinline__ float box_area_rn(const float4& a) {
+  return __fmul_rn(fmaxf(__fsub_rn(a.z, a.x), 0.f), fmaxf(__fsub_rn(a.w, a.y), 0.f));
+}
+__device__ __forceinline__ bool iou_gt(const float4& a, float area_a, const float4& b, float area_b, float thr) {
+  const float w = fmaxf(__fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x)), 0.f);
+  const float h = fmaxf(__fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y)), 0.f);
+  const float inter = __fmul_rn(w, h);
+  const float uni = __fsub_rn(__fadd_rn(area_a, area_b), inter);
+  const float iou = __fdiv_rn(inter, __fadd_rn(uni, 1e-9f));
+  return iou > thr;
+}
+
+struct NmsSmem {
+  float4 kbox[TOPK_MAX];
+  float karea[TOPK_MAX];
+  int klabel[TOPK_MAX];
+  float4 cbox[NMS_CH];
+  float carea[NMS_CH];
+  int clabel[NMS_CH];
+  int cidx[NMS_CH];
+  unsigned alive[NMS_CH / 32];
+  unsigned mask[NMS_CH][NMS_CH / 32];
+  int n_cand, n_kept, done;
+};
+
+// boxes [B,N,4], scores [B,N], labels [B,N] or null.  A candidate is valid when
+// (n_valid ? i < n_valid[b] : true) && (use_conf ? score > conf : true).
+// sort_g: per-image global scratch of npad u64 (used when the keys do not fit in smem).
+__global__ void __launch_bounds__(NT)
+nms_kernel(const float* __restrict__ boxes, const float* __restrict__ scores, const int* __restrict__ labels,
+           const int* __restrict__ n_valid, int N, int npad, int use_conf, float conf, float thr, int max_keep,
+           int classwise, int sort_in_smem, unsigned long long* sort_g, int* __restrict__ keep,
+           int* __restrict__ keep_count, float* __restrict__ out_rows) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  NmsSmem& S = *reinterpret_cast<NmsSmem*>(smem_raw);
+  unsigned long long* sort_s = reinterpret_cast<unsigned long long*>(smem_raw + ((sizeof(NmsSmem) + 15) / 16) * 16);
+  const int b = blockIdx.x;
+  const float4* bx = reinterpret_cast<const float4*>(boxes) + (long long)b * N;
+  const float* sc = scores + (long long)b * N;
+  const int* lb = labels ? labels + (long long)b * N : nullptr;
+  const int nv = n_valid ? min(n_valid[b], N) : N;
+  unsigned long long* sb = sort_in_smem ? sort_s : sort_g + (long long)b * npad;
+
+  if (threadIdx.x == 0) { S.n_cand = 0; S.n_kept = 0; S.done = 0; }
+  __syncthreads();
+  // ---- compaction of valid candidates (order is irrelevant: the sort key carries the index)
+  for (int i = threadIdx.x; i < nv; i += blockDim.x) {
+    const float s = sc[i];
+    if (!use_conf || s > conf)
+      sb[atomicAdd(&S.n_cand, 1)] = ((unsigned long long)orderable(s) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)i);
+  }
+  __syncthreads();
+  const int n = S.n_cand;
+  const int P = next_pow2(n > 1 ? n : 1);
+  for (int i = n + threadIdx.x; i < P; i += blockDim.x) sb[i] = 0;
+  __syncthreads();
+  block_bitonic_desc(sb, P);
+
+  int* keepb = keep + (long long)b * max_keep;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int WORDS = NMS_CH / 32;
+
+  for (int c0 = 0; c0 < n; c0 += NMS_CH) {
+    const int m = min(NMS_CH, n - c0);
+    for (int i = threadIdx.x; i < NMS_CH; i += blockDim.x) {
+      if (i < m) {
+        const int idx = (int)(0xFFFFFFFFu - (unsigned)(sb[c0 + i] & 0xFFFFFFFFull));
+        const float4 v = bx[idx];
+        S.cidx[i] = idx;
+        S.cbox[i] = v;
+        S.carea[i] = box_area_rn(v);
+        S.clabel[i] = lb ? lb[idx] : 0;
+      }
+    }
+    for (int i = threadIdx.x; i < WORDS; i += blockDim.x) {
+      const int lo = i * 32;
+      S.alive[i] = m >= lo + 32 ? 0xFFFFFFFFu : (m > lo ? ((1u << (m - lo)) - 1u) : 0u);
+    }
+    __syncthreads();
+    // ---- (A) suppression by the kept set: one warp per candidate, lanes stride the kept list
+    const int nk = S.n_kept;
+    if (nk > 0) {
+      for (int i = warp; i < m; i += NT / 32) {
+        const float4 v = S.cbox[i];
+        const float av = S.carea[i];
+        const int lv = S.clabel[i];
+        bool hit = false;
+        for (int j = lane; j < nk && !hit; j += 32)
+          hit = (!classwise || S.klabel[j] == lv) && iou_gt(S.kbox[j], S.karea[j], v, av, thr);
+        if (__any_sync(0xFFFFFFFFu, hit) && lane == 0) atomicAnd(&S.alive[i >> 5], ~(1u << (i & 31)));
+      }
+    }
+    // ---- (B) intra-chunk bitmask: bit j of mask[i] set iff j > i and i suppresses j
+    for (int t = threadIdx.x; t < m * WORDS; t += blockDim.x) {
+      const int i = t / WORDS, wj = t - i * WORDS;
+      unsigned bits = 0;
+      if (wj * 32 + 31 > i) {
+        const float4 v = S.cbox[i];
+        const float av = S.carea[i];
+        const int lv = S.clabel[i];
+        const int jend = min(32, m - wj * 32);
+        for (int jj = 0; jj < jend; ++jj) {
+          const int j = wj * 32 + jj;
+          if (j > i && (!classwise || S.clabel[j] == lv) && iou_gt(v, av, S.cbox[j], S.carea[j], thr)) bits |= 1u << jj;
+        }
+      }
+      S.mask[i][wj] = bits;
+    }
+    __syncthreads();
+    // ---- (C) sequential scan by warp 0: lane w owns word w of the "removed" set
+    if (warp == 0) {
+      unsigned removed = lane < WORDS ? ~S.alive[lane] : 0xFFFFFFFFu;
+      int kept = S.n_kept;
+      for (int wi = 0; wi < (m + 31) / 32 && kept < max_keep; ++wi) {
+        // candidates of word wi that are still alive form the work list; resolve in order
+        unsigned cur = __shfl_sync(0xFFFFFFFFu, removed, wi);
+        for (int bit = 0; bit < 32 && kept < max_keep; ++bit) {
+          const int i = wi * 32 + bit;
+          if (i >= m) break;
+          if (cur & (1u << bit)) continue;
+          // keep i
+          if (lane == 0) {
+            S.kbox[kept] = S.cbox[i];
+            S.karea[kept] = S.carea[i];
+            S.klabel[kept] = S.clabel[i];
+            keepb[kept] = S.cidx[i];
+          }
+          ++kept;
+          if (lane < WORDS) removed |= S.mask[i][lane];
+          cur = __shfl_sync(0xFFFFFFFFu, removed, wi);
+        }
+      }
+      if (lane == 0) {
+        S.n_kept = kept;
+        if (kept >= max_keep) S.done = 1;
+      }
+    }
+    __syncthreads();
+    if (S.done) break;
+  }
+  __syncthreads();
+  const int kept = S.n_kept;
+  if (threadIdx.x == 0) keep_count[b] = kept;
+  for (int r = kept + threadIdx.x; r < max_keep; r += blockDim.x) keepb[r] = -1;
+  if (out_rows) {
+    for (int r = threadIdx.x; r < max_keep; r += blockDim.x) {
+      float* o = out_rows + ((long long)b * max_keep + r) * 6;
+      if (r < kept) {
+        const int idx = keepb[r];
+        const float4 v = S.kbox[r];
+        o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+        o[4] = sc[idx];
+        o[5] = (float)S.klabel[r];
+      } else {
+        o[0] = o[1] = o[2] = o[3] = o[4] = o[5] = 0.f;
+      }
+    }
+  }
+}
+
+int32_t make_levels(const ly_levels* in, Levels& lv) {
+  LY_CHECK_ARG(in && in->n_levels >= 1 && in->n_levels <= 4, "decode: n_levels must be 1..4");
+  LY_CHECK_ARG(in->B >= 1 && in->nc >= 1 && in->reg_max >= 1, "decode: bad B/nc/reg_max");
+  lv.n = in->n_levels; lv.B = in->B; lv.nc = in->nc; lv.reg_max = in->reg_max;
+  lv.direct = in->direct; lv.clamp_h = in->clamp_h; lv.clamp_w = in->clamp_w;
+  int off = 0;
+  for (int i = 0; i < 4; ++i) {
+    if (i < lv.n) {
+      LY_CHECK_ARG(in->preds[i] && in->H[i] > 0 && in->W[i] > 0, "decode: bad level %d", i);
+      lv.p[i] = in->preds[i]; lv.H[i] = in->H[i]; lv.W[i] = in->W[i]; lv.stride[i] = in->stride[i];
+      lv.off[i] = off;
+      off += in->H[i] * in->W[i];
+    } else {
+      lv.p[i] = nullptr; lv.H[i] = lv.W[i] = lv.stride[i] = 0; lv.off[i] = 0x7FFFFFFF;
+    }
+  }
+  lv.A = off;
+  return LY_OK;
+}
+
+inline long long rup256(long long v) { return (v + 255) / 256 * 256; }
+inline int pow2_ge(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+
+struct Scratch {
+  float* boxes; float* best; int* label; float* s2; unsigned long long* sortbuf; int* keep; int* count;
+  long long total;
+};
+
+Scratch carve(void* base, int B, int A, int nc, int max_det) {
+  Scratch s;
+  long long o = 0;
+  auto take = [&](long long bytes) { long long r = o; o += rup256(bytes); return (char*)base + r; };
+  s.boxes = (float*)take((long long)B * A * 16);
+  s.best = (float*)take((long long)B * A * 4);
+  s.label = (int*)take((long long)B * A * 4);
+  s.s2 = (float*)take((long long)B * (max_det < A ? max_det : A) * nc * 4);
+  s.sortbuf = (unsigned long long*)take((long long)B * pow2_ge(A) * 8);
+  s.keep = (int*)take((long long)B * max_det * 4);
+  s.count = (int*)take((long long)B * 4);
+  s.total = o;
+  return s;
+}
+
+constexpr int kSmemSortMaxKeys = 16384;  // 128 KB of keys next to ~65 KB of NMS state
+
+int32_t run_nms(const float* boxes, const float* scores, const int* labels, const int* n_valid, int B, int N,
+                int use_conf, float conf, float thr, int max_keep, int classwise, unsigned long long* sort_g,
+                int* keep, int* keep_count, float* out_rows, cudaStream_t st) {
+  LY_CHECK_ARG(max_keep >= 1 && max_keep <= TOPK_MAX, "nms: max_keep must be in 1..%d", TOPK_MAX);
+  const int npad = pow2_ge(N);
+  const int in_smem = npad <= kSmemSortMaxKeys;
+  const size_t smem = ((sizeof(NmsSmem) + 15) / 16) * 16 + (in_smem ? (size_t)npad * 8 : 0);
+  static bool attr_set = false;
+  if (!attr_set) {
+    LY_CUDA(cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  nms_kernel<<<B, NT, smem, st>>>(boxes, scores, labels, n_valid, N, npad, use_conf, conf, thr, max_keep, classwise,
+                                  in_smem, sort_g, keep, keep_count, out_rows);
+  return post_launch("nms");
+}
+
+}  // namespace
+
+}  // namespace ly
+
+using namespace ly;
+
+extern "C" int64_t ly_decode_scratch_bytes(const ly_levels* in, int32_t max_det) {
+  Levels lv;
+  if (make_levels(in, lv) != LY_OK || max_det < 1) return -1;
+  return carve(nullptr, lv.B, lv.A, lv.nc, max_det).total;
+}
+
+extern "C" int32_t ly_decode_topk(const ly_levels* in, int32_t max_det, float* out, int32_t* out_anchor, int32_t* out_cls,
+                                  void* scratch, int64_t scratch_bytes, void* stream) {
+  Levels lv;
+  int32_t rc = make_levels(in, lv);
+  if (rc != LY_OK) return rc;
+  LY_CHECK_ARG(!lv.direct, "decode_topk: DFL layout only");
+  LY_CHECK_ARG(max_det >= 1 && max_det <= TOPK_MAX, "decode_topk: max_det must be in 1..%d", TOPK_MAX);
+  LY_CHECK_ARG(out && scratch, "decode_topk: null pointer");
+  Scratch s = carve(scratch, lv.B, lv.A, lv.nc, max_det);
+  LY_CHECK_ARG(scratch_bytes >= s.total, "decode_topk: scratch too small (%lld < %lld)", (long long)scratch_bytes, s.total);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int k = max_det < lv.A ? max_det : lv.A;
+  dim3 g1((lv.A + 255) / 256, lv.B);
+  dfl_kernel<<<g1, 256, 0, st>>>(lv, s.boxes, s.best, s.label);
+  rc = post_launch("dfl_decode");
+  if (rc != LY_OK) return rc;
+  topk_kernel<<<lv.B, NT, 0, st>>>(lv, k, s.boxes, s.best, s.s2, out, out_anchor, out_cls);
+  return post_launch("topk");
+}
+
+extern "C" int32_t ly_decode_nms(const ly_levels* in, float conf_thresh, float iou_thresh, int32_t max_det, int32_t classwise,
+                                 float* out, int32_t* out_count, int32_t* out_anchor, void* scratch, int64_t scratch_bytes,
+                                 void* stream) {
+  Levels lv;
+  int32_t rc = make_levels(in, lv);
+  if (rc != LY_OK) return rc;
+  LY_CHECK_ARG(out && out_count && scratch, "decode_nms: null pointer");
+  LY_CHECK_ARG(max_det >= 1 && max_det <= TOPK_MAX, "decode_nms: max_det must be in 1..%d", TOPK_MAX);
+  Scratch s = carve(scratch, lv.B, lv.A, lv.nc, max_det);
+  LY_CHECK_ARG(scratch_bytes >= s.total, "decode_nms: scratch too small (%lld < %lld)", (long long)scratch_bytes, s.total);
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 g1((lv.A + 255) / 256, lv.B);
+  dfl_kernel<<<g1, 256, 0, st>>>(lv, s.boxes, s.best, s.label);
+  rc = post_launch("dfl_decode");
+  if (rc != LY_OK) return rc;
+  return run_nms(s.boxes, s.best, s.label, nullptr, lv.B, lv.A, 1, conf_thresh, iou_thresh, max_det, classwise, s.sortbuf,
+                 out_anchor ? out_anchor : s.keep, out_count, out, st);
+}
+
+extern "C" int64_t ly_nms_scratch_bytes(int32_t B, int32_t N) {
+  if (B < 1 || N < 1) return -1;
+  return rup256((long long)B * pow2_ge(N) * 8);
+}
+
+extern "C" int32_t ly_nms(const float* boxes, const float* scores, const int32_t* labels, const int32_t* n_valid, int32_t B,
+                          int32_t N, float iou_thresh, int32_t max_keep, int32_t classwise, int32_t* keep,
+                          int32_t* keep_count, void* scratch, int64_t scratch_bytes, void* stream) {
+  LY_CHECK_ARG(boxes && scores && keep && keep_count && scratch, "nms: null pointer");
+  LY_CHECK_ARG(B >= 1 && N >= 1, "nms: B and N must be >= 1");
+  LY_CHECK_ARG(!classwise || labels, "nms: classwise needs labels");
+  LY_CHECK_ARG(scratch_bytes >= ly_nms_scratch_bytes(B, N), "nms: scratch too small");
+  return run_nms(boxes, scores, labels, n_valid, B, N, 0, 0.f, iou_thresh, max_keep, classwise,
+                 (unsigned long long*)scratch, keep, keep_count, nullptr, (cudaStream_t)stream);
+}

@@ -1,0 +1,149 @@
+"""Executes a lowered plan on the GPU through the C ABI.
+
+Host-side runtime of the hot path: owns the device copy of the packed parameters,
+one workspace per (batch, H, W) shape, the native ``ly_plan`` (tensor maps encoded
+once) and optional CUDA-graph capture of the whole forward.  PyTorch is used only
+for device memory and streams.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+from typing import Callable, Dict, List, Optional, Tuple
+
+import torch
+
+from . import _native as N
+from .plan import Op, PlanBuilder, View
+
+_KIND = {"stem": N.OP_STEM, "conv": N.OP_CONV, "dw": N.OP_DW, "pool": N.OP_POOL, "up": N.OP_UP,
+         "attn": N.OP_ATTN, "export": N.OP_EXPORT, "import": N.OP_IMPORT}
+
+
+def _view(v: Optional[View], base: int) -> N.LyView:
+    if v is None:
+        return N.LyView(None, 0, 0, 0, 0, 0)
+    return N.LyView(base + v.buf.offset, v.H, v.W, v.buf.C, v.c0, v.c)
+
+
+@dataclass
+class Compiled:
+    pb: PlanBuilder
+    B: int
+    workspace: torch.Tensor
+    handle: C.c_void_p
+    out_keys: List[Tuple[str, int]]
+    n_launches: int
+
+
+class Engine:
+    """One per (model, dtype).  ``emit`` fills a PlanBuilder for a batch of ``B`` images."""
+
+    def __init__(self, emit: Callable[[PlanBuilder], None], device: torch.device, dtype: str = "bf16",
+                 conv_impl: Optional[str] = None):
+        if device.type != "cuda":
+            raise RuntimeError("leanyolo_b200 runs on CUDA (sm_100a) only; there is no CPU path")
+        self.emit, self.device, self.dtype = emit, device, dtype
+        impl = conv_impl or os.environ.get("LEANYOLO_CONV_IMPL", "auto")
+        self.impl = N.IMPL_SIMT if impl == "simt" else N.IMPL_AUTO
+        self.lib = N.lib()
+        with torch.cuda.device(device):
+            sms = C.c_int32(0)
+            N.check(self.lib.ly_device_check(C.byref(sms)), "ly_device_check")
+        self.sm_count = sms.value
+        self._plans: Dict[Tuple[int, int, int], Compiled] = {}
+        self._w: Optional[torch.Tensor] = None
+        self._b: Optional[torch.Tensor] = None
+        self._graphs: Dict[Tuple, Tuple[torch.cuda.CUDAGraph, torch.Tensor, Dict]] = {}
+
+    # ------------------------------------------------------------------ build
+    def compile(self, B: int, H: int, W: int) -> Compiled:
+        key = (B, H, W)
+        if key in self._plans:
+            return self._plans[key]
+        pb = PlanBuilder(B, H, W, self.dtype)
+        self.emit(pb)
+        w, b = pb.finalize_params()
+        if self._w is None:
+            self._w, self._b = w.to(self.device), b.to(self.device)
+        else:
+            assert self._w.numel() == w.numel() and self._b.numel() == b.numel(), "parameter packing is shape dependent"
+        ws = torch.empty(max(pb.ws_bytes, 1024), dtype=torch.uint8, device=self.device)
+        out_keys = sorted(pb.outputs.keys())
+        slots = {k: i + 1 for i, k in enumerate(out_keys)}
+        arr = (N.LyOp * len(pb.ops))()
+        base, wbase, bbase = ws.data_ptr(), self._w.data_ptr(), self._b.data_ptr()
+        esz = pb.esize
+        dt = N.LY_BF16 if self.dtype == "bf16" else N.LY_F32
+        for i, op in enumerate(pb.ops):
+            o = arr[i]
+            o.kind, o.dtype, o.B = _KIND[op.kind], dt, B
+            o.k, o.stride, o.act, o.impl = op.k, op.stride, int(op.act), self.impl
+            o.src, o.dst, o.res = _view(op.src, base), _view(op.dst, base), _view(op.res, base)
+            o.ext_slot = -1
+            if op.kind == "stem":
+                o.w, o.bias = bbase + 4 * op.w_off, bbase + 4 * op.b_off
+                for j in range(3):
+                    o.sub[j], o.div[j] = op.extra["sub"][j], op.extra["div"][j]
+                o.ext_slot = 0
+            elif op.w_off >= 0:
+                o.w, o.bias = wbase + esz * op.w_off, bbase + 4 * op.b_off
+            if op.attn is not None:
+                o.nh, o.kdp, o.hd, o.scale = op.attn
+            if op.nchw is not None:
+                name, level, c0, c, ctot = op.nchw
+                o.nchw_ctot, o.nchw_c0, o.nchw_c = ctot, c0, c
+                o.ext_slot = slots[(name, level)]
+        handle = C.c_void_p()
+        with torch.cuda.device(self.device):
+            N.check(self.lib.ly_plan_create(arr, len(pb.ops), C.byref(handle)), "ly_plan_create")
+        comp = Compiled(pb, B, ws, handle, out_keys, len(pb.ops))
+        self._plans[key] = comp
+        return comp
+
+    # ------------------------------------------------------------------ run
+    def _launch(self, comp: Compiled, x: torch.Tensor, outs: Dict[Tuple[str, int], torch.Tensor], img0: int) -> None:
+        ext = (C.c_void_p * (1 + len(comp.out_keys)))()
+        ext[0] = x.data_ptr()
+        for i, k in enumerate(comp.out_keys):
+            ext[i + 1] = outs[k].data_ptr()
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        N.check(self.lib.ly_plan_run(comp.handle, ext, len(ext), img0, C.c_void_p(stream)), "ly_plan_run")
+
+    def alloc_outputs(self, B: int, H: int, W: int, sub: int) -> Dict[Tuple[str, int], torch.Tensor]:
+        comp = self.compile(sub, H, W)
+        return {k: torch.empty((B, c, h, w), dtype=torch.float32, device=self.device)
+                for k, (c, h, w) in comp.pb.outputs.items()}
+
+    def run(self, x: torch.Tensor, sub_batch: Optional[int] = None,
+            outs: Optional[Dict[Tuple[str, int], torch.Tensor]] = None) -> Dict[Tuple[str, int], torch.Tensor]:
+        """x: [B,3,H,W] fp32 contiguous on the engine's device.  Returns {(name, level): NCHW fp32}."""
+        assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 4 and x.shape[1] == 3
+        B, _, H, W = x.shape
+        sub = min(B, sub_batch) if sub_batch else B
+        with torch.cuda.device(self.device):
+            if outs is None:
+                outs = self.alloc_outputs(B, H, W, sub)
+            for img0 in range(0, B, sub):
+                n = min(sub, B - img0)
+                self._launch(self.compile(n, H, W), x, outs, img0)
+        return outs
+
+    def launches_per_forward(self, B: int, H: int, W: int, sub_batch: Optional[int] = None) -> int:
+        sub = min(B, sub_batch) if sub_batch else B
+        total = 0
+        for img0 in range(0, B, sub):
+            total += self.compile(min(sub, B - img0), H, W).n_launches
+        return total
+
+    def close(self) -> None:
+        for comp in self._plans.values():
+            self.lib.ly_plan_destroy(comp.handle)
+        self._plans.clear()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,158 @@
+"""YOLOv10 model façade: the reference's ``nn.Module`` surface over the CUDA plan.
+
+``model(x)`` and ``model.decode_forward(raw)`` keep the reference contract
+(leanyolo/models/yolov10/yolov10s.py:105-144): eval forward returns the three
+contiguous NCHW fp32 one2many head tensors and caches both branches in
+``_eval_branches``; ``decode_forward`` runs the top-k decode on the one2one
+branch.  All arithmetic happens in hand-written sm_100a kernels
+(``csrc/``); there is no PyTorch or CPU compute fallback.
+
+Extras that do not change the reference surface:
+* ``model.precision``  "bf16" (tensor-core hot path) or "fp32" (CUDA-core check mode).
+* ``model.detect(x)``  forward + GPU top-k decode returning a fixed ``[B,k,6]`` tensor.
+* ``model.sub_batch``  images per plan sweep (keeps producer->consumer tensors in L2).
+"""
+from __future__ import annotations
+
+import os
+from typing import Dict, List, Optional, Sequence
+
+import torch
+import torch.nn as nn
+
+from . import postprocess as PP
+from .engine import Engine
+from .modules import Backbone, Detect, Neck
+from .variants import REG_MAX, STRIDES, VARIANTS, Variant
+
+
+class YOLOv10(nn.Module):
+    variant: Variant
+
+    def __init__(self, *, class_names: Sequence[str], in_channels: int = 3,
+                 input_norm_subtract: Sequence[float] = (0.0, 0.0, 0.0),
+                 input_norm_divide: Sequence[float] = (255.0, 255.0, 255.0)):
+        super().__init__()
+        if in_channels != 3:
+            raise ValueError("leanyolo_b200 supports 3-channel RGB input only")
+        self.class_names = list(class_names)
+        self.register_buffer("input_subtract", torch.tensor(list(input_norm_subtract), dtype=torch.float32).view(1, 3, 1, 1))
+        self.register_buffer("input_divide", torch.tensor(list(input_norm_divide), dtype=torch.float32).view(1, 3, 1, 1))
+        v = self.variant
+        self.backbone = Backbone(v, in_channels)
+        self.neck = Neck(v, *self.backbone.out_c)
+        self.head = Detect(len(self.class_names), self.neck.out_c, REG_MAX)
+        self.precision = os.environ.get("LEANYOLO_PRECISION", "bf16")
+        sb = os.environ.get("LEANYOLO_SUB_BATCH")
+        self.sub_batch: Optional[int] = int(sb) if sb else None
+        self._engines: Dict[tuple, Engine] = {}
+        self._eval_branches: Dict[str, List[torch.Tensor]] = {}
+
+    # ---- class tables kept for callers that introspect them (yolov10s.py:62-65)
+    @property
+    def CH(self):
+        return dict(enumerate(self.variant.width))
+
+    @property
+    def HCH(self):
+        return dict(self.variant.neck)
+
+    @property
+    def REPS(self):
+        return dict(self.variant.reps)
+
+    # ------------------------------------------------------------------ lowering
+    def emit(self, pb, taps: bool = False) -> None:
+        """Lower the whole eval forward (both head branches) into ``pb``."""
+        bb, nk, hd = self.backbone, self.neck, self.head
+        w0, b0 = bb.cv0.folded()
+        x = pb.stem(w0, b0, self.input_subtract.flatten().tolist(), self.input_divide.flatten().tolist())
+        cats = nk.concat_buffers(pb, pb.H // 8, pb.W // 8)
+        c3w, c4w, c5w, h13, h16, h19, _ = nk.widths
+        c3, c4, c5 = bb.emit(pb, x, cats["cat_p3"].view(h13, c3w), cats["cat_p4"].view(c5w, c4w),
+                             cats["cat_n5"].view(h19, c5w))
+        p3, p4, p5 = nk.emit(pb, cats)
+        if taps:
+            for name, v, c in (("c3", c3, c3w), ("c4", c4, c4w), ("c5", c5, c5w), ("p3", p3, nk.out_c[0]),
+                               ("p4", p4, nk.out_c[1]), ("p5", p5, nk.out_c[2])):
+                pb.export_nchw(v, name, c)
+        hd.emit_branch(pb, (p3, p4, p5), hd.cv2, hd.cv3, "one2many")
+        hd.emit_branch(pb, (p3, p4, p5), hd.one2one_cv2, hd.one2one_cv3, "one2one")
+
+    def invalidate(self) -> None:
+        """Drop packed weights / plans (call after mutating parameters in place)."""
+        for e in self._engines.values():
+            e.close()
+        self._engines.clear()
+
+    def load_state_dict(self, *args, **kwargs):
+        ret = super().load_state_dict(*args, **kwargs)
+        self.invalidate()
+        return ret
+
+    def _apply(self, fn, *args, **kwargs):
+        ret = super()._apply(fn, *args, **kwargs)
+        self.invalidate()
+        return ret
+
+    def engine(self, device: torch.device, taps: bool = False) -> Engine:
+        prec = "f32" if self.precision in ("fp32", "f32", "float32") else "bf16"
+        key = (str(device), prec, taps)
+        if key not in self._engines:
+            self._engines[key] = Engine(lambda pb: self.emit(pb, taps), device, prec)
+        return self._engines[key]
+
+    # ------------------------------------------------------------------ reference surface
+    def _run(self, x: torch.Tensor, taps: bool = False):
+        if self.training:
+            raise NotImplementedError("leanyolo_b200 is inference-only: call model.eval() first "
+                                      "(training stays with the reference implementation)")
+        dev = self.input_subtract.device
+        if dev.type != "cuda" or not x.is_cuda:
+            raise RuntimeError("leanyolo_b200 runs on CUDA (sm_100a) only: move the model and the input to the GPU; "
+                               "there is no CPU fallback")
+        if x.dim() != 4 or x.shape[1] != 3 or x.shape[2] % 32 or x.shape[3] % 32:
+            raise ValueError("expected input [B,3,H,W] with H and W multiples of 32")
+        x = x.detach().to(dtype=torch.float32).contiguous()
+        return self.engine(dev, taps).run(x, self.sub_batch)
+
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor):
+        outs = self._run(x)
+        self._eval_branches = {k: [outs[(k, i)] for i in range(self.head.nl)] for k in ("one2many", "one2one")}
+        return self._eval_branches["one2many"]
+
+    @torch.no_grad()
+    def forward_with_taps(self, x: torch.Tensor) -> Dict[str, torch.Tensor]:
+        """Forward that also exports c3,c4,c5,p3,p4,p5 as NCHW fp32 (the reference fidelity taps)."""
+        outs = self._run(x, taps=True)
+        res = {k: outs[(k, 0)] for k in ("c3", "c4", "c5", "p3", "p4", "p5")}
+        for k in ("one2many", "one2one"):
+            res[k] = [outs[(k, i)] for i in range(self.head.nl)]
+        return res
+
+    @torch.no_grad()
+    def decode_forward(self, raw):
+        if isinstance(raw, dict):
+            seq = raw.get("one2one", raw.get("one2many"))
+        else:
+            seq = getattr(self, "_eval_branches", {}).get("one2one", raw)
+        return PP.decode_v10_official_topk(seq, num_classes=len(self.class_names), strides=STRIDES)
+
+    @torch.no_grad()
+    def detect(self, x: torch.Tensor, max_det: int = 300) -> torch.Tensor:
+        """forward + top-k decode, detections ``[B, min(max_det, A), 6]`` left on the device."""
+        self.forward(x)
+        out, _, _ = PP.topk_raw(self._eval_branches["one2one"], num_classes=len(self.class_names), strides=STRIDES,
+                                max_det=max_det)
+        return out
+
+
+def _make(name: str):
+    return type("YOLOv10" + name[-1], (YOLOv10,), {"variant": VARIANTS[name], "__doc__": f"{name} (see variants.py)"})
+
+
+YOLOv10n, YOLOv10s, YOLOv10m = _make("yolov10n"), _make("yolov10s"), _make("yolov10m")
+YOLOv10b, YOLOv10l, YOLOv10x = _make("yolov10b"), _make("yolov10l"), _make("yolov10x")
+MODEL_CLASSES = {"yolov10n": YOLOv10n, "yolov10s": YOLOv10s, "yolov10m": YOLOv10m,
+                 "yolov10b": YOLOv10b, "yolov10l": YOLOv10l, "yolov10x": YOLOv10x}

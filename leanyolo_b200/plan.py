@@ -1,0 +1,229 @@
+"""Lowering target: a flat list of kernel ops over NHWC buffers in one workspace.
+
+``PlanBuilder`` is filled by the ``emit`` methods in ``modules.py``.  It owns
+
+* the buffer table (NHWC, channel count padded to a multiple of 16, byte offsets
+  into a single workspace allocation),
+* the packed parameter blob (BN-folded, re-parameterised, re-ordered weights in
+  the storage dtype; biases always fp32), and
+* the op list (``Op``) that ``engine.py`` serialises into ``ly_op`` structs for
+  the C-ABI (include/leanyolo_b200.h).
+
+Data layout in HBM: activations ``[B, H, W, Ctot]`` (channels innermost) in bf16
+(or fp32 in check mode); a concat is one buffer and every producer writes its
+channel slice; a split is a channel-offset view.  Dense weights are
+``[Cout_pad][kh][kw][Cin_pad]`` (K-major rows: the B operand of the implicit
+GEMM); depthwise weights are ``[kh*kw][C_pad]``.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+CH_ALIGN = 16
+BUF_ALIGN = 1024
+
+
+def _rup(x: int, a: int) -> int:
+    return (x + a - 1) // a * a
+
+
+@dataclass
+class Buf:
+    id: int
+    H: int
+    W: int
+    C: int          # padded channel count == pixel pitch in elements
+    offset: int     # bytes into the workspace
+
+    def view(self, c0: int = 0, c: Optional[int] = None) -> "View":
+        c = self.C - c0 if c is None else _rup(c, CH_ALIGN)
+        assert c0 % 8 == 0 and c0 + c <= self.C, (c0, c, self.C)
+        return View(self, c0, c)
+
+
+@dataclass
+class View:
+    buf: Buf
+    c0: int
+    c: int
+
+    @property
+    def H(self):
+        return self.buf.H
+
+    @property
+    def W(self):
+        return self.buf.W
+
+    def sub(self, c0: int, c: int) -> "View":
+        assert c0 + c <= self.c and c0 % 8 == 0
+        return View(self.buf, self.c0 + c0, c)
+
+
+@dataclass
+class Op:
+    kind: str                       # stem | conv | dw | pool | up | attn | export
+    src: Optional[View] = None
+    dst: Optional[View] = None
+    res: Optional[View] = None
+    w_off: int = -1                 # element offset into the weight blob (storage dtype)
+    b_off: int = -1                 # element offset into the fp32 bias blob
+    k: int = 1
+    stride: int = 1
+    act: bool = False
+    cin: int = 0                    # real (unpadded) channel counts, for FLOP accounting
+    cout: int = 0
+    nchw: Optional[Tuple[str, int, int, int, int]] = None   # (tensor name, level, c0, c, ctot)
+    attn: Optional[Tuple[int, int, int, float]] = None      # (nh, kdp, hd, scale)
+    extra: dict = field(default_factory=dict)
+
+
+class PlanBuilder:
+    def __init__(self, B: int, H: int, W: int, dtype: str = "bf16"):
+        assert dtype in ("bf16", "f32")
+        assert H % 32 == 0 and W % 32 == 0, "input H, W must be multiples of 32 (neck concat, SURVEY App. C.10)"
+        self.B, self.H, self.W, self.dtype = B, H, W, dtype
+        self.esize = 2 if dtype == "bf16" else 4
+        self.bufs: List[Buf] = []
+        self.ops: List[Op] = []
+        self.ws_bytes = 0
+        self._w: List[torch.Tensor] = []   # fp64 chunks, cast at finalize
+        self._w_len = 0
+        self._b: List[torch.Tensor] = []
+        self._b_len = 0
+        self.outputs: Dict[Tuple[str, int], Tuple[int, int, int]] = {}   # (name, level) -> (C, H, W)
+
+    # ---------------------------------------------------------------- buffers
+    def buffer(self, H: int, W: int, C: int) -> Buf:
+        C = _rup(C, CH_ALIGN)
+        b = Buf(len(self.bufs), H, W, C, self.ws_bytes)
+        self.ws_bytes += _rup(self.B * H * W * C * self.esize, BUF_ALIGN)
+        self.bufs.append(b)
+        return b
+
+    # ---------------------------------------------------------------- params
+    def _add_w(self, w: torch.Tensor) -> int:
+        off = self._w_len
+        pad = (-w.numel()) % 64          # keep every weight block 128-byte aligned (TMA base address)
+        self._w.append(torch.cat([w.reshape(-1).double(), torch.zeros(pad, dtype=torch.float64)]))
+        self._w_len += w.numel() + pad
+        return off
+
+    def _add_b(self, b: torch.Tensor) -> int:
+        off = self._b_len
+        pad = (-b.numel()) % 4
+        self._b.append(torch.cat([b.reshape(-1).double(), torch.zeros(pad, dtype=torch.float64)]))
+        self._b_len += b.numel() + pad
+        return off
+
+    def finalize_params(self) -> Tuple[torch.Tensor, torch.Tensor]:
+        wdt = torch.bfloat16 if self.dtype == "bf16" else torch.float32
+        w = torch.cat(self._w).to(torch.float32).to(wdt) if self._w else torch.zeros(0, dtype=wdt)
+        b = torch.cat(self._b).to(torch.float32) if self._b else torch.zeros(0)
+        return w, b
+
+    # ---------------------------------------------------------------- ops
+    def stem(self, w: torch.Tensor, b: torch.Tensor, sub: Sequence[float], div: Sequence[float]) -> View:
+        """3x3 stride-2 conv on the user's NCHW fp32 image, normalisation applied in the
+        loader (zero padding happens AFTER normalisation in the reference, yolov10s.py:107-113,
+        so a non-zero ``subtract`` cannot be folded into a bias)."""
+        cout, cin = w.shape[0], w.shape[1]
+        assert cin == 3 and w.shape[2:] == (3, 3)
+        dst = self.buffer(self.H // 2, self.W // 2, cout).view()
+        wp = torch.zeros(dst.c, 27, dtype=torch.float64)
+        wp[:cout] = w.permute(0, 2, 3, 1).reshape(cout, 27)      # [co][ky][kx][ci]
+        bp = torch.zeros(dst.c, dtype=torch.float64)
+        bp[:cout] = b
+        op = Op("stem", dst=dst, k=3, stride=2, act=True, cin=3, cout=cout,
+                extra=dict(sub=[float(v) for v in sub], div=[float(v) for v in div]))
+        # stem weights are consumed by CUDA cores in fp32 regardless of the storage dtype
+        op.w_off, op.b_off = self._add_b(wp), self._add_b(bp)
+        self.ops.append(op)
+        return dst
+
+    def conv(self, src: View, w: torch.Tensor, b: torch.Tensor, *, k: int, stride: int, act: bool,
+             dst: Optional[View] = None, res: Optional[View] = None, out_perm: Optional[List[int]] = None,
+             nchw: Optional[Tuple[str, int, int, int, int]] = None) -> Optional[View]:
+        cout, cin = w.shape[0], w.shape[1]
+        assert w.shape[2] == w.shape[3] == k and k in (1, 3) and stride in (1, 2)
+        assert cin <= src.c < cin + CH_ALIGN, (cin, src.c)
+        if out_perm is not None:
+            wn = torch.zeros(len(out_perm), *w.shape[1:], dtype=torch.float64)
+            bn = torch.zeros(len(out_perm), dtype=torch.float64)
+            idx = torch.tensor(out_perm)
+            m = idx >= 0
+            wn[m], bn[m] = w[idx[m]], b[idx[m]]
+            w, b, cout = wn, bn, len(out_perm)
+        cpad = _rup(cout, CH_ALIGN)
+        Ho, Wo = src.H // stride, src.W // stride
+        if nchw is None:
+            if dst is None:
+                dst = self.buffer(Ho, Wo, cout).view()
+            assert dst.c == cpad and (dst.H, dst.W) == (Ho, Wo), (dst.c, cpad, dst.H, Ho)
+        else:
+            name, level, c0, c, ctot = nchw
+            self.outputs[(name, level)] = (ctot, Ho, Wo)
+        wp = torch.zeros(cpad, k, k, src.c, dtype=torch.float64)
+        wp[:cout, :, :, :cin] = w.permute(0, 2, 3, 1)
+        bp = torch.zeros(cpad, dtype=torch.float64)
+        bp[:cout] = b
+        if res is not None:
+            assert res.c == cpad and (res.H, res.W) == (Ho, Wo)
+        self.ops.append(Op("conv", src=src, dst=dst, res=res, w_off=self._add_w(wp), b_off=self._add_b(bp),
+                           k=k, stride=stride, act=act, cin=cin, cout=cout, nchw=nchw,
+                           extra=dict(cpad=cpad)))
+        return dst
+
+    def dwconv(self, src: View, w: torch.Tensor, b: torch.Tensor, *, k: int, stride: int, act: bool,
+               dst: Optional[View] = None, res: Optional[View] = None) -> View:
+        c = w.shape[0]
+        assert w.shape[1] == 1 and w.shape[2] == w.shape[3] == k and k in (3, 7)
+        assert c <= src.c < c + CH_ALIGN
+        Ho, Wo = (src.H + stride - 1) // stride, (src.W + stride - 1) // stride
+        if dst is None:
+            dst = self.buffer(Ho, Wo, c).view()
+        assert dst.c == src.c and (dst.H, dst.W) == (Ho, Wo)
+        wp = torch.zeros(k * k, src.c, dtype=torch.float64)
+        wp[:, :c] = w.reshape(c, k * k).t()
+        bp = torch.zeros(src.c, dtype=torch.float64)
+        bp[:c] = b
+        if res is not None:
+            assert res.c == dst.c and (res.H, res.W) == (Ho, Wo)
+        self.ops.append(Op("dw", src=src, dst=dst, res=res, w_off=self._add_w(wp), b_off=self._add_b(bp),
+                           k=k, stride=stride, act=act, cin=c, cout=c))
+        return dst
+
+    def sppf_pool(self, cat: Buf, c: int) -> None:
+        """cat[..., c:4c] <- three chained 5x5/s1/p2 max-pools of cat[..., 0:c] (windows 5, 9, 13)."""
+        assert cat.C == 4 * c and c % 8 == 0
+        self.ops.append(Op("pool", src=cat.view(0, c), dst=cat.view(c, 3 * c), cin=c, cout=3 * c))
+
+    def upsample2x(self, src: View, dst: View) -> None:
+        assert dst.c == src.c and (dst.H, dst.W) == (2 * src.H, 2 * src.W)
+        self.ops.append(Op("up", src=src, dst=dst, cin=src.c, cout=src.c))
+
+    def attention(self, qkv: View, *, nh: int, kdp: int, hd: int, scale: float) -> View:
+        assert qkv.c == 2 * nh * kdp + nh * hd
+        dst = self.buffer(qkv.H, qkv.W, nh * hd).view()
+        self.ops.append(Op("attn", src=qkv, dst=dst, attn=(nh, kdp, hd, scale), cin=qkv.c, cout=nh * hd))
+        return dst
+
+    def export_nchw(self, src: View, name: str, c: int) -> None:
+        """Debug / sub-module taps: NHWC storage -> public NCHW fp32 tensor."""
+        self.outputs[(name, 0)] = (c, src.H, src.W)
+        self.ops.append(Op("export", src=src, nchw=(name, 0, 0, c, c), cin=c, cout=c))
+
+    # ---------------------------------------------------------------- accounting
+    def dense_flops(self) -> int:
+        """2*MAC of the dense convs per image (the tensor-pipe-eligible work)."""
+        f = 0
+        for op in self.ops:
+            if op.kind == "conv":
+                Ho, Wo = op.src.H // op.stride, op.src.W // op.stride
+                f += 2 * Ho * Wo * op.cout * op.cin * op.k * op.k
+            elif op.kind == "stem":
+                f += 2 * op.dst.H * op.dst.W * op.cout * 27
+        return f

@@ -1,0 +1,164 @@
+"""GPU-resident detection tail behind the reference's decode functions.
+
+Mirrors ``leanyolo.models.yolov10.postprocess`` (same names, keyword arguments,
+return structure and edge-case behaviour) but every stage — DFL expectation,
+anchor decode, sigmoid, two-stage top-k, greedy IoU NMS — runs in the CUDA
+kernels of ``csrc/decode.cu`` through the C ABI.  No CPU fallback: CPU tensors
+are rejected.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _native as N
+
+MAX_DET_LIMIT = 1024  # per-CTA sort buffers in decode.cu
+
+
+def _levels(preds: Sequence[torch.Tensor], num_classes: int, strides: Sequence[int], img_size=None, nms_path=False):
+    assert len(preds) == len(strides), "preds and strides length mismatch"
+    if len(preds) > 4:
+        raise ValueError("at most 4 pyramid levels are supported")
+    p0 = preds[0]
+    if not p0.is_cuda:
+        raise RuntimeError("leanyolo_b200 decodes on CUDA only (no CPU fallback); move the head tensors to the GPU")
+    keep = []
+    lv = N.LyLevels()
+    b, c = p0.shape[0], p0.shape[1]
+    direct = bool(nms_path and c == 4 + num_classes)
+    reg_max = 1 if direct else (c - num_classes) // 4
+    if not direct:
+        assert 4 * reg_max + num_classes == c, "Invalid channel layout for v10 head"
+    for i, (p, s) in enumerate(zip(preds, strides)):
+        assert p.shape[0] == b and p.shape[1] == c and p.device == p0.device
+        q = p.detach()
+        if q.dtype != torch.float32 or not q.is_contiguous():
+            q = q.float().contiguous()
+        keep.append(q)
+        lv.preds[i] = q.data_ptr()
+        lv.H[i], lv.W[i], lv.stride[i] = q.shape[2], q.shape[3], int(s)
+    lv.n_levels, lv.B, lv.nc, lv.reg_max = len(preds), b, int(num_classes), int(reg_max)
+    lv.direct = int(direct)
+    if direct and img_size is not None:
+        lv.clamp_h, lv.clamp_w = int(img_size[0]), int(img_size[1])
+    return lv, keep, sum(int(p.shape[2] * p.shape[3]) for p in preds)
+
+
+def _stream(device) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+@torch.no_grad()
+def topk_raw(preds: Sequence[torch.Tensor], *, num_classes: int, strides: Sequence[int] = (8, 16, 32),
+             max_det: int = 300) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """Fixed-shape result: (dets [B,k,6], anchor [B,k] int32, cls [B,k] int32)."""
+    if not 1 <= max_det <= MAX_DET_LIMIT:
+        raise ValueError(f"max_det must be in 1..{MAX_DET_LIMIT}")
+    lib = N.lib()
+    lv, keep, A = _levels(preds, num_classes, strides)
+    dev = keep[0].device
+    k = min(max_det, A)
+    with torch.cuda.device(dev):
+        nbytes = lib.ly_decode_scratch_bytes(C.byref(lv), max_det)
+        scratch = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        out = torch.empty((lv.B, k, 6), dtype=torch.float32, device=dev)
+        anchor = torch.empty((lv.B, k), dtype=torch.int32, device=dev)
+        cls = torch.empty((lv.B, k), dtype=torch.int32, device=dev)
+        N.check(lib.ly_decode_topk(C.byref(lv), max_det, out.data_ptr(), anchor.data_ptr(), cls.data_ptr(),
+                                   scratch.data_ptr(), nbytes, _stream(dev)), "ly_decode_topk")
+        scratch.record_stream(torch.cuda.current_stream(dev))
+    return out, anchor, cls
+
+
+@torch.no_grad()
+def decode_v10_official_topk(
+    preds: Sequence[torch.Tensor],
+    *,
+    num_classes: int,
+    strides: Sequence[int] = (8, 16, 32),
+    max_det: int = 300,
+    conf_thresh: Optional[float] = None,   # accepted and ignored, like the reference
+    iou_thresh: Optional[float] = None,
+    img_size: Optional[Tuple[int, int]] = None,
+) -> List[List[torch.Tensor]]:
+    """Drop-in for ``decode_v10_official_topk`` (postprocess.py:166-261): always
+    ``min(max_det, A)`` rows per image, score-descending, no threshold, no clamp."""
+    out, _, _ = topk_raw(preds, num_classes=num_classes, strides=strides, max_det=max_det)
+    return [[out[i]] for i in range(out.shape[0])]
+
+
+@torch.no_grad()
+def nms_raw(preds: Sequence[torch.Tensor], *, num_classes: int, strides: Sequence[int] = (8, 16, 32),
+            conf_thresh: float = 0.25, iou_thresh: float = 0.45, max_det: int = 300,
+            img_size: Optional[Tuple[int, int]] = None, classwise: bool = False):
+    """Fixed-shape result: (dets [B,max_det,6] zero padded, count [B] int32, anchor [B,max_det] int32, -1 padded)."""
+    if not 1 <= max_det <= MAX_DET_LIMIT:
+        raise ValueError(f"max_det must be in 1..{MAX_DET_LIMIT}")
+    lib = N.lib()
+    lv, keep, A = _levels(preds, num_classes, strides, img_size, nms_path=True)
+    dev = keep[0].device
+    with torch.cuda.device(dev):
+        nbytes = lib.ly_decode_scratch_bytes(C.byref(lv), max_det)
+        scratch = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        out = torch.empty((lv.B, max_det, 6), dtype=torch.float32, device=dev)
+        count = torch.empty((lv.B,), dtype=torch.int32, device=dev)
+        anchor = torch.empty((lv.B, max_det), dtype=torch.int32, device=dev)
+        N.check(lib.ly_decode_nms(C.byref(lv), float(conf_thresh), float(iou_thresh), max_det, int(classwise),
+                                  out.data_ptr(), count.data_ptr(), anchor.data_ptr(), scratch.data_ptr(), nbytes,
+                                  _stream(dev)), "ly_decode_nms")
+        scratch.record_stream(torch.cuda.current_stream(dev))
+    return out, count, anchor
+
+
+@torch.no_grad()
+def decode_v10_predictions(
+    preds: Sequence[torch.Tensor],
+    *,
+    num_classes: int,
+    strides: Sequence[int] = (8, 16, 32),
+    conf_thresh: float = 0.25,
+    iou_thresh: float = 0.45,
+    max_det: int = 300,
+    img_size: Optional[Tuple[int, int]] = None,
+    classwise: bool = False,
+) -> List[List[torch.Tensor]]:
+    """Drop-in for ``decode_v10_predictions`` (postprocess.py:47-163): ragged
+    ``[n_i, 6]`` per image, empty images give ``torch.empty((0, 6))``.  The
+    default is class-agnostic suppression, which is what the reference code does;
+    ``classwise=True`` restricts suppression to equal labels."""
+    out, count, _ = nms_raw(preds, num_classes=num_classes, strides=strides, conf_thresh=conf_thresh,
+                            iou_thresh=iou_thresh, max_det=max_det, img_size=img_size, classwise=classwise)
+    counts = count.tolist()  # the only device->host sync of the decode
+    return [[out[i, :n]] if n > 0 else [torch.empty((0, 6), device=out.device)] for i, n in enumerate(counts)]
+
+
+@torch.no_grad()
+def nms(boxes: torch.Tensor, scores: torch.Tensor, iou_thresh: float, *, labels: Optional[torch.Tensor] = None,
+        max_keep: Optional[int] = None) -> torch.Tensor:
+    """Drop-in for ``leanyolo.utils.box_ops.nms`` on CUDA tensors: keep indices
+    (int64) into the input order, score-descending.  ``labels`` switches to
+    class-wise suppression.  ``max_keep`` (<= 1024) truncates; None keeps up to 1024."""
+    if not boxes.is_cuda:
+        raise RuntimeError("leanyolo_b200 nms runs on CUDA only (no CPU fallback)")
+    n = boxes.shape[0]
+    if n == 0:
+        return torch.zeros((0,), dtype=torch.long, device=boxes.device)
+    mk = min(max_keep or MAX_DET_LIMIT, MAX_DET_LIMIT)
+    lib = N.lib()
+    dev = boxes.device
+    with torch.cuda.device(dev):
+        b = boxes.detach().float().contiguous()
+        s = scores.detach().float().contiguous()
+        l = labels.detach().to(torch.int32).contiguous() if labels is not None else None
+        nbytes = lib.ly_nms_scratch_bytes(1, n)
+        scratch = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        keep = torch.empty((1, mk), dtype=torch.int32, device=dev)
+        cnt = torch.empty((1,), dtype=torch.int32, device=dev)
+        N.check(lib.ly_nms(b.data_ptr(), s.data_ptr(), l.data_ptr() if l is not None else None, None, 1, n,
+                           float(iou_thresh), mk, int(l is not None), keep.data_ptr(), cnt.data_ptr(),
+                           scratch.data_ptr(), nbytes, _stream(dev)), "ly_nms")
+        k = int(cnt.item())
+    return keep[0, :k].to(torch.long)

@@ -1,0 +1,124 @@
+"""Generate tests/golden/* by running the REAL reference (build container only).
+
+    python oracle/make_golden.py            # needs /root/reference
+
+The reference (jremillard/leanyolo) is pure Python, importable here but absent on the
+GPU box, so its outputs on seeded inputs are committed as small fixtures.  Weights and
+inputs are regenerated from seeds by ``leanyolo_b200.synth`` on both sides, so only the
+reference's OUTPUTS are stored.  Nothing under tests/, smoke() or bench.py reads
+/root/reference at run time.
+
+Fixtures
+  state_keys.json            state_dict key order + shapes of the six reference variants
+  forward_<variant>.pt       reference eval forward @64x64, batch 1: c3..p5 taps (module
+                             outputs) and both head branches
+  decode_topk.pt             reference decode_v10_official_topk on seeded logits (2 images,
+                             640x640 pyramid, nc=80) + reg_max=1 / max_det edge cases
+  decode_nms.pt              reference decode_v10_predictions (two threshold settings)
+  nms.pt                     reference box_ops.nms keep indices on seeded boxes
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.environ.get("LEANYOLO_REFERENCE", "/root/reference")
+sys.path.insert(0, ROOT)
+sys.path.insert(0, REF)
+
+from leanyolo.models import get_model as ref_get_model  # noqa: E402  (the reference)
+from leanyolo.models.yolov10.postprocess import decode_v10_official_topk, decode_v10_predictions  # noqa: E402
+from leanyolo.utils.box_ops import nms as ref_nms  # noqa: E402
+
+from leanyolo_b200.synth import synth_head_logits, synth_images, synth_state_dict  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+VARIANTS = ["yolov10n", "yolov10s", "yolov10m", "yolov10b", "yolov10l", "yolov10x"]
+NAMES = [f"class{i}" for i in range(80)]
+GAIN = 1.25
+
+
+def min_rel_gap(v: torch.Tensor) -> float:
+    """Smallest gap between consecutive (descending) values, in units of fp32 ulps at that value."""
+    d = (v[:-1] - v[1:]).double()
+    ulp = torch.finfo(torch.float32).eps * v[:-1].abs().clamp(min=1e-30).double()
+    return float((d / ulp).min())
+
+
+def main() -> None:
+    os.makedirs(OUT, exist_ok=True)
+    torch.manual_seed(0)
+    keys = {}
+    for vi, name in enumerate(VARIANTS):
+        model = ref_get_model(name, weights=None, class_names=NAMES).eval()
+        keys[name] = [[k, list(v.shape)] for k, v in model.state_dict().items()]
+        sd = synth_state_dict(model.state_dict(), seed=100 + vi, gain=GAIN)
+        model.load_state_dict(sd, strict=True)
+        x = synth_images(1, 64, 64, seed=200 + vi)
+        taps = {}
+        with torch.no_grad():
+            xin = x.float() / model.input_divide
+            c3, c4, c5 = model.backbone(xin)
+            p3, p4, p5 = model.neck(c3, c4, c5)
+            taps.update(c3=c3, c4=c4, c5=c5, p3=p3, p4=p4, p5=p5)
+            one2many = model(x)
+            one2one = model._eval_branches["one2one"]
+            dets = model.decode_forward(one2many)
+        torch.save({"seed_weights": 100 + vi, "seed_input": 200 + vi, "gain": GAIN, "hw": 64,
+                    "taps": {k: v.clone() for k, v in taps.items()},
+                    "one2many": [t.clone() for t in one2many], "one2one": [t.clone() for t in one2one],
+                    "dets_scores": dets[0][0][:, 4].clone()},
+                   os.path.join(OUT, f"forward_{name}.pt"))
+        print(name, "ok", [tuple(t.shape) for t in one2many])
+    with open(os.path.join(OUT, "state_keys.json"), "w") as f:
+        json.dump(keys, f)
+
+    # ---- decode: top-k
+    hw = [(80, 80), (40, 40), (20, 20)]
+    logits = synth_head_logits(2, 80, hw, seed=11)
+    topk = decode_v10_official_topk(logits, num_classes=80, strides=(8, 16, 32))
+    out = torch.stack([d[0] for d in topk])
+    gaps = [min_rel_gap(out[i, :, 4]) for i in range(2)]
+    small = synth_head_logits(1, 5, [(6, 8)], reg_max=8, seed=12)
+    small_out = decode_v10_official_topk(small, num_classes=5, strides=(8,), max_det=10)[0][0]
+    rm1 = synth_head_logits(1, 3, [(4, 4), (2, 2), (1, 1)], reg_max=1, seed=13)
+    rm1_out = decode_v10_official_topk(rm1, num_classes=3, strides=(8, 16, 32))[0][0]
+    torch.save({"seed": 11, "nc": 80, "hw": hw, "out": out, "min_gap_ulps": gaps,
+                "small": {"seed": 12, "nc": 5, "hw": [(6, 8)], "reg_max": 8, "max_det": 10, "out": small_out,
+                          "min_gap_ulps": min_rel_gap(small_out[:, 4])},
+                "regmax1": {"seed": 13, "nc": 3, "hw": [(4, 4), (2, 2), (1, 1)], "out": rm1_out}},
+               os.path.join(OUT, "decode_topk.pt"))
+    print("topk gaps (ulps):", gaps)
+
+    # ---- decode: NMS (class-agnostic, as the reference code does)
+    nms_cases = {}
+    for tag, conf, iou, seed, mean in (("default", 0.25, 0.45, 21, -3.0), ("stress", 0.001, 0.7, 22, -2.0)):
+        lg = synth_head_logits(2, 80, hw, seed=seed, cls_mean=mean)
+        res = decode_v10_predictions(lg, num_classes=80, strides=(8, 16, 32), conf_thresh=conf, iou_thresh=iou, max_det=300)
+        nms_cases[tag] = {"seed": seed, "cls_mean": mean, "conf": conf, "iou": iou, "out": [r[0] for r in res]}
+        print("nms", tag, [tuple(r[0].shape) for r in res])
+    empty = decode_v10_predictions(synth_head_logits(1, 80, hw, seed=23, cls_mean=-12.0), num_classes=80,
+                                   strides=(8, 16, 32), conf_thresh=0.25, iou_thresh=0.45)
+    nms_cases["empty"] = {"seed": 23, "cls_mean": -12.0, "conf": 0.25, "iou": 0.45, "out": [r[0] for r in empty]}
+    torch.save({"hw": hw, "nc": 80, "cases": nms_cases}, os.path.join(OUT, "decode_nms.pt"))
+
+    # ---- plain NMS on explicit boxes
+    g = torch.Generator().manual_seed(31)
+    n = 3000
+    xy = torch.rand(n, 2, generator=g) * 600
+    wh = torch.rand(n, 2, generator=g) * 120 + 4
+    boxes = torch.cat((xy, xy + wh), 1)
+    scores = (torch.randperm(n, generator=g).float() + 0.5) / n   # all distinct: no tie ambiguity
+    keep = {str(thr): ref_nms(boxes, scores, thr) for thr in (0.3, 0.5, 0.7)}
+    torch.save({"seed": 31, "n": n, "keep": keep}, os.path.join(OUT, "nms.pt"))
+    print("nms keep sizes", {k: int(v.numel()) for k, v in keep.items()})
+    total = sum(os.path.getsize(os.path.join(OUT, f)) for f in os.listdir(OUT))
+    print(f"golden dir: {total / 1e6:.2f} MB")
+
+
+if __name__ == "__main__":
+    main()

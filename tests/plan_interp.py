@@ -1,0 +1,95 @@
+"""TEST INFRASTRUCTURE: a torch-CPU interpreter of the lowered op list.
+
+Executes ``PlanBuilder.ops`` exactly as the C ABI defines them (NHWC buffers, packed
+weights, channel-offset views, residual-after-activation) so the *lowering* — BN
+folding, RepVGGDW merge, qkv re-ordering, concat/split offsets, in-place PSA updates —
+can be checked against the oracle without a GPU.  Never imported by the product.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+
+from leanyolo_b200.plan import PlanBuilder
+
+
+def run_plan(pb: PlanBuilder, x: torch.Tensor, quant=None):
+    """x: [B,3,H,W] fp32.  quant: optional fn applied to every stored activation
+    (e.g. bf16 round-trip) to emulate the storage dtype."""
+    q = quant or (lambda t: t)
+    w_blob, b_blob = pb.finalize_params()
+    w_blob = w_blob.float()
+    B = x.shape[0]
+    bufs = {b.id: torch.zeros(B, b.H, b.W, b.C) for b in pb.bufs}
+    outs = {k: torch.zeros(B, c, h, w) for k, (c, h, w) in pb.outputs.items()}
+
+    def rd(v):
+        return bufs[v.buf.id][..., v.c0:v.c0 + v.c]
+
+    def wr(v, t):
+        bufs[v.buf.id][..., v.c0:v.c0 + v.c] = q(t)
+
+    for op in pb.ops:
+        if op.kind == "stem":
+            cp = op.dst.c
+            w = b_blob[op.w_off:op.w_off + cp * 27].view(cp, 3, 3, 3).permute(0, 3, 1, 2)   # [co][ky][kx][ci] -> OIHW
+            bias = b_blob[op.b_off:op.b_off + cp]
+            sub = torch.tensor(op.extra["sub"]).view(1, 3, 1, 1)
+            div = torch.tensor(op.extra["div"]).view(1, 3, 1, 1)
+            y = F.silu(F.conv2d((x - sub) / div, w, bias, 2, 1))
+            wr(op.dst, y.permute(0, 2, 3, 1))
+        elif op.kind == "conv":
+            cin, k = op.src.c, op.k
+            cp = op.extra["cpad"]
+            w = w_blob[op.w_off:op.w_off + cp * k * k * cin].view(cp, k, k, cin).permute(0, 3, 1, 2)
+            bias = b_blob[op.b_off:op.b_off + cp]
+            y = F.conv2d(rd(op.src).permute(0, 3, 1, 2), w, bias, op.stride, k // 2)
+            if op.act:
+                y = F.silu(y)
+            y = y.permute(0, 2, 3, 1)
+            if op.res is not None:
+                y = y + rd(op.res)
+            if op.dst is not None:
+                wr(op.dst, y)
+            if op.nchw is not None:
+                name, level, c0, c, _ = op.nchw
+                outs[(name, level)][:, c0:c0 + c] = y[..., :c].permute(0, 3, 1, 2)
+        elif op.kind == "dw":
+            c, k = op.src.c, op.k
+            w = w_blob[op.w_off:op.w_off + k * k * c].view(k, k, c).permute(2, 0, 1).unsqueeze(1)
+            bias = b_blob[op.b_off:op.b_off + c]
+            y = F.conv2d(rd(op.src).permute(0, 3, 1, 2), w, bias, op.stride, k // 2, 1, c)
+            if op.act:
+                y = F.silu(y)
+            y = y.permute(0, 2, 3, 1)
+            if op.res is not None:
+                y = y + rd(op.res)
+            wr(op.dst, y)
+        elif op.kind == "pool":
+            c = op.src.c
+            t = rd(op.src).permute(0, 3, 1, 2)
+            y1 = F.max_pool2d(t, 5, 1, 2)
+            y2 = F.max_pool2d(y1, 5, 1, 2)
+            y3 = F.max_pool2d(y2, 5, 1, 2)
+            wr(op.dst, torch.cat([y1, y2, y3], 1).permute(0, 2, 3, 1))
+        elif op.kind == "up":
+            t = rd(op.src).permute(0, 3, 1, 2)
+            wr(op.dst, F.interpolate(t, scale_factor=2.0, mode="nearest").permute(0, 2, 3, 1))
+        elif op.kind == "attn":
+            nh, kdp, hd, scale = op.attn
+            t = rd(op.src)
+            Bn, H, W, _ = t.shape
+            n = H * W
+            t = t.reshape(Bn, n, -1)
+            qq = t[..., :nh * kdp].view(Bn, n, nh, kdp).permute(0, 2, 1, 3)
+            kk = t[..., nh * kdp:2 * nh * kdp].view(Bn, n, nh, kdp).permute(0, 2, 1, 3)
+            vv = t[..., 2 * nh * kdp:2 * nh * kdp + nh * hd].view(Bn, n, nh, hd).permute(0, 2, 1, 3)
+            att = ((qq @ kk.transpose(-1, -2)) * scale).softmax(-1)
+            o = (att @ vv).permute(0, 2, 1, 3).reshape(Bn, H, W, nh * hd)
+            wr(op.dst, o)
+        elif op.kind == "export":
+            name, level, c0, c, _ = op.nchw
+            outs[(name, level)][:] = rd(op.src)[..., :c].permute(0, 3, 1, 2)
+        else:
+            raise NotImplementedError(op.kind)
+    return outs
