@@ -107,6 +107,11 @@ LY_API int32_t ly_launch(const ly_op* op, void* stream);
 typedef struct ly_plan ly_plan;
 LY_API int32_t ly_plan_create(const ly_op* ops, int32_t n_ops, ly_plan** out);
 LY_API int32_t ly_plan_run(ly_plan* plan, float* const* ext, int32_t n_ext, int32_t img0, void* stream);
+/* Same as ly_plan_run, with a CUDA event between consecutive launches: fills
+ * h_ms[n_ops] (HOST array) with each op's device time and h_is_tc[n_ops] (may be
+ * NULL) with 1 for tcgen05 convs.  Synchronises the stream.  Measurement only. */
+LY_API int32_t ly_plan_profile(ly_plan* plan, float* const* ext, int32_t n_ext, int32_t img0, void* stream,
+                               float* h_ms, int32_t* h_is_tc);
 LY_API int32_t ly_plan_num_launches(const ly_plan* plan);
 LY_API void ly_plan_destroy(ly_plan* plan);
 

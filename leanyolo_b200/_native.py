@@ -48,6 +48,8 @@ PROTOTYPES = {
     "ly_launch": (C.c_int32, [C.POINTER(LyOp), C.c_void_p]),
     "ly_plan_create": (C.c_int32, [C.POINTER(LyOp), C.c_int32, C.POINTER(C.c_void_p)]),
     "ly_plan_run": (C.c_int32, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_void_p]),
+    "ly_plan_profile": (C.c_int32, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_void_p,
+                                    C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
     "ly_plan_num_launches": (C.c_int32, [C.c_void_p]),
     "ly_plan_destroy": (None, [C.c_void_p]),
     "ly_decode_scratch_bytes": (C.c_int64, [C.POINTER(LyLevels), C.c_int32]),

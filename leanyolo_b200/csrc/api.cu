@@ -124,10 +124,10 @@ int32_t ly_plan_create(const ly_op* ops, int32_t n_ops, ly_plan** out) {
   return LY_OK;
 }
 
-int32_t ly_plan_run(ly_plan* pl, float* const* ext, int32_t n_ext, int32_t img0, void* stream) {
-  LY_CHECK_ARG(pl != nullptr, "ly_plan_run: null plan");
-  cudaStream_t s = (cudaStream_t)stream;
+static int32_t plan_run_impl(ly_plan* pl, float* const* ext, int32_t n_ext, int32_t img0, cudaStream_t s,
+                             cudaEvent_t* ev) {
   for (size_t i = 0; i < pl->ops.size(); ++i) {
+    if (ev) cudaEventRecord(ev[i], s);
     const ly_op& op = pl->ops[i];
     float* nchw = op.nchw;
     if (op.ext_slot >= 0) {
@@ -155,7 +155,33 @@ int32_t ly_plan_run(ly_plan* pl, float* const* ext, int32_t n_ext, int32_t img0,
       return rc;
     }
   }
+  if (ev) cudaEventRecord(ev[pl->ops.size()], s);
   return LY_OK;
+}
+
+int32_t ly_plan_run(ly_plan* pl, float* const* ext, int32_t n_ext, int32_t img0, void* stream) {
+  LY_CHECK_ARG(pl != nullptr, "ly_plan_run: null plan");
+  return plan_run_impl(pl, ext, n_ext, img0, (cudaStream_t)stream, nullptr);
+}
+
+int32_t ly_plan_profile(ly_plan* pl, float* const* ext, int32_t n_ext, int32_t img0, void* stream, float* h_ms,
+                        int32_t* h_is_tc) {
+  LY_CHECK_ARG(pl != nullptr && h_ms != nullptr, "ly_plan_profile: null argument");
+  const size_t n = pl->ops.size();
+  std::vector<cudaEvent_t> ev(n + 1);
+  for (auto& e : ev) LY_CUDA(cudaEventCreate(&e));
+  int32_t rc = plan_run_impl(pl, ext, n_ext, img0, (cudaStream_t)stream, ev.data());
+  if (rc == LY_OK) {
+    cudaError_t e = cudaEventSynchronize(ev[n]);
+    if (e != cudaSuccess) { set_error("ly_plan_profile: %s", cudaGetErrorString(e)); rc = LY_E_CUDA; }
+  }
+  if (rc == LY_OK)
+    for (size_t i = 0; i < n; ++i) {
+      cudaEventElapsedTime(&h_ms[i], ev[i], ev[i + 1]);
+      if (h_is_tc) h_is_tc[i] = pl->tc[i] ? 1 : 0;
+    }
+  for (auto& e : ev) cudaEventDestroy(e);
+  return rc;
 }
 
 int32_t ly_plan_num_launches(const ly_plan* pl) { return pl ? (int32_t)pl->ops.size() : 0; }

@@ -130,6 +130,54 @@ class Engine:
                 self._launch(self.compile(n, H, W), x, outs, img0)
         return outs
 
+    def profile(self, x: torch.Tensor, sub_batch: Optional[int] = None):
+        """Per-op device times (ms) of one forward via CUDA events between launches.
+        Returns a list of dicts {kind, ms, flops, bytes, tc, k, stride, cin, cout, hw}."""
+        B, _, H, W = x.shape
+        sub = min(B, sub_batch) if sub_batch else B
+        rows = []
+        with torch.cuda.device(self.device):
+            outs = self.alloc_outputs(B, H, W, sub)
+            for img0 in range(0, B, sub):
+                n = min(sub, B - img0)
+                comp = self.compile(n, H, W)
+                ext = (C.c_void_p * (1 + len(comp.out_keys)))()
+                ext[0] = x.data_ptr()
+                for i, k in enumerate(comp.out_keys):
+                    ext[i + 1] = outs[k].data_ptr()
+                ms = (C.c_float * comp.n_launches)()
+                tc = (C.c_int32 * comp.n_launches)()
+                stream = torch.cuda.current_stream(self.device).cuda_stream
+                N.check(self.lib.ly_plan_profile(comp.handle, ext, len(ext), img0, C.c_void_p(stream), ms, tc), "ly_plan_profile")
+                es = comp.pb.esize
+                for i, op in enumerate(comp.pb.ops):
+                    flops = byts = 0
+                    if op.kind == "conv":
+                        Ho, Wo = op.src.H // op.stride, op.src.W // op.stride
+                        flops = 2 * n * Ho * Wo * op.cout * op.cin * op.k * op.k
+                        byts = n * (op.src.H * op.src.W * op.src.c * es + Ho * Wo * op.extra["cpad"] * (es if op.dst is not None else 4)
+                                    + (Ho * Wo * op.extra["cpad"] * es if op.res is not None else 0))
+                    elif op.kind == "stem":
+                        flops = 2 * n * op.dst.H * op.dst.W * op.cout * 27
+                        byts = n * (3 * 4 * op.dst.H * op.dst.W * 4 + op.dst.H * op.dst.W * op.dst.c * es)
+                    elif op.kind == "dw":
+                        byts = n * es * (op.src.H * op.src.W * op.src.c + op.dst.H * op.dst.W * op.dst.c * (2 if op.res is not None else 1))
+                    elif op.kind == "pool":
+                        byts = n * es * op.src.H * op.src.W * op.src.c * 4
+                    elif op.kind == "up":
+                        byts = n * es * op.dst.H * op.dst.W * op.dst.c * 5 // 4
+                    elif op.kind == "attn":
+                        nh, kdp, hd, _ = op.attn
+                        t = op.src.H * op.src.W
+                        flops = 2 * n * nh * t * t * (kdp + hd)
+                        byts = n * es * t * (op.src.c + op.dst.c)
+                    elif op.kind == "export":
+                        byts = n * op.src.H * op.src.W * op.cin * (es + 4)
+                    rows.append(dict(kind=op.kind, ms=float(ms[i]), flops=flops, bytes=byts, tc=int(tc[i]), k=op.k,
+                                     stride=op.stride, cin=op.cin, cout=op.cout,
+                                     hw=(op.src.H if op.src is not None else op.dst.H * 2)))
+        return rows
+
     def launches_per_forward(self, B: int, H: int, W: int, sub_batch: Optional[int] = None) -> int:
         sub = min(B, sub_batch) if sub_batch else B
         total = 0

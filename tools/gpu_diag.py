@@ -1,0 +1,160 @@
+"""Bring-up diagnostic: run every GPU parity check in crash-isolated subprocesses.
+
+    python tools/gpu_diag.py [--filter SUBSTR] [--out gpurun_out/diag.json]
+
+A CUDA fault (trap, illegal address) is sticky for its process, so checks run in a
+worker subprocess; when the worker dies the parent records the failure and continues
+with the remaining checks in a fresh worker.  Assertion failures do not kill the worker.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def registry():
+    import gpu_checks as G
+    import gpu_checks_decode as D
+    import gpu_checks_model as M
+
+    R = []
+
+    def add(_n, fn, **kw):
+        R.append((_n, fn, kw))
+
+    # CUDA-core conv (check mode + bring-up)
+    add("simt_f32_3x3", G.check_conv, dtype="f32", impl="simt", cin=32, cout=48, k=3)
+    add("simt_f32_1x1_s2_res", G.check_conv, dtype="f32", impl="simt", cin=64, cout=80, k=1, stride=2, res=True)
+    add("simt_bf16_3x3_views", G.check_conv, dtype="bf16", impl="simt", cin=32, cout=32, k=3, src_off=16, src_extra=16, dst_off=32, dst_extra=16)
+    add("simt_f32_nchw", G.check_conv, dtype="f32", impl="simt", cin=64, cout=80, k=1, act=False, nchw=True, nchw_c=77)
+    # tensor-core conv: start with the simplest shape, then widen
+    add("tc_1x1_64_64", G.check_conv, cin=64, cout=64, k=1, H=16, W=16, B=2)
+    add("tc_1x1_64_64_noact", G.check_conv, cin=64, cout=64, k=1, act=False)
+    add("tc_1x1_128_256", G.check_conv, cin=128, cout=256, k=1)
+    add("tc_1x1_k32", G.check_conv, cin=32, cout=64, k=1)
+    add("tc_1x1_k16", G.check_conv, cin=16, cout=32, k=1)
+    add("tc_1x1_k48_n48", G.check_conv, cin=48, cout=48, k=1)
+    add("tc_1x1_512_512_ntiles", G.check_conv, cin=512, cout=512, k=1, H=8, W=8)
+    add("tc_1x1_576_576", G.check_conv, cin=576, cout=576, k=1, H=8, W=8)
+    add("tc_1x1_tail_M", G.check_conv, cin=64, cout=64, k=1, H=5, W=7, B=3)
+    add("tc_3x3_64_64", G.check_conv, cin=64, cout=64, k=3, H=16, W=16)
+    add("tc_3x3_32_32", G.check_conv, cin=32, cout=32, k=3, H=32, W=32)
+    add("tc_3x3_16_16", G.check_conv, cin=16, cout=16, k=3, H=32, W=32)
+    add("tc_3x3_128_128_nonres", G.check_conv, cin=128, cout=128, k=3, H=16, W=16)
+    add("tc_3x3_s2", G.check_conv, cin=64, cout=128, k=3, stride=2, H=32, W=32)
+    add("tc_3x3_s2_k32", G.check_conv, cin=32, cout=64, k=3, stride=2, H=32, W=32)
+    add("tc_3x3_20x20_b3", G.check_conv, cin=64, cout=64, k=3, H=20, W=20, B=3)
+    add("tc_3x3_40x40_b3", G.check_conv, cin=64, cout=64, k=3, H=40, W=40, B=3)
+    add("tc_3x3_odd_10x6", G.check_conv, cin=64, cout=64, k=3, H=10, W=6, B=5)
+    add("tc_3x3_res", G.check_conv, cin=64, cout=64, k=3, res=True)
+    add("tc_3x3_views", G.check_conv, cin=64, cout=64, k=3, src_off=64, src_extra=64, dst_off=128, dst_extra=64)
+    add("tc_1x1_inplace_res", G.check_conv, cin=128, cout=64, k=1, act=False, inplace_res=True, dst_off=64, dst_extra=0)
+    add("tc_1x1_nchw_80", G.check_conv, cin=128, cout=80, k=1, act=False, nchw=True)
+    add("tc_1x1_nchw_pad77", G.check_conv, cin=64, cout=80, k=1, act=False, nchw=True, nchw_c=77)
+    add("tc_3x3_big", G.check_conv, cin=64, cout=64, k=3, H=160, W=160, B=4)
+    add("tc_1x1_big", G.check_conv, cin=256, cout=128, k=1, H=80, W=80, B=8)
+    # bandwidth kernels
+    for dt in ("bf16", "f32"):
+        add(f"dw3_{dt}", G.check_dw, dtype=dt, k=3)
+        add(f"dw3_s2_res_{dt}", G.check_dw, dtype=dt, k=3, stride=2, res=True, act=False)
+        add(f"dw7_{dt}", G.check_dw, dtype=dt, k=7, H=20, W=20)
+        add(f"pool_{dt}", G.check_pool, dtype=dt)
+        add(f"up_{dt}", G.check_up, dtype=dt)
+        add(f"attn_32_64_{dt}", G.check_attn, dtype=dt)
+        add(f"attn_36_72_{dt}", G.check_attn, dtype=dt, kd=36, hd=72, H=8, W=8)
+        add(f"stem_{dt}", G.check_stem, dtype=dt)
+        add(f"stem_norm_{dt}", G.check_stem, dtype=dt, cout=48, sub=(10.0, 20.0, 30.0), div=(58.0, 57.0, 59.0))
+        add(f"export_import_{dt}", G.check_export_import, dtype=dt)
+    # decode tail
+    add("topk_golden", D.check_topk_golden)
+    add("topk_vs_oracle_b4", D.check_topk_vs_oracle, B=4, seed=3)
+    add("topk_small_levels", D.check_topk_vs_oracle, B=2, seed=4, hw=[(6, 8)], nc=5, reg_max=8, max_det=10, strides=(8,))
+    add("topk_regmax1", D.check_topk_vs_oracle, B=1, seed=5, hw=[(4, 4), (2, 2), (1, 1)], nc=3, reg_max=1)
+    add("nms_exact_3000", D.check_nms_exact, n=3000)
+    add("nms_exact_classwise", D.check_nms_exact, n=2000, classwise=True)
+    add("nms_exact_9000_global_sort", D.check_nms_exact, n=20000, thr=0.6)
+    add("nms_golden", D.check_nms_golden)
+    add("decode_nms_default", D.check_decode_nms, conf=0.25, iou=0.45, cls_mean=-3.0, seed=21)
+    add("decode_nms_stress", D.check_decode_nms, conf=0.001, iou=0.7, cls_mean=-2.0, seed=22)
+    add("decode_nms_empty", D.check_decode_nms, conf=0.25, iou=0.45, cls_mean=-12.0, seed=23)
+    add("decode_nms_direct", D.check_decode_nms_direct)
+    # whole model
+    for name in ("yolov10n", "yolov10s"):
+        add(f"model_{name}_f32", M.check_model, name=name, precision="fp32", hw=64, B=2)
+        add(f"model_{name}_bf16_simt", M.check_model, name=name, precision="bf16", hw=64, B=2, conv_impl="simt")
+        add(f"model_{name}_bf16", M.check_model, name=name, precision="bf16", hw=64, B=2)
+    for name in ("yolov10m", "yolov10b", "yolov10l", "yolov10x"):
+        add(f"model_{name}_bf16", M.check_model, name=name, precision="bf16", hw=64, B=2)
+        add(f"model_{name}_f32", M.check_model, name=name, precision="fp32", hw=64, B=1)
+    add("model_s_bf16_320", M.check_model, name="yolov10s", precision="bf16", hw=320, B=2)
+    add("model_s_golden", M.check_model_golden, name="yolov10s")
+    add("model_s_subbatch_graph", M.check_subbatch_and_graph, name="yolov10s")
+    add("model_s_decode_e2e", M.check_decode_e2e, name="yolov10s")
+    return R
+
+
+def worker(names):
+    import torch  # noqa: F401
+    reg = {n: (f, kw) for n, f, kw in registry()}
+    for n in names:
+        f, kw = reg[n]
+        t = time.time()
+        try:
+            res = f(**kw)
+            print("RESULT " + json.dumps({"name": n, "ok": True, "res": res, "s": round(time.time() - t, 2)}), flush=True)
+        except AssertionError as e:
+            print("RESULT " + json.dumps({"name": n, "ok": False, "err": "ASSERT: " + str(e)[:300], "s": round(time.time() - t, 2)}), flush=True)
+        except Exception as e:  # CUDA errors are sticky: stop this worker
+            print("RESULT " + json.dumps({"name": n, "ok": False, "err": f"{type(e).__name__}: {str(e)[:400]}", "fatal": True}), flush=True)
+            return
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--worker", default=None)
+    ap.add_argument("--filter", default="")
+    ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "diag.json"))
+    ap.add_argument("--timeout", type=int, default=300)
+    a = ap.parse_args()
+    if a.worker is not None:
+        worker(a.worker.split(","))
+        return
+    names = [n for n, _, _ in registry() if a.filter in n]
+    results = []
+    todo = list(names)
+    while todo:
+        try:
+            p = subprocess.run([sys.executable, __file__, "--worker", ",".join(todo)], capture_output=True, text=True, timeout=a.timeout)
+            out, err = p.stdout, p.stderr
+        except subprocess.TimeoutExpired as e:
+            out = (e.stdout or b"").decode() if isinstance(e.stdout, bytes) else (e.stdout or "")
+            err = "TIMEOUT"
+        done = [json.loads(l[7:]) for l in out.splitlines() if l.startswith("RESULT ")]
+        results += done
+        finished = {d["name"] for d in done}
+        rest = [n for n in todo if n not in finished]
+        if done and done[-1].get("fatal"):
+            done[-1]["stderr"] = err[-600:]
+        elif rest:  # worker died without reporting (trap / segfault / timeout) on rest[0]
+            results.append({"name": rest[0], "ok": False, "err": "worker died: " + err[-600:]})
+            rest = rest[1:]
+        todo = rest
+    os.makedirs(os.path.dirname(a.out), exist_ok=True)
+    json.dump(results, open(a.out, "w"), indent=1)
+    bad = [r for r in results if not r["ok"]]
+    for r in results:
+        print(("PASS " if r["ok"] else "FAIL ") + r["name"] + "  " + (json.dumps(r.get("res")) if r["ok"] else r["err"].replace("\n", " | ")[:500]))
+    print(f"{len(results) - len(bad)}/{len(results)} checks passed")
+    sys.exit(1 if bad else 0)
+
+
+if __name__ == "__main__":
+    main()
