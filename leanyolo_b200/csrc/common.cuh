@@ -44,6 +44,8 @@ inline int32_t post_launch(const char* what) {
 int32_t launch_stem(const ly_op& op, cudaStream_t s);
 int32_t launch_conv_simt(const ly_op& op, cudaStream_t s);
 int32_t launch_dw(const ly_op& op, cudaStream_t s);
+int32_t launch_dw_tma(const ly_op& op, cudaStream_t s);   // bf16, TMA-staged (dw_tma.cu)
+bool dw_tma_supported(const ly_op& op);
 int32_t launch_pool(const ly_op& op, cudaStream_t s);
 int32_t launch_up(const ly_op& op, cudaStream_t s);
 int32_t launch_attn(const ly_op& op, cudaStream_t s);

@@ -17,18 +17,20 @@
 //   (dC0, dCtot) of the consumer's concat buffer, the input tensor map starts at the
 //   producer's channel offset, the shortcut is read in the epilogue.
 // * Persistent: one CTA per SM, static round-robin over (pixel-brick, n-tile) tiles.
-//   Warp roles: 0 = TMA producer, 1 = MMA issuer (+TMEM alloc), 2..5 = epilogue.
+//   Warp roles: 0 = TMA producer, 1 = MMA issuer (+TMEM alloc), 2..9 = epilogue.
 //
 // Reference semantics: leanyolo/models/yolov10/layers.py:51-88 (Conv = conv+BN+SiLU).
 #include <cuda.h>
 #include <string.h>
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace ly {
 
 namespace {
 
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;   // TMA warp + MMA warp + 8 epilogue warps
+constexpr int kMaxCout = 1024;   // bias vector staged in shared memory
 constexpr int kMaxStages = 12;
 constexpr uint32_t kSmemBudget = 200 * 1024;
 
@@ -55,54 +57,6 @@ struct Params {
   int cin_pad;
 };
 
-// ------------------------------------------------------------------------------ PTX glue
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-// Bounded wait: a protocol bug must trap (error to the host), never hang the GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done = 0;
-  unsigned long long t0 = 0;
-  for (uint32_t it = 0;; ++it) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (done) return;
-    if ((it & 1023u) == 1023u) {
-      unsigned long long t;
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-      if (t0 == 0) t0 = t;
-      else if (t - t0 > 4000000000ull) {  // 4 s
-        printf("conv_tc: mbarrier timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
-        __trap();
-      }
-    }
-  }
-}
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1)
-      : "memory");
-}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
@@ -125,6 +79,14 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// SiLU(x) = x*sigmoid(x) = h + h*tanh(h), h = x/2: one MUFU op (tanh.approx, rel. err 2^-11)
+__device__ __forceinline__ float silu_tanh(float x) {
+  const float h = 0.5f * x;
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(h, t, h);
+}
 
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred = 0;
@@ -154,6 +116,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __shared__ __align__(16) float s_bias[kMaxCout];
+  for (int i = threadIdx.x; i < p.tiles_n * p.block_n; i += kThreads) s_bias[i] = p.bias[i];
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmA) : "memory");
@@ -164,7 +128,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), 4);
+      mbar_init(tempty_bar(s), 8);
     }
     mbar_init(bres_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -248,9 +212,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       }
     }
   } else {
-    // ============================== epilogue (4 warps) ========================
-    const int q = warp & 3;            // TMEM lane quarter this warp may read
-    const int row = q * 32 + lane;     // row of the 128-pixel tile owned by this thread
+    // ============================== epilogue (8 warps) ========================
+    // warp -> (TMEM lane quarter q = warp % 4, column half); a thread owns one pixel row and
+    // walks its columns in 16-wide chunks, the TMEM load of chunk i+1 in flight while chunk i
+    // is activated and stored.  The accumulator stage is released as soon as the last chunk
+    // sits in registers, so the MMA warp can start tile i+2 while this tile is still stored.
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int nchunks = p.block_n >> 4;
+    const int c_half = (nchunks + 1) >> 1;
+    const int cbeg = half ? c_half : 0, cend = half ? nchunks : c_half;
+    const int row = q * 32 + lane;
     const int dw = row % p.tw;
     const int dh = (row / p.tw) % p.th;
     const int db = row / (p.tw * p.th);
@@ -273,16 +245,27 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       const __nv_bfloat16* rrow = p.res ? p.res + lin * p.rCtot + p.rC0 + n0 : nullptr;
       long long nchw_b = 0, nchw_rem = 0;
       if (p.nchw) { nchw_b = lin / p.hw_real; nchw_rem = lin - nchw_b * p.hw_real; }
-      for (int c = 0; c < p.block_n; c += 16) {
+      uint32_t nxt[16];
+      if (cbeg < cend) tmem_ld16(taddr + cbeg * 16, nxt);
+      for (int ch = cbeg; ch < cend; ++ch) {
+        const int c = ch * 16;
         uint32_t r[16];
-        tmem_ld16(taddr + c, r);
         tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) r[j] = nxt[j];
+        if (ch + 1 < cend) {
+          tmem_ld16(taddr + c + 16, nxt);
+        } else {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar(as));
+        }
         if (valid) {
           float v[16];
-          const float4* bp = reinterpret_cast<const float4*>(p.bias + n0 + c);
+          const float4* bp = reinterpret_cast<const float4*>(s_bias + n0 + c);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const float4 bb = __ldg(bp + j);
+            const float4 bb = bp[j];
             v[4 * j + 0] = __uint_as_float(r[4 * j + 0]) + bb.x;
             v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + bb.y;
             v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + bb.z;
@@ -290,7 +273,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           }
           if (p.act) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = silu_f(v[j]);
+            for (int j = 0; j < 16; ++j) v[j] = silu_tanh(v[j]);
           }
           if (rrow) {
             float rv[16];
@@ -312,9 +295,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           }
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(as));
+      if (cbeg >= cend) {   // this warp has no columns (narrow N): still release the stage
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(as));
+      }
       if (++as == 2) { as = 0; aphase ^= 1u; }
     }
   }
@@ -328,22 +313,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 }
 
 // ------------------------------------------------------------------------- host side
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn get_encode() {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void* sym = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(sym);
-  }
-  return fn;
-}
-
 int pow2_ge(int v) { int p = 32; while (p < v) p <<= 1; return p; }
 
 }  // namespace
@@ -367,6 +336,7 @@ int32_t conv_tc_prepare(const ly_op& op, ConvTcState** out) {
   LY_CHECK_ARG(conv_tc_supported(op), "conv_tc: unsupported op (bf16, k in {1,3}, stride in {1,2}, 16-channel granularity)");
   LY_CHECK_ARG(op.src.ptr && op.w && op.bias && (op.dst.ptr || op.nchw), "conv_tc: null pointer");
   LY_CHECK_ARG(op.src.H % op.stride == 0 && op.src.W % op.stride == 0, "conv_tc: H,W must divide by the stride");
+  LY_CHECK_ARG((op.dst.ptr ? op.dst.c : op.nchw_c) <= kMaxCout, "conv_tc: Cout > %d not supported", kMaxCout);
   EncodeTiledFn encode = get_encode();
   if (!encode) { set_error("conv_tc: cuTensorMapEncodeTiled entry point not available"); return LY_E_CUDA; }
 
@@ -476,7 +446,8 @@ int32_t conv_tc_prepare(const ly_op& op, ConvTcState** out) {
   st->grid = p.total_tiles < sms ? p.total_tiles : sms;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         227 * 1024 - (int)sizeof(float) * kMaxCout - 1024 /* static smem: s_bias */);
     if (e != cudaSuccess) { delete st; set_error("conv_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e)); return LY_E_CUDA; }
     attr_set = true;
   }

@@ -1,0 +1,261 @@
+// Depthwise k x k convolution (bf16 hot path), TMA-staged.
+//
+// The op is HBM-bound (reads and writes every activation once, ~9-49 MACs per element), so
+// the kernel is built around keeping many bytes in flight without spending registers on
+// them: a producer warp streams (channel-block x halo-tile) boxes of the NHWC input into a
+// shared-memory ring with 4-D TMA tile loads (out-of-image halo = hardware zero fill = the
+// conv's zero padding), 4 compute warps consume them.  A compute thread owns one 16-byte
+// channel vector of a horizontal strip of SL output pixels: every input vector it reads from
+// shared memory feeds up to K outputs, weights for the current filter row live in registers,
+// accumulation is fp32.  Persistent grid, static round-robin over tiles.
+//
+// Reference semantics: Conv(g=C) + BN (+SiLU) (+shortcut), leanyolo/models/yolov10/layers.py
+// :51-88, 274-300, 455; RepVGGDW arrives here already merged into one 7x7 (modules.py).
+#include <string.h>
+#include "common.cuh"
+#include "tma.cuh"
+
+namespace ly {
+
+namespace {
+
+constexpr int kComputeThreads = 128;
+constexpr int kThreadsDw = kComputeThreads + 32;
+constexpr int kMaxStagesDw = 6;
+
+struct DwParams {
+  CUtensorMap tmIn;
+  int tiles_x, tiles_y, tiles_c, total_tiles;
+  int Ho, Wo, C;
+  int stages, stage_bytes, box_bytes;
+  int act;
+  const __nv_bfloat16* w;
+  const float* bias;
+  __nv_bfloat16* dst; int dCtot, dC0;
+  const __nv_bfloat16* res; int rCtot, rC0;
+};
+
+__device__ __forceinline__ void unpack8(const uint4& v, float* f) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __bfloat1622float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+
+template <int K, int S, int CBV, int TW_T, int TH_T>
+__global__ void __launch_bounds__(kThreadsDw) dw_tma_kernel(const __grid_constant__ DwParams p) {
+  constexpr int CB = CBV * 8;                       // channels per block
+  constexpr int IWt = (TW_T - 1) * S + K, IHt = (TH_T - 1) * S + K;
+  constexpr int NW = kComputeThreads / CBV;         // pixel workers
+  constexpr int SL = TW_T * TH_T / NW;              // outputs per worker (a horizontal strip)
+  constexpr int SPR = TW_T / SL;                    // strips per tile row
+  constexpr int IWS = (SL - 1) * S + K;             // input columns a strip touches
+  static_assert(SL >= 1 && SL * NW == TW_T * TH_T && SPR * SL == TW_T, "bad dw tile configuration");
+  (void)IHt;
+
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  __shared__ __align__(8) unsigned long long bars[2 * kMaxStagesDw];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 127u) & ~127u;
+  const uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bar0 = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (kMaxStagesDw + s); };
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmIn) : "memory");
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), kComputeThreads / 32);
+    }
+    fence_barrier_init();
+  }
+  __syncthreads();
+
+  if (warp == kComputeThreads / 32) {
+    // ------------------------------------------------ producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        int t = tile;
+        const int xt = t % p.tiles_x; t /= p.tiles_x;
+        const int yt = t % p.tiles_y; t /= p.tiles_y;
+        const int ct = t % p.tiles_c;
+        const int b = t / p.tiles_c;
+        mbar_wait(empty_bar(stage), phase ^ 1u);
+        mbar_expect_tx(full_bar(stage), (uint32_t)p.box_bytes);
+        tma_load_4d(smem_base + stage * p.stage_bytes, &p.tmIn, full_bar(stage), ct * CB, xt * TW_T * S - K / 2,
+                    yt * TH_T * S - K / 2, b);
+        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+      }
+    }
+    return;
+  }
+
+  // -------------------------------------------------- compute
+  const int cv = threadIdx.x % CBV;
+  const int wk = threadIdx.x / CBV;
+  const int sy = wk / SPR;
+  const int sx0 = (wk % SPR) * SL;
+  int stage = 0;
+  uint32_t phase = 0;
+  for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    int t = tile;
+    const int xt = t % p.tiles_x; t /= p.tiles_x;
+    const int yt = t % p.tiles_y; t /= p.tiles_y;
+    const int ct = t % p.tiles_c;
+    const int b = t / p.tiles_c;
+    const int c = ct * CB + cv * 8;
+
+    float acc[SL][8];
+    {
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + c));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + c + 4));
+#pragma unroll
+      for (int x = 0; x < SL; ++x) {
+        acc[x][0] = b0.x; acc[x][1] = b0.y; acc[x][2] = b0.z; acc[x][3] = b0.w;
+        acc[x][4] = b1.x; acc[x][5] = b1.y; acc[x][6] = b1.z; acc[x][7] = b1.w;
+      }
+    }
+    mbar_wait(full_bar(stage), phase);
+    const uint8_t* tile_s = smem_gen + stage * p.stage_bytes;
+#pragma unroll
+    for (int ky = 0; ky < K; ++ky) {
+      float wv[K][8];
+#pragma unroll
+      for (int kx = 0; kx < K; ++kx) {
+        const uint4 raw = __ldg(reinterpret_cast<const uint4*>(p.w + (ky * K + kx) * p.C + c));
+        unpack8(raw, wv[kx]);
+      }
+      const uint8_t* row_s = tile_s + ((size_t)((sy * S + ky) * IWt + sx0 * S) * CB + cv * 8) * 2;
+#pragma unroll
+      for (int ix = 0; ix < IWS; ++ix) {
+        float in[8];
+        unpack8(*reinterpret_cast<const uint4*>(row_s + (size_t)ix * CB * 2), in);
+#pragma unroll
+        for (int kx = 0; kx < K; ++kx) {
+          const int d = ix - kx;
+          if (d >= 0 && d % S == 0 && d / S < SL) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[d / S][j] = fmaf(in[j], wv[kx][j], acc[d / S][j]);
+          }
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty_bar(stage));   // this warp is done reading the stage
+    if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+
+    const int oy = yt * TH_T + sy;
+    if (oy < p.Ho) {
+#pragma unroll
+      for (int x = 0; x < SL; ++x) {
+        const int ox = xt * TW_T + sx0 + x;
+        if (ox >= p.Wo) continue;
+        const long long opix = ((long long)b * p.Ho + oy) * p.Wo + ox;
+        if (p.act) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[x][j] = silu_f(acc[x][j]);
+        }
+        if (p.res) {
+          float rv[8];
+          load_vec<__nv_bfloat16>(p.res + opix * p.rCtot + p.rC0 + c, rv);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[x][j] += rv[j];
+        }
+        store_vec<__nv_bfloat16>(p.dst + opix * p.dCtot + p.dC0 + c, acc[x]);
+      }
+    }
+  }
+}
+
+template <int K, int S, int CBV, int TW_T, int TH_T>
+int32_t launch_cfg(const ly_op& op, cudaStream_t st) {
+  constexpr int CB = CBV * 8;
+  constexpr int IWt = (TW_T - 1) * S + K, IHt = (TH_T - 1) * S + K;
+  EncodeTiledFn encode = get_encode();
+  if (!encode) { set_error("dw_tma: cuTensorMapEncodeTiled entry point not available"); return LY_E_CUDA; }
+  DwParams p;
+  memset(&p, 0, sizeof(p));
+  p.Ho = op.dst.H; p.Wo = op.dst.W; p.C = op.src.c;
+  p.tiles_x = (p.Wo + TW_T - 1) / TW_T;
+  p.tiles_y = (p.Ho + TH_T - 1) / TH_T;
+  p.tiles_c = p.C / CB;
+  const long long total = (long long)p.tiles_x * p.tiles_y * p.tiles_c * op.B;
+  LY_CHECK_ARG(total <= 0x7FFFFFFF, "dw_tma: too many tiles");
+  p.total_tiles = (int)total;
+  p.box_bytes = IWt * IHt * CB * 2;
+  p.stage_bytes = (p.box_bytes + 127) / 128 * 128;
+  int stages = (100 * 1024) / p.stage_bytes;   // <= ~100 KB per CTA so that two CTAs share an SM
+  if (stages > kMaxStagesDw) stages = kMaxStagesDw;
+  LY_CHECK_ARG(stages >= 2, "dw_tma: tile does not fit in shared memory");
+  p.stages = stages;
+  p.act = op.act;
+  p.w = (const __nv_bfloat16*)op.w; p.bias = op.bias;
+  p.dst = (__nv_bfloat16*)op.dst.ptr; p.dCtot = op.dst.ctot; p.dC0 = op.dst.c0;
+  p.res = (const __nv_bfloat16*)op.res.ptr; p.rCtot = op.res.ctot; p.rC0 = op.res.c0;
+  {
+    char* base = (char*)op.src.ptr + (size_t)op.src.c0 * 2;
+    cuuint64_t dims[4] = {(cuuint64_t)op.src.c, (cuuint64_t)op.src.W, (cuuint64_t)op.src.H, (cuuint64_t)op.B};
+    cuuint64_t strides[3] = {(cuuint64_t)op.src.ctot * 2, (cuuint64_t)op.src.ctot * 2 * op.src.W,
+                             (cuuint64_t)op.src.ctot * 2 * op.src.W * op.src.H};
+    cuuint32_t box[4] = {CB, IWt, IHt, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = encode(&p.tmIn, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("dw_tma: cuTensorMapEncodeTiled failed with %d", (int)r); return LY_E_CUDA; }
+  }
+  const size_t smem = (size_t)p.stages * p.stage_bytes + 128;
+  static bool attr_set = false;
+  if (!attr_set) {
+    LY_CUDA(cudaFuncSetAttribute(dw_tma_kernel<K, S, CBV, TW_T, TH_T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  const int sms = sm_count();
+  // two CTAs per SM when they fit: more loads in flight, epilogue of one overlaps compute of the other
+  int grid = 2 * sms;
+  if (grid > p.total_tiles) grid = p.total_tiles;
+  dw_tma_kernel<K, S, CBV, TW_T, TH_T><<<grid, kThreadsDw, smem, st>>>(p);
+  return post_launch("dwconv_tma");
+}
+
+// waste of covering an Ho x Wo map with TW x TH tiles (1.0 = none)
+double cover(int Ho, int Wo, int tw, int th) {
+  return (double)((Wo + tw - 1) / tw * tw) * ((Ho + th - 1) / th * th) / ((double)Ho * Wo);
+}
+
+}  // namespace
+
+bool dw_tma_supported(const ly_op& op) {
+  if (op.dtype != LY_BF16) return false;
+  if (!((op.k == 3 && (op.stride == 1 || op.stride == 2)) || (op.k == 7 && op.stride == 1))) return false;
+  if (op.src.c % 16 || op.src.c0 % 8 || op.src.ctot % 8 || op.dst.c0 % 8 || op.dst.ctot % 8) return false;
+  if (op.res.ptr && (op.res.c0 % 8 || op.res.ctot % 8)) return false;
+  if (reinterpret_cast<uintptr_t>(op.src.ptr) % 16) return false;
+  return true;
+}
+
+int32_t launch_dw_tma(const ly_op& op, cudaStream_t s) {
+  const int C = op.src.c;
+  const int cbv = C % 64 == 0 ? 8 : (C % 32 == 0 ? 4 : 2);
+  const bool wide = cover(op.dst.H, op.dst.W, 20, 4) < cover(op.dst.H, op.dst.W, 16, op.stride == 2 ? 4 : 8);
+  if (op.k == 3 && op.stride == 1) {
+    if (cbv == 8) return wide ? launch_cfg<3, 1, 8, 20, 4>(op, s) : launch_cfg<3, 1, 8, 16, 8>(op, s);
+    if (cbv == 4) return launch_cfg<3, 1, 4, 16, 8>(op, s);
+    return launch_cfg<3, 1, 2, 16, 8>(op, s);
+  }
+  if (op.k == 3 && op.stride == 2) {
+    if (cbv == 8) return wide ? launch_cfg<3, 2, 8, 20, 4>(op, s) : launch_cfg<3, 2, 8, 16, 4>(op, s);
+    if (cbv == 4) return launch_cfg<3, 2, 4, 16, 4>(op, s);
+    return launch_cfg<3, 2, 2, 16, 4>(op, s);
+  }
+  if (cbv == 8) return wide ? launch_cfg<7, 1, 8, 20, 4>(op, s) : launch_cfg<7, 1, 8, 16, 8>(op, s);
+  if (cbv == 4) return launch_cfg<7, 1, 4, 16, 8>(op, s);
+  return launch_cfg<7, 1, 2, 16, 8>(op, s);
+}
+
+}  // namespace ly

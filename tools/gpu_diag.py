@@ -73,6 +73,22 @@ def registry():
         add(f"stem_{dt}", G.check_stem, dtype=dt)
         add(f"stem_norm_{dt}", G.check_stem, dtype=dt, cout=48, sub=(10.0, 20.0, 30.0), div=(58.0, 57.0, 59.0))
         add(f"export_import_{dt}", G.check_export_import, dtype=dt)
+    # TMA-staged depthwise: every tile configuration / channel-block width
+    add("dwtma_3_c64_80", G.check_dw, k=3, c=64, H=80, W=80)
+    add("dwtma_3_c128_20_res", G.check_dw, k=3, c=128, H=20, W=20, res=True)
+    add("dwtma_3_c256_40", G.check_dw, k=3, c=256, H=40, W=40, B=3)
+    add("dwtma_3_c96", G.check_dw, k=3, c=96, H=24, W=24)
+    add("dwtma_3_c48", G.check_dw, k=3, c=48, H=24, W=24)
+    add("dwtma_3_odd", G.check_dw, k=3, c=64, H=13, W=27, B=3)
+    add("dwtma_3s2_c256_80", G.check_dw, k=3, stride=2, c=256, H=80, W=80, act=False)
+    add("dwtma_3s2_c64_40", G.check_dw, k=3, stride=2, c=64, H=40, W=40, act=False)
+    add("dwtma_3s2_c96", G.check_dw, k=3, stride=2, c=96, H=24, W=24)
+    add("dwtma_3s2_c48_odd", G.check_dw, k=3, stride=2, c=48, H=14, W=22)
+    add("dwtma_7_c512_20", G.check_dw, k=7, c=512, H=20, W=20)
+    add("dwtma_7_c64_40", G.check_dw, k=7, c=64, H=40, W=40)
+    add("dwtma_7_c96", G.check_dw, k=7, c=96, H=16, W=16)
+    add("dwtma_7_c48", G.check_dw, k=7, c=48, H=16, W=16)
+    add("stem_odd_sizes", G.check_stem, H=96, W=160, cout=16, B=3)
     # decode tail
     add("topk_golden", D.check_topk_golden)
     add("topk_vs_oracle_b4", D.check_topk_vs_oracle, B=4, seed=3)
