@@ -36,6 +36,9 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found (set NVCC=/path/to/nvcc)")
 
 
+EXTRA = os.environ.get("LY_NVCC_EXTRA", "").split()   # e.g. -DLY_TC_PROFILE
+
+
 def _sources():
     return sorted(CSRC.glob("*.cu"))
 
@@ -45,7 +48,7 @@ def _fingerprint() -> str:
     for f in sorted(list(CSRC.glob("*")) + [PKG.parent / "include" / "leanyolo_b200.h"]):
         h.update(f.name.encode())
         h.update(f.read_bytes())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(" ".join(NVCC_FLAGS + EXTRA).encode())
     return h.hexdigest()
 
 
@@ -57,7 +60,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     objs = []
     for src in _sources():
         obj = OUT_DIR / (src.stem + ".o")
-        cmd = [_nvcc(), *[f for f in NVCC_FLAGS if f != "-shared"], "-c", str(src), "-o", str(obj)]
+        cmd = [_nvcc(), *[f for f in NVCC_FLAGS if f != "-shared"], *EXTRA, "-c", str(src), "-o", str(obj)]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if verbose or r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)

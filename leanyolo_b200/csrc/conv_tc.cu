@@ -2,17 +2,23 @@
 //
 //   D[M = B*Ho*Wo, N = Cout] = A[M, K = k*k*Cin] * W[N, K]^T  (+bias, SiLU, +residual)
 //
-// * A is never materialised: for every filter tap (r,s) and channel block the producer
-//   issues ONE 4-D TMA tile load (C, W, H, B) of the NHWC activation at the shifted
-//   coordinate; out-of-bounds (padding) elements are zero-filled by the TMA unit and a
-//   stride-2 conv is the tensor map's elementStrides = 2.  The tile of 128 output pixels
-//   is a (tw x th x tb) brick chosen per layer so that feature maps tile without waste
-//   (e.g. 16x8x1 @160^2, 8x8x2 @40^2, 4x4x8 @20^2); 1x1/s1 layers collapse to a flat
-//   [M, C] matrix.
+// * A is never materialised.  The producer warp issues 4-D TMA tile loads (C, W, H, B) of
+//   the NHWC activation; out-of-bounds (padding) elements are zero-filled by the TMA unit and
+//   a stride-2 conv is the tensor map's elementStrides = 2.  The tile of 128 output pixels is
+//   a (tw x th x tb) brick chosen per layer so that feature maps tile without waste; 1x1/s1
+//   layers collapse to a flat [M, C] matrix.
+//     classic mode : one box per (filter tap, channel block)          -> 9 loads / block for 3x3
+//     halo mode    : 3x3 stride 1, brick 8 x 16: one box of 8 x 18 pixels per (kx, channel
+//                    block); the three ky taps are the same shared-memory tile viewed 8 rows
+//                    (= one swizzle atom) further down -> 3 loads / block.  The TMA unit is
+//                    request-rate bound on these strided 64/128-byte rows (measured ~5 cycles
+//                    per row), so this is what moves the 3x3 layers towards the MMA roofline.
 // * MMA: tcgen05.mma.cta_group::1.kind::f16, M=128, N=BLOCK_N (<=256), K=16 per
-//   instruction, bf16 x bf16 -> fp32 accumulators in TMEM (double-buffered so the
-//   epilogue of tile i overlaps the MMAs of tile i+1).  Operands are K-major in shared
-//   memory with the 32/64/128-byte swizzle that matches the channel block (16/32/64).
+//   instruction, bf16 x bf16 -> fp32 accumulators in TMEM (double-buffered so the epilogue of
+//   tile i overlaps the MMAs of tile i+1).  Operands are K-major in shared memory with the
+//   32/64/128-byte swizzle that matches the channel block (16/32/64).
+// * Weights: resident in shared memory for the whole kernel when they fit (<= 96 KB),
+//   otherwise streamed through their own ring, one box per (tap, channel block).
 // * concat / split / residual are epilogue addressing: the output goes to a channel slice
 //   (dC0, dCtot) of the consumer's concat buffer, the input tensor map starts at the
 //   producer's channel offset, the shortcut is read in the epilogue.
@@ -21,6 +27,7 @@
 //
 // Reference semantics: leanyolo/models/yolov10/layers.py:51-88 (Conv = conv+BN+SiLU).
 #include <cuda.h>
+#include <stdlib.h>
 #include <string.h>
 #include "common.cuh"
 #include "tma.cuh"
@@ -29,9 +36,9 @@ namespace ly {
 
 namespace {
 
-constexpr int kThreads = 320;   // TMA warp + MMA warp + 8 epilogue warps
+constexpr int kThreads = 320;    // TMA warp + MMA warp + 8 epilogue warps
 constexpr int kMaxCout = 1024;   // bias vector staged in shared memory
-constexpr int kMaxStages = 12;
+constexpr int kMaxStages = 12;   // per ring
 constexpr uint32_t kSmemBudget = 200 * 1024;
 
 struct Params {
@@ -44,9 +51,13 @@ struct Params {
   int hw_real;             // Ho*Wo of the real tensor (NCHW addressing)
   int k, stride, pad;
   int kc, kc_blocks, num_kb;
+  int halo;                // 1: halo mode (3 taps share one A box)
+  int tpa, num_ka;         // taps per A stage, A loads per tile
+  int a_tap_stride;        // bytes between the windows of successive taps inside an A stage
   int block_n, tmem_cols;
-  int stages, a_stage, b_stage;   // bytes (stage strides)
-  int b_box;                      // bytes one B TMA box delivers (<= b_stage)
+  int a_stages, b_stages;
+  int a_stage, b_stage;    // stage strides in bytes
+  int a_box, b_box;        // bytes one TMA box delivers
   int b_resident;
   uint32_t idesc, desc_hi;
   int act;
@@ -98,21 +109,98 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// Optional per-role cycle accounting (-DLY_TC_PROFILE): CTA 0 prints where each role waited.
+#ifdef LY_TC_PROFILE
+#define PROF_DECL(name) long long name = 0
+#define PROF_T0() const long long t0__ = clock64()
+#define PROF_ADD(name) name += clock64() - t0__
+#else
+#define PROF_DECL(name)
+#define PROF_T0()
+#define PROF_ADD(name)
+#endif
+
+// barrier addresses inside the barrier block (see the carve-up in the kernel)
+__device__ __forceinline__ uint32_t bar_afull(uint32_t bb, int s) { return bb + 8u * s; }
+__device__ __forceinline__ uint32_t bar_aempty(uint32_t bb, int s) { return bb + 8u * (kMaxStages + s); }
+__device__ __forceinline__ uint32_t bar_bfull(uint32_t bb, int s) { return bb + 8u * (2 * kMaxStages + s); }
+__device__ __forceinline__ uint32_t bar_bempty(uint32_t bb, int s) { return bb + 8u * (3 * kMaxStages + s); }
+__device__ __forceinline__ uint32_t bar_tfull(uint32_t bb, int s) { return bb + 8u * (4 * kMaxStages + s); }
+__device__ __forceinline__ uint32_t bar_tempty(uint32_t bb, int s) { return bb + 8u * (4 * kMaxStages + 2 + s); }
+__device__ __forceinline__ uint32_t bar_bres(uint32_t bb) { return bb + 8u * (4 * kMaxStages + 4); }
+
+// The single MMA-issuing thread.  Specialised on the k-steps per channel block, the taps per
+// A stage and weight residency so that the issue loop is straight-line code: a descriptor is
+// (constant high word | 14-bit address field), and stepping K by 16 elements or moving to the
+// next tap / stage is an integer add on the low word.  (Measured: a clean issue loop sustains
+// one M=128 MMA every ~50 cycles for N <= 64; anything slower is issue overhead.)
+template <int KSTEPS, int TPA, bool BRES>
+__device__ __forceinline__ void mma_role(const Params& p, uint32_t a_base, uint32_t b_base, uint32_t bb, uint32_t tmem_base) {
+  const uint32_t hi = p.desc_hi, idesc = p.idesc;
+  const int num_ka = p.num_ka, a_stages = p.a_stages, b_stages = p.b_stages, total = p.total_tiles;
+  const uint32_t a_stage16 = (uint32_t)p.a_stage >> 4, b_stage16 = (uint32_t)p.b_stage >> 4, tap16 = (uint32_t)p.a_tap_stride >> 4;
+  const uint32_t a_lo0 = (a_base >> 4) | (1u << 16), b_lo0 = (b_base >> 4) | (1u << 16);
+  const uint32_t block_n = (uint32_t)p.block_n;
+  if (BRES) {
+    mbar_wait(bar_bres(bb), 0);
+    tc_fence_after();
+  }
+  int sa = 0, sb = 0, as = 0;
+  uint32_t pa = 0, pb = 0, aphase = 0;
+  for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+    mbar_wait(bar_tempty(bb, as), aphase ^ 1u);
+    tc_fence_after();
+    const uint32_t d_tmem = tmem_base + (uint32_t)as * block_n;
+    for (int ka = 0; ka < num_ka; ++ka) {
+      mbar_wait(bar_afull(bb, sa), pa);
+      tc_fence_after();
+      const uint32_t alo = a_lo0 + (uint32_t)sa * a_stage16;
+#pragma unroll
+      for (int tt = 0; tt < TPA; ++tt) {
+        uint32_t blo;
+        if (BRES) {
+          blo = b_lo0 + (uint32_t)(ka * TPA + tt) * b_stage16;
+        } else {
+          mbar_wait(bar_bfull(bb, sb), pb);
+          tc_fence_after();
+          blo = b_lo0 + (uint32_t)sb * b_stage16;
+        }
+#pragma unroll
+        for (int kk = 0; kk < KSTEPS; ++kk) {
+          const uint64_t da = ((uint64_t)hi << 32) | (uint64_t)(alo + tt * tap16 + 2 * kk);
+          const uint64_t db = ((uint64_t)hi << 32) | (uint64_t)(blo + 2 * kk);
+          umma_bf16(d_tmem, da, db, idesc, (tt | kk) != 0 ? 1u : (ka != 0 ? 1u : 0u));
+        }
+        if (!BRES) {
+          umma_commit(bar_bempty(bb, sb));
+          if (++sb == b_stages) { sb = 0; pb ^= 1u; }
+        }
+      }
+      umma_commit(bar_aempty(bb, sa));
+      if (++sa == a_stages) { sa = 0; pa ^= 1u; }
+    }
+    umma_commit(bar_tfull(bb, as));
+    if (++as == 2) { as = 0; aphase ^= 1u; }
+  }
+}
+
 // ------------------------------------------------------------------------------- kernel
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // carve: [A stages][B stages or resident B][barriers]
+  // carve: [A ring][B ring or resident B][barriers]
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_base = smem_base;
-  const uint32_t b_base = a_base + (uint32_t)p.stages * p.a_stage;
-  const uint32_t b_bytes_total = p.b_resident ? (uint32_t)p.num_kb * p.b_stage : (uint32_t)p.stages * p.b_stage;
+  const uint32_t b_base = a_base + (uint32_t)p.a_stages * p.a_stage;
+  const uint32_t b_bytes_total = p.b_resident ? (uint32_t)p.num_kb * p.b_stage : (uint32_t)p.b_stages * p.b_stage;
   const uint32_t bar_base = b_base + b_bytes_total;
-  auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (kMaxStages + s); };
-  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + s); };
-  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + 2 + s); };
-  const uint32_t bres_bar = bar_base + 8u * (2 * kMaxStages + 4);
-  const uint32_t tmem_slot = bar_base + 8u * (2 * kMaxStages + 5);
+  auto afull_bar = [&](int s) { return bar_base + 8u * s; };
+  auto aempty_bar = [&](int s) { return bar_base + 8u * (kMaxStages + s); };
+  auto bfull_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + s); };
+  auto bempty_bar = [&](int s) { return bar_base + 8u * (3 * kMaxStages + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (4 * kMaxStages + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (4 * kMaxStages + 2 + s); };
+  const uint32_t bres_bar = bar_base + 8u * (4 * kMaxStages + 4);
+  const uint32_t tmem_slot = bar_base + 8u * (4 * kMaxStages + 5);
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -122,17 +210,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmB) : "memory");
-    for (int s = 0; s < p.stages; ++s) {
-      mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+    for (int s = 0; s < kMaxStages; ++s) {
+      mbar_init(afull_bar(s), 1);
+      mbar_init(aempty_bar(s), 1);
+      mbar_init(bfull_bar(s), 1);
+      mbar_init(bempty_bar(s), 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
       mbar_init(tempty_bar(s), 8);
     }
     mbar_init(bres_bar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    fence_barrier_init();
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)p.tmem_cols)
@@ -147,16 +236,42 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   if (warp == 0) {
     // ============================== TMA producer ==============================
     if (elect_one()) {
+      // k-block order (shared with the MMA issuer, which simply counts k-blocks):
+      //   classic: for tap (ky, kx): for cb            halo: for cb: for kx: [A box], ky = 0..2
+      const int KK = p.k, kcb = p.kc_blocks, kc = p.kc, cin = p.cin_pad;
       if (p.b_resident) {
         mbar_expect_tx(bres_bar, (uint32_t)p.num_kb * p.b_box);
-        for (int kb = 0; kb < p.num_kb; ++kb) {
-          const int tap = kb / p.kc_blocks, cb = kb - tap * p.kc_blocks;
-          tma_load_2d(b_base + kb * p.b_stage, &p.tmB, bres_bar, tap * p.cin_pad + cb * p.kc, 0);
+        uint32_t dstb = b_base;
+        if (p.halo) {
+          for (int cb = 0; cb < kcb; ++cb)
+            for (int kx = 0; kx < 3; ++kx)
+              for (int ky = 0; ky < 3; ++ky, dstb += p.b_stage)
+                tma_load_2d(dstb, &p.tmB, bres_bar, (ky * 3 + kx) * cin + cb * kc, 0);
+        } else {
+          for (int tap = 0; tap < KK * KK; ++tap)
+            for (int cb = 0; cb < kcb; ++cb, dstb += p.b_stage) tma_load_2d(dstb, &p.tmB, bres_bar, tap * cin + cb * kc, 0);
         }
       }
-      int stage = 0;
-      uint32_t phase = 0;
-      const uint32_t tx = p.a_stage + (p.b_resident ? 0 : p.b_box);
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      PROF_DECL(w_aempty); PROF_DECL(w_bempty); PROF_DECL(p_total);
+#ifdef LY_TC_PROFILE
+      const long long pstart = clock64();
+#endif
+      const bool bres = p.b_resident != 0;
+      const uint32_t a_box = (uint32_t)p.a_box, b_box = (uint32_t)p.b_box;
+      auto load_a = [&](int c0, int w, int h, int b) {
+        { PROF_T0(); mbar_wait(aempty_bar(sa), pa ^ 1u); PROF_ADD(w_aempty); }
+        mbar_expect_tx(afull_bar(sa), a_box);
+        tma_load_4d(a_base + sa * p.a_stage, &p.tmA, afull_bar(sa), c0, w, h, b);
+        if (++sa == p.a_stages) { sa = 0; pa ^= 1u; }
+      };
+      auto load_b = [&](int kcol, int n0) {
+        { PROF_T0(); mbar_wait(bempty_bar(sb), pb ^ 1u); PROF_ADD(w_bempty); }
+        mbar_expect_tx(bfull_bar(sb), b_box);
+        tma_load_2d(b_base + sb * p.b_stage, &p.tmB, bfull_bar(sb), kcol, n0);
+        if (++sb == p.b_stages) { sb = 0; pb ^= 1u; }
+      };
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         int t = tile;
         const int nt = t % p.tiles_n; t /= p.tiles_n;
@@ -164,52 +279,42 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         const int ht = t % p.tiles_h;
         const int bt = t / p.tiles_h;
         const int w0 = wt * p.tw * p.stride - p.pad, h0 = ht * p.th * p.stride - p.pad, b0 = bt * p.tb;
-        for (int kb = 0; kb < p.num_kb; ++kb) {
-          const int tap = kb / p.kc_blocks, cb = kb - tap * p.kc_blocks;
-          const int r = tap / p.k, s = tap - r * p.k;
-          mbar_wait(empty_bar(stage), phase ^ 1u);
-          mbar_expect_tx(full_bar(stage), tx);
-          tma_load_4d(a_base + stage * p.a_stage, &p.tmA, full_bar(stage), cb * p.kc, w0 + s, h0 + r, b0);
-          if (!p.b_resident)
-            tma_load_2d(b_base + stage * p.b_stage, &p.tmB, full_bar(stage), tap * p.cin_pad + cb * p.kc, nt * p.block_n);
-          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+        const int n0 = nt * p.block_n;
+        if (p.halo) {
+          // the box starts one row above the brick and is th+2 rows tall; ky selects a window of it
+          for (int cb = 0; cb < kcb; ++cb)
+            for (int kx = 0; kx < 3; ++kx) {
+              load_a(cb * kc, w0 + kx, h0, b0);
+              if (!bres)
+                for (int ky = 0; ky < 3; ++ky) load_b((ky * 3 + kx) * cin + cb * kc, n0);
+            }
+        } else {
+          for (int ky = 0; ky < KK; ++ky)
+            for (int kx = 0; kx < KK; ++kx)
+              for (int cb = 0; cb < kcb; ++cb) {
+                load_a(cb * kc, w0 + kx, h0 + ky, b0);
+                if (!bres) load_b((ky * KK + kx) * cin + cb * kc, n0);
+              }
         }
       }
+#ifdef LY_TC_PROFILE
+      p_total = clock64() - pstart;
+      if (blockIdx.x == 0) printf("[tc prof] producer: total %lld wait_aempty %lld wait_bempty %lld\n", p_total, w_aempty, w_bempty);
+#endif
     }
   } else if (warp == 1) {
     // ============================== MMA issuer ================================
     if (elect_one()) {
-      if (p.b_resident) {
-        mbar_wait(bres_bar, 0);
-        tc_fence_after();
-      }
-      int stage = 0;
-      uint32_t phase = 0;
-      int as = 0;
-      uint32_t aphase = 0;
       const int ksteps = p.kc / 16;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        mbar_wait(tempty_bar(as), aphase ^ 1u);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(as * p.block_n);
-        for (int kb = 0; kb < p.num_kb; ++kb) {
-          mbar_wait(full_bar(stage), phase);
-          tc_fence_after();
-          const uint32_t a_addr = a_base + stage * p.a_stage;
-          const uint32_t b_addr = p.b_resident ? b_base + kb * p.b_stage : b_base + stage * p.b_stage;
-          const uint64_t hi = (uint64_t)p.desc_hi << 32;
-#pragma unroll 4
-          for (int kk = 0; kk < ksteps; ++kk) {
-            const uint64_t da = hi | (uint64_t)(((a_addr + kk * 32) >> 4) & 0x3FFFu) | (1ull << 16);
-            const uint64_t db = hi | (uint64_t)(((b_addr + kk * 32) >> 4) & 0x3FFFu) | (1ull << 16);
-            umma_bf16(d_tmem, da, db, p.idesc, (kb | kk) != 0 ? 1u : 0u);
-          }
-          umma_commit(empty_bar(stage));
-          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
-        }
-        umma_commit(tfull_bar(as));
-        if (++as == 2) { as = 0; aphase ^= 1u; }
-      }
+#define LY_MMA_CASE(KS)                                                                       \
+  if (ksteps == KS) {                                                                         \
+    if (p.tpa == 3) { if (p.b_resident) mma_role<KS, 3, true>(p, a_base, b_base, bar_base, tmem_base);   \
+                      else mma_role<KS, 3, false>(p, a_base, b_base, bar_base, tmem_base); }  \
+    else            { if (p.b_resident) mma_role<KS, 1, true>(p, a_base, b_base, bar_base, tmem_base);   \
+                      else mma_role<KS, 1, false>(p, a_base, b_base, bar_base, tmem_base); }  \
+  }
+      LY_MMA_CASE(4) else LY_MMA_CASE(2) else LY_MMA_CASE(1)
+#undef LY_MMA_CASE
     }
   } else {
     // ============================== epilogue (8 warps) ========================
@@ -228,6 +333,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     const int db = row / (p.tw * p.th);
     int as = 0;
     uint32_t aphase = 0;
+    PROF_DECL(w_tfull);
+#ifdef LY_TC_PROFILE
+    const long long estart = clock64();
+#endif
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       int t = tile;
       const int nt = t % p.tiles_n; t /= p.tiles_n;
@@ -238,7 +347,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       const bool valid = w < p.Wo && h < p.Ho && b < p.Bo;
       const long long lin = ((long long)b * p.Ho + h) * p.Wo + w;
       const int n0 = nt * p.block_n;
-      mbar_wait(tfull_bar(as), aphase);
+      { PROF_T0(); mbar_wait(tfull_bar(as), aphase); PROF_ADD(w_tfull); }
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.block_n);
       __nv_bfloat16* drow = p.dst ? p.dst + lin * p.dCtot + p.dC0 + n0 : nullptr;
@@ -302,6 +411,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       }
       if (++as == 2) { as = 0; aphase ^= 1u; }
     }
+#ifdef LY_TC_PROFILE
+    if (blockIdx.x == 0 && lane == 0 && (warp == 2 || warp == 6))
+      printf("[tc prof] epilogue warp %d: total %lld wait_tfull %lld\n", warp, clock64() - estart, w_tfull);
+#endif
   }
 
   tc_fence_before();
@@ -314,6 +427,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 
 // ------------------------------------------------------------------------- host side
 int pow2_ge(int v) { int p = 32; while (p < v) p <<= 1; return p; }
+
+int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
 
 }  // namespace
 
@@ -364,6 +482,7 @@ int32_t conv_tc_prepare(const ly_op& op, ConvTcState** out) {
   int dimW, dimH, dimB;
   if (flat) { dimW = op.B * Ho * Wo; dimH = 1; dimB = 1; } else { dimW = Wo; dimH = Ho; dimB = op.B; }
   int best_tw = 128, best_th = 1, best_tb = 1;
+  double best_cover = 1e30;
   {
     double best_cost = 1e30;
     for (int tw = 128; tw >= 1; tw >>= 1)
@@ -373,8 +492,14 @@ int32_t conv_tc_prepare(const ly_op& op, ConvTcState** out) {
         const double cover = (double)((dimW + tw - 1) / tw * tw) * ((dimH + th - 1) / th * th) * ((dimB + tb - 1) / tb * tb);
         // prefer wide bricks (longer contiguous runs) on ties, penalise batch-spanning bricks slightly
         const double cost = cover * (1.0 + 1e-3 * (tb > 1) + 1e-4 * (128 / tw));
-        if (cost < best_cost) { best_cost = cost; best_tw = tw; best_th = th; best_tb = tb; }
+        if (cost < best_cost) { best_cost = cost; best_cover = cover; best_tw = tw; best_th = th; best_tb = tb; }
       }
+  }
+  // halo mode: 3x3 stride 1 with the 8 x 16 brick, unless that brick wastes > 35 % more pixels
+  static const int halo_ok = env_int("LY_TC_HALO", 1);
+  if (halo_ok && op.k == 3 && op.stride == 1) {
+    const double cover = (double)((dimW + 7) / 8 * 8) * ((dimH + 15) / 16 * 16) * dimB;
+    if (cover <= 1.35 * best_cover) { p.halo = 1; best_tw = 8; best_th = 16; best_tb = 1; }
   }
   p.tw = best_tw; p.th = best_th; p.tb = best_tb;
   p.Wo = dimW; p.Ho = dimH; p.Bo = dimB;
@@ -384,22 +509,36 @@ int32_t conv_tc_prepare(const ly_op& op, ConvTcState** out) {
   const long long total = (long long)p.tiles_w * p.tiles_h * p.tiles_b * p.tiles_n;
   if (total > 0x7FFFFFFF) { delete st; set_error("conv_tc: too many tiles"); return LY_E_ARG; }
   p.total_tiles = (int)total;
+  p.tpa = p.halo ? 3 : 1;
+  p.num_ka = p.num_kb / p.tpa;
+  const int a_rows = p.halo ? 8 * 18 : 128;
+  p.a_tap_stride = 8 * p.kc * 2;           // 8 rows = one swizzle atom down
 
   // shared-memory pipeline
-  p.a_stage = 128 * p.kc * 2;
+  p.a_box = a_rows * p.kc * 2;
+  p.a_stage = (p.a_box + 1023) / 1024 * 1024;
   p.b_box = bn * p.kc * 2;
   p.b_stage = (p.b_box + 1023) / 1024 * 1024;
   const long long b_all = (long long)p.num_kb * p.b_stage;
-  static int resident_ok = -1;
-  if (resident_ok < 0) { const char* e = getenv("LY_TC_B_RESIDENT"); resident_ok = e ? atoi(e) : 1; }
+  static const int resident_ok = env_int("LY_TC_B_RESIDENT", 1);
   p.b_resident = (resident_ok && p.tiles_n == 1 && b_all <= 96 * 1024) ? 1 : 0;
-  const uint32_t bar_bytes = 8 * (2 * kMaxStages + 8);
-  long long avail = (long long)kSmemBudget - bar_bytes - 1024 - (p.b_resident ? b_all : 0);
-  int stages = (int)(avail / (p.a_stage + (p.b_resident ? 0 : p.b_stage)));
-  if (stages > kMaxStages) stages = kMaxStages;
-  if (stages < 2) { delete st; set_error("conv_tc: tile does not fit in shared memory"); return LY_E_ARG; }
-  p.stages = stages;
-  st->smem = 1024 + (size_t)stages * p.a_stage + (p.b_resident ? (size_t)b_all : (size_t)stages * p.b_stage) + bar_bytes;
+  const uint32_t bar_bytes = 8 * (4 * kMaxStages + 8);
+  const long long avail = (long long)kSmemBudget - bar_bytes - 1024 - (p.b_resident ? b_all : 0);
+  if (p.b_resident) {
+    p.a_stages = (int)(avail / p.a_stage);
+    p.b_stages = 1;
+  } else {
+    // split the budget so that both rings hold about the same number of k-blocks
+    const long long per_kb = p.a_stage / p.tpa + p.b_stage;
+    long long kbs = avail / per_kb;
+    p.a_stages = (int)(kbs / p.tpa);
+    if (p.a_stages < 2) p.a_stages = 2;
+    p.b_stages = (int)((avail - (long long)p.a_stages * p.a_stage) / p.b_stage);
+  }
+  if (p.a_stages > kMaxStages) p.a_stages = kMaxStages;
+  if (p.b_stages > kMaxStages) p.b_stages = kMaxStages;
+  if (p.a_stages < 2 || (!p.b_resident && p.b_stages < 2)) { delete st; set_error("conv_tc: tile does not fit in shared memory"); return LY_E_ARG; }
+  st->smem = 1024 + (size_t)p.a_stages * p.a_stage + (p.b_resident ? (size_t)b_all : (size_t)p.b_stages * p.b_stage) + bar_bytes;
   if (st->smem < 120 * 1024) st->smem = 120 * 1024;  // force one CTA per SM (TMEM allocations must not contend)
 
   // descriptors
@@ -420,9 +559,8 @@ int32_t conv_tc_prepare(const ly_op& op, ConvTcState** out) {
       dims[0] = Cin; dims[1] = op.src.W; dims[2] = op.src.H; dims[3] = op.B;
       strides[0] = (cuuint64_t)op.src.ctot * 2; strides[1] = strides[0] * op.src.W; strides[2] = strides[1] * op.src.H;
     }
-    box[0] = p.kc; box[1] = p.tw * op.stride; box[2] = p.th * op.stride; box[3] = p.tb;
+    box[0] = p.kc; box[1] = p.tw * op.stride; box[2] = (p.halo ? p.th + 2 : p.th * op.stride); box[3] = p.tb;
     estr[0] = 1; estr[1] = op.stride; estr[2] = op.stride; estr[3] = 1;
-    // a brick may not exceed the tensor extent in box units the driver rejects; clamp is not needed: OOB is legal
     CUresult r = encode(&p.tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         tswz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { delete st; set_error("conv_tc: cuTensorMapEncodeTiled(A) failed with %d", (int)r); return LY_E_CUDA; }
