@@ -56,6 +56,7 @@ enum {
 enum {
   LY_IMPL_AUTO = 0,   /* bf16: tcgen05/TMEM/TMA implicit GEMM; f32: CUDA-core check kernel */
   LY_IMPL_SIMT = 1,   /* force the CUDA-core tiled kernel (bring-up / bisecting only)      */
+  LY_STEM_IN_U8 = 2,  /* STEM only: the external image tensor is uint8 NCHW instead of fp32 */
 };
 
 /* A channel slice [c0, c0+c) of an NHWC buffer whose pixel pitch is `ctot` elements. */

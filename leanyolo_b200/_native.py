@@ -12,7 +12,7 @@ LIB_PATH = Path(__file__).resolve().parent / "_lib" / "libleanyolo_b200.so"
 
 LY_BF16, LY_F32 = 0, 1
 OP_STEM, OP_CONV, OP_DW, OP_POOL, OP_UP, OP_ATTN, OP_EXPORT, OP_IMPORT = 1, 2, 3, 4, 5, 6, 7, 8
-IMPL_AUTO, IMPL_SIMT = 0, 1
+IMPL_AUTO, IMPL_SIMT, STEM_IN_U8 = 0, 1, 2
 
 
 class LyView(C.Structure):

@@ -138,7 +138,8 @@ static int32_t plan_run_impl(ly_plan* pl, float* const* ext, int32_t n_ext, int3
       else if (op.kind == LY_OP_IMPORT) per_img = (long long)op.nchw_ctot * op.dst.H * op.dst.W;
       else if (op.kind == LY_OP_EXPORT) per_img = (long long)op.nchw_ctot * op.src.H * op.src.W;
       else per_img = (long long)op.nchw_ctot * (op.src.H / op.stride) * (op.src.W / op.stride);
-      nchw = ext[op.ext_slot] + (long long)img0 * per_img;
+      const long long esz = (op.kind == LY_OP_STEM && op.impl == LY_STEM_IN_U8) ? 1 : 4;
+      nchw = reinterpret_cast<float*>(reinterpret_cast<char*>(ext[op.ext_slot]) + (long long)img0 * per_img * esz);
     }
     int32_t rc;
     if (pl->tc[i]) {

@@ -19,9 +19,9 @@ constexpr int ST_TW = 64, ST_TH = 4;       // output tile per CTA; each thread o
 constexpr int ST_IW = 2 * ST_TW + 1, ST_IH = 2 * ST_TH + 1;
 constexpr int ST_THREADS = ST_TW / 2 * ST_TH;
 
-template <typename T>
+template <typename T, typename TIn>
 __global__ void __launch_bounds__(ST_THREADS)
-stem_kernel(const float* __restrict__ x, int H, int W, T* __restrict__ dst, int dCtot, int dC0, int Cpad,
+stem_kernel(const TIn* __restrict__ x, int H, int W, T* __restrict__ dst, int dCtot, int dC0, int Cpad,
             const float* __restrict__ w, const float* __restrict__ bias,
             float s0, float s1, float s2, float d0, float d1, float d2) {
   extern __shared__ __align__(16) float smem[];
@@ -52,11 +52,11 @@ stem_kernel(const float* __restrict__ x, int H, int W, T* __restrict__ dst, int 
       const int c = line / ST_IH, iy = line - c * ST_IH;
       const int hi = hi0 + iy;
       const bool rok = line < 3 * ST_IH && hi >= 0 && hi < H;
-      const float* rp = x + (((long long)b * 3 + (rok ? c : 0)) * H + (rok ? hi : 0)) * W;
+      const TIn* rp = x + (((long long)b * 3 + (rok ? c : 0)) * H + (rok ? hi : 0)) * W;
 #pragma unroll
       for (int k = 0; k < CPL; ++k) {
         const int ix = lane + 32 * k, wi = wi0 + ix;
-        v[l][k] = (rok && ix < ST_IW && wi >= 0 && wi < W) ? __ldg(rp + wi) : 0.f;
+        v[l][k] = (rok && ix < ST_IW && wi >= 0 && wi < W) ? (float)__ldg(rp + wi) : 0.f;
       }
     }
 #pragma unroll
@@ -352,17 +352,19 @@ int32_t launch_stem(const ly_op& op, cudaStream_t s) {
   LY_CHECK_ARG(op.dst.W % 2 == 0, "stem: output width must be even");
   dim3 grid((op.dst.W + ST_TW - 1) / ST_TW, (op.dst.H + ST_TH - 1) / ST_TH, op.B);
   size_t smem = (3 * ST_IH * ST_IW + 28 * Cpad) * sizeof(float);
+#define LY_STEM(T, TIN)                                                                                              \
+  stem_kernel<T, TIN><<<grid, ST_THREADS, smem, s>>>((const TIN*)op.nchw, H, W, (T*)op.dst.ptr, op.dst.ctot, op.dst.c0, \
+                                                     Cpad, (const float*)op.w, op.bias, op.sub[0], op.sub[1], op.sub[2], \
+                                                     op.div[0], op.div[1], op.div[2])
+  const bool u8 = op.impl == LY_STEM_IN_U8;
   if (op.dtype == LY_F32) {
     LY_CHECK_ARG(aligned16<float>(op.dst), "stem: dst not 16-byte aligned");
-    stem_kernel<float><<<grid, ST_THREADS, smem, s>>>(op.nchw, H, W, (float*)op.dst.ptr, op.dst.ctot, op.dst.c0, Cpad,
-                                                         (const float*)op.w, op.bias, op.sub[0], op.sub[1], op.sub[2],
-                                                         op.div[0], op.div[1], op.div[2]);
+    if (u8) LY_STEM(float, uint8_t); else LY_STEM(float, float);
   } else {
     LY_CHECK_ARG(aligned16<__nv_bfloat16>(op.dst), "stem: dst not 16-byte aligned");
-    stem_kernel<__nv_bfloat16><<<grid, ST_THREADS, smem, s>>>(op.nchw, H, W, (__nv_bfloat16*)op.dst.ptr, op.dst.ctot,
-                                                                 op.dst.c0, Cpad, (const float*)op.w, op.bias, op.sub[0],
-                                                                 op.sub[1], op.sub[2], op.div[0], op.div[1], op.div[2]);
+    if (u8) LY_STEM(__nv_bfloat16, uint8_t); else LY_STEM(__nv_bfloat16, float);
   }
+#undef LY_STEM
   return post_launch("stem");
 }
 

@@ -52,14 +52,14 @@ class Engine:
             sms = C.c_int32(0)
             N.check(self.lib.ly_device_check(C.byref(sms)), "ly_device_check")
         self.sm_count = sms.value
-        self._plans: Dict[Tuple[int, int, int], Compiled] = {}
+        self._plans: Dict[Tuple[int, int, int, bool], Compiled] = {}
         self._w: Optional[torch.Tensor] = None
         self._b: Optional[torch.Tensor] = None
         self._graphs: Dict[Tuple, Tuple[torch.cuda.CUDAGraph, torch.Tensor, Dict]] = {}
 
     # ------------------------------------------------------------------ build
-    def compile(self, B: int, H: int, W: int) -> Compiled:
-        key = (B, H, W)
+    def compile(self, B: int, H: int, W: int, in_u8: bool = False) -> Compiled:
+        key = (B, H, W, in_u8)
         if key in self._plans:
             return self._plans[key]
         pb = PlanBuilder(B, H, W, self.dtype)
@@ -87,6 +87,8 @@ class Engine:
                 for j in range(3):
                     o.sub[j], o.div[j] = op.extra["sub"][j], op.extra["div"][j]
                 o.ext_slot = 0
+                if in_u8:
+                    o.impl = N.STEM_IN_U8
             elif op.w_off >= 0:
                 o.w, o.bias = wbase + esz * op.w_off, bbase + 4 * op.b_off
             if op.attn is not None:
@@ -118,8 +120,9 @@ class Engine:
 
     def run(self, x: torch.Tensor, sub_batch: Optional[int] = None,
             outs: Optional[Dict[Tuple[str, int], torch.Tensor]] = None) -> Dict[Tuple[str, int], torch.Tensor]:
-        """x: [B,3,H,W] fp32 contiguous on the engine's device.  Returns {(name, level): NCHW fp32}."""
-        assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 4 and x.shape[1] == 3
+        """x: [B,3,H,W] fp32 or uint8, contiguous, on the engine's device.  Returns {(name, level): NCHW fp32}."""
+        assert x.is_cuda and x.dtype in (torch.float32, torch.uint8) and x.is_contiguous() and x.dim() == 4 and x.shape[1] == 3
+        u8 = x.dtype == torch.uint8
         B, _, H, W = x.shape
         sub = min(B, sub_batch) if sub_batch else B
         with torch.cuda.device(self.device):
@@ -127,7 +130,7 @@ class Engine:
                 outs = self.alloc_outputs(B, H, W, sub)
             for img0 in range(0, B, sub):
                 n = min(sub, B - img0)
-                self._launch(self.compile(n, H, W), x, outs, img0)
+                self._launch(self.compile(n, H, W, u8), x, outs, img0)
         return outs
 
     def profile(self, x: torch.Tensor, sub_batch: Optional[int] = None):

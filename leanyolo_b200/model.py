@@ -113,7 +113,10 @@ class YOLOv10(nn.Module):
                                "there is no CPU fallback")
         if x.dim() != 4 or x.shape[1] != 3 or x.shape[2] % 32 or x.shape[3] % 32:
             raise ValueError("expected input [B,3,H,W] with H and W multiples of 32")
-        x = x.detach().to(dtype=torch.float32).contiguous()
+        x = x.detach()
+        if x.dtype != torch.uint8:     # uint8 images go straight to the stem kernel (x.float() happens in its loader)
+            x = x.to(dtype=torch.float32)
+        x = x.contiguous()
         return self.engine(dev, taps).run(x, self.sub_batch)
 
     @torch.no_grad()

@@ -79,7 +79,10 @@ def check_subbatch_and_graph(name="yolov10s"):
     m.sub_batch = 2
     part = m(x)
     for a, b in zip(full, part):
-        assert torch.equal(a, b), "sub-batched sweep differs from one-shot forward"
+        # not bit-identical: the pixel brick (hence the order in which taps are accumulated) is
+        # chosen per batch size; the difference is fp32 summation order, far below bf16 rounding
+        err = float((a - b).abs().max() / a.abs().max())
+        assert err < 5e-3, f"sub-batched sweep differs from one-shot forward by {err:.2e}"
     m.sub_batch = None
     eng = m.engine(torch.device(DEV))
     outs = eng.alloc_outputs(5, 64, 64, 5)
@@ -118,4 +121,10 @@ def check_decode_e2e(name="yolov10s"):
         assert torch.allclose(a[:, 4], b[:, 4], atol=2e-6)
     fixed = m.detect(x)
     assert fixed.shape == (2, min(300, A), 6)
+    # uint8 images are consumed by the stem kernel directly and must equal the x.float() path
+    x8 = x.to(torch.uint8)
+    a = [t.clone() for t in m(x8)]
+    b = m(x8.float())
+    for u, v in zip(a, b):
+        assert torch.equal(u, v), "uint8 input path differs from the float path"
     return {}
