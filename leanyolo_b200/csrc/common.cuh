@@ -65,6 +65,14 @@ int sm_count();
 #ifdef __CUDACC__
 
 __device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+// SiLU(x) = x*sigmoid(x) = h + h*tanh(h), h = x/2: one MUFU op (tanh.approx, rel. err 2^-11),
+// used by the bf16 hot-path epilogues (the result is rounded to bf16 = 2^-9 anyway)
+__device__ __forceinline__ float silu_tanh(float x) {
+  const float h = 0.5f * x;
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(h, t, h);
+}
 // check-mode SiLU: full-precision expf and IEEE division (1e-4 parity vs the fp32 oracle)
 __device__ __forceinline__ float silu_precise(float x) { return x / (1.0f + expf(-x)); }
 

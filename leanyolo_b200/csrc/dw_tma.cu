@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(kThreadsDw) dw_tma_kernel(const __grid_constan
         const long long opix = ((long long)b * p.Ho + oy) * p.Wo + ox;
         if (p.act) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) acc[x][j] = silu_f(acc[x][j]);
+          for (int j = 0; j < 8; ++j) acc[x][j] = silu_tanh(acc[x][j]);
         }
         if (p.res) {
           float rv[8];
@@ -190,8 +190,9 @@ int32_t launch_cfg(const ly_op& op, cudaStream_t st) {
   p.total_tiles = (int)total;
   p.box_bytes = IWt * IHt * CB * 2;
   p.stage_bytes = (p.box_bytes + 127) / 128 * 128;
-  int stages = (100 * 1024) / p.stage_bytes;   // <= ~100 KB per CTA so that two CTAs share an SM
+  int stages = (72 * 1024) / p.stage_bytes;   // <= ~72 KB per CTA so that three CTAs share an SM
   if (stages > kMaxStagesDw) stages = kMaxStagesDw;
+  if (stages < 2 && 2 * p.stage_bytes <= 200 * 1024) stages = 2;   // big 7x7 halo tiles: two CTAs per SM instead
   LY_CHECK_ARG(stages >= 2, "dw_tma: tile does not fit in shared memory");
   p.stages = stages;
   p.act = op.act;
@@ -216,8 +217,8 @@ int32_t launch_cfg(const ly_op& op, cudaStream_t st) {
     attr_set = true;
   }
   const int sms = sm_count();
-  // two CTAs per SM when they fit: more loads in flight, epilogue of one overlaps compute of the other
-  int grid = 2 * sms;
+  // three CTAs per SM when they fit: more loads in flight, epilogue of one overlaps compute of the other
+  int grid = 3 * sms;
   if (grid > p.total_tiles) grid = p.total_tiles;
   dw_tma_kernel<K, S, CBV, TW_T, TH_T><<<grid, kThreadsDw, smem, st>>>(p);
   return post_launch("dwconv_tma");
