@@ -59,6 +59,7 @@ struct Params {
   int a_stage, b_stage;    // stage strides in bytes
   int a_box, b_box;        // bytes one TMA box delivers
   int b_resident;
+  int res_slot;            // bytes of private smem per epilogue thread for the prefetched shortcut (0 = direct loads)
   uint32_t idesc, desc_hi;
   int act;
   __nv_bfloat16* dst; int dCtot, dC0;
@@ -329,6 +330,33 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 #ifdef LY_TC_PROFILE
     const long long estart = clock64();
 #endif
+    // Shortcut (residual) operand: each thread cp.async's its own 32 bytes per chunk of the
+    // NEXT tile into a private shared-memory slot while it works on the current tile, so the
+    // DRAM latency of the uncoalesced shortcut read is off the epilogue's critical path
+    // (measured: a C2f bottleneck at 160^2 spent 35 % of its samples waiting for that load).
+    const uint32_t r_base = bar_base + 8u * (4 * kMaxStages + 8);
+    const uint32_t rslot = r_base + (uint32_t)(threadIdx.x - 64) * p.res_slot;
+    const uint32_t rstage = 256u * p.res_slot;
+    auto res_prefetch = [&](int tile_idx, uint32_t dst) {
+      if (tile_idx < p.total_tiles) {
+        int t = tile_idx;
+        const int nt = t % p.tiles_n; t /= p.tiles_n;
+        const int wt = t % p.tiles_w; t /= p.tiles_w;
+        const int ht = t % p.tiles_h;
+        const int bt = t / p.tiles_h;
+        const int w = wt * p.tw + dw, h = ht * p.th + dh, b = bt * p.tb + db;
+        if (w < p.Wo && h < p.Ho && b < p.Bo) {
+          const __nv_bfloat16* rr = p.res + (((long long)b * p.Ho + h) * p.Wo + w) * p.rCtot + p.rC0 + nt * p.block_n;
+          for (int ch = cbeg; ch < cend; ++ch) {
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (ch - cbeg) * 32), "l"(rr + ch * 16) : "memory");
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (ch - cbeg) * 32 + 16), "l"(rr + ch * 16 + 8) : "memory");
+          }
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    uint32_t rs = 0;
+    if (p.res_slot) res_prefetch(blockIdx.x, rslot);
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       int t = tile;
       const int nt = t % p.tiles_n; t /= p.tiles_n;
@@ -339,6 +367,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       const bool valid = w < p.Wo && h < p.Ho && b < p.Bo;
       const long long lin = ((long long)b * p.Ho + h) * p.Wo + w;
       const int n0 = nt * p.block_n;
+      if (p.res_slot) {
+        res_prefetch(tile + gridDim.x, rslot + (rs ^ 1u) * rstage);
+        asm volatile("cp.async.wait_group 1;" ::: "memory");   // this tile's shortcut has landed
+      }
+      const uint8_t* rsm = smem_raw + ((rslot + rs * rstage) - smem_u32(smem_raw));
       { PROF_T0(); mbar_wait(tfull_bar(as), aphase); PROF_ADD(w_tfull); }
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.block_n);
@@ -378,8 +411,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           }
           if (rrow) {
             float rv[16];
-            load_vec<__nv_bfloat16>(rrow + c, rv);
-            load_vec<__nv_bfloat16>(rrow + c + 8, rv + 8);
+            if (p.res_slot) {
+              load_vec<__nv_bfloat16>(reinterpret_cast<const __nv_bfloat16*>(rsm + (ch - cbeg) * 32), rv);
+              load_vec<__nv_bfloat16>(reinterpret_cast<const __nv_bfloat16*>(rsm + (ch - cbeg) * 32 + 16), rv + 8);
+            } else {
+              load_vec<__nv_bfloat16>(rrow + c, rv);
+              load_vec<__nv_bfloat16>(rrow + c + 8, rv + 8);
+            }
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] += rv[j];
           }
@@ -402,7 +440,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         if (lane == 0) mbar_arrive(tempty_bar(as));
       }
       if (++as == 2) { as = 0; aphase ^= 1u; }
+      rs ^= 1u;
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
 #ifdef LY_TC_PROFILE
     if (blockIdx.x == 0 && lane == 0 && (warp == 2 || warp == 6))
       printf("[tc prof] epilogue warp %d: total %lld wait_tfull %lld\n", warp, clock64() - estart, w_tfull);
@@ -515,7 +555,11 @@ int32_t conv_tc_prepare(const ly_op& op, ConvTcState** out) {
   static const int resident_ok = env_int("LY_TC_B_RESIDENT", 1);
   p.b_resident = (resident_ok && p.tiles_n == 1 && b_all <= 96 * 1024) ? 1 : 0;
   const uint32_t bar_bytes = 8 * (4 * kMaxStages + 8);
-  const long long avail = (long long)kSmemBudget - bar_bytes - 1024 - (p.b_resident ? b_all : 0);
+  // shortcut prefetch slots: 2 stages x 256 epilogue threads x (chunks per warp x 32 B); only while small
+  static const int res_prefetch_ok = env_int("LY_TC_RES_PREFETCH", 1);
+  p.res_slot = (op.res.ptr && res_prefetch_ok && bn <= 128) ? ((bn / 16 + 1) / 2) * 32 : 0;
+  const long long res_bytes = 2LL * 256 * p.res_slot;
+  const long long avail = (long long)kSmemBudget - bar_bytes - 1024 - res_bytes - (p.b_resident ? b_all : 0);
   if (p.b_resident) {
     p.a_stages = (int)(avail / p.a_stage);
     p.b_stages = 1;
@@ -530,7 +574,8 @@ int32_t conv_tc_prepare(const ly_op& op, ConvTcState** out) {
   if (p.a_stages > kMaxStages) p.a_stages = kMaxStages;
   if (p.b_stages > kMaxStages) p.b_stages = kMaxStages;
   if (p.a_stages < 2 || (!p.b_resident && p.b_stages < 2)) { delete st; set_error("conv_tc: tile does not fit in shared memory"); return LY_E_ARG; }
-  st->smem = 1024 + (size_t)p.a_stages * p.a_stage + (p.b_resident ? (size_t)b_all : (size_t)p.b_stages * p.b_stage) + bar_bytes;
+  st->smem = 1024 + (size_t)p.a_stages * p.a_stage + (p.b_resident ? (size_t)b_all : (size_t)p.b_stages * p.b_stage) + bar_bytes +
+             (size_t)res_bytes;
   if (st->smem < 120 * 1024) st->smem = 120 * 1024;  // force one CTA per SM (TMEM allocations must not contend)
 
   // descriptors
