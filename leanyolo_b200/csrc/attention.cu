@@ -8,6 +8,7 @@
 // Channel layout of the qkv buffer (re-ordered at weight-pack time, modules.py):
 //   [ q: nh x kdp | k: nh x kdp | v: nh x hd ]   (kdp = key_dim padded to 8, pad = zeros)
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace ly {
 
@@ -122,6 +123,203 @@ attn_kernel(const T* __restrict__ qkv, int N, int sCtot, int sC0, int nh, T* __r
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// bf16 hot path: flash-style attention on the warp-level tensor-core path.  The op is 0.5 %
+// of the model's FLOPs on a 20x20 map (N = 400 tokens, 4 heads): far too small for a
+// tcgen05/TMEM pipeline to amortise, so each warp owns 16 query rows and runs
+// mma.sync.m16n8k16 (bf16 x bf16 -> fp32) for both S = Q K^T and O = P V, with the online
+// softmax kept in registers between them (S accumulator fragments are re-packed in place as
+// the A operand of the second MMA).  K/V blocks of 64 keys are double-buffered in shared
+// memory with cp.async (zero-filled past N and in the padded key columns); V^T fragments
+// come from ldmatrix.trans.  5 warps per CTA = 80 queries: N = 400 tiles with no waste.
+// ---------------------------------------------------------------------------------------
+constexpr int AT_WARPS = 5;
+constexpr int AT_KB = 64;    // keys per shared-memory block
+
+__device__ __forceinline__ void mma_bf16_16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool pred) {
+  const int sz = pred ? 16 : 0;   // src-size 0 => 16 bytes of zeros
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+
+template <int KDP, int HD>
+__global__ void __launch_bounds__(AT_WARPS * 32)
+attn_mma_kernel(const __nv_bfloat16* __restrict__ qkv, int N, int sCtot, int sC0, int nh, __nv_bfloat16* __restrict__ out,
+                int dCtot, int dC0, float scale_log2e) {
+  constexpr int KD16 = (KDP + 15) / 16 * 16;
+  constexpr int KS = KD16 / 16;                    // k-steps of Q K^T
+  constexpr int NT = HD / 8;                       // n-tiles of the output
+  constexpr int KPITCH = KD16 * 2 + 16;            // bytes; (pitch / 4) mod 8 == 4 => conflict-free fragment loads
+  constexpr int VPITCH = HD * 2 + (((HD * 2 / 16) & 1) ? 0 : 16);   // odd number of 16-byte units per row
+  constexpr int KCH = KD16 * 2 / 16, VCH = HD * 2 / 16;             // 16-byte chunks per row
+  constexpr int STAGE = AT_KB * (KPITCH + VPITCH);
+  static_assert(HD % 8 == 0 && KDP % 8 == 0, "head dims must be multiples of 8");
+  __shared__ __align__(16) uint8_t sm[2 * STAGE];
+
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const __nv_bfloat16* base = qkv + (long long)b * N * sCtot + sC0;
+  const int qoff = h * KDP, koff = nh * KDP + h * KDP, voff = 2 * nh * KDP + h * HD;
+  const uint32_t sm_u = smem_u32(sm);
+
+  auto load_block = [&](int blk, int stage) {
+    const int m0 = blk * AT_KB;
+    const uint32_t ks = sm_u + stage * STAGE, vs = ks + AT_KB * KPITCH;
+    for (int i = threadIdx.x; i < AT_KB * (KCH + VCH); i += AT_WARPS * 32) {
+      const int r = i / (KCH + VCH), c = i - r * (KCH + VCH);
+      const bool rok = m0 + r < N;
+      const __nv_bfloat16* row = base + (long long)(rok ? m0 + r : 0) * sCtot;
+      if (c < KCH) cp_async16(ks + r * KPITCH + c * 16, row + koff + (c * 8 < KDP ? c * 8 : 0), rok && c * 8 < KDP);
+      else cp_async16(vs + r * VPITCH + (c - KCH) * 16, row + voff + (c - KCH) * 8, rok);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  const int nblk = (N + AT_KB - 1) / AT_KB;
+  load_block(0, 0);
+
+  // Q fragments (A operand), straight from global memory: rows g / g+8 of this warp's 16 queries
+  const int n0 = (blockIdx.x * AT_WARPS + warp) * 16;
+  uint32_t qa[KS][4];
+  {
+    const int r0 = n0 + g, r1 = n0 + g + 8;
+    const __nv_bfloat16* q0 = base + (long long)(r0 < N ? r0 : 0) * sCtot + qoff;
+    const __nv_bfloat16* q1 = base + (long long)(r1 < N ? r1 : 0) * sCtot + qoff;
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+      const int c0 = ks * 16 + 2 * t, c1 = c0 + 8;
+      qa[ks][0] = (r0 < N && c0 < KDP) ? *reinterpret_cast<const uint32_t*>(q0 + c0) : 0u;
+      qa[ks][1] = (r1 < N && c0 < KDP) ? *reinterpret_cast<const uint32_t*>(q1 + c0) : 0u;
+      qa[ks][2] = (r0 < N && c1 < KDP) ? *reinterpret_cast<const uint32_t*>(q0 + c1) : 0u;
+      qa[ks][3] = (r1 < N && c1 < KDP) ? *reinterpret_cast<const uint32_t*>(q1 + c1) : 0u;
+    }
+  }
+  float o[NT][4];
+#pragma unroll
+  for (int i = 0; i < NT; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+  float m0r = -INFINITY, m1r = -INFINITY, l0 = 0.f, l1 = 0.f;   // running max (log2 domain) / partial sums, rows g and g+8
+
+  for (int blk = 0; blk < nblk; ++blk) {
+    if (blk + 1 < nblk) {
+      load_block(blk + 1, (blk + 1) & 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    const uint8_t* ks_p = sm + (blk & 1) * STAGE;
+    const uint32_t vs_u = sm_u + (blk & 1) * STAGE + AT_KB * KPITCH;
+
+    float s[AT_KB / 8][4];
+#pragma unroll
+    for (int j = 0; j < AT_KB / 8; ++j) {
+      s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+      const uint8_t* kr = ks_p + (j * 8 + g) * KPITCH + 4 * t;
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(kr + ks * 32);
+        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(kr + ks * 32 + 16);
+        mma_bf16_16816(s[j], qa[ks], b0, b1);
+      }
+    }
+    // scale into the log2 domain, mask keys past N, block row max
+    const int kbase = blk * AT_KB + 2 * t;
+    float bm0 = -INFINITY, bm1 = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < AT_KB / 8; ++j) {
+      const int key = kbase + j * 8;
+      s[j][0] = key < N ? s[j][0] * scale_log2e : -INFINITY;
+      s[j][1] = key + 1 < N ? s[j][1] * scale_log2e : -INFINITY;
+      s[j][2] = key < N ? s[j][2] * scale_log2e : -INFINITY;
+      s[j][3] = key + 1 < N ? s[j][3] * scale_log2e : -INFINITY;
+      bm0 = fmaxf(bm0, fmaxf(s[j][0], s[j][1]));
+      bm1 = fmaxf(bm1, fmaxf(s[j][2], s[j][3]));
+    }
+    bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 1));
+    bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 2));
+    bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 1));
+    bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 2));
+    const float nm0 = fmaxf(m0r, bm0), nm1 = fmaxf(m1r, bm1);   // finite: every block holds >= 1 valid key
+    const float c0 = ex2(m0r - nm0), c1 = ex2(m1r - nm1);        // first block: ex2(-inf) = 0
+    m0r = nm0; m1r = nm1;
+    l0 *= c0; l1 *= c1;
+#pragma unroll
+    for (int i = 0; i < NT; ++i) { o[i][0] *= c0; o[i][1] *= c0; o[i][2] *= c1; o[i][3] *= c1; }
+#pragma unroll
+    for (int j = 0; j < AT_KB / 8; ++j) {
+      s[j][0] = ex2(s[j][0] - nm0); s[j][1] = ex2(s[j][1] - nm0);
+      s[j][2] = ex2(s[j][2] - nm1); s[j][3] = ex2(s[j][3] - nm1);
+      l0 += s[j][0] + s[j][1];
+      l1 += s[j][2] + s[j][3];
+    }
+    // O += P V : P (bf16) re-packed from the S fragments; V^T fragments through ldmatrix.trans
+#pragma unroll
+    for (int kk = 0; kk < AT_KB / 16; ++kk) {
+      uint32_t pa[4];
+      pa[0] = pack_bf16(s[2 * kk][0], s[2 * kk][1]);
+      pa[1] = pack_bf16(s[2 * kk][2], s[2 * kk][3]);
+      pa[2] = pack_bf16(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+      pa[3] = pack_bf16(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+      const uint32_t vrow = vs_u + (kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * VPITCH;
+#pragma unroll
+      for (int dt = 0; dt + 1 < NT; dt += 2) {
+        uint32_t b0, b1, b2, b3;
+        asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(b0), "=r"(b1), "=r"(b2), "=r"(b3)
+                     : "r"(vrow + (dt * 8 + (lane >> 4) * 8) * 2));
+        mma_bf16_16816(o[dt], pa, b0, b1);
+        mma_bf16_16816(o[dt + 1], pa, b2, b3);
+      }
+      if (NT & 1) {
+        uint32_t b0, b1;
+        asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];"
+                     : "=r"(b0), "=r"(b1)
+                     : "r"(vrow + (NT - 1) * 16));
+        mma_bf16_16816(o[NT - 1], pa, b0, b1);
+      }
+    }
+    __syncthreads();   // everyone is done with this stage before it is refilled
+  }
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+  const int r0 = n0 + g, r1 = n0 + g + 8;
+  __nv_bfloat16* o0 = out + ((long long)b * N + r0) * dCtot + dC0 + h * HD + 2 * t;
+  __nv_bfloat16* o1 = out + ((long long)b * N + r1) * dCtot + dC0 + h * HD + 2 * t;
+#pragma unroll
+  for (int i = 0; i < NT; ++i) {
+    if (r0 < N) *reinterpret_cast<uint32_t*>(o0 + i * 8) = pack_bf16(o[i][0] * i0, o[i][1] * i0);
+    if (r1 < N) *reinterpret_cast<uint32_t*>(o1 + i * 8) = pack_bf16(o[i][2] * i1, o[i][3] * i1);
+  }
+}
+
+template <int KDP, int HD>
+int32_t run_mma(const ly_op& op, cudaStream_t s) {
+  const int N = op.src.H * op.src.W;
+  dim3 grid((N + AT_WARPS * 16 - 1) / (AT_WARPS * 16), op.nh, op.B);
+  attn_mma_kernel<KDP, HD><<<grid, AT_WARPS * 32, 0, s>>>((const __nv_bfloat16*)op.src.ptr, N, op.src.ctot, op.src.c0, op.nh,
+                                                           (__nv_bfloat16*)op.dst.ptr, op.dst.ctot, op.dst.c0,
+                                                           op.scale * 1.4426950408889634f);
+  return post_launch("psa_attention_mma");
+}
+
 template <typename T, int KDP, int HD>
 int32_t run(const ly_op& op, cudaStream_t s) {
   const int N = op.src.H * op.src.W;
@@ -139,12 +337,13 @@ int32_t launch_attn(const ly_op& op, cudaStream_t s) {
   LY_CHECK_ARG(op.src.c0 % 8 == 0 && op.dst.c0 % 8 == 0 && op.src.ctot % 8 == 0 && op.dst.ctot % 8 == 0,
                "attention: views must be 16-byte aligned");
   const bool f32 = op.dtype == LY_F32;
+  const bool simt = f32 || op.impl == LY_IMPL_SIMT;
   if (op.kdp == 32 && op.hd == 64)
-    return f32 ? run<float, 32, 64>(op, s) : run<__nv_bfloat16, 32, 64>(op, s);
+    return f32 ? run<float, 32, 64>(op, s) : (simt ? run<__nv_bfloat16, 32, 64>(op, s) : run_mma<32, 64>(op, s));
   if (op.kdp == 40 && op.hd == 72)
-    return f32 ? run<float, 40, 72>(op, s) : run<__nv_bfloat16, 40, 72>(op, s);
+    return f32 ? run<float, 40, 72>(op, s) : (simt ? run<__nv_bfloat16, 40, 72>(op, s) : run_mma<40, 72>(op, s));
   if (op.kdp == 16 && op.hd == 32)
-    return f32 ? run<float, 16, 32>(op, s) : run<__nv_bfloat16, 16, 32>(op, s);
+    return f32 ? run<float, 16, 32>(op, s) : (simt ? run<__nv_bfloat16, 16, 32>(op, s) : run_mma<16, 32>(op, s));
   LY_CHECK_ARG(false, "attention: unsupported (key_dim_pad=%d, head_dim=%d); built: (32,64) (40,72) (16,32)", op.kdp, op.hd);
 }
 

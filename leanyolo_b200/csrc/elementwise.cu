@@ -2,6 +2,7 @@
 // stride 1 / 2), SPPF max-pool pyramid, nearest x2 upsample into a concat slice and the
 // NHWC<->NCHW boundary converters.  All NHWC with 16-byte channel vectors; templated on
 // the storage type (bf16 hot path, fp32 check mode).
+#include <type_traits>
 #include "common.cuh"
 
 namespace ly {
@@ -120,6 +121,156 @@ stem_kernel(const TIn* __restrict__ x, int H, int W, T* __restrict__ dst, int dC
 }
 
 // ---------------------------------------------------------------------------------------
+// bf16 hot-path stem: the same op as an implicit GEMM on the warp-level tensor-core path.
+// D[pixels, Cout] = A[pixels, K = 32] * W[Cout, 32]^T with K = 27 taps padded to 32; the
+// CUDA-core version above needs 864 FMAs per output pixel and ran at 1/5 of the layer's
+// HBM roofline, this one needs 12 shared-memory loads + 2*Cout/8 mma.sync per 16 pixels.
+// (K = 32 with M x N = pixels x 32 is far below what a tcgen05/TMEM pipeline can amortise;
+// the layer is bandwidth-bound: 12 B in (3 B as uint8) and 64 B out per 4 input pixels.)
+//
+// * The normalised image tile ((x - sub) / div, zero outside the image) is staged in shared
+//   memory as bf16 [3][2*TH+1][IWP].  uint8 pixels with sub = 0, div = 255 could be kept
+//   exact, but one code path serves both input types.
+// * K slots are ordered so that the two taps (kx = 0, 1) of a (channel, ky) line are one
+//   aligned 32-bit shared-memory load: slots 0..17 = 9 (c, ky) pairs, 18..26 = the kx = 2
+//   singles, 27..31 = zero weights.  IWP = 144 makes the fragment loads bank-conflict free.
+// * A warp owns one output row of the tile and walks it in 16-pixel m-tiles; the weight
+//   fragments live in registers; outputs are staged per warp and stored as 16-byte vectors.
+// ---------------------------------------------------------------------------------------
+constexpr int SM_TW = 64, SM_TH = 8;                 // output tile per CTA
+constexpr int SM_IH = 2 * SM_TH + 1;                 // input rows per channel
+constexpr int SM_IWP = 144;                          // input row pitch (elements): (IWP / 2) mod 32 == 8
+constexpr int SM_THREADS = SM_TH * 32;
+
+__device__ __forceinline__ void mma_bf16_16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// element offset of K slot k inside the staged tile, relative to the pixel's (2*py, 2*px) corner
+__device__ __forceinline__ int stem_slot_off(int k) {
+  if (k >= 27) return 0;
+  const int j = k < 18 ? (k >> 1) : k - 18, kx = k < 18 ? (k & 1) : 2;
+  return ((j / 3) * SM_IH + (j % 3)) * SM_IWP + kx;
+}
+// index of K slot k inside the packed [27] weight row ([ky][kx][c]); -1 = zero padding
+__device__ __forceinline__ int stem_slot_w(int k) {
+  if (k >= 27) return -1;
+  const int j = k < 18 ? (k >> 1) : k - 18, kx = k < 18 ? (k & 1) : 2;
+  return ((j % 3) * 3 + kx) * 3 + (j / 3);
+}
+
+template <typename TIn, int NT>
+__global__ void __launch_bounds__(SM_THREADS)
+stem_mma_kernel(const TIn* __restrict__ x, int H, int W, __nv_bfloat16* __restrict__ dst, int dCtot, int dC0,
+                const float* __restrict__ w, const float* __restrict__ bias,
+                float s0, float s1, float s2, float d0, float d1, float d2) {
+  constexpr int CP = NT * 8;                           // padded output channels
+  constexpr int OPITCH = CP * 2 + 16;                  // bytes per staged output pixel: (pitch / 4) mod 8 == 4
+  __shared__ __align__(16) __nv_bfloat16 tile[3 * SM_IH * SM_IWP];
+  __shared__ __align__(16) __nv_bfloat16 wsm[CP * 32];
+  __shared__ __align__(16) uint8_t ostage[SM_TH][16 * OPITCH];
+  const int Ho = H / 2, Wo = W / 2;
+  const int b = blockIdx.z, ho0 = blockIdx.y * SM_TH, wo0 = blockIdx.x * SM_TW;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+
+  for (int i = tid; i < CP * 32; i += SM_THREADS) {
+    const int co = i >> 5, wi = stem_slot_w(i & 31);
+    wsm[i] = __float2bfloat16_rn(wi >= 0 ? w[co * 27 + wi] : 0.f);
+  }
+  {
+    // aligned 4-element vectors: vector v of a line covers input columns 2*wo0 - 4 + 4v .. +3;
+    // tile column 0 is input column 2*wo0 - 1 (the last element of vector 0)
+    constexpr int VPL = SM_TW * 2 / 4 + 1, NV = 3 * SM_IH * VPL, PER = (NV + SM_THREADS - 1) / SM_THREADS;
+    using Vec = typename std::conditional<sizeof(TIn) == 1, uchar4, float4>::type;
+    Vec v[PER];
+    const int hi0 = 2 * ho0 - 1, wi0 = 2 * wo0 - 4;
+#pragma unroll
+    for (int it = 0; it < PER; ++it) {
+      const int i = tid + it * SM_THREADS;
+      const int line = i / VPL, vi = i - line * VPL;
+      const int c = line / SM_IH, hi = hi0 + (line - c * SM_IH), wi = wi0 + 4 * vi;
+      const bool ok = i < NV && hi >= 0 && hi < H && wi >= 0 && wi < W;
+      if (ok) v[it] = __ldg(reinterpret_cast<const Vec*>(x + (((long long)b * 3 + c) * H + hi) * W + wi));
+      else v[it] = Vec{0, 0, 0, 0};
+    }
+#pragma unroll
+    for (int it = 0; it < PER; ++it) {
+      const int i = tid + it * SM_THREADS;
+      if (i >= NV) continue;
+      const int line = i / VPL, vi = i - line * VPL;
+      const int c = line / SM_IH, hi = hi0 + (line - c * SM_IH), wi = wi0 + 4 * vi;
+      const bool ok = hi >= 0 && hi < H && wi >= 0 && wi < W;
+      const float sc = c == 0 ? s0 : (c == 1 ? s1 : s2), dc = c == 0 ? d0 : (c == 1 ? d1 : d2);
+      const float f0 = ok ? ((float)v[it].x - sc) / dc : 0.f, f1 = ok ? ((float)v[it].y - sc) / dc : 0.f;
+      const float f2 = ok ? ((float)v[it].z - sc) / dc : 0.f, f3 = ok ? ((float)v[it].w - sc) / dc : 0.f;
+      __nv_bfloat16* tp = tile + line * SM_IWP + 4 * vi - 3;   // tile column of element .x
+      if (vi > 0) {
+        tp[0] = __float2bfloat16_rn(f0);
+        *reinterpret_cast<__nv_bfloat162*>(tp + 1) = __floats2bfloat162_rn(f1, f2);
+      }
+      tp[3] = __float2bfloat16_rn(f3);
+    }
+  }
+  __syncthreads();
+
+  // weight fragments: b0 = W[co = nt*8+g][k = ks*16 + 2t, +1], b1 = ... + 8
+  uint32_t wb[NT][2][2];
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+      const uint32_t* wr = reinterpret_cast<const uint32_t*>(wsm + (nt * 8 + g) * 32 + ks * 16 + 2 * t);
+      wb[nt][ks][0] = wr[0];
+      wb[nt][ks][1] = wr[4];
+    }
+  float bv[NT][2];
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) { bv[nt][0] = bias[nt * 8 + 2 * t]; bv[nt][1] = bias[nt * 8 + 2 * t + 1]; }
+
+  // per-thread fragment offsets (elements).  k-step 0: two (kx = 0,1) pairs; k-step 1: four singles
+  const int op0 = stem_slot_off(2 * t), op1 = stem_slot_off(2 * t + 8);
+  const int os0 = stem_slot_off(16 + 2 * t), os1 = stem_slot_off(17 + 2 * t);
+  const int os2 = stem_slot_off(24 + 2 * t), os3 = stem_slot_off(25 + 2 * t);
+  const int ho = ho0 + warp;
+  const unsigned short* tl = reinterpret_cast<const unsigned short*>(tile);
+  uint8_t* og = ostage[warp];
+
+  for (int mt = 0; mt < SM_TW / 16; ++mt) {
+    const int px0 = mt * 16;
+    if (wo0 + px0 >= Wo || ho >= Ho) break;
+    const int base0 = (2 * warp) * SM_IWP + 2 * (px0 + g), base1 = base0 + 16;
+    uint32_t a[2][4];
+    a[0][0] = *reinterpret_cast<const uint32_t*>(tl + base0 + op0);
+    a[0][1] = *reinterpret_cast<const uint32_t*>(tl + base1 + op0);
+    a[0][2] = *reinterpret_cast<const uint32_t*>(tl + base0 + op1);
+    a[0][3] = *reinterpret_cast<const uint32_t*>(tl + base1 + op1);
+    a[1][0] = (uint32_t)tl[base0 + os0] | ((uint32_t)tl[base0 + os1] << 16);
+    a[1][1] = (uint32_t)tl[base1 + os0] | ((uint32_t)tl[base1 + os1] << 16);
+    a[1][2] = (uint32_t)tl[base0 + os2] | ((uint32_t)tl[base0 + os3] << 16);
+    a[1][3] = (uint32_t)tl[base1 + os2] | ((uint32_t)tl[base1 + os3] << 16);
+    __syncwarp();   // the previous m-tile's staged outputs have been read
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      float c[4] = {bv[nt][0], bv[nt][1], bv[nt][0], bv[nt][1]};
+      mma_bf16_16816(c, a[0], wb[nt][0][0], wb[nt][0][1]);
+      mma_bf16_16816(c, a[1], wb[nt][1][0], wb[nt][1][1]);
+      *reinterpret_cast<__nv_bfloat162*>(og + g * OPITCH + nt * 16 + t * 4) = __floats2bfloat162_rn(silu_tanh(c[0]), silu_tanh(c[1]));
+      *reinterpret_cast<__nv_bfloat162*>(og + (g + 8) * OPITCH + nt * 16 + t * 4) = __floats2bfloat162_rn(silu_tanh(c[2]), silu_tanh(c[3]));
+    }
+    __syncwarp();
+    __nv_bfloat16* orow = dst + (((long long)b * Ho + ho) * Wo + wo0 + px0) * dCtot + dC0;
+    for (int i = lane; i < 16 * NT; i += 32) {
+      const int px = i / NT, cv = i - px * NT;
+      if (wo0 + px0 + px < Wo)
+        *reinterpret_cast<uint4*>(orow + (long long)px * dCtot + cv * 8) = *reinterpret_cast<const uint4*>(og + px * OPITCH + cv * 16);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // Depthwise k x k conv (+bias, optional SiLU, optional residual added after the activation).
 // One thread = a TH x TW patch of output pixels x one 16-byte channel vector: every input
 // vector is loaded once per patch and reused by all the outputs that see it (k=3,s=1: 24
@@ -218,60 +369,73 @@ dw_kernel(const T* __restrict__ src, int sH, int sW, int sCtot, int sC0,
 
 // ---------------------------------------------------------------------------------------
 // SPPF pyramid: y1 = pool5(x), y2 = pool5(y1), y3 = pool5(y2) with -inf padding
-// (layers.py:210-217).  One CTA = one image x one 16-byte channel vector: the H x W plane
-// lives in shared memory and each of the three chained pools is a separable row-max /
-// column-max pass over it.  Reads channels [0,c) of the concat buffer and writes [c,2c),
-// [2c,3c), [3c,4c) of the same buffer.
+// (layers.py:210-217).  One CTA = one image x CBV 16-byte channel vectors (128 contiguous
+// bytes per pixel when CBV = 8, so global accesses are full lines): the H x W x CBV plane
+// lives in shared memory in the storage type (max is exact in bf16) and each of the three
+// chained pools is a separable row-max / column-max pass over it.  Reads channels [0,c) of
+// the concat buffer and writes [c,2c), [2c,3c), [3c,4c) of the same buffer.
 // ---------------------------------------------------------------------------------------
 template <typename T>
+__device__ __forceinline__ uint4 vmax(const uint4& a, const uint4& b);
+template <>
+__device__ __forceinline__ uint4 vmax<float>(const uint4& a, const uint4& b) {
+  uint4 r;
+  r.x = __float_as_uint(fmaxf(__uint_as_float(a.x), __uint_as_float(b.x)));
+  r.y = __float_as_uint(fmaxf(__uint_as_float(a.y), __uint_as_float(b.y)));
+  r.z = __float_as_uint(fmaxf(__uint_as_float(a.z), __uint_as_float(b.z)));
+  r.w = __float_as_uint(fmaxf(__uint_as_float(a.w), __uint_as_float(b.w)));
+  return r;
+}
+template <>
+__device__ __forceinline__ uint4 vmax<__nv_bfloat16>(const uint4& a, const uint4& b) {
+  uint4 r;
+  const __nv_bfloat162* x = reinterpret_cast<const __nv_bfloat162*>(&a);
+  const __nv_bfloat162* y = reinterpret_cast<const __nv_bfloat162*>(&b);
+  __nv_bfloat162* z = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) z[i] = __hmax2(x[i], y[i]);
+  return r;
+}
+
+template <typename T>
 __global__ void __launch_bounds__(256)
-pool_kernel(T* buf, int H, int W, int Ctot, int C0, int C) {
+pool_kernel(T* buf, int H, int W, int Ctot, int C0, int C, int cbv) {
   constexpr int V = Elem<T>::kVec;
-  extern __shared__ float psm[];            // [2][H*W][V]
-  const int HW = H * W;
-  float* cur = psm;
-  float* tmp = psm + (size_t)HW * V;
-  const int c = blockIdx.x * V;
+  extern __shared__ __align__(16) uint4 psm[];   // [2][H*W][cbv]
+  const int HW = H * W, items = HW * cbv;
+  uint4* cur = psm;
+  uint4* tmp = psm + items;
+  const int c = blockIdx.x * cbv * V;
   const int b = blockIdx.y;
   T* base = buf + (long long)b * HW * Ctot + C0 + c;
-  for (int p = threadIdx.x; p < HW; p += blockDim.x) {
-    float v[V];
-    load_vec<T>(base + (long long)p * Ctot, v);
-#pragma unroll
-    for (int j = 0; j < V; ++j) cur[p * V + j] = v[j];
+  for (int i = threadIdx.x; i < items; i += blockDim.x) {
+    const int p = i / cbv, v = i - p * cbv;
+    cur[i] = *reinterpret_cast<const uint4*>(base + (long long)p * Ctot + v * V);
   }
   __syncthreads();
   for (int stage = 1; stage <= 3; ++stage) {
-    for (int p = threadIdx.x; p < HW; p += blockDim.x) {   // row max -> tmp
-      const int y = p / W, x = p - y * W;
-      float m[V];
-#pragma unroll
-      for (int j = 0; j < V; ++j) m[j] = -INFINITY;
-      for (int dx = -2; dx <= 2; ++dx) {
-        const int xx = x + dx;
-        if (xx < 0 || xx >= W) continue;
-#pragma unroll
-        for (int j = 0; j < V; ++j) m[j] = fmaxf(m[j], cur[(y * W + xx) * V + j]);
-      }
-#pragma unroll
-      for (int j = 0; j < V; ++j) tmp[p * V + j] = m[j];
+    for (int i = threadIdx.x; i < items; i += blockDim.x) {   // row max -> tmp
+      const int p = i / cbv;
+      const int x = p % W;
+      uint4 m = cur[i];
+      if (x >= 1) m = vmax<T>(m, cur[i - cbv]);
+      if (x >= 2) m = vmax<T>(m, cur[i - 2 * cbv]);
+      if (x + 1 < W) m = vmax<T>(m, cur[i + cbv]);
+      if (x + 2 < W) m = vmax<T>(m, cur[i + 2 * cbv]);
+      tmp[i] = m;
     }
     __syncthreads();
-    for (int p = threadIdx.x; p < HW; p += blockDim.x) {   // column max -> cur (and out)
-      const int y = p / W, x = p - y * W;
-      float m[V];
-#pragma unroll
-      for (int j = 0; j < V; ++j) m[j] = -INFINITY;
-      for (int dy = -2; dy <= 2; ++dy) {
-        const int yy = y + dy;
-        if (yy < 0 || yy >= H) continue;
-#pragma unroll
-        for (int j = 0; j < V; ++j) m[j] = fmaxf(m[j], tmp[(yy * W + x) * V + j]);
-      }
-      store_vec<T>(base + (long long)p * Ctot + stage * C, m);
-      // cur is only read by the row pass, which finished before the barrier above
-#pragma unroll
-      for (int j = 0; j < V; ++j) cur[p * V + j] = m[j];
+    const int rs = W * cbv;
+    for (int i = threadIdx.x; i < items; i += blockDim.x) {   // column max -> cur (and out)
+      const int p = i / cbv, v = i - p * cbv;
+      const int y = p / W;
+      uint4 m = tmp[i];
+      if (y >= 1) m = vmax<T>(m, tmp[i - rs]);
+      if (y >= 2) m = vmax<T>(m, tmp[i - 2 * rs]);
+      if (y + 1 < H) m = vmax<T>(m, tmp[i + rs]);
+      if (y + 2 < H) m = vmax<T>(m, tmp[i + 2 * rs]);
+      *reinterpret_cast<uint4*>(base + (long long)p * Ctot + stage * C + v * V) = m;
+      cur[i] = m;   // cur is only read by the row pass, which finished before the barrier above
     }
     __syncthreads();
   }
@@ -357,6 +521,24 @@ int32_t launch_stem(const ly_op& op, cudaStream_t s) {
                                                      Cpad, (const float*)op.w, op.bias, op.sub[0], op.sub[1], op.sub[2], \
                                                      op.div[0], op.div[1], op.div[2])
   const bool u8 = op.impl == LY_STEM_IN_U8;
+  if (op.dtype == LY_BF16 && Cpad % 8 == 0 && Cpad <= 80 && W % 4 == 0 && op.dst.ctot % 8 == 0 && op.dst.c0 % 8 == 0 &&
+      reinterpret_cast<uintptr_t>(op.nchw) % 16 == 0 && reinterpret_cast<uintptr_t>(op.dst.ptr) % 16 == 0) {
+    dim3 g2((op.dst.W + SM_TW - 1) / SM_TW, (op.dst.H + SM_TH - 1) / SM_TH, op.B);
+#define LY_STEM_MMA(TIN, NT)                                                                                          \
+  stem_mma_kernel<TIN, NT><<<g2, SM_THREADS, 0, s>>>((const TIN*)op.nchw, H, W, (__nv_bfloat16*)op.dst.ptr, op.dst.ctot, \
+                                                     op.dst.c0, (const float*)op.w, op.bias, op.sub[0], op.sub[1],    \
+                                                     op.sub[2], op.div[0], op.div[1], op.div[2])
+#define LY_STEM_NT(NT)                                                 \
+  case NT:                                                             \
+    if (u8) LY_STEM_MMA(uint8_t, NT); else LY_STEM_MMA(float, NT);     \
+    return post_launch("stem_mma");
+    switch (Cpad / 8) {
+      LY_STEM_NT(2) LY_STEM_NT(4) LY_STEM_NT(6) LY_STEM_NT(8) LY_STEM_NT(10)
+      default: break;   // other widths: CUDA-core kernel below
+    }
+#undef LY_STEM_NT
+#undef LY_STEM_MMA
+  }
   if (op.dtype == LY_F32) {
     LY_CHECK_ARG(aligned16<float>(op.dst), "stem: dst not 16-byte aligned");
     if (u8) LY_STEM(float, uint8_t); else LY_STEM(float, float);
@@ -404,15 +586,18 @@ template <typename T>
 static int32_t run_pool(const ly_op& op, cudaStream_t s) {
   constexpr int V = 16 / sizeof(T);
   LY_CHECK_ARG(aligned16<T>(op.src), "pool: view must be 16-byte aligned");
-  const size_t smem = (size_t)2 * op.src.H * op.src.W * V * sizeof(float);
+  const int nvec = op.src.c / V;
+  int cbv = 8;   // channel vectors per CTA: as many as the shared-memory plane allows, dividing the channel count
+  while (cbv > 1 && (nvec % cbv != 0 || (size_t)2 * op.src.H * op.src.W * cbv * 16 > 100 * 1024)) cbv >>= 1;
+  const size_t smem = (size_t)2 * op.src.H * op.src.W * cbv * 16;
   LY_CHECK_ARG(smem <= 200 * 1024, "pool: feature map %dx%d too large for the shared-memory plane", op.src.H, op.src.W);
   static bool attr_set = false;
   if (!attr_set) {
     LY_CUDA(cudaFuncSetAttribute(pool_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set = true;
   }
-  dim3 grid(op.src.c / V, op.B);
-  pool_kernel<T><<<grid, 256, smem, s>>>((T*)op.src.ptr, op.src.H, op.src.W, op.src.ctot, op.src.c0, op.src.c);
+  dim3 grid(nvec / cbv, op.B);
+  pool_kernel<T><<<grid, 256, smem, s>>>((T*)op.src.ptr, op.src.H, op.src.W, op.src.ctot, op.src.c0, op.src.c, cbv);
   return post_launch("sppf_pool");
 }
 

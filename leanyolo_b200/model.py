@@ -76,8 +76,7 @@ class YOLOv10(nn.Module):
             for name, v, c in (("c3", c3, c3w), ("c4", c4, c4w), ("c5", c5, c5w), ("p3", p3, nk.out_c[0]),
                                ("p4", p4, nk.out_c[1]), ("p5", p5, nk.out_c[2])):
                 pb.export_nchw(v, name, c)
-        hd.emit_branch(pb, (p3, p4, p5), hd.cv2, hd.cv3, "one2many")
-        hd.emit_branch(pb, (p3, p4, p5), hd.one2one_cv2, hd.one2one_cv3, "one2one")
+        hd.emit(pb, (p3, p4, p5))
 
     def invalidate(self) -> None:
         """Drop packed weights / plans (call after mutating parameters in place)."""

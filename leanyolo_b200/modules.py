@@ -283,16 +283,28 @@ class Detect(nn.Module):
         self.one2one_cv3 = copy.deepcopy(self.cv3)
         self.dfl = DFL(reg_max) if reg_max > 1 else nn.Identity()
 
-    def emit_branch(self, pb, feats, reg: nn.ModuleList, cls: nn.ModuleList, out_name: str):
-        """Writes [reg(4*reg_max) | cls(nc)] logits of every level straight into the
-        public NCHW fp32 tensors (head.py:118-122) from the two final 1x1 epilogues."""
+    def emit(self, pb, feats):
+        """Both branches (head.py:118-135).  Each writes [reg(4*reg_max) | cls(nc)] logits of every
+        level straight into its public NCHW fp32 tensor from the two final 1x1 epilogues.  The
+        first reg conv of the two branches reads the same feature map, so the pair is ONE
+        implicit GEMM with the output channels concatenated (N = 2*c2: one pass over the
+        input, twice the MMA width); each branch then continues from its channel slice."""
+        branches = (("one2many", self.cv2, self.cv3), ("one2one", self.one2one_cv2, self.one2one_cv3))
         for i, f in enumerate(feats):
-            r = reg[i][1].emit(pb, reg[i][0].emit(pb, f))
-            fin = reg[i][2]
-            pb.conv(r, fin.weight.detach().double().cpu(), fin.bias.detach().double().cpu(), k=1, stride=1,
-                    act=False, nchw=(out_name, i, 0, 4 * self.reg_max, self.no))
-            c = cls[i][0][1].emit(pb, cls[i][0][0].emit(pb, f))
-            c = cls[i][1][1].emit(pb, cls[i][1][0].emit(pb, c))
-            fin = cls[i][2]
-            pb.conv(c, fin.weight.detach().double().cpu(), fin.bias.detach().double().cpu(), k=1, stride=1,
-                    act=False, nchw=(out_name, i, 4 * self.reg_max, self.nc, self.no))
+            folded = [reg[i][0].folded() for _, reg, _ in branches]
+            c2 = folded[0][0].shape[0]
+            if c2 % 16 == 0:
+                r01 = pb.conv(f, torch.cat([w for w, _ in folded]), torch.cat([b for _, b in folded]), k=3, stride=1, act=True)
+                firsts = [r01.sub(j * c2, c2) for j in range(len(branches))]
+            else:
+                firsts = [reg[i][0].emit(pb, f) for _, reg, _ in branches]
+            for (out_name, reg, cls), r in zip(branches, firsts):
+                r = reg[i][1].emit(pb, r)
+                fin = reg[i][2]
+                pb.conv(r, fin.weight.detach().double().cpu(), fin.bias.detach().double().cpu(), k=1, stride=1,
+                        act=False, nchw=(out_name, i, 0, 4 * self.reg_max, self.no))
+                c = cls[i][0][1].emit(pb, cls[i][0][0].emit(pb, f))
+                c = cls[i][1][1].emit(pb, cls[i][1][0].emit(pb, c))
+                fin = cls[i][2]
+                pb.conv(c, fin.weight.detach().double().cpu(), fin.bias.detach().double().cpu(), k=1, stride=1,
+                        act=False, nchw=(out_name, i, 4 * self.reg_max, self.nc, self.no))

@@ -53,6 +53,11 @@ def run(spec, iters=5):
         op.impl = N.IMPL_SIMT if kw.get("simt") else N.IMPL_AUTO
         op.src, op.dst = view(x, 0, cin), view(y, 0, cout)
         op.w, op.bias = w.data_ptr(), b.data_ptr()
+        if kw.get("nchw"):     # public NCHW fp32 output (head finals) instead of the NHWC buffer
+            o = torch.empty(B, cout, hw // s, hw // s, device=DEV)
+            op.dst = N.LyView(None, 0, 0, 0, 0, 0)
+            op.nchw, op.nchw_ctot, op.nchw_c0, op.nchw_c = o.data_ptr(), cout, 0, cout
+            keep.append(o)
         if kw.get("res"):
             r = torch.randn_like(y)
             op.res = view(r, 0, cout)
@@ -60,7 +65,7 @@ def run(spec, iters=5):
         keep += [x, w, b, y]
         M = B * (hw // s) ** 2
         flops = 2 * M * cout * cin * k * k
-        byts = B * hw * hw * cin * 2 + M * cout * 2 * (2 if kw.get("res") else 1)
+        byts = B * hw * hw * cin * 2 + M * cout * (4 if kw.get("nchw") else 2) * (2 if kw.get("res") else 1)
     elif kind == "dw":
         k, s, c = kw.get("k", 3), kw.get("s", 1), kw["c"]
         x = torch.randn(B, hw, hw, c, device=DEV).to(torch.bfloat16)
