@@ -245,6 +245,21 @@ def main():
     for d in by_kind.values():
         d["gbs"] = round(d["bytes"] / (d["ms"] / 1e3) / 1e9, 1) if d["ms"] > 0 else 0.0
         d["ms"] = round(d["ms"], 3)
+    # decode tail (DFL + two-stage top-k) timed alone on the cached one2one branch
+    from leanyolo_b200 import postprocess as PP
+    from leanyolo_b200.variants import STRIDES
+    branch = model._eval_branches["one2one"]
+    for _ in range(2):
+        PP.topk_raw(branch, num_classes=len(names), strides=STRIDES, max_det=300)
+    e0.record()
+    for _ in range(5):
+        PP.topk_raw(branch, num_classes=len(names), strides=STRIDES, max_det=300)
+    e1.record()
+    torch.cuda.synchronize()
+    dec_ms = e0.elapsed_time(e1) / 5
+    dec_bytes = sum(t.numel() * 4 for t in branch) + B * 300 * 6 * 4
+    by_kind["decode"] = {"ms": round(dec_ms, 3), "bytes": dec_bytes, "flops": 0, "launches": 2,
+                         "gbs": round(dec_bytes / (dec_ms / 1e3) / 1e9, 1)}
     if a.profile_out:
         os.makedirs(os.path.dirname(os.path.abspath(a.profile_out)), exist_ok=True)
         json.dump({"rows": rows, "by_kind": by_kind}, open(a.profile_out, "w"), indent=1)

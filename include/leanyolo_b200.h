@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define LY_ABI_VERSION 1
+#define LY_ABI_VERSION 2
 
 #if defined(LY_BUILD) && defined(__GNUC__)
 #define LY_API __attribute__((visibility("default")))
@@ -50,6 +50,8 @@ enum {
   LY_OP_ATTN = 6,     /* PSA attention core softmax(q^T k * scale) applied to v            layers.py:369-378 */
   LY_OP_EXPORT = 7,   /* NHWC storage -> public NCHW fp32 (taps / sub-module outputs)      */
   LY_OP_IMPORT = 8,   /* public NCHW fp32 -> NHWC storage (sub-module inputs)              */
+  LY_OP_DWPW = 9,     /* fused depthwise 3x3 (+BN+SiLU) -> 1x1 Conv+BN(+SiLU): the depthwise result is
+                         produced straight into the GEMM's shared-memory A tile      head.py:95-107, layers.py:256-264 */
 };
 
 /* conv implementation selector (ly_op.impl) */
@@ -84,6 +86,10 @@ typedef struct ly_op {
   float* nchw;        /* optional public NCHW fp32 tensor [B, nchw_ctot, Ho, Wo] (CONV/EXPORT dst, STEM/IMPORT src) */
   int32_t nchw_ctot, nchw_c0, nchw_c;
   int32_t ext_slot;   /* plan only: >=0 -> `nchw` is taken from ly_plan_run's ext[] table */
+  /* DWPW only: the depthwise stage that feeds the 1x1 (k, w, bias, act above describe the 1x1) */
+  const void* pre_w;      /* depthwise weights [pre_k*pre_k][C_pad] (dtype) */
+  const float* pre_bias;  /* [C_pad] fp32 */
+  int32_t pre_k, pre_act; /* depthwise filter size (3), 1 = SiLU after the depthwise bias */
 } ly_op;
 
 /* ---- library ---------------------------------------------------------- */

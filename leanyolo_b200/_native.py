@@ -10,8 +10,9 @@ from pathlib import Path
 
 LIB_PATH = Path(__file__).resolve().parent / "_lib" / "libleanyolo_b200.so"
 
+ABI_VERSION = 2
 LY_BF16, LY_F32 = 0, 1
-OP_STEM, OP_CONV, OP_DW, OP_POOL, OP_UP, OP_ATTN, OP_EXPORT, OP_IMPORT = 1, 2, 3, 4, 5, 6, 7, 8
+OP_STEM, OP_CONV, OP_DW, OP_POOL, OP_UP, OP_ATTN, OP_EXPORT, OP_IMPORT, OP_DWPW = 1, 2, 3, 4, 5, 6, 7, 8, 9
 IMPL_AUTO, IMPL_SIMT, STEM_IN_U8 = 0, 1, 2
 
 
@@ -28,6 +29,7 @@ class LyOp(C.Structure):
         ("src", LyView), ("dst", LyView), ("res", LyView),
         ("w", C.c_void_p), ("bias", C.c_void_p), ("nchw", C.c_void_p),
         ("nchw_ctot", C.c_int32), ("nchw_c0", C.c_int32), ("nchw_c", C.c_int32), ("ext_slot", C.c_int32),
+        ("pre_w", C.c_void_p), ("pre_bias", C.c_void_p), ("pre_k", C.c_int32), ("pre_act", C.c_int32),
     ]
 
 
@@ -81,7 +83,7 @@ def lib() -> C.CDLL:
         for name, (res, args) in PROTOTYPES.items():
             fn = getattr(l, name)
             fn.restype, fn.argtypes = res, args
-        if l.ly_abi_version() != 1:
+        if l.ly_abi_version() != ABI_VERSION:
             raise NativeError("libleanyolo_b200.so ABI version mismatch: rebuild")
         _lib = l
     return _lib

@@ -1,5 +1,6 @@
 // extern "C" boundary of libleanyolo_b200.so: error state, op dispatch, whole-forward plan.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 #include <vector>
 #include "common.cuh"
@@ -24,6 +25,15 @@ int sm_count() {
       n = 148;
   }
   return n;
+}
+
+bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("LY_PDL");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on == 1;
 }
 
 static int32_t check_arch() {
@@ -55,6 +65,14 @@ static int32_t dispatch(const ly_op& op, cudaStream_t s) {
       conv_tc_free(st);
       return rc;
     }
+    case LY_OP_DWPW: {
+      DwPwState* st = nullptr;
+      int32_t rc = dwpw_prepare(op, &st);
+      if (rc != LY_OK) return rc;
+      rc = dwpw_launch(st, nullptr, s);
+      dwpw_free(st);
+      return rc;
+    }
     case LY_OP_DW: return launch_dw(op, s);
     case LY_OP_POOL: return launch_pool(op, s);
     case LY_OP_UP: return launch_up(op, s);
@@ -69,12 +87,17 @@ static int32_t dispatch(const ly_op& op, cudaStream_t s) {
 
 using namespace ly;
 
+static_assert(sizeof(ly_view) == 32 && sizeof(ly_op) == 232, "ly_op layout is part of the C ABI (mirrored by ctypes in _native.py)");
+
 struct ly_plan {
   std::vector<ly_op> ops;
   std::vector<ConvTcState*> tc;   // per op (nullptr when not a tensor-core conv)
+  std::vector<DwPwState*> fz;     // per op (nullptr when not a fused dw->1x1)
   ~ly_plan() {
     for (auto* t : tc)
       if (t) conv_tc_free(t);
+    for (auto* t : fz)
+      if (t) dwpw_free(t);
   }
 };
 
@@ -105,12 +128,13 @@ int32_t ly_plan_create(const ly_op* ops, int32_t n_ops, ly_plan** out) {
   ly_plan* pl = new ly_plan();
   pl->ops.assign(ops, ops + n_ops);
   pl->tc.assign(n_ops, nullptr);
+  pl->fz.assign(n_ops, nullptr);
   for (int i = 0; i < n_ops; ++i) {
     const ly_op& op = pl->ops[i];
-    if (op.kind == LY_OP_CONV && use_tc(op)) {
+    if ((op.kind == LY_OP_CONV && use_tc(op)) || op.kind == LY_OP_DWPW) {
       ly_op tmp = op;
       if (tmp.ext_slot >= 0 && !tmp.nchw) tmp.nchw = reinterpret_cast<float*>(16);  // placeholder: real pointer comes at run time
-      rc = conv_tc_prepare(tmp, &pl->tc[i]);
+      rc = op.kind == LY_OP_DWPW ? dwpw_prepare(tmp, &pl->fz[i]) : conv_tc_prepare(tmp, &pl->tc[i]);
       if (rc != LY_OK) {
         char msg[400];
         snprintf(msg, sizeof(msg), "%s", g_err);
@@ -144,6 +168,8 @@ static int32_t plan_run_impl(ly_plan* pl, float* const* ext, int32_t n_ext, int3
     int32_t rc;
     if (pl->tc[i]) {
       rc = conv_tc_launch(pl->tc[i], op.ext_slot >= 0 ? nchw : nullptr, s);
+    } else if (pl->fz[i]) {
+      rc = dwpw_launch(pl->fz[i], op.ext_slot >= 0 ? nchw : nullptr, s);
     } else {
       ly_op tmp = op;
       tmp.nchw = nchw;
@@ -179,7 +205,7 @@ int32_t ly_plan_profile(ly_plan* pl, float* const* ext, int32_t n_ext, int32_t i
   if (rc == LY_OK)
     for (size_t i = 0; i < n; ++i) {
       cudaEventElapsedTime(&h_ms[i], ev[i], ev[i + 1]);
-      if (h_is_tc) h_is_tc[i] = pl->tc[i] ? 1 : 0;
+      if (h_is_tc) h_is_tc[i] = (pl->tc[i] || pl->fz[i]) ? 1 : 0;
     }
   for (auto& e : ev) cudaEventDestroy(e);
   return rc;

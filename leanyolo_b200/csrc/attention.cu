@@ -21,6 +21,8 @@ template <typename T, int KDP, int HD>
 __global__ void __launch_bounds__(QB)
 attn_kernel(const T* __restrict__ qkv, int N, int sCtot, int sC0, int nh, T* __restrict__ out, int dCtot, int dC0,
             float scale) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ __align__(16) float Ks[KB][KDP];
   __shared__ __align__(16) float Vs[KB][HD];
   constexpr int V = Elem<T>::kVec;
@@ -169,6 +171,8 @@ attn_mma_kernel(const __nv_bfloat16* __restrict__ qkv, int N, int sCtot, int sC0
   constexpr int STAGE = AT_KB * (KPITCH + VPITCH);
   static_assert(HD % 8 == 0 && KDP % 8 == 0, "head dims must be multiples of 8");
   __shared__ __align__(16) uint8_t sm[2 * STAGE];
+  pdl_trigger();
+  pdl_wait();
 
   const int h = blockIdx.y, b = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -314,7 +318,7 @@ template <int KDP, int HD>
 int32_t run_mma(const ly_op& op, cudaStream_t s) {
   const int N = op.src.H * op.src.W;
   dim3 grid((N + AT_WARPS * 16 - 1) / (AT_WARPS * 16), op.nh, op.B);
-  attn_mma_kernel<KDP, HD><<<grid, AT_WARPS * 32, 0, s>>>((const __nv_bfloat16*)op.src.ptr, N, op.src.ctot, op.src.c0, op.nh,
+  launch_k(attn_mma_kernel<KDP, HD>, grid, dim3(AT_WARPS * 32), 0, s, (const __nv_bfloat16*)op.src.ptr, N, op.src.ctot, op.src.c0, op.nh,
                                                            (__nv_bfloat16*)op.dst.ptr, op.dst.ctot, op.dst.c0,
                                                            op.scale * 1.4426950408889634f);
   return post_launch("psa_attention_mma");
@@ -324,7 +328,7 @@ template <typename T, int KDP, int HD>
 int32_t run(const ly_op& op, cudaStream_t s) {
   const int N = op.src.H * op.src.W;
   dim3 grid((N + QB - 1) / QB, op.nh, op.B);
-  attn_kernel<T, KDP, HD><<<grid, QB, 0, s>>>((const T*)op.src.ptr, N, op.src.ctot, op.src.c0, op.nh, (T*)op.dst.ptr,
+  launch_k(attn_kernel<T, KDP, HD>, grid, dim3(QB), 0, s, (const T*)op.src.ptr, N, op.src.ctot, op.src.c0, op.nh, (T*)op.dst.ptr,
                                               op.dst.ctot, op.dst.c0, op.scale);
   return post_launch("psa_attention");
 }

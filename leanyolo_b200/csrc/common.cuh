@@ -4,6 +4,7 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 #include <atomic>
 #include "../../include/leanyolo_b200.h"
 
@@ -59,10 +60,41 @@ int32_t conv_tc_launch(const ConvTcState* st, float* nchw_override, cudaStream_t
 void conv_tc_free(ConvTcState* st);
 bool conv_tc_supported(const ly_op& op);
 
+// fused depthwise 3x3 -> 1x1 (dwpw_tc.cu)
+struct DwPwState;
+int32_t dwpw_prepare(const ly_op& op, DwPwState** out);
+int32_t dwpw_launch(const DwPwState* st, float* nchw_override, cudaStream_t s);
+void dwpw_free(DwPwState* st);
+bool dwpw_supported(const ly_op& op);
+
 int sm_count();
+
+// Programmatic dependent launch: every kernel of the forward is launched with the
+// programmatic-stream-serialization attribute, so its CTAs are scheduled (and run their
+// prologue: barrier init, TMEM allocation, tensor-map prefetch) while the previous kernel
+// drains, and block in pdl_wait() until that kernel has completed and flushed.  Every
+// kernel launched this way MUST execute pdl_wait() before touching activations and before
+// it exits (that is what makes completion transitive along the stream).  LY_PDL=0 disables.
+bool pdl_enabled();
 
 // ---- device helpers ---------------------------------------------------------
 #ifdef __CUDACC__
+
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... Exp, typename... Act>
+inline cudaError_t launch_k(void (*kernel)(Exp...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Act&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute at;
+  memset(&at, 0, sizeof(at));
+  at.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at.val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = &at; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<Exp>(args)...);
+}
 
 __device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 // SiLU(x) = x*sigmoid(x) = h + h*tanh(h), h = x/2: one MUFU op (tanh.approx, rel. err 2^-11),

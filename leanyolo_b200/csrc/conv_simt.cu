@@ -26,6 +26,8 @@ conv_simt_kernel(const T* __restrict__ src, int sH, int sW, int sCtot, int sC0, 
                  const T* __restrict__ w, const float* __restrict__ bias,
                  float* nchw, int nCtot, int nC0, int nC,
                  int B, int Ho, int Wo, int Cout, int k, int stride, int act) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float As[TK][TM + 4];
   __shared__ float Bs[TK][TN + 4];
 
@@ -123,7 +125,7 @@ int32_t run(const ly_op& op, cudaStream_t st) {
   const int Cout = op.dst.ptr ? op.dst.c : (op.nchw_c + 15) / 16 * 16;
   const long long M = (long long)op.B * Ho * Wo;
   dim3 grid((unsigned)((M + TM - 1) / TM), (unsigned)((Cout + TN - 1) / TN));
-  conv_simt_kernel<T><<<grid, NT, 0, st>>>(
+  launch_k(conv_simt_kernel<T>, grid, dim3(NT), 0, st,
       (const T*)op.src.ptr, op.src.H, op.src.W, op.src.ctot, op.src.c0, op.src.c,
       (T*)op.dst.ptr, op.dst.ctot, op.dst.c0,
       (const T*)op.res.ptr, op.res.ctot, op.res.c0,

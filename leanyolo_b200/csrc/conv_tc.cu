@@ -23,7 +23,9 @@
 //   (dC0, dCtot) of the consumer's concat buffer, the input tensor map starts at the
 //   producer's channel offset, the shortcut is read in the epilogue.
 // * Persistent: one CTA per SM, static round-robin over (pixel-brick, n-tile) tiles.
-//   Warp roles: 0 = TMA producer, 1 = MMA issuer (+TMEM alloc), 2..9 = epilogue.
+//   Warp roles: 0 = TMA producer, 1 = MMA issuer (+TMEM alloc), 2..17 = epilogue (thin layers are
+//   bound by epilogue latency, not bandwidth: 16 warps keep 4 per scheduler to overlap TMEM loads,
+//   MUFU and stores of different chunks).
 //
 // Reference semantics: leanyolo/models/yolov10/layers.py:51-88 (Conv = conv+BN+SiLU).
 #include <cuda.h>
@@ -31,15 +33,17 @@
 #include <string.h>
 #include "common.cuh"
 #include "tma.cuh"
+#include "tc.cuh"
 
 namespace ly {
 
 namespace {
 
-constexpr int kThreads = 320;    // TMA warp + MMA warp + 8 epilogue warps
+constexpr int kEpiWarps = 16;    // 4 TMEM lane quarters x 4 column groups
+constexpr int kThreads = 64 + 32 * kEpiWarps;    // TMA warp + MMA warp + epilogue warps
 constexpr int kMaxCout = 1024;   // bias vector staged in shared memory
 constexpr int kMaxStages = 12;   // per ring
-constexpr uint32_t kSmemBudget = 200 * 1024;
+constexpr uint32_t kSmemBudget = 216 * 1024;
 
 struct Params {
   CUtensorMap tmA;
@@ -49,6 +53,7 @@ struct Params {
   int tiles_w, tiles_h, tiles_b, tiles_n, total_tiles;
   int Wo, Ho, Bo;          // (possibly collapsed) output extents used for tiling / masking
   int hw_real;             // Ho*Wo of the real tensor (NCHW addressing)
+  uint32_t mg_n, mg_w, mg_h;   // magic multipliers: x / d == __umulhi(x, mg) for the tile counts used (0: d == 1)
   int k, stride, pad;
   int kc, kc_blocks, num_kb;
   int halo;                // 1: halo mode (3 taps share one A box)
@@ -69,39 +74,6 @@ struct Params {
   int cin_pad;
 };
 
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accum) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accum)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred = 0;
-  asm volatile(
-      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
-      "elect.sync rx|px, 0xFFFFFFFF;\n\t"
-      "selp.b32 %0, 1, 0, px;\n\t}"
-      : "=r"(pred));
-  return pred != 0;
-}
-
 // Optional per-role cycle accounting (-DLY_TC_PROFILE): CTA 0 prints where each role waited.
 #ifdef LY_TC_PROFILE
 #define PROF_DECL(name) long long name = 0
@@ -121,6 +93,14 @@ __device__ __forceinline__ uint32_t bar_bempty(uint32_t bb, int s) { return bb +
 __device__ __forceinline__ uint32_t bar_tfull(uint32_t bb, int s) { return bb + 8u * (4 * kMaxStages + s); }
 __device__ __forceinline__ uint32_t bar_tempty(uint32_t bb, int s) { return bb + 8u * (4 * kMaxStages + 2 + s); }
 __device__ __forceinline__ uint32_t bar_bres(uint32_t bb) { return bb + 8u * (4 * kMaxStages + 4); }
+
+// tile index -> (n tile, brick) without integer division (magic multipliers from the host)
+__device__ __forceinline__ void split_tile(const Params& p, int tile_idx, int& nt, int& wt, int& ht, int& bt) {
+  uint32_t t = (uint32_t)tile_idx;   // multiplier 0 encodes a divisor of 1
+  uint32_t qn = p.mg_n ? __umulhi(t, p.mg_n) : t; nt = (int)(t - qn * (uint32_t)p.tiles_n); t = qn;
+  uint32_t qw = p.mg_w ? __umulhi(t, p.mg_w) : t; wt = (int)(t - qw * (uint32_t)p.tiles_w); t = qw;
+  uint32_t qh = p.mg_h ? __umulhi(t, p.mg_h) : t; ht = (int)(t - qh * (uint32_t)p.tiles_h); bt = (int)qh;
+}
 
 // The single MMA-issuing thread.  Specialised on the k-steps per channel block, the taps per
 // A stage and weight residency so that the issue loop is straight-line code: a descriptor is
@@ -197,8 +177,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_trigger();   // the next kernel's CTAs may be scheduled as SMs drain (they block in their own pdl_wait)
   __shared__ __align__(16) float s_bias[kMaxCout];
-  for (int i = threadIdx.x; i < p.tiles_n * p.block_n; i += kThreads) s_bias[i] = p.bias[i];
+  for (int i = threadIdx.x; i < p.tiles_n * p.block_n; i += kThreads) s_bias[i] = p.act ? 0.5f * p.bias[i] : p.bias[i];
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmA) : "memory");
@@ -211,7 +192,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), 8);
+      mbar_init(tempty_bar(s), kEpiWarps);
     }
     mbar_init(bres_bar, 1);
     fence_barrier_init();
@@ -221,6 +202,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  // everything above touched only parameters (weights' bias, tensor maps) and on-chip state;
+  // activations written by the previous kernel are read from here on
+  pdl_wait();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -266,11 +250,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         if (++sb == p.b_stages) { sb = 0; pb ^= 1u; }
       };
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        int t = tile;
-        const int nt = t % p.tiles_n; t /= p.tiles_n;
-        const int wt = t % p.tiles_w; t /= p.tiles_w;
-        const int ht = t % p.tiles_h;
-        const int bt = t / p.tiles_h;
+        int nt, wt, ht, bt;
+        split_tile(p, tile, nt, wt, ht, bt);
         const int w0 = wt * p.tw * p.stride - p.pad, h0 = ht * p.th * p.stride - p.pad, b0 = bt * p.tb;
         const int n0 = nt * p.block_n;
         if (p.halo) {
@@ -310,16 +291,19 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 #undef LY_MMA_CASE
     }
   } else {
-    // ============================== epilogue (8 warps) ========================
-    // warp -> (TMEM lane quarter q = warp % 4, column half); a thread owns one pixel row and
-    // walks its columns in 16-wide chunks, the TMEM load of chunk i+1 in flight while chunk i
-    // is activated and stored.  The accumulator stage is released as soon as the last chunk
-    // sits in registers, so the MMA warp can start tile i+2 while this tile is still stored.
+    // ============================== epilogue (16 warps) =======================
+    // warp -> (TMEM lane quarter q = warp % 4, column group cg = (warp - 2) / 4).  A thread owns
+    // one pixel row; in round i the four warps of a quarter take the 16-column chunks 4i+cg.
+    // The TMEM load of round i+1 is in flight while round i is activated and stored; the
+    // accumulator stage is released as soon as the last chunk sits in registers.
+    // (Measured dead ends for the NHWC store: a TMA store from a swizzled staging tile and a
+    // shared-memory transpose to 128-byte coalesced stores were both slower than storing
+    // 2 x 16 bytes per lane straight from the TMEM layout: the extra barrier per tile costs more
+    // than the partial-sector writes, and the TMA unit is already row-rate bound on the loads.)
     const int q = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int cg = (warp - 2) >> 2;
     const int nchunks = p.block_n >> 4;
-    const int c_half = (nchunks + 1) >> 1;
-    const int cbeg = half ? c_half : 0, cend = half ? nchunks : c_half;
+    const int rounds = (nchunks + 3) >> 2;
     const int row = q * 32 + lane;
     const int dw = row % p.tw;
     const int dh = (row / p.tw) % p.th;
@@ -330,26 +314,24 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 #ifdef LY_TC_PROFILE
     const long long estart = clock64();
 #endif
+    auto split = [&](int tile_idx, int& nt, int& wt, int& ht, int& bt) { split_tile(p, tile_idx, nt, wt, ht, bt); };
     // Shortcut (residual) operand: each thread cp.async's its own 32 bytes per chunk of the
     // NEXT tile into a private shared-memory slot while it works on the current tile, so the
     // DRAM latency of the uncoalesced shortcut read is off the epilogue's critical path
     // (measured: a C2f bottleneck at 160^2 spent 35 % of its samples waiting for that load).
     const uint32_t r_base = bar_base + 8u * (4 * kMaxStages + 8);
     const uint32_t rslot = r_base + (uint32_t)(threadIdx.x - 64) * p.res_slot;
-    const uint32_t rstage = 256u * p.res_slot;
+    const uint32_t rstage = (uint32_t)(32 * kEpiWarps) * p.res_slot;
     auto res_prefetch = [&](int tile_idx, uint32_t dst) {
       if (tile_idx < p.total_tiles) {
-        int t = tile_idx;
-        const int nt = t % p.tiles_n; t /= p.tiles_n;
-        const int wt = t % p.tiles_w; t /= p.tiles_w;
-        const int ht = t % p.tiles_h;
-        const int bt = t / p.tiles_h;
+        int nt, wt, ht, bt;
+        split(tile_idx, nt, wt, ht, bt);
         const int w = wt * p.tw + dw, h = ht * p.th + dh, b = bt * p.tb + db;
         if (w < p.Wo && h < p.Ho && b < p.Bo) {
           const __nv_bfloat16* rr = p.res + (((long long)b * p.Ho + h) * p.Wo + w) * p.rCtot + p.rC0 + nt * p.block_n;
-          for (int ch = cbeg; ch < cend; ++ch) {
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (ch - cbeg) * 32), "l"(rr + ch * 16) : "memory");
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (ch - cbeg) * 32 + 16), "l"(rr + ch * 16 + 8) : "memory");
+          for (int i = 0, ch = cg; ch < nchunks; ++i, ch += 4) {
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + i * 32), "l"(rr + ch * 16) : "memory");
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + i * 32 + 16), "l"(rr + ch * 16 + 8) : "memory");
           }
         }
       }
@@ -357,12 +339,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     };
     uint32_t rs = 0;
     if (p.res_slot) res_prefetch(blockIdx.x, rslot);
+    const float pre = p.act ? 0.5f : 1.0f;   // SiLU(x) = h + h*tanh(h), h = x/2: the halving rides on the bias FMA
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      int t = tile;
-      const int nt = t % p.tiles_n; t /= p.tiles_n;
-      const int wt = t % p.tiles_w; t /= p.tiles_w;
-      const int ht = t % p.tiles_h;
-      const int bt = t / p.tiles_h;
+      int nt, wt, ht, bt;
+      split(tile, nt, wt, ht, bt);
       const int w = wt * p.tw + dw, h = ht * p.th + dh, b = bt * p.tb + db;
       const bool valid = w < p.Wo && h < p.Ho && b < p.Bo;
       const long long lin = ((long long)b * p.Ho + h) * p.Wo + w;
@@ -375,45 +355,50 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       { PROF_T0(); mbar_wait(tfull_bar(as), aphase); PROF_ADD(w_tfull); }
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.block_n);
-      __nv_bfloat16* drow = p.dst ? p.dst + lin * p.dCtot + p.dC0 + n0 : nullptr;
-      const __nv_bfloat16* rrow = p.res ? p.res + lin * p.rCtot + p.rC0 + n0 : nullptr;
-      long long nchw_b = 0, nchw_rem = 0;
-      if (p.nchw) { nchw_b = lin / p.hw_real; nchw_rem = lin - nchw_b * p.hw_real; }
+      __nv_bfloat16* drow = (p.dst && valid) ? p.dst + lin * p.dCtot + p.dC0 + n0 : nullptr;
+      const __nv_bfloat16* rrow = (p.res && valid) ? p.res + lin * p.rCtot + p.rC0 + n0 : nullptr;
+      float* nrow = nullptr;
+      if (p.nchw && valid) {
+        const uint32_t nb = (uint32_t)lin / (uint32_t)p.hw_real;        // image index, pixel inside the image
+        nrow = p.nchw + ((long long)nb * p.nCtot + p.nC0 + n0) * p.hw_real + ((uint32_t)lin - nb * (uint32_t)p.hw_real);
+      }
       uint32_t nxt[16];
-      if (cbeg < cend) tmem_ld16(taddr + cbeg * 16, nxt);
-      for (int ch = cbeg; ch < cend; ++ch) {
+      if (cg < nchunks) tmem_ld16(taddr + cg * 16, nxt);
+      bool released = false;
+      for (int rd = 0; rd < rounds; ++rd) {
+        const int ch = rd * 4 + cg;
         const int c = ch * 16;
-        uint32_t r[16];
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 16; ++j) r[j] = nxt[j];
-        if (ch + 1 < cend) {
-          tmem_ld16(taddr + c + 16, nxt);
-        } else {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(tempty_bar(as));
-        }
-        if (valid) {
-          float v[16];
+        const bool has = ch < nchunks;
+        float v[16];
+        if (has) {
+          tmem_ld_wait();
           const float4* bp = reinterpret_cast<const float4*>(s_bias + n0 + c);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const float4 bb = bp[j];
-            v[4 * j + 0] = __uint_as_float(r[4 * j + 0]) + bb.x;
-            v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + bb.y;
-            v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + bb.z;
-            v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + bb.w;
+            v[4 * j + 0] = fmaf(__uint_as_float(nxt[4 * j + 0]), pre, bb.x);
+            v[4 * j + 1] = fmaf(__uint_as_float(nxt[4 * j + 1]), pre, bb.y);
+            v[4 * j + 2] = fmaf(__uint_as_float(nxt[4 * j + 2]), pre, bb.z);
+            v[4 * j + 3] = fmaf(__uint_as_float(nxt[4 * j + 3]), pre, bb.w);
           }
+          if (ch + 4 < nchunks) tmem_ld16(taddr + c + 64, nxt);   // next round's chunk, in flight during the activation
+        }
+        if (!released && ch + 4 >= nchunks) {   // this warp's last TMEM load has completed (or it has none)
+          released = true;
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar(as));
+        }
+        if (has) {
           if (p.act) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = silu_tanh(v[j]);
+            for (int j = 0; j < 16; ++j) v[j] = silu_from_half(v[j]);
           }
           if (rrow) {
             float rv[16];
             if (p.res_slot) {
-              load_vec<__nv_bfloat16>(reinterpret_cast<const __nv_bfloat16*>(rsm + (ch - cbeg) * 32), rv);
-              load_vec<__nv_bfloat16>(reinterpret_cast<const __nv_bfloat16*>(rsm + (ch - cbeg) * 32 + 16), rv + 8);
+              load_vec<__nv_bfloat16>(reinterpret_cast<const __nv_bfloat16*>(rsm + rd * 32), rv);
+              load_vec<__nv_bfloat16>(reinterpret_cast<const __nv_bfloat16*>(rsm + rd * 32 + 16), rv + 8);
             } else {
               load_vec<__nv_bfloat16>(rrow + c, rv);
               load_vec<__nv_bfloat16>(rrow + c + 8, rv + 8);
@@ -421,23 +406,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] += rv[j];
           }
+          if (nrow) {
+            float* np = nrow + (long long)c * p.hw_real;
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (n0 + c + j < p.nC) np[(long long)j * p.hw_real] = v[j];
+          }
           if (drow) {
             store_vec<__nv_bfloat16>(drow + c, v);
             store_vec<__nv_bfloat16>(drow + c + 8, v + 8);
           }
-          if (p.nchw) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const int n = n0 + c + j;
-              if (n < p.nC) p.nchw[(nchw_b * p.nCtot + p.nC0 + n) * (long long)p.hw_real + nchw_rem] = v[j];
-            }
-          }
         }
-      }
-      if (cbeg >= cend) {   // this warp has no columns (narrow N): still release the stage
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar(as));
       }
       if (++as == 2) { as = 0; aphase ^= 1u; }
       rs ^= 1u;
@@ -541,6 +520,15 @@ int32_t conv_tc_prepare(const ly_op& op, ConvTcState** out) {
   const long long total = (long long)p.tiles_w * p.tiles_h * p.tiles_b * p.tiles_n;
   if (total > 0x7FFFFFFF) { delete st; set_error("conv_tc: too many tiles"); return LY_E_ARG; }
   p.total_tiles = (int)total;
+  {
+    // x / d == __umulhi(x, floor(2^32 / d) + 1) whenever x * d < 2^32; 0 encodes d == 1
+    auto magic = [](uint32_t d) -> uint32_t { return d <= 1 ? 0u : (uint32_t)((1ull << 32) / d + 1); };
+    p.mg_n = magic((uint32_t)p.tiles_n); p.mg_w = magic((uint32_t)p.tiles_w); p.mg_h = magic((uint32_t)p.tiles_h);
+    const unsigned long long lim = 1ull << 32, tmax = (unsigned long long)total + 2ull * sm_count();
+    if (tmax * p.tiles_n >= lim || tmax * p.tiles_w >= lim || tmax * p.tiles_h >= lim || (unsigned long long)dimW * dimH * dimB >= lim) {
+      delete st; set_error("conv_tc: problem too large for 32-bit tile arithmetic"); return LY_E_ARG;
+    }
+  }
   p.tpa = p.halo ? 3 : 1;
   p.num_ka = p.num_kb / p.tpa;
   const int a_rows = p.halo ? 8 * 18 : 128;
@@ -555,10 +543,10 @@ int32_t conv_tc_prepare(const ly_op& op, ConvTcState** out) {
   static const int resident_ok = env_int("LY_TC_B_RESIDENT", 1);
   p.b_resident = (resident_ok && p.tiles_n == 1 && b_all <= 96 * 1024) ? 1 : 0;
   const uint32_t bar_bytes = 8 * (4 * kMaxStages + 8);
-  // shortcut prefetch slots: 2 stages x 256 epilogue threads x (chunks per warp x 32 B); only while small
+  // shortcut prefetch slots: 2 stages x 512 epilogue threads x (chunks per warp x 32 B); only while small
   static const int res_prefetch_ok = env_int("LY_TC_RES_PREFETCH", 1);
-  p.res_slot = (op.res.ptr && res_prefetch_ok && bn <= 128) ? ((bn / 16 + 1) / 2) * 32 : 0;
-  const long long res_bytes = 2LL * 256 * p.res_slot;
+  p.res_slot = (op.res.ptr && res_prefetch_ok && bn <= 128) ? ((bn / 16 + 3) / 4) * 32 : 0;   // one 32-byte chunk per round
+  const long long res_bytes = 2LL * 32 * kEpiWarps * p.res_slot;
   const long long avail = (long long)kSmemBudget - bar_bytes - 1024 - res_bytes - (p.b_resident ? b_all : 0);
   if (p.b_resident) {
     p.a_stages = (int)(avail / p.a_stage);
@@ -638,9 +626,9 @@ int32_t conv_tc_launch(const ConvTcState* st, float* nchw_override, cudaStream_t
   if (nchw_override) {
     Params p = st->p;
     p.nchw = nchw_override;
-    conv_tc_kernel<<<st->grid, kThreads, st->smem, s>>>(p);
+    launch_k(conv_tc_kernel, dim3(st->grid), dim3(kThreads), st->smem, s, p);
   } else {
-    conv_tc_kernel<<<st->grid, kThreads, st->smem, s>>>(st->p);
+    launch_k(conv_tc_kernel, dim3(st->grid), dim3(kThreads), st->smem, s, st->p);
   }
   return post_launch("conv_tc");
 }

@@ -24,6 +24,7 @@ namespace {
 constexpr int TOPK_MAX = 1024;   // max_det supported by the per-CTA sort buffers
 constexpr int NMS_CH = 512;      // candidates per NMS chunk
 constexpr int NT = 1024;
+constexpr int NT_TOPK = 512;     // top-k: 3 CTAs per SM so that a batch of 256 images is one wave
 
 struct Levels {
   const float* p[4];
@@ -42,6 +43,10 @@ __device__ __forceinline__ int level_of(const Levels& lv, int g) {
 }
 
 // ------------------------------------------------------------------------------------ DFL
+// LABEL = false (top-k path): only the best class SCORE is needed, and sigmoid is monotonic,
+// so it is sigmoid(max logit): 1 sigmoid per anchor instead of nc.  The NMS path needs the
+// reference's argmax over the sigmoid VALUES (first maximum wins, ties included): LABEL = true.
+template <bool LABEL>
 __global__ void __launch_bounds__(256)
 dfl_kernel(Levels lv, float* __restrict__ boxes, float* __restrict__ best, int* __restrict__ label) {
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
@@ -86,14 +91,21 @@ dfl_kernel(Levels lv, float* __restrict__ boxes, float* __restrict__ best, int* 
   const float* c = p + (long long)creg * HW;
   float bs = -1.f;
   int bl = 0;
-  for (int i = 0; i < lv.nc; ++i) {
-    const float v = sigmoid_precise(c[(long long)i * HW]);
-    if (v > bs) { bs = v; bl = i; }   // first maximum wins, like torch.max
+  if (LABEL) {
+    for (int i = 0; i < lv.nc; ++i) {
+      const float v = sigmoid_precise(c[(long long)i * HW]);
+      if (v > bs) { bs = v; bl = i; }   // first maximum wins, like torch.max
+    }
+  } else {
+    float mx = -INFINITY;
+#pragma unroll 8
+    for (int i = 0; i < lv.nc; ++i) mx = fmaxf(mx, c[(long long)i * HW]);
+    bs = sigmoid_precise(mx);
   }
   const long long o = (long long)b * lv.A + g;
   reinterpret_cast<float4*>(boxes)[o] = make_float4(x1, y1, x2, y2);
   best[o] = bs;
-  label[o] = bl;
+  if (LABEL) label[o] = bl;
 }
 
 // ------------------------------------------------------------------- block-wide primitives
@@ -163,7 +175,7 @@ __device__ __forceinline__ int next_pow2(int v) {
 }
 
 // ----------------------------------------------------------------------------------- top-k
-__global__ void __launch_bounds__(NT)
+__global__ void __launch_bounds__(NT_TOPK, 3)
 topk_kernel(Levels lv, int k, const float* __restrict__ boxes, const float* __restrict__ best, float* s2,
             float* __restrict__ out, int* __restrict__ out_anchor, int* __restrict__ out_cls) {
   __shared__ unsigned long long sortbuf[TOPK_MAX];
@@ -481,10 +493,10 @@ extern "C" int32_t ly_decode_topk(const ly_levels* in, int32_t max_det, float* o
   cudaStream_t st = (cudaStream_t)stream;
   const int k = max_det < lv.A ? max_det : lv.A;
   dim3 g1((lv.A + 255) / 256, lv.B);
-  dfl_kernel<<<g1, 256, 0, st>>>(lv, s.boxes, s.best, s.label);
+  dfl_kernel<false><<<g1, 256, 0, st>>>(lv, s.boxes, s.best, s.label);
   rc = post_launch("dfl_decode");
   if (rc != LY_OK) return rc;
-  topk_kernel<<<lv.B, NT, 0, st>>>(lv, k, s.boxes, s.best, s.s2, out, out_anchor, out_cls);
+  topk_kernel<<<lv.B, NT_TOPK, 0, st>>>(lv, k, s.boxes, s.best, s.s2, out, out_anchor, out_cls);
   return post_launch("topk");
 }
 
@@ -500,7 +512,7 @@ extern "C" int32_t ly_decode_nms(const ly_levels* in, float conf_thresh, float i
   LY_CHECK_ARG(scratch_bytes >= s.total, "decode_nms: scratch too small (%lld < %lld)", (long long)scratch_bytes, s.total);
   cudaStream_t st = (cudaStream_t)stream;
   dim3 g1((lv.A + 255) / 256, lv.B);
-  dfl_kernel<<<g1, 256, 0, st>>>(lv, s.boxes, s.best, s.label);
+  dfl_kernel<true><<<g1, 256, 0, st>>>(lv, s.boxes, s.best, s.label);
   rc = post_launch("dfl_decode");
   if (rc != LY_OK) return rc;
   return run_nms(s.boxes, s.best, s.label, nullptr, lv.B, lv.A, 1, conf_thresh, iou_thresh, max_det, classwise, s.sortbuf,

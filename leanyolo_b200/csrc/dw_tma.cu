@@ -73,6 +73,8 @@ __global__ void __launch_bounds__(kThreadsDw) dw_tma_kernel(const __grid_constan
     }
     fence_barrier_init();
   }
+  pdl_trigger();
+  pdl_wait();
   __syncthreads();
 
   if (warp == kComputeThreads / 32) {
@@ -220,7 +222,7 @@ int32_t launch_cfg(const ly_op& op, cudaStream_t st) {
   // three CTAs per SM when they fit: more loads in flight, epilogue of one overlaps compute of the other
   int grid = 3 * sms;
   if (grid > p.total_tiles) grid = p.total_tiles;
-  dw_tma_kernel<K, S, CBV, TW_T, TH_T><<<grid, kThreadsDw, smem, st>>>(p);
+  launch_k(dw_tma_kernel<K, S, CBV, TW_T, TH_T>, dim3(grid), dim3(kThreadsDw), smem, st, p);
   return post_launch("dwconv_tma");
 }
 

@@ -25,6 +25,8 @@ __global__ void __launch_bounds__(ST_THREADS)
 stem_kernel(const TIn* __restrict__ x, int H, int W, T* __restrict__ dst, int dCtot, int dC0, int Cpad,
             const float* __restrict__ w, const float* __restrict__ bias,
             float s0, float s1, float s2, float d0, float d1, float d2) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ __align__(16) float smem[];
   float* ws = smem;                           // [27][Cpad]  (transposed from [Cpad][27])
   float* bs = ws + 27 * Cpad;                 // [Cpad]
@@ -172,6 +174,8 @@ stem_mma_kernel(const TIn* __restrict__ x, int H, int W, __nv_bfloat16* __restri
   __shared__ __align__(16) __nv_bfloat16 tile[3 * SM_IH * SM_IWP];
   __shared__ __align__(16) __nv_bfloat16 wsm[CP * 32];
   __shared__ __align__(16) uint8_t ostage[SM_TH][16 * OPITCH];
+  pdl_trigger();
+  pdl_wait();
   const int Ho = H / 2, Wo = W / 2;
   const int b = blockIdx.z, ho0 = blockIdx.y * SM_TH, wo0 = blockIdx.x * SM_TW;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
@@ -284,6 +288,8 @@ dw_kernel(const T* __restrict__ src, int sH, int sW, int sCtot, int sC0,
           T* __restrict__ dst, int dCtot, int dC0, const T* res, int rCtot, int rC0,
           const T* __restrict__ w, const float* __restrict__ bias,
           int C, int Ho, int Wo, int act, int px, int py, long long total) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int V = Elem<T>::kVec;
   constexpr int IH = (TH - 1) * S + K, IW = (TW - 1) * S + K;
   const int cv = C / V;
@@ -401,6 +407,8 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 pool_kernel(T* buf, int H, int W, int Ctot, int C0, int C, int cbv) {
   constexpr int V = Elem<T>::kVec;
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ __align__(16) uint4 psm[];   // [2][H*W][cbv]
   const int HW = H * W, items = HW * cbv;
   uint4* cur = psm;
@@ -446,6 +454,8 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 up_kernel(const T* __restrict__ src, int sH, int sW, int sCtot, int sC0, T* __restrict__ dst, int dCtot, int dC0,
           int C, long long total) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int V = Elem<T>::kVec;
   const int cv = C / V;
   const int dH = 2 * sH, dW = 2 * sW;
@@ -467,6 +477,8 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 export_kernel(const T* __restrict__ src, int HW, int sCtot, int sC0, float* __restrict__ out, int nCtot, int nC0,
               int nC, long long total) {
+  pdl_trigger();
+  pdl_wait();
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
     const int p = (int)(idx % HW);
@@ -482,6 +494,8 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 import_kernel(const float* __restrict__ in, int HW, int nCtot, int nC0, int nC, T* __restrict__ dst, int dCtot,
               int dC0, int C, long long total) {
+  pdl_trigger();
+  pdl_wait();
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(idx % C);
@@ -517,7 +531,7 @@ int32_t launch_stem(const ly_op& op, cudaStream_t s) {
   dim3 grid((op.dst.W + ST_TW - 1) / ST_TW, (op.dst.H + ST_TH - 1) / ST_TH, op.B);
   size_t smem = (3 * ST_IH * ST_IW + 28 * Cpad) * sizeof(float);
 #define LY_STEM(T, TIN)                                                                                              \
-  stem_kernel<T, TIN><<<grid, ST_THREADS, smem, s>>>((const TIN*)op.nchw, H, W, (T*)op.dst.ptr, op.dst.ctot, op.dst.c0, \
+  launch_k(stem_kernel<T, TIN>, grid, dim3(ST_THREADS), smem, s, (const TIN*)op.nchw, H, W, (T*)op.dst.ptr, op.dst.ctot, op.dst.c0, \
                                                      Cpad, (const float*)op.w, op.bias, op.sub[0], op.sub[1], op.sub[2], \
                                                      op.div[0], op.div[1], op.div[2])
   const bool u8 = op.impl == LY_STEM_IN_U8;
@@ -525,7 +539,7 @@ int32_t launch_stem(const ly_op& op, cudaStream_t s) {
       reinterpret_cast<uintptr_t>(op.nchw) % 16 == 0 && reinterpret_cast<uintptr_t>(op.dst.ptr) % 16 == 0) {
     dim3 g2((op.dst.W + SM_TW - 1) / SM_TW, (op.dst.H + SM_TH - 1) / SM_TH, op.B);
 #define LY_STEM_MMA(TIN, NT)                                                                                          \
-  stem_mma_kernel<TIN, NT><<<g2, SM_THREADS, 0, s>>>((const TIN*)op.nchw, H, W, (__nv_bfloat16*)op.dst.ptr, op.dst.ctot, \
+  launch_k(stem_mma_kernel<TIN, NT>, g2, dim3(SM_THREADS), 0, s, (const TIN*)op.nchw, H, W, (__nv_bfloat16*)op.dst.ptr, op.dst.ctot, \
                                                      op.dst.c0, (const float*)op.w, op.bias, op.sub[0], op.sub[1],    \
                                                      op.sub[2], op.div[0], op.div[1], op.div[2])
 #define LY_STEM_NT(NT)                                                 \
@@ -556,7 +570,7 @@ static int32_t run_dw_cfg(const ly_op& op, cudaStream_t s) {
   const int Ho = op.dst.H, Wo = op.dst.W;
   const int px = (Wo + TW - 1) / TW, py = (Ho + TH - 1) / TH;
   const long long total = (long long)op.B * py * px * (op.src.c / V);
-  dw_kernel<T, K, S, TH, TW><<<grid_for(total, 128), 128, 0, s>>>(
+  launch_k(dw_kernel<T, K, S, TH, TW>, dim3(grid_for(total, 128)), dim3(128), 0, s,
       (const T*)op.src.ptr, op.src.H, op.src.W, op.src.ctot, op.src.c0, (T*)op.dst.ptr, op.dst.ctot, op.dst.c0,
       (const T*)op.res.ptr, op.res.ctot, op.res.c0, (const T*)op.w, op.bias, op.src.c, Ho, Wo, op.act, px, py, total);
   return post_launch("dwconv");
@@ -597,7 +611,7 @@ static int32_t run_pool(const ly_op& op, cudaStream_t s) {
     attr_set = true;
   }
   dim3 grid(nvec / cbv, op.B);
-  pool_kernel<T><<<grid, 256, smem, s>>>((T*)op.src.ptr, op.src.H, op.src.W, op.src.ctot, op.src.c0, op.src.c, cbv);
+  launch_k(pool_kernel<T>, grid, dim3(256), smem, s, (T*)op.src.ptr, op.src.H, op.src.W, op.src.ctot, op.src.c0, op.src.c, cbv);
   return post_launch("sppf_pool");
 }
 
@@ -612,7 +626,7 @@ static int32_t run_up(const ly_op& op, cudaStream_t s) {
   constexpr int V = 16 / sizeof(T);
   LY_CHECK_ARG(aligned16<T>(op.src) && aligned16<T>(op.dst), "upsample: views must be 16-byte aligned");
   const long long total = (long long)op.B * op.dst.H * op.dst.W * (op.src.c / V);
-  up_kernel<T><<<grid_for(total), 256, 0, s>>>((const T*)op.src.ptr, op.src.H, op.src.W, op.src.ctot, op.src.c0,
+  launch_k(up_kernel<T>, dim3(grid_for(total)), dim3(256), 0, s, (const T*)op.src.ptr, op.src.H, op.src.W, op.src.ctot, op.src.c0,
                                                (T*)op.dst.ptr, op.dst.ctot, op.dst.c0, op.src.c, total);
   return post_launch("upsample2x");
 }
@@ -628,10 +642,10 @@ int32_t launch_export(const ly_op& op, cudaStream_t s) {
   const int HW = op.src.H * op.src.W;
   const long long total = (long long)op.B * op.nchw_c * HW;
   if (op.dtype == LY_F32)
-    export_kernel<float><<<grid_for(total), 256, 0, s>>>((const float*)op.src.ptr, HW, op.src.ctot, op.src.c0, op.nchw,
+    launch_k(export_kernel<float>, dim3(grid_for(total)), dim3(256), 0, s, (const float*)op.src.ptr, HW, op.src.ctot, op.src.c0, op.nchw,
                                                          op.nchw_ctot, op.nchw_c0, op.nchw_c, total);
   else
-    export_kernel<__nv_bfloat16><<<grid_for(total), 256, 0, s>>>((const __nv_bfloat16*)op.src.ptr, HW, op.src.ctot,
+    launch_k(export_kernel<__nv_bfloat16>, dim3(grid_for(total)), dim3(256), 0, s, (const __nv_bfloat16*)op.src.ptr, HW, op.src.ctot,
                                                                  op.src.c0, op.nchw, op.nchw_ctot, op.nchw_c0, op.nchw_c, total);
   return post_launch("export_nchw");
 }
@@ -641,10 +655,10 @@ int32_t launch_import(const ly_op& op, cudaStream_t s) {
   const int HW = op.dst.H * op.dst.W;
   const long long total = (long long)op.B * op.dst.c * HW;
   if (op.dtype == LY_F32)
-    import_kernel<float><<<grid_for(total), 256, 0, s>>>(op.nchw, HW, op.nchw_ctot, op.nchw_c0, op.nchw_c,
+    launch_k(import_kernel<float>, dim3(grid_for(total)), dim3(256), 0, s, op.nchw, HW, op.nchw_ctot, op.nchw_c0, op.nchw_c,
                                                          (float*)op.dst.ptr, op.dst.ctot, op.dst.c0, op.dst.c, total);
   else
-    import_kernel<__nv_bfloat16><<<grid_for(total), 256, 0, s>>>(op.nchw, HW, op.nchw_ctot, op.nchw_c0, op.nchw_c,
+    launch_k(import_kernel<__nv_bfloat16>, dim3(grid_for(total)), dim3(256), 0, s, op.nchw, HW, op.nchw_ctot, op.nchw_c0, op.nchw_c,
                                                                  (__nv_bfloat16*)op.dst.ptr, op.dst.ctot, op.dst.c0, op.dst.c, total);
   return post_launch("import_nchw");
 }

@@ -17,7 +17,7 @@ import torch
 from . import _native as N
 from .plan import Op, PlanBuilder, View
 
-_KIND = {"stem": N.OP_STEM, "conv": N.OP_CONV, "dw": N.OP_DW, "pool": N.OP_POOL, "up": N.OP_UP,
+_KIND = {"stem": N.OP_STEM, "conv": N.OP_CONV, "dw": N.OP_DW, "dwpw": N.OP_DWPW, "pool": N.OP_POOL, "up": N.OP_UP,
          "attn": N.OP_ATTN, "export": N.OP_EXPORT, "import": N.OP_IMPORT}
 
 
@@ -91,6 +91,9 @@ class Engine:
                     o.impl = N.STEM_IN_U8
             elif op.w_off >= 0:
                 o.w, o.bias = wbase + esz * op.w_off, bbase + 4 * op.b_off
+            if op.kind == "dwpw":
+                o.pre_w, o.pre_bias = wbase + esz * op.extra["pre_w_off"], bbase + 4 * op.extra["pre_b_off"]
+                o.pre_k, o.pre_act = 3, int(op.extra["pre_act"])
             if op.attn is not None:
                 o.nh, o.kdp, o.hd, o.scale = op.attn
             if op.nchw is not None:
@@ -155,7 +158,7 @@ class Engine:
                 es = comp.pb.esize
                 for i, op in enumerate(comp.pb.ops):
                     flops = byts = 0
-                    if op.kind == "conv":
+                    if op.kind in ("conv", "dwpw"):
                         Ho, Wo = op.src.H // op.stride, op.src.W // op.stride
                         flops = 2 * n * Ho * Wo * op.cout * op.cin * op.k * op.k
                         byts = n * (op.src.H * op.src.W * op.src.c * es + Ho * Wo * op.extra["cpad"] * (es if op.dst is not None else 4)

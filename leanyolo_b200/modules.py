@@ -52,6 +52,16 @@ class ConvBN(nn.Module):
         return pb.dwconv(src, w, b, k=self.k, stride=self.s, act=self.act, dst=dst, res=res)
 
 
+def emit_dw_pw(pb, dw: "ConvBN", pw: "ConvBN", src, dst=None):
+    """dw3x3 (+SiLU) followed by a 1x1: one fused launch when the tensor-core kernel takes the
+    pair (bf16, stride 1, C % 64 == 0, Cout <= 256), otherwise the two separate ops."""
+    if dw.g > 1 and pw.g == 1 and pw.k == 1 and pw.s == 1 and pb.dwpw_fusable(src, dw.conv.in_channels, pw.conv.out_channels, dw.k, dw.s):
+        dw_w, dw_b = dw.folded()
+        pw_w, pw_b = pw.folded()
+        return pb.dwpw(src, dw_w, dw_b, pw_w, pw_b, dw_act=dw.act, act=pw.act, dst=dst)
+    return pw.emit(pb, dw.emit(pb, src), dst)
+
+
 class Bottleneck(nn.Module):
     def __init__(self, c: int, shortcut: bool):
         super().__init__()
@@ -91,9 +101,11 @@ class CIB(nn.Module):
         )
 
     def emit(self, pb, src, dst):
-        y = src
-        for m in list(self.cv1)[:4]:
-            y = m.emit(pb, y)
+        y = emit_dw_pw(pb, self.cv1[0], self.cv1[1], src)
+        if isinstance(self.cv1[2], RepVGGDW):
+            y = self.cv1[3].emit(pb, self.cv1[2].emit(pb, y))
+        else:
+            y = emit_dw_pw(pb, self.cv1[2], self.cv1[3], y)
         return self.cv1[4].emit(pb, y, dst, res=src)  # C2fCIB always shortcut=True, c_in == c_out
 
 
@@ -303,8 +315,8 @@ class Detect(nn.Module):
                 fin = reg[i][2]
                 pb.conv(r, fin.weight.detach().double().cpu(), fin.bias.detach().double().cpu(), k=1, stride=1,
                         act=False, nchw=(out_name, i, 0, 4 * self.reg_max, self.no))
-                c = cls[i][0][1].emit(pb, cls[i][0][0].emit(pb, f))
-                c = cls[i][1][1].emit(pb, cls[i][1][0].emit(pb, c))
+                c = emit_dw_pw(pb, cls[i][0][0], cls[i][0][1], f)
+                c = emit_dw_pw(pb, cls[i][1][0], cls[i][1][1], c)
                 fin = cls[i][2]
                 pb.conv(c, fin.weight.detach().double().cpu(), fin.bias.detach().double().cpu(), k=1, stride=1,
                         act=False, nchw=(out_name, i, 4 * self.reg_max, self.nc, self.no))

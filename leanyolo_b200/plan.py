@@ -65,7 +65,7 @@ class View:
 
 @dataclass
 class Op:
-    kind: str                       # stem | conv | dw | pool | up | attn | export
+    kind: str                       # stem | conv | dw | dwpw | pool | up | attn | export
     src: Optional[View] = None
     dst: Optional[View] = None
     res: Optional[View] = None
@@ -196,6 +196,40 @@ class PlanBuilder:
                            k=k, stride=stride, act=act, cin=c, cout=c))
         return dst
 
+    def dwpw_fusable(self, src: View, c: int, cout: int, k: int, stride: int) -> bool:
+        """dw k x k -> 1x1 pairs the fused tensor-core kernel takes (csrc/dwpw_tc.cu)."""
+        import os
+        if os.environ.get("LEANYOLO_FUSE_DWPW", "1") == "0":
+            return False
+        return (self.dtype == "bf16" and k == 3 and stride == 1 and src.c % 64 == 0 and src.c == c
+                and _rup(cout, CH_ALIGN) <= 256)
+
+    def dwpw(self, src: View, dw_w: torch.Tensor, dw_b: torch.Tensor, pw_w: torch.Tensor, pw_b: torch.Tensor, *,
+             dw_act: bool, act: bool, dst: Optional[View] = None,
+             nchw: Optional[Tuple[str, int, int, int, int]] = None) -> Optional[View]:
+        """act2(pw(act1(dw3x3(src)))) as ONE launch: the depthwise result feeds the 1x1 GEMM through
+        shared memory and never reaches HBM."""
+        c = dw_w.shape[0]
+        cout, cin = pw_w.shape[0], pw_w.shape[1]
+        assert dw_w.shape[1:] == (1, 3, 3) and pw_w.shape[2:] == (1, 1) and cin == c == src.c
+        cpad = _rup(cout, CH_ALIGN)
+        if nchw is None:
+            if dst is None:
+                dst = self.buffer(src.H, src.W, cout).view()
+            assert dst.c == cpad and (dst.H, dst.W) == (src.H, src.W)
+        else:
+            name, level, c0, cc, ctot = nchw
+            self.outputs[(name, level)] = (ctot, src.H, src.W)
+        dwp = dw_w.reshape(c, 9).t().contiguous()                      # [9][C]
+        wp = torch.zeros(cpad, 1, 1, src.c, dtype=torch.float64)
+        wp[:cout, :, :, :cin] = pw_w.permute(0, 2, 3, 1)
+        bp = torch.zeros(cpad, dtype=torch.float64)
+        bp[:cout] = pw_b
+        self.ops.append(Op("dwpw", src=src, dst=dst, w_off=self._add_w(wp), b_off=self._add_b(bp), k=1, stride=1, act=act,
+                           cin=cin, cout=cout, nchw=nchw,
+                           extra=dict(cpad=cpad, pre_w_off=self._add_w(dwp), pre_b_off=self._add_b(dw_b), pre_act=dw_act)))
+        return dst
+
     def sppf_pool(self, cat: Buf, c: int) -> None:
         """cat[..., c:4c] <- three chained 5x5/s1/p2 max-pools of cat[..., 0:c] (windows 5, 9, 13)."""
         assert cat.C == 4 * c and c % 8 == 0
@@ -221,7 +255,7 @@ class PlanBuilder:
         """2*MAC of the dense convs per image (the tensor-pipe-eligible work)."""
         f = 0
         for op in self.ops:
-            if op.kind == "conv":
+            if op.kind in ("conv", "dwpw"):
                 Ho, Wo = op.src.H // op.stride, op.src.W // op.stride
                 f += 2 * Ho * Wo * op.cout * op.cin * op.k * op.k
             elif op.kind == "stem":

@@ -131,6 +131,56 @@ def check_dw(dtype="bf16", B=2, H=12, W=12, c=64, k=3, stride=1, act=True, res=F
     return {"relmax": e}
 
 
+def check_dwpw(B=2, H=20, W=20, c=128, cout=128, dw_act=True, act=True, src_off=0, src_extra=0, dst_off=0, dst_extra=0,
+               nchw=False, nchw_c=None, seed=0):
+    """fused depthwise 3x3 -> 1x1 (bf16 only) against torch fp32 on the quantised operands, with the
+    depthwise result rounded to bf16 like the kernel hands it to the GEMM."""
+    g = torch.Generator().manual_seed(seed)
+    tdt = torch.bfloat16
+    xs = torch.randn(B, H, W, src_off + c + src_extra, generator=g).to(tdt)
+    dww = (torch.randn(9, c, generator=g) / 3).to(tdt)
+    dwb = torch.randn(c, generator=g) * 0.2
+    w = (torch.randn(cout, 1, 1, c, generator=g) / math.sqrt(c)).to(tdt)
+    bias = torch.randn(cout, generator=g)
+    y = F.conv2d(xs[..., src_off:src_off + c].float().permute(0, 3, 1, 2), dww.float().t().reshape(c, 1, 3, 3), dwb, 1, 1, 1, c)
+    if dw_act:
+        y = F.silu(y)
+    y = y.to(tdt).float()
+    y = F.conv2d(y, w.float().permute(0, 3, 1, 2), bias)
+    if act:
+        y = F.silu(y)
+    y = y.permute(0, 2, 3, 1)
+    dst_tot = dst_off + cout + dst_extra
+    d0 = torch.randn(B, H, W, dst_tot, generator=g).to(tdt)
+    x_d, dww_d, dwb_d, w_d, b_d, d_d = xs.to(DEV), dww.to(DEV), dwb.to(DEV), w.to(DEV).contiguous(), bias.to(DEV), d0.to(DEV)
+    op = N.LyOp()
+    op.kind, op.dtype, op.B, op.k, op.stride, op.act, op.ext_slot = N.OP_DWPW, N.LY_BF16, B, 1, 1, int(act), -1
+    op.pre_k, op.pre_act = 3, int(dw_act)
+    op.pre_w, op.pre_bias = dww_d.data_ptr(), dwb_d.data_ptr()
+    op.src = view(x_d, src_off, c)
+    op.w, op.bias = w_d.data_ptr(), b_d.data_ptr()
+    out_nchw = None
+    if nchw:
+        cr = nchw_c or cout
+        out_nchw = torch.zeros(B, cr + 3, H, W, device=DEV)
+        op.nchw, op.nchw_ctot, op.nchw_c0, op.nchw_c = out_nchw.data_ptr(), cr + 3, 2, cr
+    else:
+        op.dst = view(d_d, dst_off, cout)
+    launch(op)
+    if nchw:
+        e = relmax(out_nchw[:, 2:2 + cr].permute(0, 2, 3, 1).cpu(), y[..., :cr])
+        assert float(out_nchw[:, :2].abs().max()) == 0 and float(out_nchw[:, 2 + cr:].abs().max()) == 0, "nchw overrun"
+    else:
+        got = d_d.cpu()
+        e = relmax(got[..., dst_off:dst_off + cout], y)
+        if dst_off:
+            assert torch.equal(got[..., :dst_off], d0[..., :dst_off]), "clobbered channels before slice"
+        if dst_extra:
+            assert torch.equal(got[..., dst_off + cout:], d0[..., dst_off + cout:]), "clobbered channels after slice"
+    assert e < 2e-2, f"dwpw relmax {e:.3e}"
+    return {"relmax": e}
+
+
 def check_pool(dtype="bf16", B=2, H=20, W=20, c=32, seed=0):
     code, tdt = _dt(dtype)
     g = torch.Generator().manual_seed(seed)

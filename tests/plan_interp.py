@@ -54,6 +54,24 @@ def run_plan(pb: PlanBuilder, x: torch.Tensor, quant=None):
             if op.nchw is not None:
                 name, level, c0, c, _ = op.nchw
                 outs[(name, level)][:, c0:c0 + c] = y[..., :c].permute(0, 3, 1, 2)
+        elif op.kind == "dwpw":
+            c, cp = op.src.c, op.extra["cpad"]
+            dww = w_blob[op.extra["pre_w_off"]:op.extra["pre_w_off"] + 9 * c].view(3, 3, c).permute(2, 0, 1).unsqueeze(1)
+            dwb = b_blob[op.extra["pre_b_off"]:op.extra["pre_b_off"] + c]
+            y = F.conv2d(rd(op.src).permute(0, 3, 1, 2), dww, dwb, 1, 1, 1, c)
+            if op.extra["pre_act"]:
+                y = F.silu(y)
+            y = q(y)   # the fused kernel hands the depthwise result to the GEMM in the storage dtype
+            w = w_blob[op.w_off:op.w_off + cp * c].view(cp, 1, 1, c).permute(0, 3, 1, 2)
+            y = F.conv2d(y, w, b_blob[op.b_off:op.b_off + cp])
+            if op.act:
+                y = F.silu(y)
+            y = y.permute(0, 2, 3, 1)
+            if op.dst is not None:
+                wr(op.dst, y)
+            if op.nchw is not None:
+                name, level, c0, cc, _ = op.nchw
+                outs[(name, level)][:, c0:c0 + cc] = y[..., :cc].permute(0, 3, 1, 2)
         elif op.kind == "dw":
             c, k = op.src.c, op.k
             w = w_blob[op.w_off:op.w_off + k * k * c].view(k, k, c).permute(2, 0, 1).unsqueeze(1)

@@ -77,6 +77,20 @@ def run(spec, iters=5):
         op.w, op.bias = w.data_ptr(), b.data_ptr()
         keep += [x, w, b, y]
         byts = (x.numel() + y.numel()) * 2
+    elif kind == "dwpw":
+        c, cout = kw["c"], kw["cout"]
+        x = torch.randn(B, hw, hw, c, device=DEV).to(torch.bfloat16)
+        dww = (torch.randn(9, c, device=DEV) / 3).to(torch.bfloat16)
+        dwb = torch.randn(c, device=DEV)
+        w = (torch.randn(cout, 1, 1, c, device=DEV) / math.sqrt(c)).to(torch.bfloat16)
+        b = torch.randn(cout, device=DEV)
+        y = torch.empty(B, hw, hw, cout, device=DEV, dtype=torch.bfloat16)
+        op.kind, op.k, op.stride, op.act, op.pre_k, op.pre_act = N.OP_DWPW, 1, 1, kw.get("act", 1), 3, 1
+        op.src, op.dst = view(x), view(y)
+        op.w, op.bias, op.pre_w, op.pre_bias = w.data_ptr(), b.data_ptr(), dww.data_ptr(), dwb.data_ptr()
+        keep += [x, dww, dwb, w, b, y]
+        flops = 2 * B * hw * hw * cout * c
+        byts = (x.numel() + y.numel()) * 2
     elif kind == "pool":
         c = kw["c"]
         buf = torch.randn(B, hw, hw, 4 * c, device=DEV).to(torch.bfloat16)

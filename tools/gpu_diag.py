@@ -89,6 +89,16 @@ def registry():
     add("dwtma_7_c96", G.check_dw, k=7, c=96, H=16, W=16)
     add("dwtma_7_c48", G.check_dw, k=7, c=48, H=16, W=16)
     add("stem_odd_sizes", G.check_stem, H=96, W=160, cout=16, B=3)
+    # fused depthwise -> 1x1 (tensor-core): every map size of the head, k-block counts 1..8, views, NCHW
+    add("dwpw_128_128_20", G.check_dwpw, c=128, cout=128, H=20, W=20)
+    add("dwpw_128_128_80", G.check_dwpw, c=128, cout=128, H=80, W=80, B=3)
+    add("dwpw_256_128_40", G.check_dwpw, c=256, cout=128, H=40, W=40, B=2)
+    add("dwpw_512_128_20", G.check_dwpw, c=512, cout=128, H=20, W=20, B=3)
+    add("dwpw_64_80_odd", G.check_dwpw, c=64, cout=80, H=13, W=27, B=3)
+    add("dwpw_64_256_noact", G.check_dwpw, c=64, cout=256, H=16, W=16, dw_act=False, act=False)
+    add("dwpw_192_192_views", G.check_dwpw, c=192, cout=192, H=24, W=24, src_off=64, src_extra=64, dst_off=64, dst_extra=32)
+    add("dwpw_128_80_nchw", G.check_dwpw, c=128, cout=80, H=20, W=20, act=False, nchw=True, nchw_c=77)
+    add("dwpw_big", G.check_dwpw, c=128, cout=128, H=80, W=80, B=16)
     # decode tail
     add("topk_golden", D.check_topk_golden)
     add("topk_vs_oracle_b4", D.check_topk_vs_oracle, B=4, seed=3)
