@@ -4,10 +4,10 @@
 // the kernel is built around keeping many bytes in flight without spending registers on
 // them: a producer warp streams (channel-block x halo-tile) boxes of the NHWC input into a
 // shared-memory ring with 4-D TMA tile loads (out-of-image halo = hardware zero fill = the
-// conv's zero padding), 4 compute warps consume them.  A compute thread owns one 16-byte
-// channel vector of a horizontal strip of SL output pixels: every input vector it reads from
-// shared memory feeds up to K outputs, weights for the current filter row live in registers,
-// accumulation is fp32.  Persistent grid, static round-robin over tiles.
+// conv's zero padding), up to 8 compute warps consume them: a warp owns a 4x4 patch of output
+// pixels and a lane 2 of the box's 64 channels, accumulation is fp32.  Persistent grid, static
+// round-robin over tiles.  Channel counts that are not a multiple of 64 take the register-tiled
+// CUDA-core kernel in elementwise.cu.
 //
 // Reference semantics: Conv(g=C) + BN (+SiLU) (+shortcut), leanyolo/models/yolov10/layers.py
 // :51-88, 274-300, 455; RepVGGDW arrives here already merged into one 7x7 (modules.py).
@@ -19,11 +19,257 @@ namespace ly {
 
 namespace {
 
-constexpr int kComputeThreads = 128;
-constexpr int kThreadsDw = kComputeThreads + 32;
+constexpr int kMaxDwWarps = 8;
 constexpr int kMaxStagesDw = 6;
 
 struct DwParams {
+  CUtensorMap tmIn;
+  int npx, npy, tw, th, iwt, iht;          // tile = npx x npy patches of 4x4 outputs; raw box iwt x iht pixels
+  int tiles_x, tiles_y, tiles_c, total_tiles;
+  int Ho, Wo, C;
+  int stages, stage_bytes, box_bytes;
+  int act;
+  const __nv_bfloat16* w;
+  const float* bias;
+  __nv_bfloat16* dst; int dCtot, dC0;
+  const __nv_bfloat16* res; int rCtot, rC0;
+};
+
+__device__ __forceinline__ float2 bf2_to_f2(uint32_t raw) {
+  return make_float2(__uint_as_float(raw << 16), __uint_as_float(raw & 0xffff0000u));
+}
+
+// One compute warp = one 4x4 patch of output pixels; a lane owns 2 of the tile's 64 channels, so
+// every shared-memory read is a conflict-free 128-byte pixel row, every global store / shortcut
+// load a full 128-byte line, and an input pixel is read from shared memory ~once per patch
+// (K=3: each input row once, all 9 taps in registers; K=7: one filter row of taps at a time).
+template <int K, int S>
+__global__ void __launch_bounds__(32 * (kMaxDwWarps + 1)) dw_tma_kernel(const __grid_constant__ DwParams p) {
+  constexpr int IP = 3 * S + K;                     // input patch edge: 6 (3x3 s1), 9 (3x3 s2), 10 (7x7 s1)
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  __shared__ __align__(8) unsigned long long bars[2 * kMaxStagesDw];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 127u) & ~127u;
+  const uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bar0 = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (kMaxStagesDw + s); };
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ncw = p.npx * p.npy;                    // compute warps; warp ncw is the TMA producer
+  if (threadIdx.x == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmIn) : "memory");
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), ncw);
+    }
+    fence_barrier_init();
+  }
+  pdl_trigger();
+  pdl_wait();
+  __syncthreads();
+
+  auto split = [&](int tile, int& xt, int& yt, int& ct, int& b) {
+    int t = tile;
+    xt = t % p.tiles_x; t /= p.tiles_x;
+    yt = t % p.tiles_y; t /= p.tiles_y;
+    ct = t % p.tiles_c;
+    b = t / p.tiles_c;
+  };
+
+  if (warp == ncw) {
+    // ------------------------------------------------ producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        int xt, yt, ct, b;
+        split(tile, xt, yt, ct, b);
+        mbar_wait(empty_bar(stage), phase ^ 1u);
+        mbar_expect_tx(full_bar(stage), (uint32_t)p.box_bytes);
+        tma_load_4d(smem_base + stage * p.stage_bytes, &p.tmIn, full_bar(stage), ct * 64, xt * p.tw * S - K / 2,
+                    yt * p.th * S - K / 2, b);
+        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+      }
+    }
+    return;
+  }
+
+  // -------------------------------------------------- compute
+  const int pyi = warp / p.npx, pxi = warp - pyi * p.npx;
+  int stage = 0;
+  uint32_t phase = 0;
+  for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    int xt, yt, ct, b;
+    split(tile, xt, yt, ct, b);
+    const int c = ct * 64 + 2 * lane;
+    float acc[4][4][2];
+    {
+      const float2 b2 = __ldg(reinterpret_cast<const float2*>(p.bias + c));
+#pragma unroll
+      for (int y = 0; y < 4; ++y)
+#pragma unroll
+        for (int x = 0; x < 4; ++x) { acc[y][x][0] = b2.x; acc[y][x][1] = b2.y; }
+    }
+    const uint32_t* wg = reinterpret_cast<const uint32_t*>(p.w + c);   // tap t at wg[t * C / 2]
+    const int wstride = p.C >> 1;
+    float2 wv[K <= 3 ? K * K : K];
+    if (K <= 3) {
+#pragma unroll
+      for (int t = 0; t < K * K; ++t) wv[t] = bf2_to_f2(__ldg(wg + t * wstride));
+    }
+    mbar_wait(full_bar(stage), phase);
+    // halo pixel (X, Y) of the raw tile sits at ((Y * iwt + X) * 64 + channel) * 2 bytes
+    const uint8_t* rt = smem_gen + (size_t)stage * p.stage_bytes + ((size_t)((4 * pyi * S) * p.iwt + 4 * pxi * S) * 64 + 2 * lane) * 2;
+    if (K <= 3) {
+#pragma unroll
+      for (int iy = 0; iy < IP; ++iy) {
+        float2 in[IP];
+#pragma unroll
+        for (int ix = 0; ix < IP; ++ix) in[ix] = bf2_to_f2(*reinterpret_cast<const uint32_t*>(rt + (size_t)(iy * p.iwt + ix) * 128));
+#pragma unroll
+        for (int ky = 0; ky < K; ++ky) {
+          const int d = iy - ky;
+          if (d >= 0 && d % S == 0 && d / S < 4) {
+#pragma unroll
+            for (int kx = 0; kx < K; ++kx)
+#pragma unroll
+              for (int ox = 0; ox < 4; ++ox) {
+                acc[d / S][ox][0] = fmaf(in[ox * S + kx].x, wv[ky * K + kx].x, acc[d / S][ox][0]);
+                acc[d / S][ox][1] = fmaf(in[ox * S + kx].y, wv[ky * K + kx].y, acc[d / S][ox][1]);
+              }
+          }
+        }
+      }
+    } else {
+      uint32_t wn[K];                       // next filter row, loaded one iteration ahead (L1/L2 latency off the FMA chain)
+#pragma unroll
+      for (int kx = 0; kx < K; ++kx) wn[kx] = __ldg(wg + kx * wstride);
+#pragma unroll 1
+      for (int ky = 0; ky < K; ++ky) {
+#pragma unroll
+        for (int kx = 0; kx < K; ++kx) wv[kx] = bf2_to_f2(wn[kx]);
+        if (ky + 1 < K) {
+#pragma unroll
+          for (int kx = 0; kx < K; ++kx) wn[kx] = __ldg(wg + ((ky + 1) * K + kx) * wstride);
+        }
+#pragma unroll
+        for (int oy = 0; oy < 4; ++oy) {
+          float2 in[IP];
+          const uint8_t* rr = rt + (size_t)((oy * S + ky) * p.iwt) * 128;
+#pragma unroll
+          for (int ix = 0; ix < IP; ++ix) in[ix] = bf2_to_f2(*reinterpret_cast<const uint32_t*>(rr + (size_t)ix * 128));
+#pragma unroll
+          for (int kx = 0; kx < K; ++kx)
+#pragma unroll
+            for (int ox = 0; ox < 4; ++ox) {
+              acc[oy][ox][0] = fmaf(in[ox * S + kx].x, wv[kx].x, acc[oy][ox][0]);
+              acc[oy][ox][1] = fmaf(in[ox * S + kx].y, wv[kx].y, acc[oy][ox][1]);
+            }
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty_bar(stage));   // this warp is done reading the stage
+    if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+
+#pragma unroll
+    for (int y = 0; y < 4; ++y) {
+      const int oy = yt * p.th + 4 * pyi + y;
+      if (oy >= p.Ho) continue;
+#pragma unroll
+      for (int x = 0; x < 4; ++x) {
+        const int ox = xt * p.tw + 4 * pxi + x;
+        if (ox >= p.Wo) continue;
+        const long long opix = ((long long)b * p.Ho + oy) * p.Wo + ox;
+        float v0 = acc[y][x][0], v1 = acc[y][x][1];
+        if (p.act) { v0 = silu_tanh(v0); v1 = silu_tanh(v1); }
+        if (p.res) {
+          const float2 r2 = bf2_to_f2(*reinterpret_cast<const uint32_t*>(p.res + opix * p.rCtot + p.rC0 + c));
+          v0 += r2.x; v1 += r2.y;
+        }
+        *reinterpret_cast<__nv_bfloat162*>(p.dst + opix * p.dCtot + p.dC0 + c) = __floats2bfloat162_rn(v0, v1);
+      }
+    }
+  }
+}
+
+template <int K, int S>
+int32_t launch_cfg(const ly_op& op, cudaStream_t st) {
+  EncodeTiledFn encode = get_encode();
+  if (!encode) { set_error("dw_tma: cuTensorMapEncodeTiled entry point not available"); return LY_E_CUDA; }
+  DwParams p;
+  memset(&p, 0, sizeof(p));
+  p.Ho = op.dst.H; p.Wo = op.dst.W; p.C = op.src.c;
+  // tile = npx x npy patches (one compute warp each): raw box <= 48 KB, then most patches, fewest tiles
+  {
+    long long best_key = -1;
+    for (int npx = 1; npx <= kMaxDwWarps; ++npx)
+      for (int npy = 1; npx * npy <= kMaxDwWarps; ++npy) {
+        const int tw = 4 * npx, th = 4 * npy;
+        const long long box = (long long)((tw - 1) * S + K) * ((th - 1) * S + K) * 128;
+        if (box > 48 * 1024 || (tw - 1) * S + K > 256 || (th - 1) * S + K > 256) continue;
+        const long long tiles = (long long)((p.Wo + tw - 1) / tw) * ((p.Ho + th - 1) / th);
+        // useful outputs per unit of work: total warp-patches = tiles * npx * npy (lower is better), then smaller box
+        const long long key = tiles * npx * npy * 1000000LL + tiles * 1000 + box / 1024;
+        if (best_key < 0 || key < best_key) { best_key = key; p.npx = npx; p.npy = npy; }
+      }
+    LY_CHECK_ARG(best_key >= 0, "dw_tma: no tile configuration fits");
+  }
+  p.tw = 4 * p.npx; p.th = 4 * p.npy;
+  p.iwt = (p.tw - 1) * S + K; p.iht = (p.th - 1) * S + K;
+  p.tiles_x = (p.Wo + p.tw - 1) / p.tw;
+  p.tiles_y = (p.Ho + p.th - 1) / p.th;
+  p.tiles_c = p.C / 64;
+  const long long total = (long long)p.tiles_x * p.tiles_y * p.tiles_c * op.B;
+  LY_CHECK_ARG(total <= 0x7FFFFFFF, "dw_tma: too many tiles");
+  p.total_tiles = (int)total;
+  p.box_bytes = p.iwt * p.iht * 128;
+  p.stage_bytes = (p.box_bytes + 127) / 128 * 128;
+  // K=7 is FMA/latency-bound (49 taps per output): three CTAs per SM; the 3x3 kernels are
+  // bandwidth-bound: two CTAs with deeper rings
+  const int ctas_per_sm = K == 7 ? 3 : 2;
+  int stages = ((K == 7 ? 72 : 100) * 1024) / p.stage_bytes;
+  if (stages > kMaxStagesDw) stages = kMaxStagesDw;
+  if (stages < 2) stages = 2;
+  p.stages = stages;
+  p.act = op.act;
+  p.w = (const __nv_bfloat16*)op.w; p.bias = op.bias;
+  p.dst = (__nv_bfloat16*)op.dst.ptr; p.dCtot = op.dst.ctot; p.dC0 = op.dst.c0;
+  p.res = (const __nv_bfloat16*)op.res.ptr; p.rCtot = op.res.ctot; p.rC0 = op.res.c0;
+  {
+    char* base = (char*)op.src.ptr + (size_t)op.src.c0 * 2;
+    cuuint64_t dims[4] = {(cuuint64_t)op.src.c, (cuuint64_t)op.src.W, (cuuint64_t)op.src.H, (cuuint64_t)op.B};
+    cuuint64_t strides[3] = {(cuuint64_t)op.src.ctot * 2, (cuuint64_t)op.src.ctot * 2 * op.src.W,
+                             (cuuint64_t)op.src.ctot * 2 * op.src.W * op.src.H};
+    cuuint32_t box[4] = {64, (cuuint32_t)p.iwt, (cuuint32_t)p.iht, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = encode(&p.tmIn, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("dw_tma: cuTensorMapEncodeTiled failed with %d", (int)r); return LY_E_CUDA; }
+  }
+  const size_t smem = (size_t)p.stages * p.stage_bytes + 128;
+  static bool attr_set = false;
+  if (!attr_set) {
+    LY_CUDA(cudaFuncSetAttribute(dw_tma_kernel<K, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  const int sms = sm_count();
+  int grid = ctas_per_sm * sms;
+  if (grid > p.total_tiles) grid = p.total_tiles;
+  launch_k(dw_tma_kernel<K, S>, dim3(grid), dim3(32 * (p.npx * p.npy + 1)), smem, st, p);
+  return post_launch("dwconv_tma");
+}
+
+// ---------------------------------------------------------------------------------------
+// 3x3 stride 1: a compute thread owns one 16-byte channel vector of a horizontal strip of SL
+// output pixels (fewer, wider stores per output than the patch kernel above, which wins on
+// the small stride-1 maps that remain after the dw->1x1 fusion).
+// ---------------------------------------------------------------------------------------
+constexpr int kComputeThreads = 128;
+constexpr int kThreadsDw = kComputeThreads + 32;
+constexpr int kMaxStagesV = 6;
+
+struct DwVParams {
   CUtensorMap tmIn;
   int tiles_x, tiles_y, tiles_c, total_tiles;
   int Ho, Wo, C;
@@ -46,7 +292,7 @@ __device__ __forceinline__ void unpack8(const uint4& v, float* f) {
 }
 
 template <int K, int S, int CBV, int TW_T, int TH_T>
-__global__ void __launch_bounds__(kThreadsDw) dw_tma_kernel(const __grid_constant__ DwParams p) {
+__global__ void __launch_bounds__(kThreadsDw) dw_strip_kernel(const __grid_constant__ DwVParams p) {
   constexpr int CB = CBV * 8;                       // channels per block
   constexpr int IWt = (TW_T - 1) * S + K, IHt = (TH_T - 1) * S + K;
   constexpr int NW = kComputeThreads / CBV;         // pixel workers
@@ -57,12 +303,12 @@ __global__ void __launch_bounds__(kThreadsDw) dw_tma_kernel(const __grid_constan
   (void)IHt;
 
   extern __shared__ __align__(128) uint8_t smem_raw[];
-  __shared__ __align__(8) unsigned long long bars[2 * kMaxStagesDw];
+  __shared__ __align__(8) unsigned long long bars[2 * kMaxStagesV];
   const uint32_t smem_base = (smem_u32(smem_raw) + 127u) & ~127u;
   const uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   const uint32_t bar0 = smem_u32(bars);
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
-  auto empty_bar = [&](int s) { return bar0 + 8u * (kMaxStagesDw + s); };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (kMaxStagesV + s); };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -176,12 +422,12 @@ __global__ void __launch_bounds__(kThreadsDw) dw_tma_kernel(const __grid_constan
 }
 
 template <int K, int S, int CBV, int TW_T, int TH_T>
-int32_t launch_cfg(const ly_op& op, cudaStream_t st) {
+int32_t launch_strip(const ly_op& op, cudaStream_t st) {
   constexpr int CB = CBV * 8;
   constexpr int IWt = (TW_T - 1) * S + K, IHt = (TH_T - 1) * S + K;
   EncodeTiledFn encode = get_encode();
   if (!encode) { set_error("dw_tma: cuTensorMapEncodeTiled entry point not available"); return LY_E_CUDA; }
-  DwParams p;
+  DwVParams p;
   memset(&p, 0, sizeof(p));
   p.Ho = op.dst.H; p.Wo = op.dst.W; p.C = op.src.c;
   p.tiles_x = (p.Wo + TW_T - 1) / TW_T;
@@ -193,7 +439,7 @@ int32_t launch_cfg(const ly_op& op, cudaStream_t st) {
   p.box_bytes = IWt * IHt * CB * 2;
   p.stage_bytes = (p.box_bytes + 127) / 128 * 128;
   int stages = (72 * 1024) / p.stage_bytes;   // <= ~72 KB per CTA so that three CTAs share an SM
-  if (stages > kMaxStagesDw) stages = kMaxStagesDw;
+  if (stages > kMaxStagesV) stages = kMaxStagesV;
   if (stages < 2 && 2 * p.stage_bytes <= 200 * 1024) stages = 2;   // big 7x7 halo tiles: two CTAs per SM instead
   LY_CHECK_ARG(stages >= 2, "dw_tma: tile does not fit in shared memory");
   p.stages = stages;
@@ -215,14 +461,14 @@ int32_t launch_cfg(const ly_op& op, cudaStream_t st) {
   const size_t smem = (size_t)p.stages * p.stage_bytes + 128;
   static bool attr_set = false;
   if (!attr_set) {
-    LY_CUDA(cudaFuncSetAttribute(dw_tma_kernel<K, S, CBV, TW_T, TH_T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    LY_CUDA(cudaFuncSetAttribute(dw_strip_kernel<K, S, CBV, TW_T, TH_T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set = true;
   }
   const int sms = sm_count();
   // three CTAs per SM when they fit: more loads in flight, epilogue of one overlaps compute of the other
   int grid = 3 * sms;
   if (grid > p.total_tiles) grid = p.total_tiles;
-  launch_k(dw_tma_kernel<K, S, CBV, TW_T, TH_T>, dim3(grid), dim3(kThreadsDw), smem, st, p);
+  launch_k(dw_strip_kernel<K, S, CBV, TW_T, TH_T>, dim3(grid), dim3(kThreadsDw), smem, st, p);
   return post_launch("dwconv_tma");
 }
 
@@ -236,29 +482,19 @@ double cover(int Ho, int Wo, int tw, int th) {
 bool dw_tma_supported(const ly_op& op) {
   if (op.dtype != LY_BF16) return false;
   if (!((op.k == 3 && (op.stride == 1 || op.stride == 2)) || (op.k == 7 && op.stride == 1))) return false;
-  if (op.src.c % 16 || op.src.c0 % 8 || op.src.ctot % 8 || op.dst.c0 % 8 || op.dst.ctot % 8) return false;
+  if (op.src.c % 64 || op.src.c0 % 8 || op.src.ctot % 8 || op.dst.c0 % 8 || op.dst.ctot % 8) return false;
   if (op.res.ptr && (op.res.c0 % 8 || op.res.ctot % 8)) return false;
   if (reinterpret_cast<uintptr_t>(op.src.ptr) % 16) return false;
   return true;
 }
 
 int32_t launch_dw_tma(const ly_op& op, cudaStream_t s) {
-  const int C = op.src.c;
-  const int cbv = C % 64 == 0 ? 8 : (C % 32 == 0 ? 4 : 2);
-  const bool wide = cover(op.dst.H, op.dst.W, 20, 4) < cover(op.dst.H, op.dst.W, 16, op.stride == 2 ? 4 : 8);
   if (op.k == 3 && op.stride == 1) {
-    if (cbv == 8) return wide ? launch_cfg<3, 1, 8, 20, 4>(op, s) : launch_cfg<3, 1, 8, 16, 8>(op, s);
-    if (cbv == 4) return launch_cfg<3, 1, 4, 16, 8>(op, s);
-    return launch_cfg<3, 1, 2, 16, 8>(op, s);
+    const bool wide = cover(op.dst.H, op.dst.W, 20, 4) < cover(op.dst.H, op.dst.W, 16, 8);
+    return wide ? launch_strip<3, 1, 8, 20, 4>(op, s) : launch_strip<3, 1, 8, 16, 8>(op, s);
   }
-  if (op.k == 3 && op.stride == 2) {
-    if (cbv == 8) return wide ? launch_cfg<3, 2, 8, 20, 4>(op, s) : launch_cfg<3, 2, 8, 16, 4>(op, s);
-    if (cbv == 4) return launch_cfg<3, 2, 4, 16, 4>(op, s);
-    return launch_cfg<3, 2, 2, 16, 4>(op, s);
-  }
-  if (cbv == 8) return wide ? launch_cfg<7, 1, 8, 20, 4>(op, s) : launch_cfg<7, 1, 8, 16, 8>(op, s);
-  if (cbv == 4) return launch_cfg<7, 1, 4, 16, 8>(op, s);
-  return launch_cfg<7, 1, 2, 16, 8>(op, s);
+  if (op.k == 3 && op.stride == 2) return launch_cfg<3, 2>(op, s);
+  return launch_cfg<7, 1>(op, s);
 }
 
 }  // namespace ly
