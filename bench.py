@@ -126,6 +126,11 @@ def main():
         }))
         return
 
+    # stdout carries exactly ONE JSON line: anything libraries print to fd 1 meanwhile (NCCL prints its
+    # version there at communicator init) goes to stderr instead
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     from leanyolo_b200 import _native, get_model
@@ -156,20 +161,29 @@ def main():
     for _ in range(max(a.warmup, 3)):
         step(x)
     torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
+    # the clock sampler starts BEFORE the barrier: every rank must enter the timed region together
+    # (a rank that starts late makes the others wait in the first all-gather)
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
         time.sleep(0.3)
+    if world > 1:
+        dist.barrier()
+        step(x)
+        torch.cuda.synchronize()
+        dist.barrier()
     launches0 = lib.ly_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(a.steps + 1)]
     e0.record()
-    for _ in range(a.steps):
+    marks[0].record()
+    for i in range(a.steps):
         det = step(x)
+        marks[i + 1].record()
     e1.record()
     torch.cuda.synchronize()
+    per_step = [marks[i].elapsed_time(marks[i + 1]) for i in range(a.steps)]
     launches = lib.ly_launch_count() - launches0
     if world > 1:
         dist.barrier()
@@ -232,14 +246,14 @@ def main():
     eng = model.engine(dev)
     rows = eng.profile(x, model.sub_batch)
     rows = eng.profile(x, model.sub_batch)   # second pass: warm
-    tc = [r for r in rows if r["tc"]]
+    tc = [r for r in rows if r["tc"] and r["kind"] == "conv"]
     tc_ms = sum(r["ms"] for r in tc)
     tc_flops = sum(r["flops"] for r in tc)
     all_ms = sum(r["ms"] for r in rows)
     achieved = tc_flops / (tc_ms / 1e3) / 1e12 if tc_ms > 0 else 0.0
     by_kind = {}
     for r in rows:
-        k = "conv_tc" if r["tc"] else r["kind"]
+        k = "conv_tc" if (r["tc"] and r["kind"] == "conv") else r["kind"]
         d = by_kind.setdefault(k, {"ms": 0.0, "bytes": 0, "flops": 0, "launches": 0})
         d["ms"] += r["ms"]; d["bytes"] += r["bytes"]; d["flops"] += r["flops"]; d["launches"] += 1
     for d in by_kind.values():
@@ -263,8 +277,15 @@ def main():
     if a.profile_out:
         os.makedirs(os.path.dirname(os.path.abspath(a.profile_out)), exist_ok=True)
         json.dump({"rows": rows, "by_kind": by_kind}, open(a.profile_out, "w"), indent=1)
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if os.path.exists(tp) and a.model == "yolov10s" and B == 256 and S == 640:
+        traffic = json.load(open(tp))["conv_tc_kernel"]["dram_bytes_per_launch"]   # ncu capture of this workload
+    alg_bytes = sum(r["bytes"] for r in tc) / max(len(tc), 1)
     roofline = {"bound": "tensor", "kernel": "conv_tc_kernel", "achieved": round(achieved, 1), "peak": peaks["tf_sust"],
-                "unit": "TFLOP/s", "frac": round(achieved / peaks["tf_sust"], 4), "traffic": None,
+                "unit": "TFLOP/s", "frac": round(achieved / peaks["tf_sust"], 4), "traffic": traffic,
+                "traffic_unit": "DRAM bytes per launch (ncu dram read+write, profiles/r1_ncu_launch_summary.txt)",
+                "algorithmic_bytes_per_launch": int(alg_bytes),
                 "peak_source": peaks["src"] + " (bf16_tflops_sustained: kernel timed inside a long step)",
                 "launches_per_step": len(tc), "share_of_step": round(tc_ms / all_ms, 3) if all_ms else None,
                 "by_kind": by_kind,
@@ -279,6 +300,7 @@ def main():
     out = {
         "metric": "images/sec (fwd+decode)", "value": round(value, 1), "unit": "images/s", "n_gpus": world,
         "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": round(ms_total / a.steps, 3),
+        "ms_per_step_min_max": [round(min(per_step), 3), round(max(per_step), 3)],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": workload, "global_batch": world * B, "parallelism": f"dp{world} (shard by image)",
                    "l2": "inputs larger than L2 (1.26 GB fp32 per step), no flush needed",
@@ -290,7 +312,10 @@ def main():
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
     }
-    print(json.dumps(out))
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
+    print(json.dumps(out), flush=True)
+    os.dup2(2, 1)
     if world > 1:
         dist.destroy_process_group()
 

@@ -8,15 +8,15 @@
 //
 //   warp 0      TMA: (th+2) x (tw+2) halo box of 64 input channels per k-block (zero padding =
 //               hardware OOB fill) into a raw ring; 1x1 weight slab [Cout x 64] into a B ring
-//   warps 10-17 depthwise producers: a warp owns a 4x4 patch of output pixels, a lane 2 of the 64
+//   warps 10-25 depthwise producers: a warp owns a 4x2 patch of output pixels, a lane 2 of the 64
 //               channels; fp32 accumulate, SiLU, bf16, written as the 128-byte-swizzled A tile
 //               (row = pixel of the tile, 64 channels = one swizzle row)
 //   warp 1      tcgen05.mma M=128 x N=Cout x K=64 per k-block into a double-buffered TMEM
 //               accumulator
 //   warps 2-9   epilogue: TMEM -> bias (+SiLU) -> bf16 NHWC slice (or the public NCHW fp32)
 //
-// The tile is a rectangle of up to 8 such patches of one image (16x8 on 80x80 maps, 8x16 on
-// 40x40, 20x4 on 20x20); rows of the M=128 MMA past tw*th are never written and are masked in
+// The tile is a rectangle of up to 16 such patches of one image (16x8 on 80x80 maps, 20x6 on
+// 40x40 and 20x20); rows of the M=128 MMA past tw*th are never written and are masked in
 // the epilogue.
 #include <cuda.h>
 #include <string.h>
@@ -28,7 +28,8 @@ namespace ly {
 
 namespace {
 
-constexpr int kFEpWarps = 8, kFDwWarps = 8;
+constexpr int kFEpWarps = 8, kFDwWarps = 16;
+constexpr int kPH = 2;                 // patch = 4 wide x kPH tall output pixels per depthwise warp
 constexpr int kFThreads = 64 + 32 * (kFEpWarps + kFDwWarps);
 constexpr int kFMaxStages = 4;
 constexpr uint32_t kFSmemBudget = 216 * 1024;
@@ -37,7 +38,7 @@ constexpr int kFAStage = 128 * 128;   // 128 rows x 64 bf16
 struct FParams {
   CUtensorMap tmIn;   // (C, W, H, B), box (64, tw+2, th+2, 1), no swizzle
   CUtensorMap tmB;    // (K = Cin, N = Cout), box (64, block_n), 128-byte swizzle
-  int tw, th, tile_px, npx, npy;   // tile = npx x npy patches of 4x4 pixels (one depthwise warp each)
+  int tw, th, tile_px, npx, npy;   // tile = npx x npy patches of 4 x kPH pixels (one depthwise warp each)
   int tiles_x, tiles_y, total_tiles;
   uint32_t mg_x, mg_y;
   int H, W, B;
@@ -185,12 +186,13 @@ __global__ void __launch_bounds__(kFThreads, 1) dwpw_kernel(const __grid_constan
     }
   } else if (warp >= 2 + kFEpWarps) {
     // ============================== depthwise producers =======================
-    // One warp = one 4x4 patch of output pixels; a lane owns 2 of the 64 channels of the k-block.
+    // One warp = one 4x2 patch of output pixels; a lane owns 2 of the 64 channels of the k-block.
     // Every shared-memory access is then a conflict-free 128-byte row (raw tile, A tile) and an
-    // input pixel is loaded once per patch (36 loads for 16 outputs) instead of once per output
-    // row and strip.  (The first version used 16-byte channel vectors x 4-pixel strips: the four
-    // strips of a warp re-read the same weights and neighbouring pixels, the L1/shared pipe ran
-    // at 95 % and the fused kernel was slower than the two separate ones.)
+    // input pixel is loaded once per patch (24 loads for 8 outputs) instead of once per output
+    // row and strip.  (Measured steps: 16-byte channel vectors x 4-pixel strips re-read weights
+    // and neighbouring pixels, the L1/shared pipe ran at 95 % and the fused kernel was slower
+    // than the two separate ones; 8 warps x 4x4 patches were bound by the serial instruction
+    // stream of each producer warp (IPC 0.2): 16 warps x 4x2 patches; a 4-warp epilogue then became the bottleneck of the 2-k-block layers, so 8.)
     const int pw_i = warp - (2 + kFEpWarps);                 // patch index inside the tile
     const bool active = pw_i < p.npx * p.npy;
     const int pyi = pw_i / p.npx, pxi = pw_i - pyi * p.npx;
@@ -200,7 +202,7 @@ __global__ void __launch_bounds__(kFThreads, 1) dwpw_kernel(const __grid_constan
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       for (int kb = 0; kb < p.kblocks; ++kb) {
         mbar_wait(rfull(rs), rp);
-        float acc[4][4][2];
+        float acc[kPH][4][2];
         if (active) {
           const int c = kb * 64 + 2 * lane;
           float wv[9][2];
@@ -211,13 +213,13 @@ __global__ void __launch_bounds__(kFThreads, 1) dwpw_kernel(const __grid_constan
           }
           const float2 b2 = *reinterpret_cast<const float2*>(dwb + c);
 #pragma unroll
-          for (int y = 0; y < 4; ++y)
+          for (int y = 0; y < kPH; ++y)
 #pragma unroll
             for (int x = 0; x < 4; ++x) { acc[y][x][0] = b2.x; acc[y][x][1] = b2.y; }
           // halo pixel (X, Y) of the raw tile sits at ((Y * iw + X) * 64 + channel) * 2 bytes
-          const uint8_t* rt = gen + (r_base - base) + (size_t)rs * p.r_stage + ((size_t)((4 * pyi) * iw + 4 * pxi) * 64 + 2 * lane) * 2;
+          const uint8_t* rt = gen + (r_base - base) + (size_t)rs * p.r_stage + ((size_t)((kPH * pyi) * iw + 4 * pxi) * 64 + 2 * lane) * 2;
 #pragma unroll
-          for (int iy = 0; iy < 6; ++iy) {
+          for (int iy = 0; iy < kPH + 2; ++iy) {
             float in[6][2];
 #pragma unroll
             for (int ix = 0; ix < 6; ++ix) {
@@ -228,7 +230,7 @@ __global__ void __launch_bounds__(kFThreads, 1) dwpw_kernel(const __grid_constan
 #pragma unroll
             for (int ky = 0; ky < 3; ++ky) {
               const int oy = iy - ky;
-              if (oy >= 0 && oy < 4) {
+              if (oy >= 0 && oy < kPH) {
 #pragma unroll
                 for (int kx = 0; kx < 3; ++kx)
 #pragma unroll
@@ -248,13 +250,13 @@ __global__ void __launch_bounds__(kFThreads, 1) dwpw_kernel(const __grid_constan
         if (active) {
           const uint32_t ab = a_base + (uint32_t)as * kFAStage;
 #pragma unroll
-          for (int y = 0; y < 4; ++y)
+          for (int y = 0; y < kPH; ++y)
 #pragma unroll
             for (int x = 0; x < 4; ++x) {
               float v0 = acc[y][x][0], v1 = acc[y][x][1];
               if (p.pre_act) { v0 = silu_from_half(v0); v1 = silu_from_half(v1); }
               const __nv_bfloat162 h2 = __floats2bfloat162_rn(v0, v1);
-              const uint32_t r = (uint32_t)((4 * pyi + y) * p.tw + 4 * pxi + x);   // tile row = pixel index, x fastest
+              const uint32_t r = (uint32_t)((kPH * pyi + y) * p.tw + 4 * pxi + x);   // tile row = pixel index, x fastest
               const uint32_t addr = ab + r * 128u + ((((uint32_t)lane >> 2) ^ (r & 7u)) << 4) + ((uint32_t)lane & 3u) * 4u;
               asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(*reinterpret_cast<const uint32_t*>(&h2)) : "memory");
             }
@@ -266,7 +268,7 @@ __global__ void __launch_bounds__(kFThreads, 1) dwpw_kernel(const __grid_constan
       }
     }
   } else {
-    // ============================== epilogue (8 warps) ========================
+    // ============================== epilogue (2 warps per TMEM lane quarter) ==========
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
     const int nchunks = p.block_n >> 4;
@@ -377,13 +379,14 @@ int32_t dwpw_prepare(const ly_op& op, DwPwState** out) {
   p.H = H; p.W = W; p.B = op.B; p.cin = Cin; p.kblocks = Cin / 64;
   p.block_n = Cout; p.tmem_cols = f_pow2_ge(2 * Cout);
   p.pre_act = op.pre_act; p.act = op.act;
-  // tile = npx x npy patches of 4x4 pixels, at most one patch per depthwise warp: fewest tiles
+  // tile = npx x npy patches of 4 x kPH pixels, at most one patch per depthwise warp: fewest tiles
   // per image first, then the smallest halo box
   {
     long long best_tiles = 1LL << 60, best_halo = 1LL << 60;
     for (int npx = 1; npx <= kFDwWarps; ++npx)
       for (int npy = 1; npx * npy <= kFDwWarps; ++npy) {
-        const int tw = 4 * npx, th = 4 * npy;
+        const int tw = 4 * npx, th = kPH * npy;
+        if (tw * th > 128) continue;
         const long long tiles = (long long)((W + tw - 1) / tw) * ((H + th - 1) / th);
         const long long halo = (long long)(tw + 2) * (th + 2);
         if (tiles < best_tiles || (tiles == best_tiles && halo < best_halo)) {
@@ -391,7 +394,7 @@ int32_t dwpw_prepare(const ly_op& op, DwPwState** out) {
         }
       }
   }
-  p.tw = 4 * p.npx; p.th = 4 * p.npy;
+  p.tw = 4 * p.npx; p.th = kPH * p.npy;
   p.tile_px = p.tw * p.th;
   p.tiles_x = (W + p.tw - 1) / p.tw;
   p.tiles_y = (H + p.th - 1) / p.th;
