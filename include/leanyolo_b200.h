@@ -90,6 +90,11 @@ typedef struct ly_op {
   const void* pre_w;      /* depthwise weights [pre_k*pre_k][C_pad] (dtype) */
   const float* pre_bias;  /* [C_pad] fp32 */
   int32_t pre_k, pre_act; /* depthwise filter size (3), 1 = SiLU after the depthwise bias */
+  /* CONV (bf16, tensor-core path) only: half-resolution NHWC tensor [B, Ho/2, Wo/2, up.c] added to the
+   * accumulator BEFORE the activation at (h/2, w/2).  A 1x1 conv commutes with nearest x2 upsampling, so
+   * conv1x1(cat[up(a), b]) = act(W_b*b + up(W_a*a) + bias): the neck's upsample + concat never
+   * materialises (neck.py:116-121).  up.ptr == NULL: absent. */
+  ly_view up;
 } ly_op;
 
 /* ---- library ---------------------------------------------------------- */

@@ -30,6 +30,7 @@ class LyOp(C.Structure):
         ("w", C.c_void_p), ("bias", C.c_void_p), ("nchw", C.c_void_p),
         ("nchw_ctot", C.c_int32), ("nchw_c0", C.c_int32), ("nchw_c", C.c_int32), ("ext_slot", C.c_int32),
         ("pre_w", C.c_void_p), ("pre_bias", C.c_void_p), ("pre_k", C.c_int32), ("pre_act", C.c_int32),
+        ("up", LyView),
     ]
 
 

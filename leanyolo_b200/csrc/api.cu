@@ -87,7 +87,7 @@ static int32_t dispatch(const ly_op& op, cudaStream_t s) {
 
 using namespace ly;
 
-static_assert(sizeof(ly_view) == 32 && sizeof(ly_op) == 232, "ly_op layout is part of the C ABI (mirrored by ctypes in _native.py)");
+static_assert(sizeof(ly_view) == 32 && sizeof(ly_op) == 264, "ly_op layout is part of the C ABI (mirrored by ctypes in _native.py)");
 
 struct ly_plan {
   std::vector<ly_op> ops;

@@ -137,6 +137,7 @@ int32_t run(const ly_op& op, cudaStream_t st) {
 }  // namespace
 
 int32_t launch_conv_simt(const ly_op& op, cudaStream_t s) {
+  LY_CHECK_ARG(!op.up.ptr, "conv: the upsampled pre-activation addend is only implemented on the bf16 tensor-core path");
   LY_CHECK_ARG(op.k == 1 || op.k == 3, "conv: k must be 1 or 3 (got %d)", op.k);
   LY_CHECK_ARG(op.stride == 1 || op.stride == 2, "conv: stride must be 1 or 2");
   LY_CHECK_ARG(op.src.ptr && op.w && op.bias, "conv: null src/w/bias");

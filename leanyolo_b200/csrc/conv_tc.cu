@@ -69,6 +69,7 @@ struct Params {
   int act;
   __nv_bfloat16* dst; int dCtot, dC0;
   const __nv_bfloat16* res; int rCtot, rC0;
+  const __nv_bfloat16* up; int uCtot, uC0, uH, uW, Wreal;   // half-resolution pre-activation addend (upsampled x2 on the fly)
   const float* bias;
   float* nchw; int nCtot, nC0, nC;
   int cin_pad;
@@ -357,6 +358,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.block_n);
       __nv_bfloat16* drow = (p.dst && valid) ? p.dst + lin * p.dCtot + p.dC0 + n0 : nullptr;
       const __nv_bfloat16* rrow = (p.res && valid) ? p.res + lin * p.rCtot + p.rC0 + n0 : nullptr;
+      const __nv_bfloat16* urow = nullptr;
+      if (p.up && valid) {
+        // real (b, h, w) of this output pixel (the tiling of a 1x1 conv is flat), then the half-resolution source pixel
+        const uint32_t ub = (uint32_t)lin / (uint32_t)p.hw_real, urem = (uint32_t)lin - ub * (uint32_t)p.hw_real;
+        const uint32_t uh = urem / (uint32_t)p.Wreal, uw = urem - uh * (uint32_t)p.Wreal;
+        urow = p.up + (((long long)ub * p.uH + (uh >> 1)) * p.uW + (uw >> 1)) * p.uCtot + p.uC0 + n0;
+      }
       float* nrow = nullptr;
       if (p.nchw && valid) {
         const uint32_t nb = (uint32_t)lin / (uint32_t)p.hw_real;        // image index, pixel inside the image
@@ -390,6 +398,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           if (lane == 0) mbar_arrive(tempty_bar(as));
         }
         if (has) {
+          if (urow) {
+            float uv[16];
+            load_vec<__nv_bfloat16>(urow + c, uv);
+            load_vec<__nv_bfloat16>(urow + c + 8, uv + 8);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = fmaf(uv[j], pre, v[j]);
+          }
           if (p.act) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] = silu_from_half(v[j]);
@@ -458,6 +473,7 @@ bool conv_tc_supported(const ly_op& op) {
   if (op.src.c % 16 || op.src.c0 % 8 || op.src.ctot % 8) return false;
   if (op.dst.ptr && (op.dst.c % 16 || op.dst.c0 % 8 || op.dst.ctot % 8)) return false;
   if (op.res.ptr && (op.res.c0 % 8 || op.res.ctot % 8)) return false;
+  if (op.up.ptr && (op.up.c0 % 8 || op.up.ctot % 8 || op.up.H * 2 != op.src.H / op.stride || op.up.W * 2 != op.src.W / op.stride)) return false;
   return true;
 }
 
@@ -606,6 +622,7 @@ int32_t conv_tc_prepare(const ly_op& op, ConvTcState** out) {
 
   p.dst = (__nv_bfloat16*)op.dst.ptr; p.dCtot = op.dst.ctot; p.dC0 = op.dst.c0;
   p.res = (const __nv_bfloat16*)op.res.ptr; p.rCtot = op.res.ctot; p.rC0 = op.res.c0;
+  p.up = (const __nv_bfloat16*)op.up.ptr; p.uCtot = op.up.ctot; p.uC0 = op.up.c0; p.uH = op.up.H; p.uW = op.up.W; p.Wreal = Wo;
   p.bias = op.bias;
   p.nchw = op.nchw; p.nCtot = op.nchw_ctot; p.nC0 = op.nchw_c0; p.nC = op.nchw_c;
 

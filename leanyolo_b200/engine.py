@@ -62,7 +62,7 @@ class Engine:
         key = (B, H, W, in_u8)
         if key in self._plans:
             return self._plans[key]
-        pb = PlanBuilder(B, H, W, self.dtype)
+        pb = PlanBuilder(B, H, W, self.dtype, tensor_core=self.impl != N.IMPL_SIMT)
         self.emit(pb)
         w, b = pb.finalize_params()
         if self._w is None:
@@ -91,6 +91,8 @@ class Engine:
                     o.impl = N.STEM_IN_U8
             elif op.w_off >= 0:
                 o.w, o.bias = wbase + esz * op.w_off, bbase + 4 * op.b_off
+            if op.extra.get("up") is not None:
+                o.up = _view(op.extra["up"], base)
             if op.kind == "dwpw":
                 o.pre_w, o.pre_bias = wbase + esz * op.extra["pre_w_off"], bbase + 4 * op.extra["pre_b_off"]
                 o.pre_k, o.pre_act = 3, int(op.extra["pre_act"])

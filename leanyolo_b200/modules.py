@@ -120,10 +120,16 @@ class C2f(nn.Module):
         self.cv2 = ConvBN((2 + n) * c, cout, 1)
         self.m = nn.ModuleList([CIB(c, lk) if cib else Bottleneck(c, shortcut) for _ in range(n)])
 
-    def emit(self, pb, src, dst=None):
+    def emit(self, pb, src, dst=None, upcat=None):
+        """``upcat=(low, skip)``: the block's input is cat[upsample2x(low), skip] (top-down neck);
+        cv1 is then applied without materialising either (PlanBuilder.upcat_conv)."""
         c = self.c
         cat = pb.buffer(src.H, src.W, (2 + self.n) * c)
-        self.cv1.emit(pb, src, cat.view(0, 2 * c))
+        if upcat is not None:
+            w, b = self.cv1.folded()
+            pb.upcat_conv(upcat[0], upcat[1], w, b, act=self.cv1.act, dst=cat.view(0, 2 * c))
+        else:
+            self.cv1.emit(pb, src, cat.view(0, 2 * c))
         y = cat.view(c, c)
         for i, m in enumerate(self.m):
             y = m.emit(pb, y, cat.view((2 + i) * c, c))
@@ -253,10 +259,17 @@ class Neck(nn.Module):
 
     def emit(self, pb, cats):
         c3, c4, c5, h13, h16, h19, _ = self.widths
-        pb.upsample2x(cats["cat_n5"].view(h19, c5), cats["cat_p4"].view(0, c5))
-        p4a = self.p5_p4_c2f.emit(pb, cats["cat_p4"].view(), cats["cat_n4"].view(h16, h13))
-        pb.upsample2x(p4a, cats["cat_p3"].view(0, h13))
-        p3 = self.p4_p3_c2f.emit(pb, cats["cat_p3"].view())
+        c5v = cats["cat_n5"].view(h19, c5)
+        if pb.upcat_fusable():
+            # top-down path: upsample + concat + 1x1 folded into the 1x1 (conv commutes with nearest upsampling)
+            p4a = self.p5_p4_c2f.emit(pb, cats["cat_p4"].view(), cats["cat_n4"].view(h16, h13),
+                                      upcat=(c5v, cats["cat_p4"].view(c5, c4)))
+            p3 = self.p4_p3_c2f.emit(pb, cats["cat_p3"].view(), upcat=(p4a, cats["cat_p3"].view(h13, c3)))
+        else:
+            pb.upsample2x(c5v, cats["cat_p4"].view(0, c5))
+            p4a = self.p5_p4_c2f.emit(pb, cats["cat_p4"].view(), cats["cat_n4"].view(h16, h13))
+            pb.upsample2x(p4a, cats["cat_p3"].view(0, h13))
+            p3 = self.p4_p3_c2f.emit(pb, cats["cat_p3"].view())
         self.p3_down.emit(pb, p3, cats["cat_n4"].view(0, h16))
         p4 = self.p3_p4_c2f.emit(pb, cats["cat_n4"].view())
         self.p4_down.emit(pb, p4, cats["cat_n5"].view(0, h19))

@@ -82,8 +82,10 @@ class Op:
 
 
 class PlanBuilder:
-    def __init__(self, B: int, H: int, W: int, dtype: str = "bf16"):
+    def __init__(self, B: int, H: int, W: int, dtype: str = "bf16", tensor_core: bool = True):
         assert dtype in ("bf16", "f32")
+        # False: bring-up / bisecting mode (every conv on the CUDA-core kernel): no tensor-core-only fusions
+        self.tensor_core = tensor_core and dtype == "bf16"
         assert H % 32 == 0 and W % 32 == 0, "input H, W must be multiples of 32 (neck concat, SURVEY App. C.10)"
         self.B, self.H, self.W, self.dtype = B, H, W, dtype
         self.esize = 2 if dtype == "bf16" else 4
@@ -146,7 +148,8 @@ class PlanBuilder:
 
     def conv(self, src: View, w: torch.Tensor, b: torch.Tensor, *, k: int, stride: int, act: bool,
              dst: Optional[View] = None, res: Optional[View] = None, out_perm: Optional[List[int]] = None,
-             nchw: Optional[Tuple[str, int, int, int, int]] = None) -> Optional[View]:
+             nchw: Optional[Tuple[str, int, int, int, int]] = None, up: Optional[View] = None,
+             bias: bool = True) -> Optional[View]:
         cout, cin = w.shape[0], w.shape[1]
         assert w.shape[2] == w.shape[3] == k and k in (1, 3) and stride in (1, 2)
         assert cin <= src.c < cin + CH_ALIGN, (cin, src.c)
@@ -172,10 +175,28 @@ class PlanBuilder:
         bp[:cout] = b
         if res is not None:
             assert res.c == cpad and (res.H, res.W) == (Ho, Wo)
+        extra = dict(cpad=cpad)
+        if up is not None:
+            # half-resolution tensor added before the activation at (h/2, w/2): see upcat_conv()
+            assert self.dtype == "bf16" and up.c == cpad and (2 * up.H, 2 * up.W) == (Ho, Wo)
+            extra["up"] = up
         self.ops.append(Op("conv", src=src, dst=dst, res=res, w_off=self._add_w(wp), b_off=self._add_b(bp),
-                           k=k, stride=stride, act=act, cin=cin, cout=cout, nchw=nchw,
-                           extra=dict(cpad=cpad)))
+                           k=k, stride=stride, act=act, cin=cin, cout=cout, nchw=nchw, extra=extra))
         return dst
+
+    def upcat_fusable(self) -> bool:
+        import os
+        return self.tensor_core and os.environ.get("LEANYOLO_FUSE_UPCAT", "1") != "0"
+
+    def upcat_conv(self, low: View, skip: View, w: torch.Tensor, b: torch.Tensor, *, act: bool, dst: View) -> View:
+        """act(conv1x1(cat[upsample2x(low), skip])) without the upsample or the concat: a 1x1 conv
+        commutes with nearest upsampling, so the ``low`` half of the weights is applied at half
+        resolution (4x fewer pixels) and added, upsampled on the fly, before the activation of the
+        conv over ``skip`` (neck.py:116-121; cat order [up, skip])."""
+        c_low = w.shape[1] - skip.c
+        assert c_low == low.c and w.shape[2:] == (1, 1) and (2 * low.H, 2 * low.W) == (skip.H, skip.W)
+        t = self.conv(low, w[:, :c_low], torch.zeros_like(b), k=1, stride=1, act=False)
+        return self.conv(skip, w[:, c_low:], b, k=1, stride=1, act=act, dst=dst, up=t)
 
     def dwconv(self, src: View, w: torch.Tensor, b: torch.Tensor, *, k: int, stride: int, act: bool,
                dst: Optional[View] = None, res: Optional[View] = None) -> View:
@@ -201,7 +222,7 @@ class PlanBuilder:
         import os
         if os.environ.get("LEANYOLO_FUSE_DWPW", "1") == "0":
             return False
-        return (self.dtype == "bf16" and k == 3 and stride == 1 and src.c % 64 == 0 and src.c == c
+        return (self.tensor_core and k == 3 and stride == 1 and src.c % 64 == 0 and src.c == c
                 and _rup(cout, CH_ALIGN) <= 256)
 
     def dwpw(self, src: View, dw_w: torch.Tensor, dw_b: torch.Tensor, pw_w: torch.Tensor, pw_b: torch.Tensor, *,

@@ -43,7 +43,7 @@ def rel_l2(a: torch.Tensor, b: torch.Tensor) -> float:
 # ------------------------------------------------------------------------------- dense conv
 def check_conv(dtype="bf16", impl="auto", B=2, H=16, W=16, cin=64, cout=64, k=3, stride=1, act=True, res=False,
                src_off=0, src_extra=0, dst_off=0, dst_extra=0, nchw=False, inplace_res=False, seed=0, nchw_c=None,
-               tol=None):
+               tol=None, up=False):
     code, tdt = _dt(dtype)
     g = torch.Generator().manual_seed(seed)
     Ho, Wo = H // stride, W // stride
@@ -56,6 +56,10 @@ def check_conv(dtype="bf16", impl="auto", B=2, H=16, W=16, cin=64, cout=64, k=3,
     # reference on the quantised operands, fp32 math
     xin = xs[..., src_off:src_off + cin].float().permute(0, 3, 1, 2)
     y = F.conv2d(xin, w.float().permute(0, 3, 1, 2), bias, stride, k // 2)
+    ups = None
+    if up:   # half-resolution pre-activation addend, upsampled x2 on the fly (channel slice of a wider buffer)
+        ups = torch.randn(B, Ho // 2, Wo // 2, 16 + cout, generator=g).to(tdt)
+        y = y + F.interpolate(ups[..., 16:].float().permute(0, 3, 1, 2), scale_factor=2.0, mode="nearest")
     if act:
         y = F.silu(y)
     y = y.permute(0, 2, 3, 1)
@@ -83,6 +87,9 @@ def check_conv(dtype="bf16", impl="auto", B=2, H=16, W=16, cin=64, cout=64, k=3,
     elif res:
         r_d = rs.to(DEV)
         op.res = view(r_d, 0, cout)
+    if up:
+        u_d = ups.to(DEV)
+        op.up = view(u_d, 16, cout)
     launch(op)
     tol = tol if tol is not None else (2e-2 if dtype == "bf16" else 1e-4)
     if nchw:

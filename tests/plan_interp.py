@@ -44,6 +44,8 @@ def run_plan(pb: PlanBuilder, x: torch.Tensor, quant=None):
             w = w_blob[op.w_off:op.w_off + cp * k * k * cin].view(cp, k, k, cin).permute(0, 3, 1, 2)
             bias = b_blob[op.b_off:op.b_off + cp]
             y = F.conv2d(rd(op.src).permute(0, 3, 1, 2), w, bias, op.stride, k // 2)
+            if op.extra.get("up") is not None:      # half-resolution pre-activation addend
+                y = y + F.interpolate(rd(op.extra["up"]).permute(0, 3, 1, 2), scale_factor=2.0, mode="nearest")
             if op.act:
                 y = F.silu(y)
             y = y.permute(0, 2, 3, 1)

@@ -208,7 +208,7 @@ def test_shared_library_exports_every_declared_symbol():
     for sym in declared:
         assert hasattr(lib, sym), sym
     assert N.lib().ly_abi_version() == N.ABI_VERSION
-    assert ctypes.sizeof(N.LyView) == 32 and ctypes.sizeof(N.LyOp) == 232
+    assert ctypes.sizeof(N.LyView) == 32 and ctypes.sizeof(N.LyOp) == 264
 
 
 # ------------------------------------------------------------------ lowering vs oracle
@@ -272,5 +272,15 @@ def test_plan_is_pure_views_no_copy_ops_and_counts_flops():
     # 87 dense convs in the reference = stem + 86 GEMM convs, of which the first reg conv of the two
     # head branches is one GEMM per level (-3) and 12 follow a depthwise conv in a fused dw->1x1
     # launch; RepVGGDW pairs merged: 24 dw -> 22, 12 of them inside the fused launches
-    assert kinds == {"stem": 1, "conv": 71, "dw": 10, "dwpw": 12, "pool": 1, "attn": 1, "up": 2}
-    assert abs(pb.dense_flops() / 1e9 - 24.625) < 0.01   # dense GFLOP / image
+    # the two upsample+concat+1x1 of the top-down neck are 2 convs each (half-resolution part + skip part), no upsample op
+    assert kinds == {"stem": 1, "conv": 73, "dw": 10, "dwpw": 12, "pool": 1, "attn": 1}
+    # the reference does 24.625 dense GFLOP / image; applying the upsampled half of the
+    # two neck 1x1 convs at half resolution removes 0.629 of them
+    assert abs(pb.dense_flops() / 1e9 - 23.996) < 0.01
+    os.environ["LEANYOLO_FUSE_UPCAT"] = "0"
+    try:
+        pb2 = PlanBuilder(1, 640, 640, "bf16")
+        m.emit(pb2)
+    finally:
+        del os.environ["LEANYOLO_FUSE_UPCAT"]
+    assert abs(pb2.dense_flops() / 1e9 - 24.625) < 0.01 and sum(op.kind == "up" for op in pb2.ops) == 2

@@ -59,6 +59,9 @@ def registry():
     add("tc_1x1_inplace_res", G.check_conv, cin=128, cout=64, k=1, act=False, inplace_res=True, dst_off=64, dst_extra=0)
     add("tc_1x1_nchw_80", G.check_conv, cin=128, cout=80, k=1, act=False, nchw=True)
     add("tc_1x1_nchw_pad77", G.check_conv, cin=64, cout=80, k=1, act=False, nchw=True, nchw_c=77)
+    add("tc_1x1_up_128", G.check_conv, cin=128, cout=128, k=1, H=16, W=24, B=3, up=True)
+    add("tc_1x1_up_256_noact", G.check_conv, cin=64, cout=256, k=1, H=20, W=20, act=False, up=True)
+    add("tc_1x1_up_views", G.check_conv, cin=128, cout=64, k=1, H=8, W=8, up=True, src_off=256, dst_off=0, dst_extra=64)
     add("tc_3x3_big", G.check_conv, cin=64, cout=64, k=3, H=160, W=160, B=4)
     add("tc_1x1_big", G.check_conv, cin=256, cout=128, k=1, H=80, W=80, B=8)
     # bandwidth kernels
