@@ -8,9 +8,11 @@
 //   a (tw x th x tb) brick chosen per layer so that feature maps tile without waste; 1x1/s1
 //   layers collapse to a flat [M, C] matrix.
 //     classic mode : one box per (filter tap, channel block)          -> 9 loads / block for 3x3
-//     halo mode    : 3x3 stride 1, brick 8 x 16: one box of 8 x 18 pixels per (kx, channel
+//     halo mode    : 3x3, brick 8 x 16: one box of 8 x 18 pixels per (kx, channel
 //                    block); the three ky taps are the same shared-memory tile viewed 8 rows
-//                    (= one swizzle atom) further down -> 3 loads / block.  The TMA unit is
+//                    (= one swizzle atom) further down -> 3 loads / block.  Stride 2: the box
+//                    holds 8 (every other) columns x 33 rows and the A descriptor's 8-row
+//                    group stride is doubled, so output row oy reads stored row 2*oy + ky.  The TMA unit is
 //                    request-rate bound on these strided 64/128-byte rows (measured ~5 cycles
 //                    per row), so this is what moves the 3x3 layers towards the MMA roofline.
 // * MMA: tcgen05.mma.cta_group::1.kind::f16, M=128, N=BLOCK_N (<=256), K=16 per
@@ -65,7 +67,7 @@ struct Params {
   int a_box, b_box;        // bytes one TMA box delivers
   int b_resident;
   int res_slot;            // bytes of private smem per epilogue thread for the prefetched shortcut (0 = direct loads)
-  uint32_t idesc, desc_hi;
+  uint32_t idesc, desc_hi, desc_hi_a;   // desc_hi_a: A operand (its 8-row group stride doubles in stride-2 halo mode)
   int act;
   __nv_bfloat16* dst; int dCtot, dC0;
   const __nv_bfloat16* res; int rCtot, rC0;
@@ -110,7 +112,7 @@ __device__ __forceinline__ void split_tile(const Params& p, int tile_idx, int& n
 // one M=128 MMA every ~50 cycles for N <= 64; anything slower is issue overhead.)
 template <int KSTEPS, int TPA, bool BRES>
 __device__ __forceinline__ void mma_role(const Params& p, uint32_t a_base, uint32_t b_base, uint32_t bb, uint32_t tmem_base) {
-  const uint32_t hi = p.desc_hi, idesc = p.idesc;
+  const uint32_t hi = p.desc_hi, hi_a = p.desc_hi_a, idesc = p.idesc;
   const int num_ka = p.num_ka, a_stages = p.a_stages, b_stages = p.b_stages, total = p.total_tiles;
   const uint32_t a_stage16 = (uint32_t)p.a_stage >> 4, b_stage16 = (uint32_t)p.b_stage >> 4, tap16 = (uint32_t)p.a_tap_stride >> 4;
   const uint32_t a_lo0 = (a_base >> 4) | (1u << 16), b_lo0 = (b_base >> 4) | (1u << 16);
@@ -141,7 +143,7 @@ __device__ __forceinline__ void mma_role(const Params& p, uint32_t a_base, uint3
         }
 #pragma unroll
         for (int kk = 0; kk < KSTEPS; ++kk) {
-          const uint64_t da = ((uint64_t)hi << 32) | (uint64_t)(alo + tt * tap16 + 2 * kk);
+          const uint64_t da = ((uint64_t)hi_a << 32) | (uint64_t)(alo + tt * tap16 + 2 * kk);
           const uint64_t db = ((uint64_t)hi << 32) | (uint64_t)(blo + 2 * kk);
           umma_bf16(d_tmem, da, db, idesc, (tt | kk) != 0 ? 1u : (ka != 0 ? 1u : 0u));
         }
@@ -524,7 +526,10 @@ int32_t conv_tc_prepare(const ly_op& op, ConvTcState** out) {
   }
   // halo mode: 3x3 stride 1 with the 8 x 16 brick, unless that brick wastes > 35 % more pixels
   static const int halo_ok = env_int("LY_TC_HALO", 1);
-  if (halo_ok && op.k == 3 && op.stride == 1) {
+  static const int halo2_ok = env_int("LY_TC_HALO_S2", 1);
+  // (stride 2: only for 64-byte channel rows, where the TMA request rate binds: 32->64 @320^2 0.65 -> 0.51 ms;
+  //  with 128-byte rows the classic 9-load mode is as fast or faster)
+  if (halo_ok && op.k == 3 && (op.stride == 1 || (halo2_ok && p.kc <= 32))) {
     const double cover = (double)((dimW + 7) / 8 * 8) * ((dimH + 15) / 16 * 16) * dimB;
     if (cover <= 1.35 * best_cover) { p.halo = 1; best_tw = 8; best_th = 16; best_tb = 1; }
   }
@@ -547,7 +552,9 @@ int32_t conv_tc_prepare(const ly_op& op, ConvTcState** out) {
   }
   p.tpa = p.halo ? 3 : 1;
   p.num_ka = p.num_kb / p.tpa;
-  const int a_rows = p.halo ? 8 * 18 : 128;
+  // halo box: 8 output columns x all the input rows the 16 output rows touch (18 at stride 1, 33 at stride 2)
+  const int halo_rows = (16 - 1) * op.stride + 3;
+  const int a_rows = p.halo ? 8 * halo_rows : 128;
   p.a_tap_stride = 8 * p.kc * 2;           // 8 rows = one swizzle atom down
 
   // shared-memory pipeline
@@ -586,6 +593,10 @@ int32_t conv_tc_prepare(const ly_op& op, ConvTcState** out) {
   const int swz = p.kc == 64 ? 2 : (p.kc == 32 ? 4 : 6);       // UMMA LayoutType: SW128 / SW64 / SW32
   const uint32_t sbo = (uint32_t)(8 * p.kc * 2) >> 4;          // 8-row group stride, 16-byte units
   p.desc_hi = (sbo & 0x3FFFu) | (1u << 14) /*version = 1 (sm_100)*/ | ((uint32_t)swz << 29);
+  // stride-2 halo mode: output row oy of the brick reads input row 2*oy + ky, so consecutive 8-pixel
+  // row groups of the A operand are TWO stored groups apart
+  const uint32_t sbo_a = sbo * (uint32_t)((p.halo && op.stride == 2) ? 2 : 1);
+  p.desc_hi_a = (sbo_a & 0x3FFFu) | (1u << 14) | ((uint32_t)swz << 29);
   p.idesc = (1u << 4) /*D=f32*/ | (1u << 7) /*A=bf16*/ | (1u << 10) /*B=bf16*/ | ((uint32_t)(bn >> 3) << 17) | ((128u >> 4) << 24);
 
   const CUtensorMapSwizzle tswz = p.kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (p.kc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
@@ -604,8 +615,8 @@ int32_t conv_tc_prepare(const ly_op& op, ConvTcState** out) {
     // pixel would otherwise cost a 128-byte DRAM fetch (measured: 2x read traffic on C2f slices)
     const CUtensorMapL2promotion a_promo = p.kc == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
                                           : (p.kc == 32 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : CU_TENSOR_MAP_L2_PROMOTION_NONE);
-    box[0] = p.kc; box[1] = p.tw * op.stride; box[2] = (p.halo ? p.th + 2 : p.th * op.stride); box[3] = p.tb;
-    estr[0] = 1; estr[1] = op.stride; estr[2] = op.stride; estr[3] = 1;
+    box[0] = p.kc; box[1] = p.tw * op.stride; box[2] = (p.halo ? halo_rows : p.th * op.stride); box[3] = p.tb;
+    estr[0] = 1; estr[1] = op.stride; estr[2] = p.halo ? 1 : op.stride; estr[3] = 1;   // halo: every input row is loaded
     CUresult r = encode(&p.tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         tswz, a_promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { delete st; set_error("conv_tc: cuTensorMapEncodeTiled(A) failed with %d", (int)r); return LY_E_CUDA; }

@@ -46,7 +46,9 @@ __device__ __forceinline__ int level_of(const Levels& lv, int g) {
 // LABEL = false (top-k path): only the best class SCORE is needed, and sigmoid is monotonic,
 // so it is sigmoid(max logit): 1 sigmoid per anchor instead of nc.  The NMS path needs the
 // reference's argmax over the sigmoid VALUES (first maximum wins, ties included): LABEL = true.
-template <bool LABEL>
+// RM = 16: the standard reg_max with the 16 bin loads of a side issued together (fully unrolled);
+// RM = 0: any reg_max, rolled loops.
+template <bool LABEL, int RM>
 __global__ void __launch_bounds__(256)
 dfl_kernel(Levels lv, float* __restrict__ boxes, float* __restrict__ best, int* __restrict__ label) {
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
@@ -75,13 +77,26 @@ dfl_kernel(Levels lv, float* __restrict__ boxes, float* __restrict__ best, int* 
 #pragma unroll
     for (int side = 0; side < 4; ++side) {
       const float* q = p + (long long)side * lv.reg_max * HW;
-      float mx = -INFINITY;
-      for (int i = 0; i < lv.reg_max; ++i) mx = fmaxf(mx, q[(long long)i * HW]);
-      float den = 0.f, num = 0.f;
-      for (int i = 0; i < lv.reg_max; ++i) {
-        const float e = expf(q[(long long)i * HW] - mx);
-        den += e;
-        num += e * (float)i;
+      float mx = -INFINITY, den = 0.f, num = 0.f;
+      if (RM > 0) {
+        float t[RM > 0 ? RM : 1];
+#pragma unroll
+        for (int i = 0; i < RM; ++i) t[i] = __ldg(q + (long long)i * HW);
+#pragma unroll
+        for (int i = 0; i < RM; ++i) mx = fmaxf(mx, t[i]);
+#pragma unroll
+        for (int i = 0; i < RM; ++i) {
+          const float e = expf(t[i] - mx);
+          den += e;
+          num += e * (float)i;
+        }
+      } else {
+        for (int i = 0; i < lv.reg_max; ++i) mx = fmaxf(mx, q[(long long)i * HW]);
+        for (int i = 0; i < lv.reg_max; ++i) {
+          const float e = expf(q[(long long)i * HW] - mx);
+          den += e;
+          num += e * (float)i;
+        }
       }
       d[side] = num / den;
     }
@@ -493,7 +508,8 @@ extern "C" int32_t ly_decode_topk(const ly_levels* in, int32_t max_det, float* o
   cudaStream_t st = (cudaStream_t)stream;
   const int k = max_det < lv.A ? max_det : lv.A;
   dim3 g1((lv.A + 255) / 256, lv.B);
-  dfl_kernel<false><<<g1, 256, 0, st>>>(lv, s.boxes, s.best, s.label);
+  if (lv.reg_max == 16) dfl_kernel<false, 16><<<g1, 256, 0, st>>>(lv, s.boxes, s.best, s.label);
+  else dfl_kernel<false, 0><<<g1, 256, 0, st>>>(lv, s.boxes, s.best, s.label);
   rc = post_launch("dfl_decode");
   if (rc != LY_OK) return rc;
   topk_kernel<<<lv.B, NT_TOPK, 0, st>>>(lv, k, s.boxes, s.best, s.s2, out, out_anchor, out_cls);
@@ -512,7 +528,8 @@ extern "C" int32_t ly_decode_nms(const ly_levels* in, float conf_thresh, float i
   LY_CHECK_ARG(scratch_bytes >= s.total, "decode_nms: scratch too small (%lld < %lld)", (long long)scratch_bytes, s.total);
   cudaStream_t st = (cudaStream_t)stream;
   dim3 g1((lv.A + 255) / 256, lv.B);
-  dfl_kernel<true><<<g1, 256, 0, st>>>(lv, s.boxes, s.best, s.label);
+  if (lv.reg_max == 16) dfl_kernel<true, 16><<<g1, 256, 0, st>>>(lv, s.boxes, s.best, s.label);
+  else dfl_kernel<true, 0><<<g1, 256, 0, st>>>(lv, s.boxes, s.best, s.label);
   rc = post_launch("dfl_decode");
   if (rc != LY_OK) return rc;
   return run_nms(s.boxes, s.best, s.label, nullptr, lv.B, lv.A, 1, conf_thresh, iou_thresh, max_det, classwise, s.sortbuf,

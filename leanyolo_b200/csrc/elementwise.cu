@@ -165,7 +165,7 @@ __device__ __forceinline__ int stem_slot_w(int k) {
 }
 
 template <typename TIn, int NT>
-__global__ void __launch_bounds__(SM_THREADS)
+__global__ void __launch_bounds__(SM_THREADS, 4)
 stem_mma_kernel(const TIn* __restrict__ x, int H, int W, __nv_bfloat16* __restrict__ dst, int dCtot, int dC0,
                 const float* __restrict__ w, const float* __restrict__ bias,
                 float s0, float s1, float s2, float d0, float d1, float d2) {

@@ -51,6 +51,8 @@ def registry():
     add("tc_3x3_128_128_nonres", G.check_conv, cin=128, cout=128, k=3, H=16, W=16)
     add("tc_3x3_s2", G.check_conv, cin=64, cout=128, k=3, stride=2, H=32, W=32)
     add("tc_3x3_s2_k32", G.check_conv, cin=32, cout=64, k=3, stride=2, H=32, W=32)
+    add("tc_3x3_s2_80_b3", G.check_conv, cin=64, cout=128, k=3, stride=2, H=80, W=80, B=3)
+    add("tc_3x3_s2_k128_odd", G.check_conv, cin=128, cout=64, k=3, stride=2, H=24, W=40, B=2, res=True)
     add("tc_3x3_20x20_b3", G.check_conv, cin=64, cout=64, k=3, H=20, W=20, B=3)
     add("tc_3x3_40x40_b3", G.check_conv, cin=64, cout=64, k=3, H=40, W=40, B=3)
     add("tc_3x3_odd_10x6", G.check_conv, cin=64, cout=64, k=3, H=10, W=6, B=5)
