@@ -325,13 +325,22 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     const uint32_t r_base = bar_base + 8u * (4 * kMaxStages + 8);
     const uint32_t rslot = r_base + (uint32_t)(threadIdx.x - 64) * p.res_slot;
     const uint32_t rstage = (uint32_t)(32 * kEpiWarps) * p.res_slot;
+    // The half-resolution addend of the folded upsample+concat 1x1 (p.up) goes through the same slots.
     auto res_prefetch = [&](int tile_idx, uint32_t dst) {
       if (tile_idx < p.total_tiles) {
         int nt, wt, ht, bt;
         split(tile_idx, nt, wt, ht, bt);
         const int w = wt * p.tw + dw, h = ht * p.th + dh, b = bt * p.tb + db;
         if (w < p.Wo && h < p.Ho && b < p.Bo) {
-          const __nv_bfloat16* rr = p.res + (((long long)b * p.Ho + h) * p.Wo + w) * p.rCtot + p.rC0 + nt * p.block_n;
+          const uint32_t lin32 = ((uint32_t)b * (uint32_t)p.Ho + (uint32_t)h) * (uint32_t)p.Wo + (uint32_t)w;
+          const __nv_bfloat16* rr;
+          if (p.up) {
+            const uint32_t ub = lin32 / (uint32_t)p.hw_real, urem = lin32 - ub * (uint32_t)p.hw_real;
+            const uint32_t uh = urem / (uint32_t)p.Wreal, uw = urem - uh * (uint32_t)p.Wreal;
+            rr = p.up + (((long long)ub * p.uH + (uh >> 1)) * p.uW + (uw >> 1)) * p.uCtot + p.uC0 + nt * p.block_n;
+          } else {
+            rr = p.res + (long long)lin32 * p.rCtot + p.rC0 + nt * p.block_n;
+          }
           for (int i = 0, ch = cg; ch < nchunks; ++i, ch += 4) {
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + i * 32), "l"(rr + ch * 16) : "memory");
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + i * 32 + 16), "l"(rr + ch * 16 + 8) : "memory");
@@ -361,7 +370,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       __nv_bfloat16* drow = (p.dst && valid) ? p.dst + lin * p.dCtot + p.dC0 + n0 : nullptr;
       const __nv_bfloat16* rrow = (p.res && valid) ? p.res + lin * p.rCtot + p.rC0 + n0 : nullptr;
       const __nv_bfloat16* urow = nullptr;
-      if (p.up && valid) {
+      const bool has_up = p.up && valid;
+      if (has_up && !p.res_slot) {
         // real (b, h, w) of this output pixel (the tiling of a 1x1 conv is flat), then the half-resolution source pixel
         const uint32_t ub = (uint32_t)lin / (uint32_t)p.hw_real, urem = (uint32_t)lin - ub * (uint32_t)p.hw_real;
         const uint32_t uh = urem / (uint32_t)p.Wreal, uw = urem - uh * (uint32_t)p.Wreal;
@@ -386,10 +396,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const float4 bb = bp[j];
-            v[4 * j + 0] = fmaf(__uint_as_float(nxt[4 * j + 0]), pre, bb.x);
-            v[4 * j + 1] = fmaf(__uint_as_float(nxt[4 * j + 1]), pre, bb.y);
-            v[4 * j + 2] = fmaf(__uint_as_float(nxt[4 * j + 2]), pre, bb.z);
-            v[4 * j + 3] = fmaf(__uint_as_float(nxt[4 * j + 3]), pre, bb.w);
+            ffma2(v[4 * j + 0], v[4 * j + 1], __uint_as_float(nxt[4 * j + 0]), __uint_as_float(nxt[4 * j + 1]), pre, pre, bb.x, bb.y);
+            ffma2(v[4 * j + 2], v[4 * j + 3], __uint_as_float(nxt[4 * j + 2]), __uint_as_float(nxt[4 * j + 3]), pre, pre, bb.z, bb.w);
           }
           if (ch + 4 < nchunks) tmem_ld16(taddr + c + 64, nxt);   // next round's chunk, in flight during the activation
         }
@@ -400,16 +408,21 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           if (lane == 0) mbar_arrive(tempty_bar(as));
         }
         if (has) {
-          if (urow) {
+          if (has_up) {
             float uv[16];
-            load_vec<__nv_bfloat16>(urow + c, uv);
-            load_vec<__nv_bfloat16>(urow + c + 8, uv + 8);
+            if (p.res_slot) {
+              load_vec<__nv_bfloat16>(reinterpret_cast<const __nv_bfloat16*>(rsm + rd * 32), uv);
+              load_vec<__nv_bfloat16>(reinterpret_cast<const __nv_bfloat16*>(rsm + rd * 32 + 16), uv + 8);
+            } else {
+              load_vec<__nv_bfloat16>(urow + c, uv);
+              load_vec<__nv_bfloat16>(urow + c + 8, uv + 8);
+            }
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = fmaf(uv[j], pre, v[j]);
+            for (int j = 0; j < 16; j += 2) ffma2(v[j], v[j + 1], uv[j], uv[j + 1], pre, pre, v[j], v[j + 1]);
           }
           if (p.act) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = silu_from_half(v[j]);
+            for (int j = 0; j < 16; j += 2) silu2_from_half(v[j], v[j + 1]);
           }
           if (rrow) {
             float rv[16];
@@ -421,7 +434,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
               load_vec<__nv_bfloat16>(rrow + c + 8, rv + 8);
             }
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] += rv[j];
+            for (int j = 0; j < 16; j += 2) fadd2(v[j], v[j + 1], v[j], v[j + 1], rv[j], rv[j + 1]);
           }
           if (nrow) {
             float* np = nrow + (long long)c * p.hw_real;
@@ -499,8 +512,10 @@ int32_t conv_tc_prepare(const ly_op& op, ConvTcState** out) {
   p.kc_blocks = Cin / p.kc;
   p.num_kb = op.k * op.k * p.kc_blocks;
   // N tile: the largest multiple of 16 that divides Cout and is <= 256
+  // (ops with a prefetched addend keep N <= 128 so that the per-thread prefetch slots stay small)
+  const int bn_max = op.up.ptr ? 128 : 256;
   int bn = 16;
-  for (int c = 16; c <= 256 && c <= Cout; c += 16)
+  for (int c = 16; c <= bn_max && c <= Cout; c += 16)
     if (Cout % c == 0) bn = c;
   p.block_n = bn;
   p.tiles_n = Cout / bn;
@@ -533,6 +548,9 @@ int32_t conv_tc_prepare(const ly_op& op, ConvTcState** out) {
     const double cover = (double)((dimW + 7) / 8 * 8) * ((dimH + 15) / 16 * 16) * dimB;
     if (cover <= 1.35 * best_cover) { p.halo = 1; best_tw = 8; best_th = 16; best_tb = 1; }
   }
+  // experiment (LY_TC_HALO_TW=4): 4-wide brick, so the ky windows start 4 rows = HALF a swizzle atom apart
+  static const int halo_tw = env_int("LY_TC_HALO_TW", 8);
+  if (p.halo && halo_tw != 8 && op.stride == 1) { best_tw = halo_tw; best_th = 128 / halo_tw; }
   p.tw = best_tw; p.th = best_th; p.tb = best_tb;
   p.Wo = dimW; p.Ho = dimH; p.Bo = dimB;
   p.tiles_w = (dimW + p.tw - 1) / p.tw;
@@ -553,9 +571,9 @@ int32_t conv_tc_prepare(const ly_op& op, ConvTcState** out) {
   p.tpa = p.halo ? 3 : 1;
   p.num_ka = p.num_kb / p.tpa;
   // halo box: 8 output columns x all the input rows the 16 output rows touch (18 at stride 1, 33 at stride 2)
-  const int halo_rows = (16 - 1) * op.stride + 3;
-  const int a_rows = p.halo ? 8 * halo_rows : 128;
-  p.a_tap_stride = 8 * p.kc * 2;           // 8 rows = one swizzle atom down
+  const int halo_rows = (p.th - 1) * op.stride + 3;
+  const int a_rows = p.halo ? p.tw * halo_rows : 128;
+  p.a_tap_stride = p.tw * p.kc * 2;        // one brick row down (tw = 8: one swizzle atom)
 
   // shared-memory pipeline
   p.a_box = a_rows * p.kc * 2;
@@ -568,7 +586,7 @@ int32_t conv_tc_prepare(const ly_op& op, ConvTcState** out) {
   const uint32_t bar_bytes = 8 * (4 * kMaxStages + 8);
   // shortcut prefetch slots: 2 stages x 512 epilogue threads x (chunks per warp x 32 B); only while small
   static const int res_prefetch_ok = env_int("LY_TC_RES_PREFETCH", 1);
-  p.res_slot = (op.res.ptr && res_prefetch_ok && bn <= 128) ? ((bn / 16 + 3) / 4) * 32 : 0;   // one 32-byte chunk per round
+  p.res_slot = (((op.res.ptr != nullptr) != (op.up.ptr != nullptr)) && res_prefetch_ok && bn <= 128) ? ((bn / 16 + 3) / 4) * 32 : 0;   // one 32-byte chunk per round
   const long long res_bytes = 2LL * 32 * kEpiWarps * p.res_slot;
   const long long avail = (long long)kSmemBudget - bar_bytes - 1024 - res_bytes - (p.b_resident ? b_all : 0);
   if (p.b_resident) {

@@ -47,6 +47,29 @@ __device__ __forceinline__ float silu_from_half(float h) {
   return fmaf(h, t, h);
 }
 
+// Packed fp32 pairs (sm_100 FFMA2 / FADD2): two IEEE fp32 operations in ONE issue slot (same
+// rounding as the scalar instructions).  The FMA pipe still spends two passes, but the thin-layer
+// epilogues and the depthwise producers are bound by the instruction issue rate, not by the pipe.
+__device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, float b0, float b1, float c0, float c1) {
+  asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1), "f"(c0), "f"(c1));
+}
+__device__ __forceinline__ void fadd2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+      "add.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+// SiLU of a pair, inputs already halved (see silu_from_half): two MUFU.TANH + one FFMA2
+__device__ __forceinline__ void silu2_from_half(float& h0, float& h1) {
+  float t0, t1;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(h0));
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(h1));
+  ffma2(h0, h1, h0, h1, t0, t1, h0, h1);
+}
+
 #endif  // __CUDACC__
 
 }  // namespace ly

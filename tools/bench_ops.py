@@ -58,6 +58,10 @@ def run(spec, iters=5):
             op.dst = N.LyView(None, 0, 0, 0, 0, 0)
             op.nchw, op.nchw_ctot, op.nchw_c0, op.nchw_c = o.data_ptr(), cout, 0, cout
             keep.append(o)
+        if kw.get("up"):      # half-resolution pre-activation addend (folded upsample + concat)
+            u = torch.randn(B, hw // s // 2, hw // s // 2, cout, device=DEV).to(torch.bfloat16)
+            op.up = view(u, 0, cout)
+            keep.append(u)
         if kw.get("res"):
             r = torch.randn_like(y)
             op.res = view(r, 0, cout)
