@@ -15,6 +15,14 @@
 //                    group stride is doubled, so output row oy reads stored row 2*oy + ky.  The TMA unit is
 //                    request-rate bound on these strided 64/128-byte rows (measured ~5 cycles
 //                    per row), so this is what moves the 3x3 layers towards the MMA roofline.
+//     band mode    : 3x3 stride 1, maps up to 254 pixels wide: ONE box per channel block holds
+//                    R+2 full padded image rows ((W+2) x (R+2) pixels, row index = y*(W+2)+x).
+//                    Output pixel m = oy*(W+2)+ox of the band reads row m + ky*(W+2) + kx for tap
+//                    (ky, kx): all nine taps are the SAME tile viewed a few rows further down
+//                    (the 128B/64B/32B swizzle is a function of the absolute shared-memory
+//                    address, so a descriptor may start at any row), and the M = 128 tiles are
+//                    consecutive runs of m.  2 of every W+2 accumulator rows are discarded, but
+//                    every input byte crosses the TMA unit (R+2)/R times instead of 3.4 times.
 // * MMA: tcgen05.mma.cta_group::1.kind::f16, M=128, N=BLOCK_N (<=256), K=16 per
 //   instruction, bf16 x bf16 -> fp32 accumulators in TMEM (double-buffered so the epilogue of
 //   tile i overlaps the MMAs of tile i+1).  Operands are K-major in shared memory with the
@@ -32,6 +40,7 @@
 // Reference semantics: leanyolo/models/yolov10/layers.py:51-88 (Conv = conv+BN+SiLU).
 #include <cuda.h>
 #include <stdlib.h>
+#include <algorithm>
 #include <string.h>
 #include "common.cuh"
 #include "tma.cuh"
@@ -58,7 +67,9 @@ struct Params {
   uint32_t mg_n, mg_w, mg_h;   // magic multipliers: x / d == __umulhi(x, mg) for the tile counts used (0: d == 1)
   int k, stride, pad;
   int kc, kc_blocks, num_kb;
-  int halo;                // 1: halo mode (3 taps share one A box)
+  int halo;                // 1: halo mode (3 taps share one A box)  2: band mode (all 9 taps share one box)
+  int band_r, band_w, band_mt, bands;   // band mode: output rows per band, padded row width W+2, M tiles per band, bands per image
+  uint32_t mg_bw, mg_bands;
   int tpa, num_ka;         // taps per A stage, A loads per tile
   int a_tap_stride;        // bytes between the windows of successive taps inside an A stage
   int block_n, tmem_cols;
@@ -160,6 +171,271 @@ __device__ __forceinline__ void mma_role(const Params& p, uint32_t a_base, uint3
   }
 }
 
+// Band mode issuer.  Unit = one band of one image; its kc_blocks A stages stay resident while every
+// (n tile, M tile) of the band is accumulated: D[mt] = sum over (cb, tap) A[stage cb, rows mt*128 + tap offset ...] * W[tap, cb].
+template <int KSTEPS, bool BRES>
+__device__ __forceinline__ void mma_role_band(const Params& p, uint32_t a_base, uint32_t b_base, uint32_t bb, uint32_t tmem_base) {
+  const uint32_t hi = p.desc_hi, idesc = p.idesc;
+  const int a_stages = p.a_stages, b_stages = p.b_stages, total = p.total_tiles, kcb = p.kc_blocks;
+  const uint32_t a_stage16 = (uint32_t)p.a_stage >> 4, b_stage16 = (uint32_t)p.b_stage >> 4;
+  const uint32_t row16 = (uint32_t)p.kc >> 3;                       // one pixel row of the tile, in 16-byte units
+  const uint32_t a_lo0 = (a_base >> 4) | (1u << 16), b_lo0 = (b_base >> 4) | (1u << 16);
+  const uint32_t block_n = (uint32_t)p.block_n;
+  const uint32_t bw16 = (uint32_t)p.band_w * row16;
+  if (BRES) {
+    mbar_wait(bar_bres(bb), 0);
+    tc_fence_after();
+  }
+  int sa = 0, sb = 0, as = 0;
+  uint32_t pa = 0, pb = 0, aphase = 0;
+  for (int unit = blockIdx.x; unit < total; unit += gridDim.x) {
+    {  // all channel blocks of this band have landed
+      int s = sa; uint32_t ph = pa;
+      for (int cb = 0; cb < kcb; ++cb) {
+        mbar_wait(bar_afull(bb, s), ph);
+        if (++s == a_stages) { s = 0; ph ^= 1u; }
+      }
+      tc_fence_after();
+    }
+    for (int nt = 0; nt < p.tiles_n; ++nt)
+      for (int mt = 0; mt < p.band_mt; ++mt) {
+        mbar_wait(bar_tempty(bb, as), aphase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)as * block_n;
+        int s = sa;
+        for (int cb = 0; cb < kcb; ++cb) {
+          const uint32_t alo = a_lo0 + (uint32_t)s * a_stage16 + (uint32_t)(mt * 128) * row16;
+#pragma unroll
+          for (int tap = 0; tap < 9; ++tap) {
+            uint32_t blo;
+            if (BRES) {
+              blo = b_lo0 + (uint32_t)(tap * kcb + cb) * b_stage16;
+            } else {
+              mbar_wait(bar_bfull(bb, sb), pb);
+              tc_fence_after();
+              blo = b_lo0 + (uint32_t)sb * b_stage16;
+            }
+            const uint32_t at = alo + (uint32_t)(tap / 3) * bw16 + (uint32_t)(tap % 3) * row16;
+#pragma unroll
+            for (int kk = 0; kk < KSTEPS; ++kk) {
+              const uint64_t da = ((uint64_t)hi << 32) | (uint64_t)(at + 2 * kk);
+              const uint64_t db = ((uint64_t)hi << 32) | (uint64_t)(blo + 2 * kk);
+              umma_bf16(d_tmem, da, db, idesc, (tap | kk) != 0 ? 1u : (cb != 0 ? 1u : 0u));
+            }
+            if (!BRES) {
+              umma_commit(bar_bempty(bb, sb));
+              if (++sb == b_stages) { sb = 0; pb ^= 1u; }
+            }
+          }
+          if (++s == a_stages) s = 0;
+        }
+        umma_commit(bar_tfull(bb, as));
+        if (++as == 2) { as = 0; aphase ^= 1u; }
+      }
+    for (int cb = 0; cb < kcb; ++cb) {   // the band's tiles are free once everything issued so far has completed
+      umma_commit(bar_aempty(bb, sa));
+      if (++sa == a_stages) { sa = 0; pa ^= 1u; }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------- epilogue
+// 16 warps: warp -> (TMEM lane quarter q = warp % 4, column group cg = (warp - 2) / 4).  A thread
+// owns one pixel row; in round i the four warps of a quarter take the 16-column chunks 4i+cg.
+// The TMEM load of round i+1 is in flight while round i is activated and stored; the accumulator
+// stage is released as soon as the last chunk sits in registers.
+// Thin layers are bound by THIS instruction stream (ncu: ~300 warp-instructions per warp and tile
+// of which ~60 are the activation math), so the role is specialised at compile time on
+//   MAP   pixel mapping: 0 flat (1x1/s1: pixel = tile*128 + row), 1 brick / halo, 2 band
+//   ADD   epilogue addend: 0 none, 1 shortcut (prefetched slots), 2 half-resolution addend
+//         (prefetched slots), 3 shortcut (direct loads), 4 half-resolution addend (direct loads)
+//   NCHW  public fp32 NCHW output instead of the NHWC bf16 buffer
+// and every address is 32-bit pixel index x 32-bit pitch (one IMAD.WIDE).
+// (Measured dead ends for the NHWC store: a TMA store from a swizzled staging tile and a
+// shared-memory transpose to 128-byte coalesced stores were both slower than storing
+// 2 x 16 bytes per lane straight from the TMEM layout: the extra barrier per tile costs more
+// than the partial-sector writes, and the TMA unit is already row-rate bound on the loads.)
+template <int MAP, int ADD, bool NCHW>
+__device__ __forceinline__ void epilogue_role(const Params& p, uint8_t* smem_raw, uint32_t bar_base, uint32_t tmem_base, const float* s_bias) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = warp & 3;
+  const int cg = (warp - 2) >> 2;
+  const int nchunks = p.block_n >> 4;
+  const int rounds = (nchunks + 3) >> 2;
+  const uint32_t row = (uint32_t)(q * 32 + lane);
+  const uint32_t dw = row % (uint32_t)p.tw;
+  const uint32_t dh = (row / (uint32_t)p.tw) % (uint32_t)p.th;
+  const uint32_t db = row / (uint32_t)(p.tw * p.th);
+  const bool act = p.act != 0;
+  const float pre = act ? 0.5f : 1.0f;   // SiLU(x) = h + h*tanh(h), h = x/2: the halving rides on the bias FMA
+  constexpr bool kSlots = ADD == 1 || ADD == 2;
+  constexpr bool kUp = ADD == 2 || ADD == 4;
+  constexpr bool kRes = ADD == 1 || ADD == 3;
+
+  // Work items in the order the issuer accumulates them: one tile per step of the persistent loop
+  // (flat / brick), or (unit, n tile, M tile) in band mode.  `it_*` is the state of the next item.
+  struct Loc { bool more, valid; uint32_t lin; int n0; };
+  int it_unit = blockIdx.x, it_nt = 0, it_mt = 0;
+  auto next_item = [&]() -> Loc {
+    Loc L;
+    L.more = it_unit < p.total_tiles;
+    L.valid = false; L.lin = 0; L.n0 = 0;
+    if (!L.more) return L;
+    if (MAP == 2) {
+      const uint32_t b = p.mg_bands ? __umulhi((uint32_t)it_unit, p.mg_bands) : (uint32_t)it_unit;
+      const uint32_t bd = (uint32_t)it_unit - b * (uint32_t)p.bands;
+      const uint32_t m = (uint32_t)it_mt * 128u + row;
+      const uint32_t oy = __umulhi(m, p.mg_bw), ox = m - oy * (uint32_t)p.band_w;
+      const uint32_t h = bd * (uint32_t)p.band_r + oy;
+      L.valid = ox < (uint32_t)p.Wo && oy < (uint32_t)p.band_r && h < (uint32_t)p.Ho;
+      L.lin = (b * (uint32_t)p.Ho + h) * (uint32_t)p.Wo + ox;
+      L.n0 = it_nt * p.block_n;
+      if (++it_mt == p.band_mt) { it_mt = 0; if (++it_nt == p.tiles_n) { it_nt = 0; it_unit += gridDim.x; } }
+    } else if (MAP == 0) {
+      const uint32_t t = (uint32_t)it_unit;
+      const uint32_t qn = p.mg_n ? __umulhi(t, p.mg_n) : t;
+      L.n0 = (int)(t - qn * (uint32_t)p.tiles_n) * p.block_n;
+      L.lin = qn * 128u + row;
+      L.valid = L.lin < (uint32_t)p.Wo;
+      it_unit += gridDim.x;
+    } else {
+      int nt, wt, ht, bt;
+      split_tile(p, it_unit, nt, wt, ht, bt);
+      const uint32_t w = (uint32_t)(wt * p.tw) + dw, h = (uint32_t)(ht * p.th) + dh, b = (uint32_t)(bt * p.tb) + db;
+      L.valid = w < (uint32_t)p.Wo && h < (uint32_t)p.Ho && b < (uint32_t)p.Bo;
+      L.lin = (b * (uint32_t)p.Ho + h) * (uint32_t)p.Wo + w;
+      L.n0 = nt * p.block_n;
+      it_unit += gridDim.x;
+    }
+    return L;
+  };
+  // half-resolution source row of output pixel `lin` (the conv is 1x1, so lin is the real pixel index)
+  auto up_row = [&](uint32_t lin, int n0) -> const __nv_bfloat16* {
+    const uint32_t ub = lin / (uint32_t)p.hw_real, urem = lin - ub * (uint32_t)p.hw_real;
+    const uint32_t uh = urem / (uint32_t)p.Wreal, uw = urem - uh * (uint32_t)p.Wreal;
+    return p.up + (size_t)((ub * (uint32_t)p.uH + (uh >> 1)) * (uint32_t)p.uW + (uw >> 1)) * (uint32_t)p.uCtot + p.uC0 + n0;
+  };
+  // Shortcut / addend operand: each thread cp.async's its own 32 bytes per chunk of the NEXT tile
+  // into a private shared-memory slot while it works on the current tile, so the DRAM latency of
+  // the uncoalesced read is off the epilogue's critical path (measured: a C2f bottleneck at 160^2
+  // spent 35 % of its samples waiting for that load).
+  const uint32_t r_base = bar_base + 8u * (4 * kMaxStages + 8);
+  const uint32_t rslot = r_base + (uint32_t)(threadIdx.x - 64) * p.res_slot;
+  const uint32_t rstage = (uint32_t)(32 * kEpiWarps) * p.res_slot;
+  auto res_prefetch = [&](const Loc& L, uint32_t dst) {
+    if (L.more && L.valid) {
+      const __nv_bfloat16* rr = kUp ? up_row(L.lin, L.n0) : p.res + (size_t)L.lin * (uint32_t)p.rCtot + p.rC0 + L.n0;
+      for (int i = 0, ch = cg; ch < nchunks; ++i, ch += 4) {
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + i * 32), "l"(rr + ch * 16) : "memory");
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + i * 32 + 16), "l"(rr + ch * 16 + 8) : "memory");
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  int as = 0;
+  uint32_t aphase = 0, rs = 0;
+  PROF_DECL(w_tfull);
+#ifdef LY_TC_PROFILE
+  const long long estart = clock64();
+#endif
+  Loc cur = next_item();
+  if (kSlots) res_prefetch(cur, rslot);
+  while (cur.more) {
+    const Loc nxtloc = next_item();
+    const bool valid = cur.valid;
+    const uint32_t lin = cur.lin;
+    const int n0 = cur.n0;
+    if (kSlots) {
+      res_prefetch(nxtloc, rslot + (rs ^ 1u) * rstage);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");   // this tile's addend has landed
+    }
+    const uint8_t* rsm = smem_raw + ((rslot + rs * rstage) - smem_u32(smem_raw));
+    const __nv_bfloat16* arow = nullptr;                     // direct-load addend row
+    if (ADD == 3 && valid) arow = p.res + (size_t)lin * (uint32_t)p.rCtot + p.rC0 + n0;
+    if (ADD == 4 && valid) arow = up_row(lin, n0);
+    __nv_bfloat16* drow = nullptr;
+    float* nrow = nullptr;
+    if (NCHW) {
+      if (valid) {
+        const uint32_t nb = lin / (uint32_t)p.hw_real;        // image index, pixel inside the image
+        nrow = p.nchw + (size_t)(nb * (uint32_t)p.nCtot + (uint32_t)(p.nC0 + n0)) * (uint32_t)p.hw_real + (lin - nb * (uint32_t)p.hw_real);
+      }
+    } else if (valid) {
+      drow = p.dst + (size_t)lin * (uint32_t)p.dCtot + p.dC0 + n0;
+    }
+    { PROF_T0(); mbar_wait(bar_tfull(bar_base, as), aphase); PROF_ADD(w_tfull); }
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.block_n);
+    uint32_t nxt[16];
+    if (cg < nchunks) tmem_ld16(taddr + cg * 16, nxt);
+    bool released = false;
+    for (int rd = 0; rd < rounds; ++rd) {
+      const int ch = rd * 4 + cg;
+      const int c = ch * 16;
+      const bool has = ch < nchunks;
+      float v[16];
+      if (has) {
+        tmem_ld_wait();
+        const float4* bp = reinterpret_cast<const float4*>(s_bias + n0 + c);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 bb = bp[j];
+          ffma2(v[4 * j + 0], v[4 * j + 1], __uint_as_float(nxt[4 * j + 0]), __uint_as_float(nxt[4 * j + 1]), pre, pre, bb.x, bb.y);
+          ffma2(v[4 * j + 2], v[4 * j + 3], __uint_as_float(nxt[4 * j + 2]), __uint_as_float(nxt[4 * j + 3]), pre, pre, bb.z, bb.w);
+        }
+        if (ch + 4 < nchunks) tmem_ld16(taddr + c + 64, nxt);   // next round's chunk, in flight during the activation
+      }
+      if (!released && ch + 4 >= nchunks) {   // this warp's last TMEM load has completed (or it has none)
+        released = true;
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_tempty(bar_base, as));
+      }
+      if (has) {
+        if (kUp && valid) {
+          float uv[16];
+          const __nv_bfloat16* src = kSlots ? reinterpret_cast<const __nv_bfloat16*>(rsm + rd * 32) : arow + c;
+          load_vec<__nv_bfloat16>(src, uv);
+          load_vec<__nv_bfloat16>(src + 8, uv + 8);
+#pragma unroll
+          for (int j = 0; j < 16; j += 2) ffma2(v[j], v[j + 1], uv[j], uv[j + 1], pre, pre, v[j], v[j + 1]);
+        }
+        if (act) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 2) silu2_from_half(v[j], v[j + 1]);
+        }
+        if (kRes && valid) {
+          float rv[16];
+          const __nv_bfloat16* src = kSlots ? reinterpret_cast<const __nv_bfloat16*>(rsm + rd * 32) : arow + c;
+          load_vec<__nv_bfloat16>(src, rv);
+          load_vec<__nv_bfloat16>(src + 8, rv + 8);
+#pragma unroll
+          for (int j = 0; j < 16; j += 2) fadd2(v[j], v[j + 1], v[j], v[j + 1], rv[j], rv[j + 1]);
+        }
+        if (NCHW) {
+          if (nrow) {
+            float* np = nrow + (size_t)c * (uint32_t)p.hw_real;
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (n0 + c + j < p.nC) np[(size_t)j * (uint32_t)p.hw_real] = v[j];
+          }
+        } else if (drow) {
+          store_vec<__nv_bfloat16>(drow + c, v);
+          store_vec<__nv_bfloat16>(drow + c + 8, v + 8);
+        }
+      }
+    }
+    if (++as == 2) { as = 0; aphase ^= 1u; }
+    rs ^= 1u;
+    cur = nxtloc;
+  }
+  if (kSlots) asm volatile("cp.async.wait_group 0;" ::: "memory");
+#ifdef LY_TC_PROFILE
+  if (blockIdx.x == 0 && lane == 0 && (warp == 2 || warp == 6))
+    printf("[tc prof] epilogue warp %d: total %lld wait_tfull %lld\n", warp, clock64() - estart, w_tfull);
+#endif
+}
+
 // ------------------------------------------------------------------------------- kernel
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -222,7 +498,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       if (p.b_resident) {
         mbar_expect_tx(bres_bar, (uint32_t)p.num_kb * p.b_box);
         uint32_t dstb = b_base;
-        if (p.halo) {
+        if (p.halo == 1) {
           for (int cb = 0; cb < kcb; ++cb)
             for (int kx = 0; kx < 3; ++kx)
               for (int ky = 0; ky < 3; ++ky, dstb += p.b_stage)
@@ -252,6 +528,25 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         tma_load_2d(b_base + sb * p.b_stage, &p.tmB, bfull_bar(sb), kcol, n0);
         if (++sb == p.b_stages) { sb = 0; pb ^= 1u; }
       };
+      if (p.halo == 2) {
+        // band mode: unit = (band, image); one box per channel block, then (if the weights stream)
+        // the weight slabs in the issuer's order.  The A boxes of the NEXT unit are requested before
+        // this unit's weight slabs so that the band prefetch runs a whole unit ahead.
+        auto unit_a = [&](int unit) {
+          const uint32_t b = p.mg_bands ? __umulhi((uint32_t)unit, p.mg_bands) : (uint32_t)unit;
+          const int band = unit - (int)b * p.bands;
+          for (int cb = 0; cb < kcb; ++cb) load_a(cb * kc, -1, band * p.band_r - 1, (int)b);
+        };
+        if ((int)blockIdx.x < p.total_tiles) unit_a(blockIdx.x);
+        for (int unit = blockIdx.x; unit < p.total_tiles; unit += gridDim.x) {
+          if (unit + (int)gridDim.x < p.total_tiles) unit_a(unit + gridDim.x);
+          if (!bres)
+            for (int nt = 0; nt < p.tiles_n; ++nt)
+              for (int mt = 0; mt < p.band_mt; ++mt)
+                for (int cb = 0; cb < kcb; ++cb)
+                  for (int tap = 0; tap < 9; ++tap) load_b(tap * cin + cb * kc, nt * p.block_n);
+        }
+      } else
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         int nt, wt, ht, bt;
         split_tile(p, tile, nt, wt, ht, bt);
@@ -283,6 +578,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     // ============================== MMA issuer ================================
     if (elect_one()) {
       const int ksteps = p.kc / 16;
+      if (p.halo == 2) {
+        if (ksteps == 4) { if (p.b_resident) mma_role_band<4, true>(p, a_base, b_base, bar_base, tmem_base); else mma_role_band<4, false>(p, a_base, b_base, bar_base, tmem_base); }
+        else if (ksteps == 2) { if (p.b_resident) mma_role_band<2, true>(p, a_base, b_base, bar_base, tmem_base); else mma_role_band<2, false>(p, a_base, b_base, bar_base, tmem_base); }
+        else { if (p.b_resident) mma_role_band<1, true>(p, a_base, b_base, bar_base, tmem_base); else mma_role_band<1, false>(p, a_base, b_base, bar_base, tmem_base); }
+      } else
 #define LY_MMA_CASE(KS)                                                                       \
   if (ksteps == KS) {                                                                         \
     if (p.tpa == 3) { if (p.b_resident) mma_role<KS, 3, true>(p, a_base, b_base, bar_base, tmem_base);   \
@@ -290,172 +590,24 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     else            { if (p.b_resident) mma_role<KS, 1, true>(p, a_base, b_base, bar_base, tmem_base);   \
                       else mma_role<KS, 1, false>(p, a_base, b_base, bar_base, tmem_base); }  \
   }
-      LY_MMA_CASE(4) else LY_MMA_CASE(2) else LY_MMA_CASE(1)
+      { LY_MMA_CASE(4) else LY_MMA_CASE(2) else LY_MMA_CASE(1) }
 #undef LY_MMA_CASE
     }
   } else {
     // ============================== epilogue (16 warps) =======================
-    // warp -> (TMEM lane quarter q = warp % 4, column group cg = (warp - 2) / 4).  A thread owns
-    // one pixel row; in round i the four warps of a quarter take the 16-column chunks 4i+cg.
-    // The TMEM load of round i+1 is in flight while round i is activated and stored; the
-    // accumulator stage is released as soon as the last chunk sits in registers.
-    // (Measured dead ends for the NHWC store: a TMA store from a swizzled staging tile and a
-    // shared-memory transpose to 128-byte coalesced stores were both slower than storing
-    // 2 x 16 bytes per lane straight from the TMEM layout: the extra barrier per tile costs more
-    // than the partial-sector writes, and the TMA unit is already row-rate bound on the loads.)
-    const int q = warp & 3;
-    const int cg = (warp - 2) >> 2;
-    const int nchunks = p.block_n >> 4;
-    const int rounds = (nchunks + 3) >> 2;
-    const int row = q * 32 + lane;
-    const int dw = row % p.tw;
-    const int dh = (row / p.tw) % p.th;
-    const int db = row / (p.tw * p.th);
-    int as = 0;
-    uint32_t aphase = 0;
-    PROF_DECL(w_tfull);
-#ifdef LY_TC_PROFILE
-    const long long estart = clock64();
-#endif
-    auto split = [&](int tile_idx, int& nt, int& wt, int& ht, int& bt) { split_tile(p, tile_idx, nt, wt, ht, bt); };
-    // Shortcut (residual) operand: each thread cp.async's its own 32 bytes per chunk of the
-    // NEXT tile into a private shared-memory slot while it works on the current tile, so the
-    // DRAM latency of the uncoalesced shortcut read is off the epilogue's critical path
-    // (measured: a C2f bottleneck at 160^2 spent 35 % of its samples waiting for that load).
-    const uint32_t r_base = bar_base + 8u * (4 * kMaxStages + 8);
-    const uint32_t rslot = r_base + (uint32_t)(threadIdx.x - 64) * p.res_slot;
-    const uint32_t rstage = (uint32_t)(32 * kEpiWarps) * p.res_slot;
-    // The half-resolution addend of the folded upsample+concat 1x1 (p.up) goes through the same slots.
-    auto res_prefetch = [&](int tile_idx, uint32_t dst) {
-      if (tile_idx < p.total_tiles) {
-        int nt, wt, ht, bt;
-        split(tile_idx, nt, wt, ht, bt);
-        const int w = wt * p.tw + dw, h = ht * p.th + dh, b = bt * p.tb + db;
-        if (w < p.Wo && h < p.Ho && b < p.Bo) {
-          const uint32_t lin32 = ((uint32_t)b * (uint32_t)p.Ho + (uint32_t)h) * (uint32_t)p.Wo + (uint32_t)w;
-          const __nv_bfloat16* rr;
-          if (p.up) {
-            const uint32_t ub = lin32 / (uint32_t)p.hw_real, urem = lin32 - ub * (uint32_t)p.hw_real;
-            const uint32_t uh = urem / (uint32_t)p.Wreal, uw = urem - uh * (uint32_t)p.Wreal;
-            rr = p.up + (((long long)ub * p.uH + (uh >> 1)) * p.uW + (uw >> 1)) * p.uCtot + p.uC0 + nt * p.block_n;
-          } else {
-            rr = p.res + (long long)lin32 * p.rCtot + p.rC0 + nt * p.block_n;
-          }
-          for (int i = 0, ch = cg; ch < nchunks; ++i, ch += 4) {
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + i * 32), "l"(rr + ch * 16) : "memory");
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + i * 32 + 16), "l"(rr + ch * 16 + 8) : "memory");
-          }
-        }
-      }
-      asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-    uint32_t rs = 0;
-    if (p.res_slot) res_prefetch(blockIdx.x, rslot);
-    const float pre = p.act ? 0.5f : 1.0f;   // SiLU(x) = h + h*tanh(h), h = x/2: the halving rides on the bias FMA
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      int nt, wt, ht, bt;
-      split(tile, nt, wt, ht, bt);
-      const int w = wt * p.tw + dw, h = ht * p.th + dh, b = bt * p.tb + db;
-      const bool valid = w < p.Wo && h < p.Ho && b < p.Bo;
-      const long long lin = ((long long)b * p.Ho + h) * p.Wo + w;
-      const int n0 = nt * p.block_n;
-      if (p.res_slot) {
-        res_prefetch(tile + gridDim.x, rslot + (rs ^ 1u) * rstage);
-        asm volatile("cp.async.wait_group 1;" ::: "memory");   // this tile's shortcut has landed
-      }
-      const uint8_t* rsm = smem_raw + ((rslot + rs * rstage) - smem_u32(smem_raw));
-      { PROF_T0(); mbar_wait(tfull_bar(as), aphase); PROF_ADD(w_tfull); }
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.block_n);
-      __nv_bfloat16* drow = (p.dst && valid) ? p.dst + lin * p.dCtot + p.dC0 + n0 : nullptr;
-      const __nv_bfloat16* rrow = (p.res && valid) ? p.res + lin * p.rCtot + p.rC0 + n0 : nullptr;
-      const __nv_bfloat16* urow = nullptr;
-      const bool has_up = p.up && valid;
-      if (has_up && !p.res_slot) {
-        // real (b, h, w) of this output pixel (the tiling of a 1x1 conv is flat), then the half-resolution source pixel
-        const uint32_t ub = (uint32_t)lin / (uint32_t)p.hw_real, urem = (uint32_t)lin - ub * (uint32_t)p.hw_real;
-        const uint32_t uh = urem / (uint32_t)p.Wreal, uw = urem - uh * (uint32_t)p.Wreal;
-        urow = p.up + (((long long)ub * p.uH + (uh >> 1)) * p.uW + (uw >> 1)) * p.uCtot + p.uC0 + n0;
-      }
-      float* nrow = nullptr;
-      if (p.nchw && valid) {
-        const uint32_t nb = (uint32_t)lin / (uint32_t)p.hw_real;        // image index, pixel inside the image
-        nrow = p.nchw + ((long long)nb * p.nCtot + p.nC0 + n0) * p.hw_real + ((uint32_t)lin - nb * (uint32_t)p.hw_real);
-      }
-      uint32_t nxt[16];
-      if (cg < nchunks) tmem_ld16(taddr + cg * 16, nxt);
-      bool released = false;
-      for (int rd = 0; rd < rounds; ++rd) {
-        const int ch = rd * 4 + cg;
-        const int c = ch * 16;
-        const bool has = ch < nchunks;
-        float v[16];
-        if (has) {
-          tmem_ld_wait();
-          const float4* bp = reinterpret_cast<const float4*>(s_bias + n0 + c);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float4 bb = bp[j];
-            ffma2(v[4 * j + 0], v[4 * j + 1], __uint_as_float(nxt[4 * j + 0]), __uint_as_float(nxt[4 * j + 1]), pre, pre, bb.x, bb.y);
-            ffma2(v[4 * j + 2], v[4 * j + 3], __uint_as_float(nxt[4 * j + 2]), __uint_as_float(nxt[4 * j + 3]), pre, pre, bb.z, bb.w);
-          }
-          if (ch + 4 < nchunks) tmem_ld16(taddr + c + 64, nxt);   // next round's chunk, in flight during the activation
-        }
-        if (!released && ch + 4 >= nchunks) {   // this warp's last TMEM load has completed (or it has none)
-          released = true;
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(tempty_bar(as));
-        }
-        if (has) {
-          if (has_up) {
-            float uv[16];
-            if (p.res_slot) {
-              load_vec<__nv_bfloat16>(reinterpret_cast<const __nv_bfloat16*>(rsm + rd * 32), uv);
-              load_vec<__nv_bfloat16>(reinterpret_cast<const __nv_bfloat16*>(rsm + rd * 32 + 16), uv + 8);
-            } else {
-              load_vec<__nv_bfloat16>(urow + c, uv);
-              load_vec<__nv_bfloat16>(urow + c + 8, uv + 8);
-            }
-#pragma unroll
-            for (int j = 0; j < 16; j += 2) ffma2(v[j], v[j + 1], uv[j], uv[j + 1], pre, pre, v[j], v[j + 1]);
-          }
-          if (p.act) {
-#pragma unroll
-            for (int j = 0; j < 16; j += 2) silu2_from_half(v[j], v[j + 1]);
-          }
-          if (rrow) {
-            float rv[16];
-            if (p.res_slot) {
-              load_vec<__nv_bfloat16>(reinterpret_cast<const __nv_bfloat16*>(rsm + rd * 32), rv);
-              load_vec<__nv_bfloat16>(reinterpret_cast<const __nv_bfloat16*>(rsm + rd * 32 + 16), rv + 8);
-            } else {
-              load_vec<__nv_bfloat16>(rrow + c, rv);
-              load_vec<__nv_bfloat16>(rrow + c + 8, rv + 8);
-            }
-#pragma unroll
-            for (int j = 0; j < 16; j += 2) fadd2(v[j], v[j + 1], v[j], v[j + 1], rv[j], rv[j + 1]);
-          }
-          if (nrow) {
-            float* np = nrow + (long long)c * p.hw_real;
-#pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (n0 + c + j < p.nC) np[(long long)j * p.hw_real] = v[j];
-          }
-          if (drow) {
-            store_vec<__nv_bfloat16>(drow + c, v);
-            store_vec<__nv_bfloat16>(drow + c + 8, v + 8);
-          }
-        }
-      }
-      if (++as == 2) { as = 0; aphase ^= 1u; }
-      rs ^= 1u;
-    }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-#ifdef LY_TC_PROFILE
-    if (blockIdx.x == 0 && lane == 0 && (warp == 2 || warp == 6))
-      printf("[tc prof] epilogue warp %d: total %lld wait_tfull %lld\n", warp, clock64() - estart, w_tfull);
-#endif
+    const int add = p.res ? (p.res_slot ? 1 : 3) : (p.up ? (p.res_slot ? 2 : 4) : 0);
+    const int map = p.halo == 2 ? 2 : ((p.k == 1 && p.stride == 1) ? 0 : 1);
+#define LY_EPI(M, A, N) epilogue_role<M, A, N>(p, smem_raw, bar_base, tmem_base, s_bias)
+#define LY_EPI_MAP(M)                                           \
+  if (p.nchw) LY_EPI(M, 0, true);                               \
+  else if (add == 0) LY_EPI(M, 0, false);                       \
+  else if (add == 1) LY_EPI(M, 1, false);                       \
+  else if (add == 2) LY_EPI(M, 2, false);                       \
+  else if (add == 3) LY_EPI(M, 3, false);                       \
+  else LY_EPI(M, 4, false);
+    if (map == 0) { LY_EPI_MAP(0) } else if (map == 1) { LY_EPI_MAP(1) } else { LY_EPI_MAP(2) }
+#undef LY_EPI_MAP
+#undef LY_EPI
   }
 
   tc_fence_before();
@@ -495,6 +647,7 @@ bool conv_tc_supported(const ly_op& op) {
 int32_t conv_tc_prepare(const ly_op& op, ConvTcState** out) {
   LY_CHECK_ARG(conv_tc_supported(op), "conv_tc: unsupported op (bf16, k in {1,3}, stride in {1,2}, 16-channel granularity)");
   LY_CHECK_ARG(op.src.ptr && op.w && op.bias && (op.dst.ptr || op.nchw), "conv_tc: null pointer");
+  LY_CHECK_ARG(!(op.nchw && (op.dst.ptr || op.res.ptr || op.up.ptr)), "conv_tc: an NCHW output takes no NHWC destination, shortcut or addend");
   LY_CHECK_ARG(op.src.H % op.stride == 0 && op.src.W % op.stride == 0, "conv_tc: H,W must divide by the stride");
   LY_CHECK_ARG((op.dst.ptr ? op.dst.c : op.nchw_c) <= kMaxCout, "conv_tc: Cout > %d not supported", kMaxCout);
   EncodeTiledFn encode = get_encode();
@@ -527,7 +680,7 @@ int32_t conv_tc_prepare(const ly_op& op, ConvTcState** out) {
   if (flat) { dimW = op.B * Ho * Wo; dimH = 1; dimB = 1; } else { dimW = Wo; dimH = Ho; dimB = op.B; }
   int best_tw = 128, best_th = 1, best_tb = 1;
   double best_cover = 1e30;
-  {
+  if (!flat) {   // flat: 128 consecutive pixels per tile (the epilogue's MAP = 0 assumes it)
     double best_cost = 1e30;
     for (int tw = 128; tw >= 1; tw >>= 1)
       for (int th = 128 / tw; th >= 1; th >>= 1) {
@@ -556,7 +709,44 @@ int32_t conv_tc_prepare(const ly_op& op, ConvTcState** out) {
   p.tiles_w = (dimW + p.tw - 1) / p.tw;
   p.tiles_h = (dimH + p.th - 1) / p.th;
   p.tiles_b = (dimB + p.tb - 1) / p.tb;
-  const long long total = (long long)p.tiles_w * p.tiles_h * p.tiles_b * p.tiles_n;
+  long long total = (long long)p.tiles_w * p.tiles_h * p.tiles_b * p.tiles_n;
+
+  // ---- band mode (3x3 stride 1): pick the band height R by a cycle model of one CTA:
+  //   MMA issue  : (32 + N/4) cycles per M=128,K=16 instruction (shared-memory operand reads; N = 256: 128)
+  //   TMA        : ~5 cycles per box row (measured request rate on 64/128-byte rows)
+  // and compare with the brick/halo tiling chosen above under the same model.
+  static const int band_ok = env_int("LY_TC_BAND", 1);   // 0 off, 1 by the model, 2 whenever it fits
+  const long long b_all_bytes = (long long)p.num_kb * ((bn * p.kc * 2 + 1023) / 1024 * 1024);
+  const bool b_res_possible = env_int("LY_TC_B_RESIDENT", 1) && p.tiles_n == 1 && b_all_bytes <= 96 * 1024;
+  if (band_ok && op.k == 3 && op.stride == 1 && Wo + 2 <= 256 && 2 * p.kc_blocks <= kMaxStages) {
+    const int sms = sm_count();
+    const double cyc_mma = (bn <= 128 ? 32.0 + bn / 4.0 : bn / 2.0) * (p.kc / 16);     // per k-block per M tile
+    const double tma_row = 5.0;
+    auto waves = [&](long long units) { return (double)((units + sms - 1) / sms); };
+    const double cost_now = waves(total) * (p.halo ? (double)std::max(p.num_kb * cyc_mma, 3.0 * p.kc_blocks * (p.tw * (p.th + 2)) * tma_row)
+                                                   : (double)std::max(p.num_kb * cyc_mma, 9.0 * p.kc_blocks * 128 * tma_row));
+    const int BW = Wo + 2;
+    const long long fixed = 8 * (4 * kMaxStages + 8) + 1024 + (op.res.ptr && bn <= 128 ? 2LL * 32 * kEpiWarps * (((bn / 16 + 3) / 4) * 32) : 0);
+    const long long b_bytes = b_res_possible ? b_all_bytes : 3LL * ((bn * p.kc * 2 + 1023) / 1024 * 1024);
+    int best_r = 0; double best_cost = 1e30;
+    for (int R = 1; R <= Ho && R + 2 <= 256; ++R) {
+      const long long stage = ((long long)(R + 2) * BW * p.kc * 2 + 1023) / 1024 * 1024;
+      if (fixed + b_bytes + 2LL * p.kc_blocks * stage > (long long)kSmemBudget) break;
+      const int mt = ((R - 1) * BW + Wo + 127) / 128;
+      const long long units = (long long)((Ho + R - 1) / R) * op.B;
+      const double unit_cost = std::max((double)p.tiles_n * mt * p.num_kb * cyc_mma, (double)p.kc_blocks * (R + 2) * BW * tma_row);
+      const double cost = waves(units) * unit_cost;
+      if (cost < best_cost) { best_cost = cost; best_r = R; }
+    }
+    if (best_r && (band_ok == 2 || best_cost < cost_now)) {
+      p.halo = 2;
+      p.band_r = best_r; p.band_w = BW;
+      p.band_mt = ((best_r - 1) * BW + Wo + 127) / 128;
+      p.bands = (Ho + best_r - 1) / best_r;
+      p.tw = 128; p.th = 1; p.tb = 1;
+      total = (long long)p.bands * op.B;
+    }
+  }
   if (total > 0x7FFFFFFF) { delete st; set_error("conv_tc: too many tiles"); return LY_E_ARG; }
   p.total_tiles = (int)total;
   {
@@ -567,12 +757,18 @@ int32_t conv_tc_prepare(const ly_op& op, ConvTcState** out) {
     if (tmax * p.tiles_n >= lim || tmax * p.tiles_w >= lim || tmax * p.tiles_h >= lim || (unsigned long long)dimW * dimH * dimB >= lim) {
       delete st; set_error("conv_tc: problem too large for 32-bit tile arithmetic"); return LY_E_ARG;
     }
+    if (p.halo == 2) {
+      // (a divisor of 1 cannot use the 0 encoding here: the kernel always multiplies)
+      p.mg_bw = (uint32_t)((1ull << 32) / (uint32_t)p.band_w + 1);
+      p.mg_bands = p.bands > 1 ? (uint32_t)((1ull << 32) / (uint32_t)p.bands + 1) : 0u;
+      if (tmax * p.bands >= lim) { delete st; set_error("conv_tc: problem too large for 32-bit tile arithmetic"); return LY_E_ARG; }
+    }
   }
-  p.tpa = p.halo ? 3 : 1;
+  p.tpa = p.halo == 1 ? 3 : 1;
   p.num_ka = p.num_kb / p.tpa;
   // halo box: 8 output columns x all the input rows the 16 output rows touch (18 at stride 1, 33 at stride 2)
   const int halo_rows = (p.th - 1) * op.stride + 3;
-  const int a_rows = p.halo ? p.tw * halo_rows : 128;
+  const int a_rows = p.halo == 2 ? (p.band_r + 2) * p.band_w : (p.halo ? p.tw * halo_rows : 128);
   p.a_tap_stride = p.tw * p.kc * 2;        // one brick row down (tw = 8: one swizzle atom)
 
   // shared-memory pipeline
@@ -589,7 +785,12 @@ int32_t conv_tc_prepare(const ly_op& op, ConvTcState** out) {
   p.res_slot = (((op.res.ptr != nullptr) != (op.up.ptr != nullptr)) && res_prefetch_ok && bn <= 128) ? ((bn / 16 + 3) / 4) * 32 : 0;   // one 32-byte chunk per round
   const long long res_bytes = 2LL * 32 * kEpiWarps * p.res_slot;
   const long long avail = (long long)kSmemBudget - bar_bytes - 1024 - res_bytes - (p.b_resident ? b_all : 0);
-  if (p.b_resident) {
+  if (p.halo == 2) {
+    // a band keeps kc_blocks stages for all of its tiles; the next band is prefetched meanwhile
+    p.a_stages = p.b_resident ? (int)(avail / p.a_stage) : 2 * p.kc_blocks;
+    p.b_stages = p.b_resident ? 1 : (int)((avail - (long long)p.a_stages * p.a_stage) / p.b_stage);
+    if (p.a_stages < 2 * p.kc_blocks) { delete st; set_error("conv_tc: band does not fit in shared memory"); return LY_E_ARG; }
+  } else if (p.b_resident) {
     p.a_stages = (int)(avail / p.a_stage);
     p.b_stages = 1;
   } else {
@@ -634,6 +835,7 @@ int32_t conv_tc_prepare(const ly_op& op, ConvTcState** out) {
     const CUtensorMapL2promotion a_promo = p.kc == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
                                           : (p.kc == 32 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : CU_TENSOR_MAP_L2_PROMOTION_NONE);
     box[0] = p.kc; box[1] = p.tw * op.stride; box[2] = (p.halo ? halo_rows : p.th * op.stride); box[3] = p.tb;
+    if (p.halo == 2) { box[1] = p.band_w; box[2] = p.band_r + 2; box[3] = 1; }
     estr[0] = 1; estr[1] = op.stride; estr[2] = p.halo ? 1 : op.stride; estr[3] = 1;   // halo: every input row is loaded
     CUresult r = encode(&p.tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         tswz, a_promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -657,6 +859,11 @@ int32_t conv_tc_prepare(const ly_op& op, ConvTcState** out) {
 
   const int sms = sm_count();
   st->grid = p.total_tiles < sms ? p.total_tiles : sms;
+  static const int debug = env_int("LY_TC_DEBUG", 0);
+  if (debug)
+    fprintf(stderr, "[conv_tc] k%d s%d %dx%d cin %d cout %d B %d: mode %d bn %d tiles_n %d kc %d a_stages %d (%d B) b_res %d b_stages %d res_slot %d "
+            "band R %d mt %d bands %d units %d smem %zu\n", op.k, op.stride, op.src.H, op.src.W, Cin, Cout, op.B, p.halo, bn, p.tiles_n, p.kc,
+            p.a_stages, p.a_stage, p.b_resident, p.b_stages, p.res_slot, p.band_r, p.band_mt, p.bands, p.total_tiles, st->smem);
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
