@@ -12,6 +12,8 @@
 // Reference semantics: Conv(g=C) + BN (+SiLU) (+shortcut), leanyolo/models/yolov10/layers.py
 // :51-88, 274-300, 455; RepVGGDW arrives here already merged into one 7x7 (modules.py).
 #include <string.h>
+#include <stdlib.h>
+#include <algorithm>
 #include "common.cuh"
 #include "tma.cuh"
 
@@ -472,6 +474,235 @@ int32_t launch_strip(const ly_op& op, cudaStream_t st) {
   return post_launch("dwconv_tma");
 }
 
+
+// ---------------------------------------------------------------------------------------
+// 7x7 stride 1 (the merged RepVGGDW of the large-kernel CIB blocks): 49 taps per output make
+// this the one FMA-bound depthwise conv.  (ncu on the generic kernel above: 40 % of the stall
+// samples on global weight loads inside the tap loop, every input row re-read from shared
+// memory once per (ky, oy) pair, issue slots 60 % busy at 31 % FMA-pipe utilisation.)  Here
+//  * a CTA keeps ONE 64-channel block for its whole life, so a lane's 49 x 2 weights and its
+//    bias stay in registers;
+//  * the loop runs over INPUT rows: a row of the halo patch is loaded and unpacked once and
+//    feeds every output row it touches;
+//  * all arithmetic is packed FFMA2 on the lane's two channels.
+// ---------------------------------------------------------------------------------------
+constexpr int kDw7Warps = 10;
+
+struct Dw7Params {
+  CUtensorMap tmIn;
+  int npx, npy, tw, th, iwt, iht;
+  int tiles_x, tiles_y, tiles_c, tiles_per_cb, ctas_per_cb;
+  int Ho, Wo, C;
+  int stages, stage_bytes, box_bytes;
+  int act;
+  const __nv_bfloat16* w;
+  const float* bias;
+  __nv_bfloat16* dst; int dCtot, dC0;
+  const __nv_bfloat16* res; int rCtot, rC0;
+};
+
+__device__ __forceinline__ void ffma2_f2(float2& d, const float2& a, const float2& b) {
+  asm("{\n\t.reg .b64 ra, rb, rc;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%0, %1};\n\t"
+      "fma.rn.f32x2 rc, ra, rb, rc;\n\tmov.b64 {%0, %1}, rc;\n\t}"
+      : "+f"(d.x), "+f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+}
+
+template <int PH>
+__global__ void __launch_bounds__(32 * (kDw7Warps + 1)) dw7_kernel(const __grid_constant__ Dw7Params p) {
+  constexpr int K = 7, IPX = 4 + K - 1, IPY = PH + K - 1;       // halo patch of a 4 x PH output patch
+  constexpr int kWBytes = 0;                                   // (weights live in registers)
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  __shared__ __align__(8) unsigned long long bars[2 * kMaxStagesDw];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 127u) & ~127u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t stage0 = smem_base + kWBytes;
+  const uint32_t bar0 = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (kMaxStagesDw + s); };
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ncw = p.npx * p.npy;                    // compute warps; warp ncw is the TMA producer
+  const int cb = blockIdx.x % p.tiles_c, cta = blockIdx.x / p.tiles_c;
+  if (threadIdx.x == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmIn) : "memory");
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), ncw);
+    }
+    fence_barrier_init();
+  }
+  pdl_trigger();
+  // weights are parameters: fetched before waiting on the previous kernel.  The lane's 49 taps stay
+  // in registers as packed bf16 pairs and are unpacked at the point of use (2 ALU ops next to 4..8
+  // FFMA2): fp32 pairs in shared memory cost one LDS.64 per tap and output row, and made the
+  // kernel shared-memory-bandwidth bound (measured 0.24 ms vs 0.30 for the generic kernel).
+  uint32_t wreg[K * K];
+  {
+    const uint32_t* wg = reinterpret_cast<const uint32_t*>(p.w + cb * 64 + 2 * lane);
+#pragma unroll
+    for (int t = 0; t < K * K; ++t) wreg[t] = __ldg(wg + (size_t)t * (p.C >> 1));
+  }
+  pdl_wait();
+  __syncthreads();
+
+  auto split = [&](int t, int& xt, int& yt, int& b) {
+    xt = t % p.tiles_x; t /= p.tiles_x;
+    yt = t % p.tiles_y;
+    b = t / p.tiles_y;
+  };
+
+  if (warp == ncw) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = cta; t < p.tiles_per_cb; t += p.ctas_per_cb) {
+        int xt, yt, b;
+        split(t, xt, yt, b);
+        mbar_wait(empty_bar(stage), phase ^ 1u);
+        mbar_expect_tx(full_bar(stage), (uint32_t)p.box_bytes);
+        tma_load_4d(stage0 + stage * p.stage_bytes, &p.tmIn, full_bar(stage), cb * 64, xt * p.tw - K / 2, yt * p.th - K / 2, b);
+        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+      }
+    }
+    return;
+  }
+  if (warp > ncw) return;
+
+  const int pyi = warp / p.npx, pxi = warp - pyi * p.npx;
+  const int c = cb * 64 + 2 * lane;
+  const float2 bias2 = __ldg(reinterpret_cast<const float2*>(p.bias + c));
+  int stage = 0;
+  uint32_t phase = 0;
+  for (int t = cta; t < p.tiles_per_cb; t += p.ctas_per_cb) {
+    int xt, yt, b;
+    split(t, xt, yt, b);
+    float2 acc[PH][4];
+#pragma unroll
+    for (int y = 0; y < PH; ++y)
+#pragma unroll
+      for (int x = 0; x < 4; ++x) acc[y][x] = bias2;
+    mbar_wait(full_bar(stage), phase);
+    // halo pixel (X, Y) of the raw tile sits at ((Y * iwt + X) * 64 + channel) * 2 bytes
+    const uint8_t* rt = smem_gen + kWBytes + (size_t)stage * p.stage_bytes + ((size_t)((PH * pyi) * p.iwt + 4 * pxi) * 64 + 2 * lane) * 2;
+#pragma unroll
+    for (int iy = 0; iy < IPY; ++iy) {
+      float2 in[IPX];
+#pragma unroll
+      for (int ix = 0; ix < IPX; ++ix) in[ix] = bf2_to_f2(*reinterpret_cast<const uint32_t*>(rt + (size_t)(iy * p.iwt + ix) * 128));
+#pragma unroll
+      for (int oy = 0; oy < PH; ++oy) {
+        const int ky = iy - oy;
+        if (ky >= 0 && ky < K) {
+#pragma unroll
+          for (int kx = 0; kx < K; ++kx) {
+            const float2 w2 = bf2_to_f2(wreg[ky * K + kx]);
+#pragma unroll
+            for (int ox = 0; ox < 4; ++ox) ffma2_f2(acc[oy][ox], in[ox + kx], w2);
+          }
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty_bar(stage));   // this warp is done reading the stage
+    if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+
+    // stores: one 64-bit base per patch, 32-bit offsets per pixel (the per-pixel 64-bit index
+    // arithmetic of the generic kernel was 30 % of this kernel's instructions)
+    const int oy0 = yt * p.th + PH * pyi, ox0 = xt * p.tw + 4 * pxi;
+    const size_t opix0 = ((size_t)b * p.Ho + oy0) * p.Wo + ox0;
+    __nv_bfloat16* dbase = p.dst + opix0 * p.dCtot + p.dC0 + c;
+    const __nv_bfloat16* rbase = p.res ? p.res + opix0 * p.rCtot + p.rC0 + c : nullptr;
+    const bool act = p.act != 0;
+#pragma unroll
+    for (int y = 0; y < PH; ++y) {
+      if (oy0 + y >= p.Ho) continue;
+#pragma unroll
+      for (int x = 0; x < 4; ++x) {
+        if (ox0 + x >= p.Wo) continue;
+        const int rel = y * p.Wo + x;
+        float v0 = acc[y][x].x, v1 = acc[y][x].y;
+        if (act) { v0 = silu_tanh(v0); v1 = silu_tanh(v1); }
+        if (rbase) {
+          const float2 r2 = bf2_to_f2(*reinterpret_cast<const uint32_t*>(rbase + rel * p.rCtot));
+          v0 += r2.x; v1 += r2.y;
+        }
+        *reinterpret_cast<__nv_bfloat162*>(dbase + rel * p.dCtot) = __floats2bfloat162_rn(v0, v1);
+      }
+    }
+  }
+}
+
+template <int PH>
+int32_t launch_dw7(const ly_op& op, cudaStream_t st) {
+  constexpr int K = 7;
+  EncodeTiledFn encode = get_encode();
+  if (!encode) { set_error("dw_tma: cuTensorMapEncodeTiled entry point not available"); return LY_E_CUDA; }
+  Dw7Params p;
+  memset(&p, 0, sizeof(p));
+  p.Ho = op.dst.H; p.Wo = op.dst.W; p.C = op.src.c;
+  {
+    long long best_key = -1;
+    for (int npx = 1; npx <= kDw7Warps; ++npx)
+      for (int npy = 1; npx * npy <= kDw7Warps; ++npy) {
+        const int tw = 4 * npx, th = PH * npy;
+        const long long box = (long long)(tw + K - 1) * (th + K - 1) * 128;
+        if (box > 40 * 1024 || tw + K - 1 > 256 || th + K - 1 > 256) continue;
+        const long long tiles = (long long)((p.Wo + tw - 1) / tw) * ((p.Ho + th - 1) / th);
+        const long long key = tiles * npx * npy * 1000000LL + tiles * 1000 + box / 1024;   // fewest warp-patches, then fewest tiles
+        if (best_key < 0 || key < best_key) { best_key = key; p.npx = npx; p.npy = npy; }
+      }
+    LY_CHECK_ARG(best_key >= 0, "dw7: no tile configuration fits");
+  }
+  p.tw = 4 * p.npx; p.th = PH * p.npy;
+  p.iwt = p.tw + K - 1; p.iht = p.th + K - 1;
+  p.tiles_x = (p.Wo + p.tw - 1) / p.tw;
+  p.tiles_y = (p.Ho + p.th - 1) / p.th;
+  p.tiles_c = p.C / 64;
+  const long long per_cb = (long long)p.tiles_x * p.tiles_y * op.B;
+  LY_CHECK_ARG(per_cb <= 0x7FFFFFFF, "dw7: too many tiles");
+  p.tiles_per_cb = (int)per_cb;
+  p.box_bytes = p.iwt * p.iht * 128;
+  p.stage_bytes = (p.box_bytes + 127) / 128 * 128;
+  // registers (the 49 packed taps + the accumulators) allow 65536 / (threads * ~170) CTAs per SM; the
+  // ring takes what shared memory is left: the loads of a 33 KB halo box take about as long as its
+  // 49-tap compute, so two stages starve (measured: 22 % of the samples in the barrier wait)
+  const int threads = 32 * (p.npx * p.npy + 1);
+  const int ctas_per_sm = std::max(1, std::min(3, 65536 / (threads * 176)));
+  static const int stages_env = getenv("LY_DW7_STAGES") ? atoi(getenv("LY_DW7_STAGES")) : 0;
+  p.stages = stages_env ? stages_env : (int)std::min<long long>(kMaxStagesDw, (200LL * 1024 / ctas_per_sm - 256) / p.stage_bytes);
+  LY_CHECK_ARG(p.stages >= 2, "dw7: tile does not fit in shared memory");
+  const size_t smem = (size_t)p.stages * p.stage_bytes + 128;
+  p.act = op.act;
+  p.w = (const __nv_bfloat16*)op.w; p.bias = op.bias;
+  p.dst = (__nv_bfloat16*)op.dst.ptr; p.dCtot = op.dst.ctot; p.dC0 = op.dst.c0;
+  p.res = (const __nv_bfloat16*)op.res.ptr; p.rCtot = op.res.ctot; p.rC0 = op.res.c0;
+  {
+    char* base = (char*)op.src.ptr + (size_t)op.src.c0 * 2;
+    cuuint64_t dims[4] = {(cuuint64_t)op.src.c, (cuuint64_t)op.src.W, (cuuint64_t)op.src.H, (cuuint64_t)op.B};
+    cuuint64_t strides[3] = {(cuuint64_t)op.src.ctot * 2, (cuuint64_t)op.src.ctot * 2 * op.src.W,
+                             (cuuint64_t)op.src.ctot * 2 * op.src.W * op.src.H};
+    cuuint32_t box[4] = {64, (cuuint32_t)p.iwt, (cuuint32_t)p.iht, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = encode(&p.tmIn, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("dw7: cuTensorMapEncodeTiled failed with %d", (int)r); return LY_E_CUDA; }
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    LY_CUDA(cudaFuncSetAttribute(dw7_kernel<PH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  // every CTA owns one channel block: the grid is a multiple of the channel-block count
+  const int sms = sm_count();
+  long long per = (long long)ctas_per_sm * sms / p.tiles_c;
+  if (per < 1) per = 1;
+  if (per > per_cb) per = per_cb;
+  p.ctas_per_cb = (int)per;
+  launch_k(dw7_kernel<PH>, dim3((unsigned)(per * p.tiles_c)), dim3(32 * (p.npx * p.npy + 1)), smem, st, p);
+  return post_launch("dwconv7");
+}
+
 // waste of covering an Ho x Wo map with TW x TH tiles (1.0 = none)
 double cover(int Ho, int Wo, int tw, int th) {
   return (double)((Wo + tw - 1) / tw * tw) * ((Ho + th - 1) / th * th) / ((double)Ho * Wo);
@@ -494,6 +725,9 @@ int32_t launch_dw_tma(const ly_op& op, cudaStream_t s) {
     return wide ? launch_strip<3, 1, 8, 20, 4>(op, s) : launch_strip<3, 1, 8, 16, 8>(op, s);
   }
   if (op.k == 3 && op.stride == 2) return launch_cfg<3, 2>(op, s);
+  static const int dw7_mode = getenv("LY_DW7") ? atoi(getenv("LY_DW7")) : 2;   // 0: generic patch kernel, 2 / 4: dw7_kernel with 4x2 / 4x4 patches
+  if (dw7_mode == 2) return launch_dw7<2>(op, s);
+  if (dw7_mode == 4) return launch_dw7<4>(op, s);
   return launch_cfg<7, 1>(op, s);
 }
 
