@@ -101,12 +101,17 @@ def main():
     ap.add_argument("--sub-batch", type=int, default=int(os.environ.get("LEANYOLO_SUB_BATCH", "0")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-out", default=None, help="write the per-op CUDA-event table (JSON) here")
+    ap.add_argument("--decode", default="topk", choices=["topk", "nms"],
+                    help="topk: decode_forward (headline); nms: decode_v10_predictions on the one2many branch (config 3)")
+    ap.add_argument("--conf", type=float, default=0.001)
+    ap.add_argument("--iou", type=float, default=0.7)
     a = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    workload = f"{a.model} {a.imgsz}x{a.imgsz} batch {a.batch}/GPU bf16 top-k decode"
+    dec_name = "top-k decode" if a.decode == "topk" else f"NMS decode (conf {a.conf}, iou {a.iou}, max-dets 300)"
+    workload = f"{a.model} {a.imgsz}x{a.imgsz} batch {a.batch}/GPU bf16 {dec_name}"
     cores = os.cpu_count() or 1
 
     if a.impl == "reference":
@@ -151,8 +156,14 @@ def main():
     x = x_u8.float()                      # resident fp32 NCHW input, 0..255 (the reference's input contract)
     gathered = [torch.empty((B, 300, 6), device=dev) for _ in range(world)] if world > 1 else None
 
+    from leanyolo_b200 import postprocess as PP
+    from leanyolo_b200.variants import STRIDES
+
     def step(inp):
-        det = model.detect(inp)           # forward (both head branches) + GPU top-k decode -> [B,300,6]
+        if a.decode == "topk":
+            det = model.detect(inp)       # forward (both head branches) + GPU top-k decode -> [B,300,6]
+        else:                             # forward + conf filter + greedy NMS on the one2many branch -> [B,300,6] zero padded
+            det, _, _ = PP.nms_raw(model(inp), num_classes=len(names), strides=STRIDES, conf_thresh=a.conf, iou_thresh=a.iou, max_det=300)
         if world > 1:
             dist.all_gather(gathered, det)   # the only collective: per-image detections (latency-bound)
         return det
@@ -260,8 +271,6 @@ def main():
         d["gbs"] = round(d["bytes"] / (d["ms"] / 1e3) / 1e9, 1) if d["ms"] > 0 else 0.0
         d["ms"] = round(d["ms"], 3)
     # decode tail (DFL + two-stage top-k) timed alone on the cached one2one branch
-    from leanyolo_b200 import postprocess as PP
-    from leanyolo_b200.variants import STRIDES
     branch = model._eval_branches["one2one"]
     for _ in range(2):
         PP.topk_raw(branch, num_classes=len(names), strides=STRIDES, max_det=300)

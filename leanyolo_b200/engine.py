@@ -35,6 +35,7 @@ class Compiled:
     handle: C.c_void_p
     out_keys: List[Tuple[str, int]]
     n_launches: int
+    in_keys: List[Tuple[str, int]] = None
 
 
 class Engine:
@@ -70,8 +71,11 @@ class Engine:
         else:
             assert self._w.numel() == w.numel() and self._b.numel() == b.numel(), "parameter packing is shape dependent"
         ws = torch.empty(max(pb.ws_bytes, 1024), dtype=torch.uint8, device=self.device)
+        # external pointer table of a run: [image | named NCHW inputs ... | NCHW outputs ...]
+        in_keys = list(pb.inputs.keys())
         out_keys = sorted(pb.outputs.keys())
-        slots = {k: i + 1 for i, k in enumerate(out_keys)}
+        in_slots = {k: i + 1 for i, k in enumerate(in_keys)}
+        slots = {k: i + 1 + len(in_keys) for i, k in enumerate(out_keys)}
         arr = (N.LyOp * len(pb.ops))()
         base, wbase, bbase = ws.data_ptr(), self._w.data_ptr(), self._b.data_ptr()
         esz = pb.esize
@@ -101,20 +105,24 @@ class Engine:
             if op.nchw is not None:
                 name, level, c0, c, ctot = op.nchw
                 o.nchw_ctot, o.nchw_c0, o.nchw_c = ctot, c0, c
-                o.ext_slot = slots[(name, level)]
+                o.ext_slot = in_slots[(name, level)] if op.kind == "import" else slots[(name, level)]
         handle = C.c_void_p()
         with torch.cuda.device(self.device):
             N.check(self.lib.ly_plan_create(arr, len(pb.ops), C.byref(handle)), "ly_plan_create")
-        comp = Compiled(pb, B, ws, handle, out_keys, len(pb.ops))
+        comp = Compiled(pb, B, ws, handle, out_keys, len(pb.ops), in_keys)
         self._plans[key] = comp
         return comp
 
     # ------------------------------------------------------------------ run
-    def _launch(self, comp: Compiled, x: torch.Tensor, outs: Dict[Tuple[str, int], torch.Tensor], img0: int) -> None:
-        ext = (C.c_void_p * (1 + len(comp.out_keys)))()
-        ext[0] = x.data_ptr()
+    def _launch(self, comp: Compiled, x: Optional[torch.Tensor], outs: Dict[Tuple[str, int], torch.Tensor], img0: int,
+                ins: Optional[Dict[Tuple[str, int], torch.Tensor]] = None) -> None:
+        n_in = len(comp.in_keys)
+        ext = (C.c_void_p * (1 + n_in + len(comp.out_keys)))()
+        ext[0] = x.data_ptr() if x is not None else None
+        for i, k in enumerate(comp.in_keys):
+            ext[i + 1] = ins[k].data_ptr()
         for i, k in enumerate(comp.out_keys):
-            ext[i + 1] = outs[k].data_ptr()
+            ext[i + 1 + n_in] = outs[k].data_ptr()
         stream = torch.cuda.current_stream(self.device).cuda_stream
         N.check(self.lib.ly_plan_run(comp.handle, ext, len(ext), img0, C.c_void_p(stream)), "ly_plan_run")
 
@@ -136,6 +144,19 @@ class Engine:
             for img0 in range(0, B, sub):
                 n = min(sub, B - img0)
                 self._launch(self.compile(n, H, W, u8), x, outs, img0)
+        return outs
+
+    def run_named(self, ins: Dict[Tuple[str, int], torch.Tensor], H: int, W: int,
+                  x: Optional[torch.Tensor] = None) -> Dict[Tuple[str, int], torch.Tensor]:
+        """Sub-module plans: inputs are named NCHW fp32 feature maps (and/or the image ``x``); H, W = image size."""
+        ts = list(ins.values()) + ([x] if x is not None else [])
+        B = ts[0].shape[0]
+        for t in ins.values():
+            assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.shape[0] == B
+        with torch.cuda.device(self.device):
+            comp = self.compile(B, H, W, False)
+            outs = {k: torch.empty((B, c, h, w), dtype=torch.float32, device=self.device) for k, (c, h, w) in comp.pb.outputs.items()}
+            self._launch(comp, x, outs, 0, ins)
         return outs
 
     def profile(self, x: torch.Tensor, sub_batch: Optional[int] = None):

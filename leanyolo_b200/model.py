@@ -15,6 +15,7 @@ Extras that do not change the reference surface:
 from __future__ import annotations
 
 import os
+import weakref
 from typing import Dict, List, Optional, Sequence
 
 import torch
@@ -47,6 +48,10 @@ class YOLOv10(nn.Module):
         self.sub_batch: Optional[int] = int(sb) if sb else None
         self._engines: Dict[tuple, Engine] = {}
         self._eval_branches: Dict[str, List[torch.Tensor]] = {}
+        # the sub-modules are callable like the reference's (model.backbone(x), model.neck(c3, c4, c5),
+        # model.head(feats), head.forward_feat(feats, cv2, cv3)): they run their slice of the plan through this model
+        for m in (self.backbone, self.neck, self.head):
+            object.__setattr__(m, "_root", weakref.ref(self))
 
     # ---- class tables kept for callers that introspect them (yolov10s.py:62-65)
     @property
@@ -77,6 +82,46 @@ class YOLOv10(nn.Module):
                                ("p4", p4, nk.out_c[1]), ("p5", p5, nk.out_c[2])):
                 pb.export_nchw(v, name, c)
         hd.emit(pb, (p3, p4, p5))
+
+    # ------------------------------------------------------------------ sub-module plans
+    def _emit_part(self, pb, part: str) -> None:
+        bb, nk, hd = self.backbone, self.neck, self.head
+        c3w, c4w, c5w, h13, h16, h19, _ = nk.widths
+        h8, w8 = pb.H // 8, pb.W // 8
+        if part == "backbone":
+            # the reference's backbone takes the already-normalised image (yolov10s.py:107-114)
+            w0, b0 = bb.cv0.folded()
+            x = pb.stem(w0, b0, [0.0, 0.0, 0.0], [1.0, 1.0, 1.0])
+            for name, v, c in zip(("c3", "c4", "c5"), bb.emit(pb, x), bb.out_c):
+                pb.export_nchw(v, name, c)
+        elif part == "neck":
+            cats = nk.concat_buffers(pb, h8, w8)
+            pb.import_nchw("c3", c3w, h8, w8, cats["cat_p3"].view(h13, c3w))
+            pb.import_nchw("c4", c4w, h8 // 2, w8 // 2, cats["cat_p4"].view(c5w, c4w))
+            pb.import_nchw("c5", c5w, h8 // 4, w8 // 4, cats["cat_n5"].view(h19, c5w))
+            for name, v, c in zip(("p3", "p4", "p5"), nk.emit(pb, cats), nk.out_c):
+                pb.export_nchw(v, name, c)
+        elif part == "head":
+            feats = [pb.import_nchw(f"p{3 + i}", c, h8 >> i, w8 >> i) for i, c in enumerate(nk.out_c)]
+            hd.emit(pb, feats)
+        else:
+            raise ValueError(part)
+
+    def _run_part(self, part: str, ins: Dict[str, torch.Tensor], hw, x: Optional[torch.Tensor] = None):
+        if self.training:
+            raise NotImplementedError("leanyolo_b200 is inference-only: call model.eval() first")
+        dev = self.input_subtract.device
+        ts = list(ins.values()) + ([x] if x is not None else [])
+        if dev.type != "cuda" or any(not t.is_cuda for t in ts):
+            raise RuntimeError("leanyolo_b200 runs on CUDA (sm_100a) only: move the model and the inputs to the GPU; "
+                               "there is no CPU fallback")
+        prec = "f32" if self.precision in ("fp32", "f32", "float32") else "bf16"
+        key = (str(dev), prec, "part:" + part)
+        if key not in self._engines:
+            self._engines[key] = Engine(lambda pb: self._emit_part(pb, part), dev, prec)
+        named = {(k, 0): v.detach().to(torch.float32).contiguous() for k, v in ins.items()}
+        xin = x.detach().to(torch.float32).contiguous() if x is not None else None
+        return self._engines[key].run_named(named, hw[0], hw[1], xin)
 
     def invalidate(self) -> None:
         """Drop packed weights / plans (call after mutating parameters in place)."""

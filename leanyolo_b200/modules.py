@@ -223,6 +223,14 @@ class Backbone(nn.Module):
         self.psa10 = PSA(w[10])
         self.out_c = (w[4], w[6], w[10])
 
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor):
+        """``model.backbone(x)`` (backbone.py:88-106): normalised NCHW image -> (C3, C4, C5) NCHW fp32."""
+        if x.dim() != 4 or x.shape[1] != 3 or x.shape[2] % 32 or x.shape[3] % 32:
+            raise ValueError("expected input [B,3,H,W] with H and W multiples of 32")
+        out = self._root()._run_part("backbone", {}, (x.shape[2], x.shape[3]), x)
+        return out[("c3", 0)], out[("c4", 0)], out[("c5", 0)]
+
     def emit(self, pb, x, c3_dst=None, c4_dst=None, c5_dst=None):
         y = self.cv1.emit(pb, x)
         y = self.cv3.emit(pb, self.c2.emit(pb, y))
@@ -245,6 +253,12 @@ class Neck(nn.Module):
         self.p4_p5_c2f = C2f(h[19] + c5, h[22], r[22], True, cib=True, lk="p4_p5" in v.lk)
         self.widths = (c3, c4, c5, h[13], h[16], h[19], h[22])
         self.out_c = (h[16], h[19], h[22])
+
+    @torch.no_grad()
+    def forward(self, c3: torch.Tensor, c4: torch.Tensor, c5: torch.Tensor):
+        """``model.neck(c3, c4, c5)`` (neck.py:102-129): NCHW fp32 in, (P3, P4, P5) NCHW fp32 out."""
+        out = self._root()._run_part("neck", {"c3": c3, "c4": c4, "c5": c5}, (8 * c3.shape[2], 8 * c3.shape[3]))
+        return out[("p3", 0)], out[("p4", 0)], out[("p5", 0)]
 
     def concat_buffers(self, pb, h8, w8):
         """The four concat inputs of the neck, allocated before the backbone runs so
@@ -307,6 +321,29 @@ class Detect(nn.Module):
         self.one2one_cv2 = copy.deepcopy(self.cv2)
         self.one2one_cv3 = copy.deepcopy(self.cv3)
         self.dfl = DFL(reg_max) if reg_max > 1 else nn.Identity()
+
+    def _run(self, x: Sequence[torch.Tensor]):
+        assert len(x) == self.nl
+        return self._root()._run_part("head", {f"p{3 + i}": t for i, t in enumerate(x)}, (8 * x[0].shape[2], 8 * x[0].shape[3]))
+
+    @torch.no_grad()
+    def forward_feat(self, x: Sequence[torch.Tensor], cv2, cv3) -> List[torch.Tensor]:
+        """head.py:118-122.  ``cv2`` / ``cv3`` select the branch: the module lists of this head (the
+        one-to-many stacks or their one-to-one copies), as the reference's callers pass them."""
+        if cv2 is self.cv2 and cv3 is self.cv3:
+            name = "one2many"
+        elif cv2 is self.one2one_cv2 and cv3 is self.one2one_cv3:
+            name = "one2one"
+        else:
+            raise ValueError("forward_feat: cv2/cv3 must be this head's (cv2, cv3) or (one2one_cv2, one2one_cv3)")
+        out = self._run(x)
+        return [out[(name, i)] for i in range(self.nl)]
+
+    @torch.no_grad()
+    def forward(self, x: Sequence[torch.Tensor]):
+        """Eval: the one2many list (head.py:124-135).  Training is out of scope (raises in the root model)."""
+        out = self._run(x)
+        return [out[("one2many", i)] for i in range(self.nl)]
 
     def emit(self, pb, feats):
         """Both branches (head.py:118-135).  Each writes [reg(4*reg_max) | cls(nc)] logits of every

@@ -97,6 +97,7 @@ class PlanBuilder:
         self._b: List[torch.Tensor] = []
         self._b_len = 0
         self.outputs: Dict[Tuple[str, int], Tuple[int, int, int]] = {}   # (name, level) -> (C, H, W)
+        self.inputs: Dict[Tuple[str, int], Tuple[int, int, int]] = {}    # external NCHW fp32 inputs besides the image
 
     # ---------------------------------------------------------------- buffers
     def buffer(self, H: int, W: int, C: int) -> Buf:
@@ -264,6 +265,16 @@ class PlanBuilder:
         assert qkv.c == 2 * nh * kdp + nh * hd
         dst = self.buffer(qkv.H, qkv.W, nh * hd).view()
         self.ops.append(Op("attn", src=qkv, dst=dst, attn=(nh, kdp, hd, scale), cin=qkv.c, cout=nh * hd))
+        return dst
+
+    def import_nchw(self, name: str, c: int, H: int, W: int, dst: Optional[View] = None) -> View:
+        """Sub-module entry (``model.neck(c3, c4, c5)``, ``model.head(feats)``): a caller's NCHW fp32
+        feature map -> NHWC storage (optionally straight into a concat slice)."""
+        if dst is None:
+            dst = self.buffer(H, W, c).view()
+        assert (dst.H, dst.W) == (H, W) and dst.c == _rup(c, CH_ALIGN)
+        self.inputs[(name, 0)] = (c, H, W)
+        self.ops.append(Op("import", dst=dst, nchw=(name, 0, 0, c, c), cin=c, cout=c))
         return dst
 
     def export_nchw(self, src: View, name: str, c: int) -> None:

@@ -128,3 +128,84 @@ def check_decode_e2e(name="yolov10s"):
     for u, v in zip(a, b):
         assert torch.equal(u, v), "uint8 input path differs from the float path"
     return {}
+
+
+def check_submodules(name="yolov10s", precision="bf16", hw=64, B=2, seed=4):
+    """The reference's component surface (tests/fidelity/test_fidelity_core.py:46-62):
+    model.backbone(x_normalised) -> (c3, c4, c5); model.neck(c3, c4, c5) -> (p3, p4, p5);
+    model.head(feats) -> one2many list; head.forward_feat(feats, cv2, cv3) selects the branch.
+    Each stage is fed the ORACLE's tensors, so the tolerances are per stage."""
+    m, sd = build(name, seed=seed, precision=precision)
+    x = synth_images(B, hw, hw, seed=seed + 10)
+    taps = {}
+    ref = O.forward(sd, x, taps=taps)
+    tol = 1e-4 if precision == "fp32" else 2e-2
+    worst = {}
+    xn = (x / 255.0).to(DEV)
+    c3, c4, c5 = m.backbone(xn)
+    for k, t in zip(("c3", "c4", "c5"), (c3, c4, c5)):
+        assert t.is_contiguous() and t.dtype == torch.float32 and t.shape == taps[k].shape
+        worst[k] = _errs(t, taps[k])
+    p = m.neck(taps["c3"].to(DEV), taps["c4"].to(DEV), taps["c5"].to(DEV))
+    for k, t in zip(("p3", "p4", "p5"), p):
+        worst[k] = _errs(t, taps[k])
+    feats = [taps[k].to(DEV) for k in ("p3", "p4", "p5")]
+    h = m.head(feats)
+    o2o = m.head.forward_feat(feats, m.head.one2one_cv2, m.head.one2one_cv3)
+    o2m = m.head.forward_feat(feats, m.head.cv2, m.head.cv3)
+    for i in range(3):
+        worst[f"head{i}"] = _errs(h[i], ref["one2many"][i])
+        worst[f"o2o{i}"] = _errs(o2o[i], ref["one2one"][i])
+        assert torch.equal(o2m[i], h[i])
+    try:
+        m.head.forward_feat(feats, m.head.cv2, m.head.one2one_cv3)
+        raise AssertionError("mixed branch stacks must be rejected")
+    except ValueError:
+        pass
+    bad = {k: v for k, v in worst.items() if v[0] >= tol or v[1] >= tol}
+    assert not bad, f"{name} {precision} sub-modules over tolerance {tol}: " + ", ".join(f"{k}={v[0]:.2e}/{v[1]:.2e}" for k, v in bad.items())
+    return {"max_relmax": max(v[0] for v in worst.values())}
+
+
+def check_config_nms(name="yolov10m", hw=640, B=2, conf=0.001, iou=0.7, max_det=300, seed=7):
+    """BASELINE config 3 at full resolution: model(x) -> decode_v10_predictions (NMS stress: with random
+    weights nearly every anchor passes conf 0.001).  The GPU NMS decode of the GPU head tensors must equal the
+    oracle's greedy NMS of the SAME tensors (the bit-exact keep-set test on identical boxes is nms_exact_*)."""
+    m, sd = build(name, seed=seed)
+    x = synth_images(B, hw, hw, seed=seed + 1).to(DEV)
+    raw = m(x)
+    got = PP.decode_v10_predictions(raw, num_classes=80, strides=(8, 16, 32), conf_thresh=conf, iou_thresh=iou, max_det=max_det)
+    ref = O.decode_nms([t.cpu() for t in raw], num_classes=80, strides=(8, 16, 32), conf_thresh=conf, iou_thresh=iou, max_det=max_det)
+    from gpu_checks_decode import _canon
+    n_tot = 0
+    for i in range(B):
+        a, b = _canon(got[i][0].cpu()), _canon(ref[i][0])
+        assert a.shape == b.shape, f"image {i}: kept {tuple(a.shape)} vs oracle {tuple(b.shape)}"
+        if a.numel():
+            # boxes are decoded on the GPU (ulp-level differences), so a borderline IoU decision may flip:
+            # identical detections for >= 99% of the rows (same bar as check_decode_nms)
+            close = ((a - b).abs().max(1)[0] < 1e-2).float().mean()
+            assert close >= 0.99, f"image {i}: only {float(close):.3f} of rows match"
+        n_tot += a.shape[0]
+    return {"kept": n_tot}
+
+
+def check_config_large(name="yolov10l", hw=1280, B=1, seed=8):
+    """BASELINE config 5 (1280x1280: 160/80/40 maps, 33600 anchors) and config 4's variant (x): bf16 head
+    tensors within 2e-2 of the fp32 oracle, then the top-k decode against the oracle on the same tensors."""
+    m, sd = build(name, seed=seed)
+    x = synth_images(B, hw, hw, seed=seed + 1)
+    ref = O.forward(sd, x)
+    raw = m(x.to(DEV))
+    worst = 0.0
+    for br, ts in (("one2many", raw), ("one2one", m._eval_branches["one2one"])):
+        for i in range(3):
+            e = _errs(ts[i], ref[br][i])
+            worst = max(worst, e[0], e[1])
+    assert worst < 2e-2, f"{name}@{hw}: {worst:.2e}"
+    dets = m.decode_forward(raw)
+    refd = O.decode_topk([t.cpu() for t in m._eval_branches["one2one"]], num_classes=80)
+    for i in range(B):
+        assert dets[i][0].shape == (300, 6)
+        assert torch.allclose(dets[i][0][:, 4].cpu(), refd[i][0][:, 4], atol=2e-6)
+    return {"max_rel": worst}

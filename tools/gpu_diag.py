@@ -129,6 +129,14 @@ def registry():
     add("model_s_golden", M.check_model_golden, name="yolov10s")
     add("model_s_subbatch_graph", M.check_subbatch_and_graph, name="yolov10s")
     add("model_s_decode_e2e", M.check_decode_e2e, name="yolov10s")
+    # the reference's component surface: backbone / neck / head / forward_feat callables
+    add("submodules_s_bf16", M.check_submodules, name="yolov10s", precision="bf16")
+    add("submodules_s_f32", M.check_submodules, name="yolov10s", precision="fp32")
+    add("submodules_m_bf16", M.check_submodules, name="yolov10m", precision="bf16", B=1)
+    # BASELINE.json configs 3-5 at their real resolutions (small batches: the CPU oracle has to follow)
+    add("config3_m_640_nms_stress", M.check_config_nms, name="yolov10m", hw=640, B=2)
+    add("config4_x_640", M.check_config_large, name="yolov10x", hw=640, B=2)
+    add("config5_l_1280", M.check_config_large, name="yolov10l", hw=1280, B=1)
     return R
 
 
