@@ -9,6 +9,11 @@ namespace ly {
 
 static thread_local char g_err[512] = "";
 std::atomic<long long> g_launches{0};
+thread_local int g_reverse = 0;
+static int reverse_enabled() {
+  static const int v = getenv("LY_REVERSE") ? atoi(getenv("LY_REVERSE")) : 0;   // measured: no gain at batch 256 (15.11 vs 15.05 ms), kept as a switch
+  return v;
+}
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -131,6 +136,7 @@ int32_t ly_plan_create(const ly_op* ops, int32_t n_ops, ly_plan** out) {
   pl->fz.assign(n_ops, nullptr);
   for (int i = 0; i < n_ops; ++i) {
     const ly_op& op = pl->ops[i];
+    g_reverse = reverse_enabled() ? (i & 1) : 0;
     if ((op.kind == LY_OP_CONV && use_tc(op)) || op.kind == LY_OP_DWPW) {
       ly_op tmp = op;
       if (tmp.ext_slot >= 0 && !tmp.nchw) tmp.nchw = reinterpret_cast<float*>(16);  // placeholder: real pointer comes at run time
@@ -144,6 +150,7 @@ int32_t ly_plan_create(const ly_op* ops, int32_t n_ops, ly_plan** out) {
       }
     }
   }
+  g_reverse = 0;
   *out = pl;
   return LY_OK;
 }
@@ -166,6 +173,7 @@ static int32_t plan_run_impl(ly_plan* pl, float* const* ext, int32_t n_ext, int3
       nchw = reinterpret_cast<float*>(reinterpret_cast<char*>(ext[op.ext_slot]) + (long long)img0 * per_img * esz);
     }
     int32_t rc;
+    g_reverse = reverse_enabled() ? (int)(i & 1) : 0;
     if (pl->tc[i]) {
       rc = conv_tc_launch(pl->tc[i], op.ext_slot >= 0 ? nchw : nullptr, s);
     } else if (pl->fz[i]) {
@@ -182,6 +190,7 @@ static int32_t plan_run_impl(ly_plan* pl, float* const* ext, int32_t n_ext, int3
       return rc;
     }
   }
+  g_reverse = 0;
   if (ev) cudaEventRecord(ev[pl->ops.size()], s);
   return LY_OK;
 }

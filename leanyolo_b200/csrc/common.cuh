@@ -69,6 +69,12 @@ bool dwpw_supported(const ly_op& op);
 
 int sm_count();
 
+// Tile traversal direction of the op being prepared / launched (set by the plan executor: ops
+// alternate).  A layer that walks its tiles in the opposite order to its producer starts on the
+// part of the producer's output that is still in the 126 MB L2 (the tensors are 100-800 MB, so a
+// same-direction walk always starts on lines that were evicted long ago).
+extern thread_local int g_reverse;
+
 // Programmatic dependent launch: every kernel of the forward is launched with the
 // programmatic-stream-serialization attribute, so its CTAs are scheduled (and run their
 // prologue: barrier init, TMEM allocation, tensor-map prefetch) while the previous kernel

@@ -86,6 +86,7 @@ struct Params {
   const float* bias;
   float* nchw; int nCtot, nC0, nC;
   int cin_pad;
+  int rev;                 // walk the tiles / units last to first (see g_reverse)
 };
 
 // Optional per-role cycle accounting (-DLY_TC_PROFILE): CTA 0 prints where each role waited.
@@ -109,8 +110,9 @@ __device__ __forceinline__ uint32_t bar_tempty(uint32_t bb, int s) { return bb +
 __device__ __forceinline__ uint32_t bar_bres(uint32_t bb) { return bb + 8u * (4 * kMaxStages + 4); }
 
 // tile index -> (n tile, brick) without integer division (magic multipliers from the host)
+__device__ __forceinline__ int phys(const Params& p, int t) { return p.rev ? p.total_tiles - 1 - t : t; }
 __device__ __forceinline__ void split_tile(const Params& p, int tile_idx, int& nt, int& wt, int& ht, int& bt) {
-  uint32_t t = (uint32_t)tile_idx;   // multiplier 0 encodes a divisor of 1
+  uint32_t t = (uint32_t)phys(p, tile_idx);   // multiplier 0 encodes a divisor of 1
   uint32_t qn = p.mg_n ? __umulhi(t, p.mg_n) : t; nt = (int)(t - qn * (uint32_t)p.tiles_n); t = qn;
   uint32_t qw = p.mg_w ? __umulhi(t, p.mg_w) : t; wt = (int)(t - qw * (uint32_t)p.tiles_w); t = qw;
   uint32_t qh = p.mg_h ? __umulhi(t, p.mg_h) : t; ht = (int)(t - qh * (uint32_t)p.tiles_h); bt = (int)qh;
@@ -282,8 +284,9 @@ __device__ __forceinline__ void epilogue_role(const Params& p, uint8_t* smem_raw
     L.valid = false; L.lin = 0; L.n0 = 0;
     if (!L.more) return L;
     if (MAP == 2) {
-      const uint32_t b = p.mg_bands ? __umulhi((uint32_t)it_unit, p.mg_bands) : (uint32_t)it_unit;
-      const uint32_t bd = (uint32_t)it_unit - b * (uint32_t)p.bands;
+      const uint32_t pu = (uint32_t)phys(p, it_unit);
+      const uint32_t b = p.mg_bands ? __umulhi(pu, p.mg_bands) : pu;
+      const uint32_t bd = pu - b * (uint32_t)p.bands;
       const uint32_t m = (uint32_t)it_mt * 128u + row;
       const uint32_t oy = __umulhi(m, p.mg_bw), ox = m - oy * (uint32_t)p.band_w;
       const uint32_t h = bd * (uint32_t)p.band_r + oy;
@@ -292,7 +295,7 @@ __device__ __forceinline__ void epilogue_role(const Params& p, uint8_t* smem_raw
       L.n0 = it_nt * p.block_n;
       if (++it_mt == p.band_mt) { it_mt = 0; if (++it_nt == p.tiles_n) { it_nt = 0; it_unit += gridDim.x; } }
     } else if (MAP == 0) {
-      const uint32_t t = (uint32_t)it_unit;
+      const uint32_t t = (uint32_t)phys(p, it_unit);
       const uint32_t qn = p.mg_n ? __umulhi(t, p.mg_n) : t;
       L.n0 = (int)(t - qn * (uint32_t)p.tiles_n) * p.block_n;
       L.lin = qn * 128u + row;
@@ -533,6 +536,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         // the weight slabs in the issuer's order.  The A boxes of the NEXT unit are requested before
         // this unit's weight slabs so that the band prefetch runs a whole unit ahead.
         auto unit_a = [&](int unit) {
+          unit = phys(p, unit);
           const uint32_t b = p.mg_bands ? __umulhi((uint32_t)unit, p.mg_bands) : (uint32_t)unit;
           const int band = unit - (int)b * p.bands;
           for (int cb = 0; cb < kcb; ++cb) load_a(cb * kc, -1, band * p.band_r - 1, (int)b);
@@ -660,6 +664,7 @@ int32_t conv_tc_prepare(const ly_op& op, ConvTcState** out) {
   const int Cout = op.dst.ptr ? op.dst.c : (op.nchw_c + 15) / 16 * 16;
   const int Ho = op.src.H / op.stride, Wo = op.src.W / op.stride;
   p.k = op.k; p.stride = op.stride; p.pad = op.k / 2; p.act = op.act; p.cin_pad = Cin;
+  p.rev = g_reverse;
   p.hw_real = Ho * Wo;
   p.kc = Cin % 64 == 0 ? 64 : (Cin % 32 == 0 ? 32 : 16);
   p.kc_blocks = Cin / p.kc;

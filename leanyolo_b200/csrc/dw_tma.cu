@@ -31,6 +31,7 @@ struct DwParams {
   int Ho, Wo, C;
   int stages, stage_bytes, box_bytes;
   int act;
+  int rev;               // walk the tiles last to first (see g_reverse)
   const __nv_bfloat16* w;
   const float* bias;
   __nv_bfloat16* dst; int dCtot, dC0;
@@ -71,7 +72,7 @@ __global__ void __launch_bounds__(32 * (kMaxDwWarps + 1)) dw_tma_kernel(const __
   __syncthreads();
 
   auto split = [&](int tile, int& xt, int& yt, int& ct, int& b) {
-    int t = tile;
+    int t = p.rev ? p.total_tiles - 1 - tile : tile;
     xt = t % p.tiles_x; t /= p.tiles_x;
     yt = t % p.tiles_y; t /= p.tiles_y;
     ct = t % p.tiles_c;
@@ -235,6 +236,7 @@ int32_t launch_cfg(const ly_op& op, cudaStream_t st) {
   if (stages < 2) stages = 2;
   p.stages = stages;
   p.act = op.act;
+  p.rev = g_reverse;
   p.w = (const __nv_bfloat16*)op.w; p.bias = op.bias;
   p.dst = (__nv_bfloat16*)op.dst.ptr; p.dCtot = op.dst.ctot; p.dC0 = op.dst.c0;
   p.res = (const __nv_bfloat16*)op.res.ptr; p.rCtot = op.res.ctot; p.rC0 = op.res.c0;
@@ -277,6 +279,7 @@ struct DwVParams {
   int Ho, Wo, C;
   int stages, stage_bytes, box_bytes;
   int act;
+  int rev;               // walk the tiles last to first (see g_reverse)
   const __nv_bfloat16* w;
   const float* bias;
   __nv_bfloat16* dst; int dCtot, dC0;
@@ -331,7 +334,7 @@ __global__ void __launch_bounds__(kThreadsDw) dw_strip_kernel(const __grid_const
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        int t = tile;
+        int t = p.rev ? p.total_tiles - 1 - tile : tile;
         const int xt = t % p.tiles_x; t /= p.tiles_x;
         const int yt = t % p.tiles_y; t /= p.tiles_y;
         const int ct = t % p.tiles_c;
@@ -354,7 +357,7 @@ __global__ void __launch_bounds__(kThreadsDw) dw_strip_kernel(const __grid_const
   int stage = 0;
   uint32_t phase = 0;
   for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-    int t = tile;
+    int t = p.rev ? p.total_tiles - 1 - tile : tile;
     const int xt = t % p.tiles_x; t /= p.tiles_x;
     const int yt = t % p.tiles_y; t /= p.tiles_y;
     const int ct = t % p.tiles_c;
@@ -446,6 +449,7 @@ int32_t launch_strip(const ly_op& op, cudaStream_t st) {
   LY_CHECK_ARG(stages >= 2, "dw_tma: tile does not fit in shared memory");
   p.stages = stages;
   p.act = op.act;
+  p.rev = g_reverse;
   p.w = (const __nv_bfloat16*)op.w; p.bias = op.bias;
   p.dst = (__nv_bfloat16*)op.dst.ptr; p.dCtot = op.dst.ctot; p.dC0 = op.dst.c0;
   p.res = (const __nv_bfloat16*)op.res.ptr; p.rCtot = op.res.ctot; p.rC0 = op.res.c0;
@@ -495,6 +499,7 @@ struct Dw7Params {
   int Ho, Wo, C;
   int stages, stage_bytes, box_bytes;
   int act;
+  int rev;               // walk the tiles last to first (see g_reverse)
   const __nv_bfloat16* w;
   const float* bias;
   __nv_bfloat16* dst; int dCtot, dC0;
@@ -547,6 +552,7 @@ __global__ void __launch_bounds__(32 * (kDw7Warps + 1)) dw7_kernel(const __grid_
   __syncthreads();
 
   auto split = [&](int t, int& xt, int& yt, int& b) {
+    if (p.rev) t = p.tiles_per_cb - 1 - t;
     xt = t % p.tiles_x; t /= p.tiles_x;
     yt = t % p.tiles_y;
     b = t / p.tiles_y;
@@ -674,6 +680,7 @@ int32_t launch_dw7(const ly_op& op, cudaStream_t st) {
   LY_CHECK_ARG(p.stages >= 2, "dw7: tile does not fit in shared memory");
   const size_t smem = (size_t)p.stages * p.stage_bytes + 128;
   p.act = op.act;
+  p.rev = g_reverse;
   p.w = (const __nv_bfloat16*)op.w; p.bias = op.bias;
   p.dst = (__nv_bfloat16*)op.dst.ptr; p.dCtot = op.dst.ctot; p.dC0 = op.dst.c0;
   p.res = (const __nv_bfloat16*)op.res.ptr; p.rCtot = op.res.ctot; p.rC0 = op.res.c0;

@@ -53,10 +53,11 @@ struct FParams {
   const float* bias;
   __nv_bfloat16* dst; int dCtot, dC0;
   float* nchw; int nCtot, nC0, nC;
+  int rev;               // walk the tiles last to first (see g_reverse)
 };
 
 __device__ __forceinline__ void f_split(const FParams& p, int tile, int& xt, int& yt, int& b) {
-  uint32_t t = (uint32_t)tile;
+  uint32_t t = (uint32_t)(p.rev ? p.total_tiles - 1 - tile : tile);
   uint32_t qx = p.mg_x ? __umulhi(t, p.mg_x) : t; xt = (int)(t - qx * (uint32_t)p.tiles_x); t = qx;
   uint32_t qy = p.mg_y ? __umulhi(t, p.mg_y) : t; yt = (int)(t - qy * (uint32_t)p.tiles_y); b = (int)qy;
 }
@@ -379,6 +380,7 @@ int32_t dwpw_prepare(const ly_op& op, DwPwState** out) {
   p.H = H; p.W = W; p.B = op.B; p.cin = Cin; p.kblocks = Cin / 64;
   p.block_n = Cout; p.tmem_cols = f_pow2_ge(2 * Cout);
   p.pre_act = op.pre_act; p.act = op.act;
+  p.rev = g_reverse;
   // tile = npx x npy patches of 4 x kPH pixels, at most one patch per depthwise warp: fewest tiles
   // per image first, then the smallest halo box
   {
