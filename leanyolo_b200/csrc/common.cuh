@@ -66,6 +66,12 @@ int32_t dwpw_prepare(const ly_op& op, DwPwState** out);
 int32_t dwpw_launch(const DwPwState* st, float* nchw_override, cudaStream_t s);
 void dwpw_free(DwPwState* st);
 bool dwpw_supported(const ly_op& op);
+// ... with the depthwise stage on the tensor cores too (dwpw_mma.cu; C <= 128, Cout <= 128): chosen by dwpw_prepare
+struct DwPwMmaState;
+int32_t dwpw_mma_prepare(const ly_op& op, DwPwMmaState** out);
+int32_t dwpw_mma_launch(const DwPwMmaState* st, float* nchw_override, cudaStream_t s);
+void dwpw_mma_free(DwPwMmaState* st);
+bool dwpw_mma_supported(const ly_op& op);
 
 int sm_count();
 

@@ -354,6 +354,7 @@ struct DwPwState {
   FParams p;
   int grid;
   size_t smem;
+  DwPwMmaState* mma = nullptr;   // set: the launch goes to dwpw_mma_kernel (depthwise stage on the tensor cores)
 };
 
 bool dwpw_supported(const ly_op& op) {
@@ -373,6 +374,12 @@ int32_t dwpw_prepare(const ly_op& op, DwPwState** out) {
   EncodeTiledFn encode = get_encode();
   if (!encode) { set_error("dwpw: cuTensorMapEncodeTiled entry point not available"); return LY_E_CUDA; }
   DwPwState* st = new DwPwState();
+  if (dwpw_mma_supported(op)) {
+    const int32_t rc = dwpw_mma_prepare(op, &st->mma);
+    if (rc != LY_OK) { delete st; return rc; }
+    *out = st;
+    return LY_OK;
+  }
   FParams& p = st->p;
   memset(&p, 0, sizeof(p));
   const int H = op.src.H, W = op.src.W, Cin = op.src.c;
@@ -463,6 +470,7 @@ int32_t dwpw_prepare(const ly_op& op, DwPwState** out) {
 }
 
 int32_t dwpw_launch(const DwPwState* st, float* nchw_override, cudaStream_t s) {
+  if (st->mma) return dwpw_mma_launch(st->mma, nchw_override, s);
   if (nchw_override) {
     FParams p = st->p;
     p.nchw = nchw_override;
@@ -473,6 +481,9 @@ int32_t dwpw_launch(const DwPwState* st, float* nchw_override, cudaStream_t s) {
   return post_launch("dwpw_tc");
 }
 
-void dwpw_free(DwPwState* st) { delete st; }
+void dwpw_free(DwPwState* st) {
+  if (st && st->mma) dwpw_mma_free(st->mma);
+  delete st;
+}
 
 }  // namespace ly

@@ -130,7 +130,7 @@ int main() {
   cudaMalloc(&d, 16);
   cudaMalloc(&sink, (size_t)148 * 320 * 64 * 4);
   const int L = 512;
-  for (int N : {32, 64, 128, 256}) {
+  for (int N : {8, 16, 32, 64, 128, 256}) {
     run<0>(N, L, d, sink);
     run<8>(N, L, d, sink);
     run<32>(N, L, d, sink);
