@@ -322,15 +322,23 @@ __device__ __forceinline__ void epilogue_role(const Params& p, uint8_t* smem_raw
   // into a private shared-memory slot while it works on the current tile, so the DRAM latency of
   // the uncoalesced read is off the epilogue's critical path (measured: a C2f bottleneck at 160^2
   // spent 35 % of its samples waiting for that load).
+  // Slot layout: piece-major ([stage][2*round + half][epilogue thread] x 16 bytes), so the 32 lanes of a
+  // warp touch 32 consecutive 16-byte words: thread-major slots (64-byte stride per lane) cost a 4-way
+  // bank conflict on every cp.async write and LDS.128 read (ncu: 11.8 M conflicts, 28 % short-scoreboard stalls).
   const uint32_t r_base = bar_base + 8u * (4 * kMaxStages + 8);
-  const uint32_t rslot = r_base + (uint32_t)(threadIdx.x - 64) * p.res_slot;
+  const uint32_t rslot = r_base + (uint32_t)(threadIdx.x - 64) * 16u;
+  constexpr uint32_t kPiece = 32u * kEpiWarps * 16u;                    // bytes between pieces
   const uint32_t rstage = (uint32_t)(32 * kEpiWarps) * p.res_slot;
+  // Half-resolution addend: horizontally adjacent output pixels (w even, w + 1) share their source pixel.  In
+  // the flat mapping they are adjacent lanes (the row width is even), so the odd lane skips its own request
+  // and reads the even lane's slot: half the scattered 32-byte L2 requests of this epilogue.
+  auto up_dup = [&](uint32_t lin) -> bool { return kUp && MAP == 0 && lane > 0 && (((lin % (uint32_t)p.Wreal) & 1u) != 0u); };
   auto res_prefetch = [&](const Loc& L, uint32_t dst) {
-    if (L.more && L.valid) {
+    if (L.more && L.valid && !up_dup(L.lin)) {
       const __nv_bfloat16* rr = kUp ? up_row(L.lin, L.n0) : p.res + (size_t)L.lin * (uint32_t)p.rCtot + p.rC0 + L.n0;
       for (int i = 0, ch = cg; ch < nchunks; ++i, ch += 4) {
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + i * 32), "l"(rr + ch * 16) : "memory");
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + i * 32 + 16), "l"(rr + ch * 16 + 8) : "memory");
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (2 * i) * kPiece), "l"(rr + ch * 16) : "memory");
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (2 * i + 1) * kPiece), "l"(rr + ch * 16 + 8) : "memory");
       }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
@@ -352,7 +360,7 @@ __device__ __forceinline__ void epilogue_role(const Params& p, uint8_t* smem_raw
       res_prefetch(nxtloc, rslot + (rs ^ 1u) * rstage);
       asm volatile("cp.async.wait_group 1;" ::: "memory");   // this tile's addend has landed
     }
-    const uint8_t* rsm = smem_raw + ((rslot + rs * rstage) - smem_u32(smem_raw));
+    const uint8_t* rsm = smem_raw + ((rslot + rs * rstage) - smem_u32(smem_raw)) - (up_dup(lin) ? 16 : 0);
     const __nv_bfloat16* arow = nullptr;                     // direct-load addend row
     if (ADD == 3 && valid) arow = p.res + (size_t)lin * (uint32_t)p.rCtot + p.rC0 + n0;
     if (ADD == 4 && valid) arow = up_row(lin, n0);
@@ -397,9 +405,13 @@ __device__ __forceinline__ void epilogue_role(const Params& p, uint8_t* smem_raw
       if (has) {
         if (kUp && valid) {
           float uv[16];
-          const __nv_bfloat16* src = kSlots ? reinterpret_cast<const __nv_bfloat16*>(rsm + rd * 32) : arow + c;
-          load_vec<__nv_bfloat16>(src, uv);
-          load_vec<__nv_bfloat16>(src + 8, uv + 8);
+          if (kSlots) {
+            load_vec<__nv_bfloat16>(reinterpret_cast<const __nv_bfloat16*>(rsm + (2 * rd) * kPiece), uv);
+            load_vec<__nv_bfloat16>(reinterpret_cast<const __nv_bfloat16*>(rsm + (2 * rd + 1) * kPiece), uv + 8);
+          } else {
+            load_vec<__nv_bfloat16>(arow + c, uv);
+            load_vec<__nv_bfloat16>(arow + c + 8, uv + 8);
+          }
 #pragma unroll
           for (int j = 0; j < 16; j += 2) ffma2(v[j], v[j + 1], uv[j], uv[j + 1], pre, pre, v[j], v[j + 1]);
         }
@@ -409,9 +421,13 @@ __device__ __forceinline__ void epilogue_role(const Params& p, uint8_t* smem_raw
         }
         if (kRes && valid) {
           float rv[16];
-          const __nv_bfloat16* src = kSlots ? reinterpret_cast<const __nv_bfloat16*>(rsm + rd * 32) : arow + c;
-          load_vec<__nv_bfloat16>(src, rv);
-          load_vec<__nv_bfloat16>(src + 8, rv + 8);
+          if (kSlots) {
+            load_vec<__nv_bfloat16>(reinterpret_cast<const __nv_bfloat16*>(rsm + (2 * rd) * kPiece), rv);
+            load_vec<__nv_bfloat16>(reinterpret_cast<const __nv_bfloat16*>(rsm + (2 * rd + 1) * kPiece), rv + 8);
+          } else {
+            load_vec<__nv_bfloat16>(arow + c, rv);
+            load_vec<__nv_bfloat16>(arow + c + 8, rv + 8);
+          }
 #pragma unroll
           for (int j = 0; j < 16; j += 2) fadd2(v[j], v[j + 1], v[j], v[j + 1], rv[j], rv[j + 1]);
         }
