@@ -87,6 +87,7 @@ struct Params {
   float* nchw; int nCtot, nC0, nC;
   int cin_pad;
   int rev;                 // walk the tiles / units last to first (see g_reverse)
+  int st256;               // NHWC rows are 32-byte aligned: one 256-bit store per 16-channel chunk
 };
 
 // Optional per-role cycle accounting (-DLY_TC_PROFILE): CTA 0 prints where each role waited.
@@ -439,8 +440,12 @@ __device__ __forceinline__ void epilogue_role(const Params& p, uint8_t* smem_raw
               if (n0 + c + j < p.nC) np[(size_t)j * (uint32_t)p.hw_real] = v[j];
           }
         } else if (drow) {
-          store_vec<__nv_bfloat16>(drow + c, v);
-          store_vec<__nv_bfloat16>(drow + c + 8, v + 8);
+          if (p.st256) {
+            store_bf16x16(drow + c, v);
+          } else {
+            store_vec<__nv_bfloat16>(drow + c, v);
+            store_vec<__nv_bfloat16>(drow + c + 8, v + 8);
+          }
         }
       }
     }
@@ -873,6 +878,8 @@ int32_t conv_tc_prepare(const ly_op& op, ConvTcState** out) {
   }
 
   p.dst = (__nv_bfloat16*)op.dst.ptr; p.dCtot = op.dst.ctot; p.dC0 = op.dst.c0;
+  static const int st256_ok = env_int("LY_ST256", 1);
+  p.st256 = st256_ok && op.dst.ptr && op.dst.ctot % 16 == 0 && op.dst.c0 % 16 == 0 && reinterpret_cast<uintptr_t>(op.dst.ptr) % 32 == 0;
   p.res = (const __nv_bfloat16*)op.res.ptr; p.rCtot = op.res.ctot; p.rC0 = op.res.c0;
   p.up = (const __nv_bfloat16*)op.up.ptr; p.uCtot = op.up.ctot; p.uC0 = op.up.c0; p.uH = op.up.H; p.uW = op.up.W; p.Wreal = Wo;
   p.bias = op.bias;

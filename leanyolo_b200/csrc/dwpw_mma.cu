@@ -77,6 +77,7 @@ struct GParams {
   const float* bias;
   __nv_bfloat16* dst; int dCtot, dC0;
   float* nchw; int nCtot, nC0, nC;
+  int st256;
 };
 
 __device__ __forceinline__ void g_split(const GParams& p, int tile, int& xt, int& yt, int& b) {
@@ -358,8 +359,12 @@ __global__ void __launch_bounds__(kThreads, 1) dwpw_mma_kernel(const __grid_cons
           for (int j = 0; j < 16; j += 2) silu2_from_half(v[j], v[j + 1]);
         }
         if (drow) {
-          store_vec<__nv_bfloat16>(drow + c, v);
-          store_vec<__nv_bfloat16>(drow + c + 8, v + 8);
+          if (p.st256) {
+            store_bf16x16(drow + c, v);
+          } else {
+            store_vec<__nv_bfloat16>(drow + c, v);
+            store_vec<__nv_bfloat16>(drow + c + 8, v + 8);
+          }
         }
         if (nrow) {
           float* np = nrow + (size_t)c * hw;
@@ -483,6 +488,8 @@ int32_t dwpw_mma_prepare(const ly_op& op, DwPwMmaState** out) {
   }
   p.dww = (const __nv_bfloat16*)op.pre_w; p.dwb = op.pre_bias; p.bias = op.bias;
   p.dst = (__nv_bfloat16*)op.dst.ptr; p.dCtot = op.dst.ctot; p.dC0 = op.dst.c0;
+  p.st256 = (getenv("LY_ST256") ? atoi(getenv("LY_ST256")) : 1) && op.dst.ptr && op.dst.ctot % 16 == 0 && op.dst.c0 % 16 == 0 &&
+            reinterpret_cast<uintptr_t>(op.dst.ptr) % 32 == 0;
   p.nchw = op.nchw; p.nCtot = op.nchw_ctot; p.nC0 = op.nchw_c0; p.nC = op.nchw_c;
   const int sms = sm_count();
   st->grid = p.total_tiles < sms ? p.total_tiles : sms;
