@@ -293,7 +293,7 @@ def main():
     alg_bytes = sum(r["bytes"] for r in tc) / max(len(tc), 1)
     roofline = {"bound": "tensor", "kernel": "conv_tc_kernel", "achieved": round(achieved, 1), "peak": peaks["tf_sust"],
                 "unit": "TFLOP/s", "frac": round(achieved / peaks["tf_sust"], 4), "traffic": traffic,
-                "traffic_unit": "DRAM bytes per launch (ncu dram read+write, profiles/r1_ncu_launch_summary.txt)",
+                "traffic_unit": "DRAM bytes per launch (ncu dram read+write, profiles/r1_final_ncu_launch_summary.txt)",
                 "algorithmic_bytes_per_launch": int(alg_bytes),
                 "peak_source": peaks["src"] + " (bf16_tflops_sustained: kernel timed inside a long step)",
                 "launches_per_step": len(tc), "share_of_step": round(tc_ms / all_ms, 3) if all_ms else None,

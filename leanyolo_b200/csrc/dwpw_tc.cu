@@ -54,6 +54,7 @@ struct FParams {
   __nv_bfloat16* dst; int dCtot, dC0;
   float* nchw; int nCtot, nC0, nC;
   int rev;               // walk the tiles last to first (see g_reverse)
+  int st256;             // 32-byte aligned NHWC rows: one 256-bit store per 16-channel chunk
 };
 
 __device__ __forceinline__ void f_split(const FParams& p, int tile, int& xt, int& yt, int& b) {
@@ -319,8 +320,12 @@ __global__ void __launch_bounds__(kFThreads, 1) dwpw_kernel(const __grid_constan
           for (int j = 0; j < 16; ++j) v[j] = silu_from_half(v[j]);
         }
         if (drow) {
-          store_vec<__nv_bfloat16>(drow + c, v);
-          store_vec<__nv_bfloat16>(drow + c + 8, v + 8);
+          if (p.st256) {
+            store_bf16x16(drow + c, v);
+          } else {
+            store_vec<__nv_bfloat16>(drow + c, v);
+            store_vec<__nv_bfloat16>(drow + c + 8, v + 8);
+          }
         }
         if (nrow) {
           float* np = nrow + (long long)c * p.H * p.W;
@@ -456,6 +461,7 @@ int32_t dwpw_prepare(const ly_op& op, DwPwState** out) {
   }
   p.dww = (const __nv_bfloat16*)op.pre_w; p.dwb = op.pre_bias; p.bias = op.bias;
   p.dst = (__nv_bfloat16*)op.dst.ptr; p.dCtot = op.dst.ctot; p.dC0 = op.dst.c0;
+  p.st256 = op.dst.ptr && op.dst.ctot % 16 == 0 && op.dst.c0 % 16 == 0 && reinterpret_cast<uintptr_t>(op.dst.ptr) % 32 == 0;
   p.nchw = op.nchw; p.nCtot = op.nchw_ctot; p.nC0 = op.nchw_c0; p.nC = op.nchw_c;
   const int sms = sm_count();
   st->grid = p.total_tiles < sms ? p.total_tiles : sms;
