@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define LY_ABI_VERSION 2
+#define LY_ABI_VERSION 3
 
 #if defined(LY_BUILD) && defined(__GNUC__)
 #define LY_API __attribute__((visibility("default")))
@@ -169,6 +169,29 @@ LY_API int64_t ly_nms_scratch_bytes(int32_t B, int32_t N);
 LY_API int32_t ly_nms(const float* boxes, const float* scores, const int32_t* labels, const int32_t* n_valid,
                int32_t B, int32_t N, float iou_thresh, int32_t max_keep, int32_t classwise,
                int32_t* keep, int32_t* keep_count, void* scratch, int64_t scratch_bytes, void* stream);
+
+/* ---- pre / post-processing around the path -------- */
+/* One source image of a letterboxed batch.  The host computes the geometry exactly as
+ * `letterbox` does (utils/letterbox.py:44-80: new_w/new_h = round(orig * r), pads split by round()). */
+typedef struct ly_lb_desc {
+  const uint8_t* src;      /* device pointer, uint8 HWC RGB                                 */
+  int64_t src_pitch;       /* bytes per source row                                          */
+  int32_t src_h, src_w;
+  int32_t new_h, new_w;    /* size after the resize (== src: plain copy)                    */
+  int32_t top, left;       /* border added above / left; the rest of the slot is border too */
+} ly_lb_desc;
+
+/* Replaces `letterbox` (utils/letterbox.py:9-91: cv2.resize INTER_LINEAR + cv2.copyMakeBorder) and the
+ * HWC->CHW transpose of tools/infer.py:112-114 for a whole batch in one launch.  `descs`: DEVICE array [B].
+ * dst: uint8 `[B,3,dst_h,dst_w]` (chw != 0, what the stem kernel consumes) or `[B,dst_h,dst_w,3]`.
+ * Bit-exact with cv2's 8-bit fixed-point bilinear.  fill: 3 bytes RGB (NULL = 114,114,114).          */
+LY_API int32_t ly_letterbox_u8(const ly_lb_desc* descs, int32_t B, uint8_t* dst, int32_t dst_h, int32_t dst_w,
+                               int32_t chw, const uint8_t* fill, void* stream);
+
+/* Replaces `unletterbox_coords` (utils/box_ops.py:96-124) for a batch of detections, in place:
+ * dets `[B,K,row]` fp32 with xyxy in the first four columns; meta `[B,6]` fp32 =
+ * (gain_w, gain_h, pad_left, pad_top, orig_h, orig_w).                                               */
+LY_API int32_t ly_unletterbox(float* dets, int32_t B, int32_t K, int32_t row, const float* meta, void* stream);
 
 #ifdef __cplusplus
 }

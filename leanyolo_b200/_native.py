@@ -10,7 +10,7 @@ from pathlib import Path
 
 LIB_PATH = Path(__file__).resolve().parent / "_lib" / "libleanyolo_b200.so"
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 LY_BF16, LY_F32 = 0, 1
 OP_STEM, OP_CONV, OP_DW, OP_POOL, OP_UP, OP_ATTN, OP_EXPORT, OP_IMPORT, OP_DWPW = 1, 2, 3, 4, 5, 6, 7, 8, 9
 IMPL_AUTO, IMPL_SIMT, STEM_IN_U8 = 0, 1, 2
@@ -42,6 +42,11 @@ class LyLevels(C.Structure):
     ]
 
 
+class LyLbDesc(C.Structure):      # mirrors `ly_lb_desc` (32 bytes)
+    _fields_ = [("src", C.c_void_p), ("src_pitch", C.c_int64), ("src_h", C.c_int32), ("src_w", C.c_int32),
+                ("new_h", C.c_int32), ("new_w", C.c_int32), ("top", C.c_int32), ("left", C.c_int32)]
+
+
 # name -> (restype, argtypes); must list every symbol declared in include/leanyolo_b200.h
 PROTOTYPES = {
     "ly_abi_version": (C.c_int32, []),
@@ -60,6 +65,8 @@ PROTOTYPES = {
                                    C.c_void_p, C.c_int64, C.c_void_p]),
     "ly_decode_nms": (C.c_int32, [C.POINTER(LyLevels), C.c_float, C.c_float, C.c_int32, C.c_int32, C.c_void_p,
                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "ly_letterbox_u8": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "ly_unletterbox": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "ly_nms_scratch_bytes": (C.c_int64, [C.c_int32, C.c_int32]),
     "ly_nms": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_float,
                            C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),

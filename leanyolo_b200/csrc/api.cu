@@ -195,6 +195,19 @@ static int32_t plan_run_impl(ly_plan* pl, float* const* ext, int32_t n_ext, int3
   return LY_OK;
 }
 
+int32_t ly_letterbox_u8(const ly_lb_desc* descs, int32_t B, uint8_t* dst, int32_t dst_h, int32_t dst_w, int32_t chw,
+                        const uint8_t* fill, void* stream) {
+  int32_t rc = check_arch();
+  if (rc != LY_OK) return rc;
+  return launch_letterbox(descs, B, dst, dst_h, dst_w, chw, fill, (cudaStream_t)stream);
+}
+
+int32_t ly_unletterbox(float* dets, int32_t B, int32_t K, int32_t row, const float* meta, void* stream) {
+  int32_t rc = check_arch();
+  if (rc != LY_OK) return rc;
+  return launch_unletterbox(dets, B, K, row, meta, (cudaStream_t)stream);
+}
+
 int32_t ly_plan_run(ly_plan* pl, float* const* ext, int32_t n_ext, int32_t img0, void* stream) {
   LY_CHECK_ARG(pl != nullptr, "ly_plan_run: null plan");
   return plan_run_impl(pl, ext, n_ext, img0, (cudaStream_t)stream, nullptr);

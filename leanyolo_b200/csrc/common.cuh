@@ -52,6 +52,9 @@ int32_t launch_up(const ly_op& op, cudaStream_t s);
 int32_t launch_attn(const ly_op& op, cudaStream_t s);
 int32_t launch_export(const ly_op& op, cudaStream_t s);
 int32_t launch_import(const ly_op& op, cudaStream_t s);
+int32_t launch_letterbox(const ly_lb_desc* descs, int32_t B, uint8_t* dst, int32_t dst_h, int32_t dst_w, int32_t chw,
+                         const uint8_t* fill, cudaStream_t s);
+int32_t launch_unletterbox(float* dets, int32_t B, int32_t K, int32_t row, const float* meta, cudaStream_t s);
 
 // tcgen05 implicit-GEMM conv: tensor maps are encoded once (prepare) and reused.
 struct ConvTcState;

@@ -1,0 +1,138 @@
+"""GPU pre/post-processing on either side of the hot path.
+
+Drop-ins for the reference's ``letterbox`` (leanyolo/utils/letterbox.py:9-91) and
+``unletterbox_coords`` (leanyolo/utils/box_ops.py:96-124) on CUDA tensors, plus the batched forms
+the serving loop of ``tools/infer.py:110-138`` needs at tens of thousands of images per second:
+
+    batch, meta = letterbox_batch(images, 640)        # list of uint8 HWC cuda tensors -> [B,3,640,640] uint8
+    dets = model.detect(batch)                        # the stem kernel consumes uint8 NCHW directly
+    unletterbox_dets(dets, meta)                      # in place, back to each image's own coordinates
+
+The geometry (scale, rounded new size, pad split) is host arithmetic restated from the reference;
+the resize is cv2's 8-bit fixed-point bilinear, bit for bit, in ``csrc/preprocess.cu``.  CUDA only:
+CPU tensors raise (no fallback).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Sequence, Tuple
+
+import torch
+
+from . import _native as N
+
+
+def letterbox_params(orig_h: int, orig_w: int, new_shape=640, auto: bool = False, scale_fill: bool = False,
+                     scaleup: bool = True, stride: int = 32):
+    """letterbox.py:44-80 -> (new_w, new_h, left, top, right, bottom, gain_w, gain_h)."""
+    if isinstance(new_shape, int):
+        tgt_h, tgt_w = new_shape, new_shape
+    else:
+        tgt_h, tgt_w = int(new_shape[0]), int(new_shape[1])
+    if scale_fill:
+        gain_w, gain_h = tgt_w / max(orig_w, 1), tgt_h / max(orig_h, 1)
+        new_w, new_h, pad_w, pad_h = tgt_w, tgt_h, 0.0, 0.0
+    else:
+        r = min(tgt_w / max(orig_w, 1), tgt_h / max(orig_h, 1))
+        if not scaleup:
+            r = min(r, 1.0)
+        new_w, new_h = int(round(orig_w * r)), int(round(orig_h * r))
+        gain_w = gain_h = r
+        pad_w, pad_h = float(tgt_w - new_w), float(tgt_h - new_h)
+        if auto and stride > 1:
+            pad_w, pad_h = pad_w % stride, pad_h % stride
+    left = int(round(pad_w / 2.0)); right = int(round(pad_w - left))
+    top = int(round(pad_h / 2.0)); bottom = int(round(pad_h - top))
+    return new_w, new_h, left, top, right, bottom, float(gain_w), float(gain_h)
+
+
+def _check_img(img: torch.Tensor) -> None:
+    if not isinstance(img, torch.Tensor) or not img.is_cuda:
+        raise RuntimeError("leanyolo_b200 letterbox runs on CUDA tensors only (no CPU fallback)")
+    if img.dtype != torch.uint8 or img.dim() != 3 or img.shape[2] != 3 or img.stride(2) != 1 or img.stride(1) != 3:
+        raise ValueError("expected a uint8 HWC RGB image tensor with packed pixels")
+    if img.shape[0] < 1 or img.shape[1] < 1 or img.shape[0] > 32767 or img.shape[1] > 32767:
+        raise ValueError("image size out of range")   # cv2's fixed-point tables are 16-bit offsets as well
+
+
+def _launch(images: Sequence[torch.Tensor], geo, out: torch.Tensor, chw: bool, color) -> None:
+    dev = out.device
+    descs = (N.LyLbDesc * len(images))()
+    for d, img, (new_w, new_h, left, top, *_rest) in zip(descs, images, geo):
+        d.src, d.src_pitch = img.data_ptr(), img.stride(0)
+        d.src_h, d.src_w, d.new_h, d.new_w, d.top, d.left = img.shape[0], img.shape[1], new_h, new_w, top, left
+    raw = torch.frombuffer(bytearray(bytes(descs)), dtype=torch.uint8)
+    fill = (C.c_uint8 * 3)(*[int(c) for c in color])
+    with torch.cuda.device(dev):
+        d_descs = raw.to(dev, non_blocking=False)
+        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        N.check(N.lib().ly_letterbox_u8(d_descs.data_ptr(), len(images), out.data_ptr(), out.shape[-2] if chw else out.shape[-3],
+                                        out.shape[-1] if chw else out.shape[-2], int(chw), fill, stream), "ly_letterbox_u8")
+        d_descs.record_stream(torch.cuda.current_stream(dev))
+
+
+@torch.no_grad()
+def letterbox(img: torch.Tensor, new_shape=640, color: Tuple[int, int, int] = (114, 114, 114), auto: bool = False,
+              scale_fill: bool = False, scaleup: bool = True, stride: int = 32):
+    """Reference signature and return value, on a CUDA uint8 HWC tensor: (img_out HWC, (gain_w, gain_h), (left, top))."""
+    _check_img(img)
+    g = letterbox_params(img.shape[0], img.shape[1], new_shape, auto, scale_fill, scaleup, stride)
+    new_w, new_h, left, top, right, bottom, gw, gh = g
+    out = torch.empty((1, new_h + top + bottom, new_w + left + right, 3), dtype=torch.uint8, device=img.device)
+    _launch([img], [g], out, False, color)
+    return out[0], (gw, gh), (left, top)
+
+
+@torch.no_grad()
+def letterbox_batch(images: Sequence[torch.Tensor], new_shape=640, color: Tuple[int, int, int] = (114, 114, 114),
+                    scale_fill: bool = False, scaleup: bool = True):
+    """B images of any sizes -> one uint8 NCHW batch ``[B,3,H,W]`` (ONE launch) + meta ``[B,6]`` fp32 on the device =
+    (gain_w, gain_h, pad_left, pad_top, orig_h, orig_w) per image, the argument of ``unletterbox_dets``."""
+    if len(images) == 0:
+        raise ValueError("empty batch")
+    for img in images:
+        _check_img(img)
+    tgt = (new_shape, new_shape) if isinstance(new_shape, int) else (int(new_shape[0]), int(new_shape[1]))
+    geo = [letterbox_params(img.shape[0], img.shape[1], tgt, False, scale_fill, scaleup) for img in images]
+    dev = images[0].device
+    out = torch.empty((len(images), 3, tgt[0], tgt[1]), dtype=torch.uint8, device=dev)
+    _launch(images, geo, out, True, color)
+    meta = torch.tensor([[g[6], g[7], g[2], g[3], img.shape[0], img.shape[1]] for g, img in zip(geo, images)],
+                        dtype=torch.float32).to(dev)
+    return out, meta
+
+
+@torch.no_grad()
+def unletterbox_dets(dets: torch.Tensor, meta: torch.Tensor) -> torch.Tensor:
+    """In place: xyxy columns of ``dets [B,K,>=4]`` fp32 back to original-image coordinates (box_ops.py:96-124)."""
+    if not dets.is_cuda or not meta.is_cuda:
+        raise RuntimeError("leanyolo_b200 unletterbox runs on CUDA tensors only (no CPU fallback)")
+    assert dets.dtype == torch.float32 and dets.dim() == 3 and dets.shape[2] >= 4 and dets.is_contiguous()
+    assert meta.dtype == torch.float32 and meta.shape == (dets.shape[0], 6) and meta.is_contiguous()
+    if dets.shape[1] == 0:
+        return dets
+    with torch.cuda.device(dets.device):
+        stream = C.c_void_p(torch.cuda.current_stream(dets.device).cuda_stream)
+        N.check(N.lib().ly_unletterbox(dets.data_ptr(), dets.shape[0], dets.shape[1], dets.shape[2], meta.data_ptr(), stream),
+                "ly_unletterbox")
+    return dets
+
+
+@torch.no_grad()
+def unletterbox_coords(boxes: torch.Tensor, gain: Tuple[float, float], pad: Tuple[int, int], to_shape: Tuple[int, int]) -> torch.Tensor:
+    """Reference signature (box_ops.py:96-101): boxes ``[N,4]`` xyxy -> new tensor in original-image coordinates."""
+    if not isinstance(boxes, torch.Tensor) or not boxes.is_cuda:
+        raise RuntimeError("leanyolo_b200 unletterbox runs on CUDA tensors only (no CPU fallback)")
+    out = boxes.detach().to(torch.float32).reshape(1, -1, 4).contiguous().clone()
+    meta = torch.tensor([[gain[0], gain[1], pad[0], pad[1], to_shape[0], to_shape[1]]], dtype=torch.float32).to(boxes.device)
+    return unletterbox_dets(out, meta).reshape(boxes.shape)
+
+
+@torch.no_grad()
+def detect_images(model, images: Sequence[torch.Tensor], imgsz: int = 640, max_det: int = 300) -> List[torch.Tensor]:
+    """The loop body of tools/infer.py:110-138 for a batch: letterbox -> forward -> top-k decode -> unletterbox.
+    Returns one ``[k,6]`` tensor per image in ITS OWN pixel coordinates."""
+    batch, meta = letterbox_batch(images, imgsz)
+    dets = model.detect(batch, max_det=max_det)
+    unletterbox_dets(dets, meta)
+    return list(dets.unbind(0))

@@ -24,6 +24,7 @@ def registry():
     import gpu_checks as G
     import gpu_checks_decode as D
     import gpu_checks_model as M
+    import gpu_checks_preprocess as PR
 
     R = []
 
@@ -137,6 +138,11 @@ def registry():
     add("config3_m_640_nms_stress", M.check_config_nms, name="yolov10m", hw=640, B=2)
     add("config4_x_640", M.check_config_large, name="yolov10x", hw=640, B=2)
     add("config5_l_1280", M.check_config_large, name="yolov10l", hw=1280, B=1)
+    # pre / post-processing around the path: bit-exact with the reference's cv2 letterbox
+    add("letterbox_golden", PR.check_letterbox_golden)
+    add("letterbox_batch_640", PR.check_letterbox_batch)
+    add("unletterbox_batch", PR.check_unletterbox_batch)
+    add("detect_images_e2e", PR.check_detect_images)
     return R
 
 
