@@ -55,20 +55,32 @@ def _check_img(img: torch.Tensor) -> None:
         raise ValueError("image size out of range")   # cv2's fixed-point tables are 16-bit offsets as well
 
 
-def _launch(images: Sequence[torch.Tensor], geo, out: torch.Tensor, chw: bool, color) -> None:
+def _descs(images: Sequence[torch.Tensor], geo, dev) -> torch.Tensor:
+    """The DEVICE array of ``ly_lb_desc`` for a batch (one small host->device copy)."""
+    import numpy as np
+    a = np.zeros(len(images), dtype=np.dtype([("src", "<u8"), ("pitch", "<i8"), ("sh", "<i4"), ("sw", "<i4"), ("nh", "<i4"),
+                                              ("nw", "<i4"), ("top", "<i4"), ("left", "<i4")]))
+    a["src"] = [img.data_ptr() for img in images]
+    a["pitch"] = [img.stride(0) for img in images]
+    a["sh"] = [img.shape[0] for img in images]
+    a["sw"] = [img.shape[1] for img in images]
+    a["nw"], a["nh"], a["left"], a["top"] = [g[0] for g in geo], [g[1] for g in geo], [g[2] for g in geo], [g[3] for g in geo]
+    assert a.dtype.itemsize == C.sizeof(N.LyLbDesc)
+    return torch.from_numpy(a.view(np.uint8)).to(dev)
+
+
+def _run(d_descs: torch.Tensor, B: int, out: torch.Tensor, chw: bool, color) -> None:
     dev = out.device
-    descs = (N.LyLbDesc * len(images))()
-    for d, img, (new_w, new_h, left, top, *_rest) in zip(descs, images, geo):
-        d.src, d.src_pitch = img.data_ptr(), img.stride(0)
-        d.src_h, d.src_w, d.new_h, d.new_w, d.top, d.left = img.shape[0], img.shape[1], new_h, new_w, top, left
-    raw = torch.frombuffer(bytearray(bytes(descs)), dtype=torch.uint8)
     fill = (C.c_uint8 * 3)(*[int(c) for c in color])
     with torch.cuda.device(dev):
-        d_descs = raw.to(dev, non_blocking=False)
         stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-        N.check(N.lib().ly_letterbox_u8(d_descs.data_ptr(), len(images), out.data_ptr(), out.shape[-2] if chw else out.shape[-3],
+        N.check(N.lib().ly_letterbox_u8(d_descs.data_ptr(), B, out.data_ptr(), out.shape[-2] if chw else out.shape[-3],
                                         out.shape[-1] if chw else out.shape[-2], int(chw), fill, stream), "ly_letterbox_u8")
         d_descs.record_stream(torch.cuda.current_stream(dev))
+
+
+def _launch(images: Sequence[torch.Tensor], geo, out: torch.Tensor, chw: bool, color) -> None:
+    _run(_descs(images, geo, out.device), len(images), out, chw, color)
 
 
 @torch.no_grad()
