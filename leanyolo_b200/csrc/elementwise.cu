@@ -3,6 +3,7 @@
 // NHWC<->NCHW boundary converters.  All NHWC with 16-byte channel vectors; templated on
 // the storage type (bf16 hot path, fp32 check mode).
 #include <type_traits>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace ly {
@@ -623,8 +624,11 @@ static int32_t run_pool(const ly_op& op, cudaStream_t s) {
   constexpr int V = 16 / sizeof(T);
   LY_CHECK_ARG(aligned16<T>(op.src), "pool: view must be 16-byte aligned");
   const int nvec = op.src.c / V;
-  int cbv = 8;   // channel vectors per CTA: as many as the shared-memory plane allows, dividing the channel count
-  while (cbv > 1 && (nvec % cbv != 0 || (size_t)2 * op.src.H * op.src.W * cbv * 16 > 100 * 1024)) cbv >>= 1;
+  // channel vectors per CTA, dividing the channel count.  The kernel is a chain of 7 barrier-separated passes over a small
+  // plane, i.e. latency-bound: smaller planes = more CTAs per SM to hide it (measured at 20x20x256, batch 256: see DESIGN)
+  static const int plane_kb = getenv("LY_POOL_PLANE_KB") ? atoi(getenv("LY_POOL_PLANE_KB")) : 52;   // 100 KB: 0.140 ms, 52: 0.102, 26: 0.107, 13: 0.122
+  int cbv = 8;
+  while (cbv > 1 && (nvec % cbv != 0 || (size_t)2 * op.src.H * op.src.W * cbv * 16 > (size_t)plane_kb * 1024)) cbv >>= 1;
   const size_t smem = (size_t)2 * op.src.H * op.src.W * cbv * 16;
   LY_CHECK_ARG(smem <= 200 * 1024, "pool: feature map %dx%d too large for the shared-memory plane", op.src.H, op.src.W);
   static bool attr_set = false;
