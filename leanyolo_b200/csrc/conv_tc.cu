@@ -88,6 +88,7 @@ struct Params {
   int cin_pad;
   int rev;                 // walk the tiles / units last to first (see g_reverse)
   int st256;               // NHWC rows are 32-byte aligned: one 256-bit store per 16-channel chunk
+  int pair;                // streamed weights: two pixel tiles (2q, 2q+1) share every weight k-block (4 accumulators in TMEM)
 };
 
 // Optional per-role cycle accounting (-DLY_TC_PROFILE): CTA 0 prints where each role waited.
@@ -168,6 +169,65 @@ __device__ __forceinline__ void mma_role(const Params& p, uint32_t a_base, uint3
       }
       umma_commit(bar_aempty(bb, sa));
       if (++sa == a_stages) { sa = 0; pa ^= 1u; }
+    }
+    umma_commit(bar_tfull(bb, as));
+    if (++as == 2) { as = 0; aphase ^= 1u; }
+  }
+}
+
+// Pair mode issuer (streamed weights, one n tile, 4 * N <= 512 TMEM columns).  The 3x3 N = 128 layers stream
+// 295 KB of weights per 128-pixel tile; at 10 TB/s of L2 -> SM bandwidth that, not the tensor pipe, bounded
+// them (3x3 128->128 @40^2: 3584 tiles x 349 KB in 0.12 ms = 10.4 TB/s).  Every weight k-block now feeds the
+// MMAs of TWO pixel tiles (consecutive A stages), halving the weight traffic per output.
+template <int KSTEPS, int TPA>
+__device__ __forceinline__ void mma_role_pair(const Params& p, uint32_t a_base, uint32_t b_base, uint32_t bb, uint32_t tmem_base) {
+  const uint32_t hi = p.desc_hi, hi_a = p.desc_hi_a, idesc = p.idesc;
+  const int num_ka = p.num_ka, a_stages = p.a_stages, b_stages = p.b_stages, total = p.total_tiles;
+  const uint32_t a_stage16 = (uint32_t)p.a_stage >> 4, b_stage16 = (uint32_t)p.b_stage >> 4, tap16 = (uint32_t)p.a_tap_stride >> 4;
+  const uint32_t a_lo0 = (a_base >> 4) | (1u << 16), b_lo0 = (b_base >> 4) | (1u << 16);
+  const uint32_t block_n = (uint32_t)p.block_n;
+  const int pairs = (total + 1) >> 1;
+  int sa = 0, sb = 0, as = 0;
+  uint32_t pa = 0, pb = 0, aphase = 0;
+  for (int q = blockIdx.x; q < pairs; q += gridDim.x) {
+    const bool two = 2 * q + 1 < total;
+    mbar_wait(bar_tempty(bb, as), aphase ^ 1u);
+    tc_fence_after();
+    const uint32_t d0 = tmem_base + (uint32_t)(2 * as) * block_n, d1 = d0 + block_n;
+    for (int ka = 0; ka < num_ka; ++ka) {
+      const int s0 = sa;
+      mbar_wait(bar_afull(bb, s0), pa);
+      if (++sa == a_stages) { sa = 0; pa ^= 1u; }
+      const int s1 = sa;
+      if (two) {
+        mbar_wait(bar_afull(bb, s1), pa);
+        if (++sa == a_stages) { sa = 0; pa ^= 1u; }
+      }
+      tc_fence_after();
+      const uint32_t alo0 = a_lo0 + (uint32_t)s0 * a_stage16, alo1 = a_lo0 + (uint32_t)s1 * a_stage16;
+#pragma unroll
+      for (int tt = 0; tt < TPA; ++tt) {
+        mbar_wait(bar_bfull(bb, sb), pb);
+        tc_fence_after();
+        const uint32_t blo = b_lo0 + (uint32_t)sb * b_stage16;
+        const uint32_t acc = (tt != 0 || ka != 0) ? 1u : 0u;
+#pragma unroll
+        for (int kk = 0; kk < KSTEPS; ++kk) {
+          const uint64_t db = ((uint64_t)hi << 32) | (uint64_t)(blo + 2 * kk);
+          umma_bf16(d0, ((uint64_t)hi_a << 32) | (uint64_t)(alo0 + tt * tap16 + 2 * kk), db, idesc, kk != 0 ? 1u : acc);
+        }
+        if (two) {
+#pragma unroll
+          for (int kk = 0; kk < KSTEPS; ++kk) {
+            const uint64_t db = ((uint64_t)hi << 32) | (uint64_t)(blo + 2 * kk);
+            umma_bf16(d1, ((uint64_t)hi_a << 32) | (uint64_t)(alo1 + tt * tap16 + 2 * kk), db, idesc, kk != 0 ? 1u : acc);
+          }
+        }
+        umma_commit(bar_bempty(bb, sb));
+        if (++sb == b_stages) { sb = 0; pb ^= 1u; }
+      }
+      umma_commit(bar_aempty(bb, s0));
+      if (two) umma_commit(bar_aempty(bb, s1));
     }
     umma_commit(bar_tfull(bb, as));
     if (++as == 2) { as = 0; aphase ^= 1u; }
@@ -277,12 +337,13 @@ __device__ __forceinline__ void epilogue_role(const Params& p, uint8_t* smem_raw
 
   // Work items in the order the issuer accumulates them: one tile per step of the persistent loop
   // (flat / brick), or (unit, n tile, M tile) in band mode.  `it_*` is the state of the next item.
-  struct Loc { bool more, valid; uint32_t lin; int n0; };
+  struct Loc { bool more, valid, first, last; uint32_t lin; int n0, sub; };
   int it_unit = blockIdx.x, it_nt = 0, it_mt = 0;
+  const bool pair = MAP == 1 && p.pair != 0;
   auto next_item = [&]() -> Loc {
     Loc L;
-    L.more = it_unit < p.total_tiles;
-    L.valid = false; L.lin = 0; L.n0 = 0;
+    L.more = pair ? 2 * it_unit < p.total_tiles : it_unit < p.total_tiles;
+    L.valid = false; L.lin = 0; L.n0 = 0; L.sub = 0; L.first = L.last = true;
     if (!L.more) return L;
     if (MAP == 2) {
       const uint32_t pu = (uint32_t)phys(p, it_unit);
@@ -304,12 +365,18 @@ __device__ __forceinline__ void epilogue_role(const Params& p, uint8_t* smem_raw
       it_unit += gridDim.x;
     } else {
       int nt, wt, ht, bt;
-      split_tile(p, it_unit, nt, wt, ht, bt);
+      int tile = it_unit;
+      if (pair) {   // it_unit counts PAIRS: tiles 2q (accumulator 0) and 2q + 1 (accumulator 1)
+        tile = 2 * it_unit + it_mt;
+        L.sub = it_mt; L.first = it_mt == 0; L.last = it_mt == 1 || tile + 1 >= p.total_tiles;
+      }
+      split_tile(p, tile, nt, wt, ht, bt);
       const uint32_t w = (uint32_t)(wt * p.tw) + dw, h = (uint32_t)(ht * p.th) + dh, b = (uint32_t)(bt * p.tb) + db;
       L.valid = w < (uint32_t)p.Wo && h < (uint32_t)p.Ho && b < (uint32_t)p.Bo;
       L.lin = (b * (uint32_t)p.Ho + h) * (uint32_t)p.Wo + w;
       L.n0 = nt * p.block_n;
-      it_unit += gridDim.x;
+      if (pair && !L.last) it_mt = 1;
+      else { it_mt = 0; it_unit += gridDim.x; }
     }
     return L;
   };
@@ -375,9 +442,9 @@ __device__ __forceinline__ void epilogue_role(const Params& p, uint8_t* smem_raw
     } else if (valid) {
       drow = p.dst + (size_t)lin * (uint32_t)p.dCtot + p.dC0 + n0;
     }
-    { PROF_T0(); mbar_wait(bar_tfull(bar_base, as), aphase); PROF_ADD(w_tfull); }
+    if (cur.first) { PROF_T0(); mbar_wait(bar_tfull(bar_base, as), aphase); PROF_ADD(w_tfull); }
     tc_fence_after();
-    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.block_n);
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(((pair ? 2 * as : as) + cur.sub) * p.block_n);
     uint32_t nxt[16];
     if (cg < nchunks) tmem_ld16(taddr + cg * 16, nxt);
     bool released = false;
@@ -399,9 +466,11 @@ __device__ __forceinline__ void epilogue_role(const Params& p, uint8_t* smem_raw
       }
       if (!released && ch + 4 >= nchunks) {   // this warp's last TMEM load has completed (or it has none)
         released = true;
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_tempty(bar_base, as));
+        if (cur.last) {                       // (pair mode: the accumulator set is free after its second tile)
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_tempty(bar_base, as));
+        }
       }
       if (has) {
         if (kUp && valid) {
@@ -449,7 +518,7 @@ __device__ __forceinline__ void epilogue_role(const Params& p, uint8_t* smem_raw
         }
       }
     }
-    if (++as == 2) { as = 0; aphase ^= 1u; }
+    if (cur.last && ++as == 2) { as = 0; aphase ^= 1u; }
     rs ^= 1u;
     cur = nxtloc;
   }
@@ -571,6 +640,33 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                 for (int cb = 0; cb < kcb; ++cb)
                   for (int tap = 0; tap < 9; ++tap) load_b(tap * cin + cb * kc, nt * p.block_n);
         }
+      } else if (p.pair) {
+        // pair mode: the A boxes of tiles 2q and 2q+1 alternate in the ring, each weight slab is requested once
+        const int pairs = (p.total_tiles + 1) >> 1;
+        for (int q = blockIdx.x; q < pairs; q += gridDim.x) {
+          const bool two = 2 * q + 1 < p.total_tiles;
+          int nt, wt, ht, bt, nt1, wt1 = 0, ht1 = 0, bt1 = 0;
+          split_tile(p, 2 * q, nt, wt, ht, bt);
+          if (two) split_tile(p, 2 * q + 1, nt1, wt1, ht1, bt1);
+          const int w0 = wt * p.tw * p.stride - p.pad, h0 = ht * p.th * p.stride - p.pad, b0 = bt * p.tb;
+          const int w1 = wt1 * p.tw * p.stride - p.pad, h1 = ht1 * p.th * p.stride - p.pad, b1 = bt1 * p.tb;
+          if (p.halo) {
+            for (int cb = 0; cb < kcb; ++cb)
+              for (int kx = 0; kx < 3; ++kx) {
+                load_a(cb * kc, w0 + kx, h0, b0);
+                if (two) load_a(cb * kc, w1 + kx, h1, b1);
+                for (int ky = 0; ky < 3; ++ky) load_b((ky * 3 + kx) * cin + cb * kc, 0);
+              }
+          } else {
+            for (int ky = 0; ky < KK; ++ky)
+              for (int kx = 0; kx < KK; ++kx)
+                for (int cb = 0; cb < kcb; ++cb) {
+                  load_a(cb * kc, w0 + kx, h0 + ky, b0);
+                  if (two) load_a(cb * kc, w1 + kx, h1 + ky, b1);
+                  load_b((ky * KK + kx) * cin + cb * kc, 0);
+                }
+          }
+        }
       } else
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         int nt, wt, ht, bt;
@@ -607,6 +703,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         if (ksteps == 4) { if (p.b_resident) mma_role_band<4, true>(p, a_base, b_base, bar_base, tmem_base); else mma_role_band<4, false>(p, a_base, b_base, bar_base, tmem_base); }
         else if (ksteps == 2) { if (p.b_resident) mma_role_band<2, true>(p, a_base, b_base, bar_base, tmem_base); else mma_role_band<2, false>(p, a_base, b_base, bar_base, tmem_base); }
         else { if (p.b_resident) mma_role_band<1, true>(p, a_base, b_base, bar_base, tmem_base); else mma_role_band<1, false>(p, a_base, b_base, bar_base, tmem_base); }
+      } else if (p.pair) {
+        if (ksteps == 4) { if (p.tpa == 3) mma_role_pair<4, 3>(p, a_base, b_base, bar_base, tmem_base); else mma_role_pair<4, 1>(p, a_base, b_base, bar_base, tmem_base); }
+        else if (ksteps == 2) { if (p.tpa == 3) mma_role_pair<2, 3>(p, a_base, b_base, bar_base, tmem_base); else mma_role_pair<2, 1>(p, a_base, b_base, bar_base, tmem_base); }
+        else { if (p.tpa == 3) mma_role_pair<1, 3>(p, a_base, b_base, bar_base, tmem_base); else mma_role_pair<1, 1>(p, a_base, b_base, bar_base, tmem_base); }
       } else
 #define LY_MMA_CASE(KS)                                                                       \
   if (ksteps == KS) {                                                                         \
@@ -744,7 +844,11 @@ int32_t conv_tc_prepare(const ly_op& op, ConvTcState** out) {
   static const int band_ok = env_int("LY_TC_BAND", 1);   // 0 off, 1 by the model, 2 whenever it fits
   const long long b_all_bytes = (long long)p.num_kb * ((bn * p.kc * 2 + 1023) / 1024 * 1024);
   const bool b_res_possible = env_int("LY_TC_B_RESIDENT", 1) && p.tiles_n == 1 && b_all_bytes <= 96 * 1024;
-  if (band_ok && op.k == 3 && op.stride == 1 && Wo + 2 <= 256 && 2 * p.kc_blocks <= kMaxStages) {
+  // pair mode: streamed weights shared by two pixel tiles (see mma_role_pair)
+  static const int pair_ok = env_int("LY_TC_PAIR", 1);
+  p.pair = (pair_ok && op.k == 3 && p.tiles_n == 1 && !b_res_possible && 4 * bn <= 512) ? 1 : 0;
+  if (p.pair) p.tmem_cols = pow2_ge(4 * bn);
+  if (band_ok && !p.pair && op.k == 3 && op.stride == 1 && Wo + 2 <= 256 && 2 * p.kc_blocks <= kMaxStages) {
     const int sms = sm_count();
     const double cyc_mma = (bn <= 128 ? 32.0 + bn / 4.0 : bn / 2.0) * (p.kc / 16);     // per k-block per M tile
     const double tma_row = 5.0;
@@ -816,6 +920,13 @@ int32_t conv_tc_prepare(const ly_op& op, ConvTcState** out) {
     p.a_stages = p.b_resident ? (int)(avail / p.a_stage) : 2 * p.kc_blocks;
     p.b_stages = p.b_resident ? 1 : (int)((avail - (long long)p.a_stages * p.a_stage) / p.b_stage);
     if (p.a_stages < 2 * p.kc_blocks) { delete st; set_error("conv_tc: band does not fit in shared memory"); return LY_E_ARG; }
+  } else if (p.pair) {
+    // one k-step of a tile pair = 2 A stages + tpa weight slabs: size both rings in whole steps
+    const long long per_step = 2LL * p.a_stage + (long long)p.tpa * p.b_stage;
+    long long steps = avail / per_step;
+    if (steps < 1) steps = 1;
+    p.a_stages = (int)(2 * steps);
+    p.b_stages = (int)((avail - (long long)p.a_stages * p.a_stage) / p.b_stage);
   } else if (p.b_resident) {
     p.a_stages = (int)(avail / p.a_stage);
     p.b_stages = 1;
@@ -886,11 +997,12 @@ int32_t conv_tc_prepare(const ly_op& op, ConvTcState** out) {
   p.nchw = op.nchw; p.nCtot = op.nchw_ctot; p.nC0 = op.nchw_c0; p.nC = op.nchw_c;
 
   const int sms = sm_count();
-  st->grid = p.total_tiles < sms ? p.total_tiles : sms;
+  const int work = p.pair ? (p.total_tiles + 1) / 2 : p.total_tiles;
+  st->grid = work < sms ? work : sms;
   static const int debug = env_int("LY_TC_DEBUG", 0);
   if (debug)
-    fprintf(stderr, "[conv_tc] k%d s%d %dx%d cin %d cout %d B %d: mode %d bn %d tiles_n %d kc %d a_stages %d (%d B) b_res %d b_stages %d res_slot %d "
-            "band R %d mt %d bands %d units %d smem %zu\n", op.k, op.stride, op.src.H, op.src.W, Cin, Cout, op.B, p.halo, bn, p.tiles_n, p.kc,
+    fprintf(stderr, "[conv_tc] k%d s%d %dx%d cin %d cout %d B %d: mode %d pair %d bn %d tiles_n %d kc %d a_stages %d (%d B) b_res %d b_stages %d res_slot %d "
+            "band R %d mt %d bands %d units %d smem %zu\n", op.k, op.stride, op.src.H, op.src.W, Cin, Cout, op.B, p.halo, p.pair, bn, p.tiles_n, p.kc,
             p.a_stages, p.a_stage, p.b_resident, p.b_stages, p.res_slot, p.band_r, p.band_mt, p.bands, p.total_tiles, st->smem);
   static bool attr_set = false;
   if (!attr_set) {
