@@ -209,3 +209,54 @@ def check_config_large(name="yolov10l", hw=1280, B=1, seed=8):
         assert dets[i][0].shape == (300, 6)
         assert torch.allclose(dets[i][0][:, 4].cpu(), refd[i][0][:, 4], atol=2e-6)
     return {"max_rel": worst}
+
+
+def check_fullsize_properties(name="yolov10s", B=256, hw=640, seed=11):
+    """BASELINE config 2 at its FULL size (batch 256 @640^2), where the CPU oracle cannot follow: size-independent
+    properties of the path.
+      * batch consistency: images run alone give the same head tensors as inside the batch of 256 (only the tile
+        mapping, hence the fp32 summation order, may differ: rel-L2 < 5e-3);
+      * top-k decode: scores descending, finite boxes, class ids integral in [0, nc), exactly max_det rows, and the
+        scores equal the 300 largest of the oracle's per-image decode for a sample of images (exact top-k selection
+        out of 8400 x 80 candidates);
+      * NMS decode (conf 0.25 / iou 0.45): per image count <= max_det, scores descending and > conf, and NO kept
+        pair with IoU > thr (the defining property of greedy class-agnostic NMS), rows past the count are zero."""
+    m, sd = build(name, seed=seed)
+    g = torch.Generator(device=DEV).manual_seed(seed)
+    x = torch.randint(0, 256, (B, 3, hw, hw), dtype=torch.uint8, device=DEV, generator=g)
+    raw = [t.clone() for t in m(x)]
+    o2o = [t.clone() for t in m._eval_branches["one2one"]]
+    det = m.detect(x)
+    assert det.shape == (B, 300, 6) and bool(torch.isfinite(det).all())
+    sc = det[:, :, 4]
+    assert bool((sc[:, :-1] >= sc[:, 1:]).all()), "top-k scores are not descending"
+    cls = det[:, :, 5]
+    assert bool(((cls == cls.round()) & (cls >= 0) & (cls < 80)).all())
+    # batch consistency + exact top-k selection on a sample
+    for i in (0, 97, B - 1):
+        alone = m(x[i:i + 1])
+        for lvl in range(3):
+            e = _errs(alone[lvl][0], raw[lvl][i].cpu())
+            assert e[1] < 5e-3, f"image {i} level {lvl}: alone vs in-batch rel-L2 {e[1]:.2e}"
+        ref = O.decode_topk([t[i:i + 1].cpu() for t in o2o], num_classes=80)[0][0]
+        assert torch.allclose(det[i, :, 4].cpu(), ref[:, 4], atol=2e-6), f"image {i}: top-k scores differ from the oracle"
+    # NMS decode of the whole batch
+    out, count, _ = PP.nms_raw(raw, num_classes=80, strides=(8, 16, 32), conf_thresh=0.25, iou_thresh=0.45, max_det=300)
+    cnt = count.cpu()
+    assert int(cnt.max()) <= 300 and int(cnt.min()) >= 0
+    out_c = out.cpu()
+    worst = 0.0
+    for i in range(B):
+        n = int(cnt[i])
+        d = out_c[i]
+        assert bool((d[n:] == 0).all()), "rows past the count must be zero"
+        if n == 0:
+            continue
+        s = d[:n, 4]
+        assert bool((s > 0.25).all()) and bool((s[:-1] >= s[1:]).all())
+        if n > 1:
+            iou = O.box_iou(d[:n, :4], d[:n, :4])
+            iou.fill_diagonal_(0)
+            worst = max(worst, float(iou.max()))
+    assert worst <= 0.45 + 1e-6, f"two kept boxes overlap with IoU {worst:.4f} > 0.45"
+    return {"max_kept_iou": worst, "mean_kept": float(cnt.float().mean())}
