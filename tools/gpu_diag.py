@@ -138,6 +138,9 @@ def registry():
     add("config3_m_640_nms_stress", M.check_config_nms, name="yolov10m", hw=640, B=2)
     add("config4_x_640", M.check_config_large, name="yolov10x", hw=640, B=2)
     add("config5_l_1280", M.check_config_large, name="yolov10l", hw=1280, B=1)
+    add("model_n_640_vs_oracle", M.check_config_large, name="yolov10n", hw=640, B=2)
+    add("model_s_640_vs_oracle", M.check_config_large, name="yolov10s", hw=640, B=2)
+    add("model_b_640_vs_oracle", M.check_config_large, name="yolov10b", hw=640, B=1)
     add("config2_s_640_b256_properties", M.check_fullsize_properties, name="yolov10s", B=256, hw=640)
     # pre / post-processing around the path: bit-exact with the reference's cv2 letterbox
     add("letterbox_golden", PR.check_letterbox_golden)
