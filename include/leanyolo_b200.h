@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define LY_ABI_VERSION 3
+#define LY_ABI_VERSION 4
 
 #if defined(LY_BUILD) && defined(__GNUC__)
 #define LY_API __attribute__((visibility("default")))
@@ -52,6 +52,10 @@ enum {
   LY_OP_IMPORT = 8,   /* public NCHW fp32 -> NHWC storage (sub-module inputs)              */
   LY_OP_DWPW = 9,     /* fused depthwise 3x3 (+BN+SiLU) -> 1x1 Conv+BN(+SiLU): the depthwise result is
                          produced straight into the GEMM's shared-memory A tile      head.py:95-107, layers.py:256-264 */
+  LY_OP_CHAIN = 10,   /* a chain of dense Conv+BN(+SiLU) stages (k in {1,3}, stride 1) run per spatial tile with every
+                         intermediate tensor held in shared memory: a whole C2f block (cv1 -> Bottleneck -> cv2,
+                         layers.py:91-173) or the 3x3 -> 1x1 tail of a box-regression stack (head.py:86-92) in ONE
+                         launch; only the block's input and output touch HBM.  Described by ly_op.chain.            */
 };
 
 /* conv implementation selector (ly_op.impl) */
@@ -68,6 +72,40 @@ typedef struct ly_view {
   int32_t ctot;
   int32_t c0, c;
 } ly_view;
+
+/* ---- LY_OP_CHAIN ---------------------------------------------------------------------------------
+ * The tile's tensors live in shared-memory REGIONS: [pixels of the tile + halo][<= 64 channels] bf16.
+ * Regions 0 .. n_in-1 are the 64-channel blocks of op.src (loaded by TMA, zero padding = OOB fill); the
+ * others are written by the stages.  A stage is one implicit GEMM over the tile: its K dimension is
+ * the list of source blocks (all the same width), its output goes to a region (zeroed outside the
+ * image, which is the next conv's zero padding) or, for the last stage, to op.dst / op.nchw.          */
+#define LY_CHAIN_MAX_STAGES 6
+#define LY_CHAIN_MAX_BLOCKS 4
+#define LY_CHAIN_MAX_REGIONS 8
+
+typedef struct ly_chain_blk {
+  int32_t region;     /* < 0: absent */
+  int32_t c0, c;      /* channels [c0, c0 + c) of the region, multiples of 16 */
+} ly_chain_blk;
+
+typedef struct ly_chain_stage {
+  int32_t k;          /* 1 or 3 (stride 1, zero padding k/2) */
+  int32_t act;        /* 1 = SiLU after bias */
+  int32_t cout;       /* multiple of 16, <= 256 */
+  int32_t n_src;      /* source blocks in weight-column order, all of width 16, 32 or 64 */
+  ly_chain_blk src[LY_CHAIN_MAX_BLOCKS];
+  ly_chain_blk dst;   /* region < 0: the last stage, written to op.dst (NHWC slice) or op.nchw */
+  ly_chain_blk res;   /* added after the activation (Bottleneck shortcut); region < 0: none */
+  const void* w;      /* bf16 [cout][k*k][sum of the source widths] */
+  const float* bias;  /* [cout] fp32 */
+} ly_chain_stage;
+
+typedef struct ly_chain {
+  int32_t n_regions, n_in;
+  int32_t region_c[LY_CHAIN_MAX_REGIONS];   /* channels per region: 16, 32 or 64 */
+  int32_t n_stages, reserved;
+  ly_chain_stage st[LY_CHAIN_MAX_STAGES];
+} ly_chain;
 
 /* One kernel launch.  Unused fields are zero. */
 typedef struct ly_op {
@@ -95,6 +133,7 @@ typedef struct ly_op {
    * conv1x1(cat[up(a), b]) = act(W_b*b + up(W_a*a) + bias): the neck's upsample + concat never
    * materialises (neck.py:116-121).  up.ptr == NULL: absent. */
   ly_view up;
+  const ly_chain* chain;  /* LY_OP_CHAIN only (HOST pointer, copied by ly_launch / ly_plan_create) */
 } ly_op;
 
 /* ---- library ---------------------------------------------------------- */

@@ -10,15 +10,31 @@ from pathlib import Path
 
 LIB_PATH = Path(__file__).resolve().parent / "_lib" / "libleanyolo_b200.so"
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 LY_BF16, LY_F32 = 0, 1
-OP_STEM, OP_CONV, OP_DW, OP_POOL, OP_UP, OP_ATTN, OP_EXPORT, OP_IMPORT, OP_DWPW = 1, 2, 3, 4, 5, 6, 7, 8, 9
+OP_STEM, OP_CONV, OP_DW, OP_POOL, OP_UP, OP_ATTN, OP_EXPORT, OP_IMPORT, OP_DWPW, OP_CHAIN = 1, 2, 3, 4, 5, 6, 7, 8, 9, 10
+CHAIN_MAX_STAGES, CHAIN_MAX_BLOCKS, CHAIN_MAX_REGIONS = 6, 4, 8
 IMPL_AUTO, IMPL_SIMT, STEM_IN_U8 = 0, 1, 2
 
 
 class LyView(C.Structure):
     _fields_ = [("ptr", C.c_void_p), ("H", C.c_int32), ("W", C.c_int32), ("ctot", C.c_int32),
                 ("c0", C.c_int32), ("c", C.c_int32)]
+
+
+class LyChainBlk(C.Structure):      # mirrors `ly_chain_blk`
+    _fields_ = [("region", C.c_int32), ("c0", C.c_int32), ("c", C.c_int32)]
+
+
+class LyChainStage(C.Structure):    # mirrors `ly_chain_stage`
+    _fields_ = [("k", C.c_int32), ("act", C.c_int32), ("cout", C.c_int32), ("n_src", C.c_int32),
+                ("src", LyChainBlk * CHAIN_MAX_BLOCKS), ("dst", LyChainBlk), ("res", LyChainBlk),
+                ("w", C.c_void_p), ("bias", C.c_void_p)]
+
+
+class LyChain(C.Structure):         # mirrors `ly_chain`
+    _fields_ = [("n_regions", C.c_int32), ("n_in", C.c_int32), ("region_c", C.c_int32 * CHAIN_MAX_REGIONS),
+                ("n_stages", C.c_int32), ("reserved", C.c_int32), ("st", LyChainStage * CHAIN_MAX_STAGES)]
 
 
 class LyOp(C.Structure):
@@ -31,6 +47,7 @@ class LyOp(C.Structure):
         ("nchw_ctot", C.c_int32), ("nchw_c0", C.c_int32), ("nchw_c", C.c_int32), ("ext_slot", C.c_int32),
         ("pre_w", C.c_void_p), ("pre_bias", C.c_void_p), ("pre_k", C.c_int32), ("pre_act", C.c_int32),
         ("up", LyView),
+        ("chain", C.POINTER(LyChain)),
     ]
 
 

@@ -78,6 +78,14 @@ static int32_t dispatch(const ly_op& op, cudaStream_t s) {
       dwpw_free(st);
       return rc;
     }
+    case LY_OP_CHAIN: {
+      ChainState* st = nullptr;
+      int32_t rc = chain_tc_prepare(op, &st);
+      if (rc != LY_OK) return rc;
+      rc = chain_tc_launch(st, nullptr, s);
+      chain_tc_free(st);
+      return rc;
+    }
     case LY_OP_DW: return launch_dw(op, s);
     case LY_OP_POOL: return launch_pool(op, s);
     case LY_OP_UP: return launch_up(op, s);
@@ -92,13 +100,17 @@ static int32_t dispatch(const ly_op& op, cudaStream_t s) {
 
 using namespace ly;
 
-static_assert(sizeof(ly_view) == 32 && sizeof(ly_op) == 264, "ly_op layout is part of the C ABI (mirrored by ctypes in _native.py)");
+static_assert(sizeof(ly_chain_stage) == 104 && sizeof(ly_chain) == 672, "ly_chain layout is part of the C ABI (mirrored by ctypes in _native.py)");
+static_assert(sizeof(ly_view) == 32 && sizeof(ly_op) == 272, "ly_op layout is part of the C ABI (mirrored by ctypes in _native.py)");
 
 struct ly_plan {
   std::vector<ly_op> ops;
   std::vector<ConvTcState*> tc;   // per op (nullptr when not a tensor-core conv)
   std::vector<DwPwState*> fz;     // per op (nullptr when not a fused dw->1x1)
+  std::vector<ChainState*> chn;   // per op (nullptr when not a fused chain)
   ~ly_plan() {
+    for (auto* t : chn)
+      if (t) chain_tc_free(t);
     for (auto* t : tc)
       if (t) conv_tc_free(t);
     for (auto* t : fz)
@@ -134,13 +146,16 @@ int32_t ly_plan_create(const ly_op* ops, int32_t n_ops, ly_plan** out) {
   pl->ops.assign(ops, ops + n_ops);
   pl->tc.assign(n_ops, nullptr);
   pl->fz.assign(n_ops, nullptr);
+  pl->chn.assign(n_ops, nullptr);
   for (int i = 0; i < n_ops; ++i) {
     const ly_op& op = pl->ops[i];
     g_reverse = reverse_enabled() ? (i & 1) : 0;
-    if ((op.kind == LY_OP_CONV && use_tc(op)) || op.kind == LY_OP_DWPW) {
+    if ((op.kind == LY_OP_CONV && use_tc(op)) || op.kind == LY_OP_DWPW || op.kind == LY_OP_CHAIN) {
       ly_op tmp = op;
       if (tmp.ext_slot >= 0 && !tmp.nchw) tmp.nchw = reinterpret_cast<float*>(16);  // placeholder: real pointer comes at run time
-      rc = op.kind == LY_OP_DWPW ? dwpw_prepare(tmp, &pl->fz[i]) : conv_tc_prepare(tmp, &pl->tc[i]);
+      rc = op.kind == LY_OP_CHAIN ? chain_tc_prepare(tmp, &pl->chn[i])
+                                  : (op.kind == LY_OP_DWPW ? dwpw_prepare(tmp, &pl->fz[i]) : conv_tc_prepare(tmp, &pl->tc[i]));
+      pl->ops[i].chain = nullptr;   // the prepared state owns a copy; the caller's description may go away
       if (rc != LY_OK) {
         char msg[400];
         snprintf(msg, sizeof(msg), "%s", g_err);
@@ -178,6 +193,8 @@ static int32_t plan_run_impl(ly_plan* pl, float* const* ext, int32_t n_ext, int3
       rc = conv_tc_launch(pl->tc[i], op.ext_slot >= 0 ? nchw : nullptr, s);
     } else if (pl->fz[i]) {
       rc = dwpw_launch(pl->fz[i], op.ext_slot >= 0 ? nchw : nullptr, s);
+    } else if (pl->chn[i]) {
+      rc = chain_tc_launch(pl->chn[i], op.ext_slot >= 0 ? nchw : nullptr, s);
     } else {
       ly_op tmp = op;
       tmp.nchw = nchw;
@@ -227,7 +244,7 @@ int32_t ly_plan_profile(ly_plan* pl, float* const* ext, int32_t n_ext, int32_t i
   if (rc == LY_OK)
     for (size_t i = 0; i < n; ++i) {
       cudaEventElapsedTime(&h_ms[i], ev[i], ev[i + 1]);
-      if (h_is_tc) h_is_tc[i] = (pl->tc[i] || pl->fz[i]) ? 1 : 0;
+      if (h_is_tc) h_is_tc[i] = (pl->tc[i] || pl->fz[i] || pl->chn[i]) ? 1 : 0;
     }
   for (auto& e : ev) cudaEventDestroy(e);
   return rc;

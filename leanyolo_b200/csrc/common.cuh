@@ -76,6 +76,13 @@ int32_t dwpw_mma_launch(const DwPwMmaState* st, float* nchw_override, cudaStream
 void dwpw_mma_free(DwPwMmaState* st);
 bool dwpw_mma_supported(const ly_op& op);
 
+// fused chain of dense conv stages with shared-memory intermediates (chain_tc.cu)
+struct ChainState;
+int32_t chain_tc_prepare(const ly_op& op, ChainState** out);
+int32_t chain_tc_launch(const ChainState* st, float* nchw_override, cudaStream_t s);
+void chain_tc_free(ChainState* st);
+bool chain_tc_supported(const ly_op& op);
+
 int sm_count();
 
 // Tile traversal direction of the op being prepared / launched (set by the plan executor: ops

@@ -113,3 +113,35 @@ def run_plan(pb: PlanBuilder, x: torch.Tensor, quant=None):
         else:
             raise NotImplementedError(op.kind)
     return outs
+
+
+def run_chain(regions, n_in, stages, x, quant=None):
+    """Reference semantics of LY_OP_CHAIN (include/leanyolo_b200.h) on whole images.
+
+    regions: channels per region; x: [B,H,W,sum(regions[:n_in])] NHWC fp32 (already in the storage
+    precision); stages: dicts {k, act, cout, src: [(region, c0, c)], dst: (region, c0, c) | None,
+    res: (region, c0, c) | None, w: [cout,k,k,Ctot] fp32, b: [cout] fp32}.  Intermediates are stored
+    through ``quant`` (the kernel keeps them as bf16 in shared memory).  Returns the last stage's
+    [B,H,W,cout] fp32 result (not quantised)."""
+    q = quant or (lambda t: t)
+    B, H, W, _ = x.shape
+    reg = [torch.zeros(B, H, W, c) for c in regions]
+    off = 0
+    for i in range(n_in):
+        reg[i] = x[..., off:off + regions[i]].clone()
+        off += regions[i]
+    y = None
+    for st in stages:
+        xin = torch.cat([reg[r][..., c0:c0 + c] for r, c0, c in st["src"]], -1).permute(0, 3, 1, 2)
+        w = st["w"].float().permute(0, 3, 1, 2)
+        y = F.conv2d(xin, w, st["b"].float(), 1, st["k"] // 2)
+        if st["act"]:
+            y = F.silu(y)
+        y = y.permute(0, 2, 3, 1)
+        if st.get("res") is not None:
+            r, c0, c = st["res"]
+            y = y + reg[r][..., c0:c0 + c]
+        if st.get("dst") is not None:
+            r, c0, c = st["dst"]
+            reg[r][..., c0:c0 + c] = q(y)
+    return y

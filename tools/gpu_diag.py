@@ -25,6 +25,7 @@ def registry():
     import gpu_checks_decode as D
     import gpu_checks_model as M
     import gpu_checks_preprocess as PR
+    import gpu_checks_chain as CH
 
     R = []
 
@@ -67,6 +68,19 @@ def registry():
     add("tc_1x1_up_views", G.check_conv, cin=128, cout=64, k=1, H=8, W=8, up=True, src_off=256, dst_off=0, dst_extra=64)
     add("tc_3x3_big", G.check_conv, cin=64, cout=64, k=3, H=160, W=160, B=4)
     add("tc_1x1_big", G.check_conv, cin=256, cout=128, k=1, H=80, W=80, B=8)
+    # fused conv chains (LY_OP_CHAIN): single stages first (bisecting), then the real blocks
+    add("chain_single_1x1_64", CH.check_chain, kind="single", k=1, cin=64, cout=64, H=16, W=16)
+    add("chain_single_3x3_64", CH.check_chain, kind="single", k=3, cin=64, cout=64, H=16, W=16)
+    add("chain_single_3x3_32", CH.check_chain, kind="single", k=3, cin=32, cout=32, H=24, W=20)
+    add("chain_single_3x3_16_n48", CH.check_chain, kind="single", k=3, cin=16, cout=48, H=12, W=28, B=3)
+    add("chain_tail_64_nchw", CH.check_chain, kind="tail", c=64, cout=64, H=20, W=20, nchw=True)
+    add("chain_tail_64_80", CH.check_chain, kind="tail", c=64, cout=64, H=80, W=80, B=3, nchw=True, nchw_c=61)
+    add("chain_tail_32_views", CH.check_chain, kind="tail", c=32, cout=48, H=24, W=40, act_last=True, src_off=32, src_extra=16, dst_off=16, dst_extra=32)
+    add("chain_two_in", CH.check_chain, kind="two_in", H=20, W=36)
+    add("chain_c2f_32", CH.check_chain, kind="c2f", c=32, H=40, W=40)
+    add("chain_c2f_32_160", CH.check_chain, kind="c2f", c=32, H=160, W=160, B=3)
+    add("chain_c2f_32_noshortcut_odd", CH.check_chain, kind="c2f", c=32, shortcut=False, H=36, W=52, B=3, src_off=64, dst_off=64, dst_extra=64)
+    add("chain_c2f_16", CH.check_chain, kind="c2f", c=16, H=48, W=48)
     # bandwidth kernels
     for dt in ("bf16", "f32"):
         add(f"dw3_{dt}", G.check_dw, dtype=dt, k=3)
