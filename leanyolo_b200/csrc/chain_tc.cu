@@ -45,6 +45,7 @@ constexpr int kMaxSt = LY_CHAIN_MAX_STAGES, kMaxBlk = LY_CHAIN_MAX_BLOCKS, kMaxR
 constexpr int kMaxMt = 8;          // M tiles per stage and tile
 constexpr int kMaxItems = kMaxSt * kMaxMt;
 constexpr int kMaxSlots = 8;
+constexpr int kMaxEntries = 1024;  // MMAs per item list (descriptor table in shared memory)
 constexpr int kNumBars = 3 + 2 * kMaxSlots + kMaxSt * kMaxMt + 1;   // + the TMEM base slot
 constexpr uint32_t kSmemMax = 227 * 1024 - 1024;                    // dynamic shared memory incl. the 1 KB alignment slack
 
@@ -72,12 +73,20 @@ struct Params {
   int tiles_x, tiles_y, total_tiles;
   uint32_t mg_pw;
   int H, W, B;
-  int n_items, x_last_item;
-  unsigned char item_stage[kMaxItems], item_mt[kMaxItems];
-  int slot_w, n_slots;
+  int n_items, early;
+  // item list of one iteration: (stage, M tile), flags bit0 = belongs to the NEXT tile of this CTA (an "early" stage
+  // hoisted into the tail of the previous tile), bit1 = reads the input frame, bit2 = last reader of the input frame;
+  // wstage/wmt: before issuing, also wait for M tiles 0..wmt of stage wstage of the CURRENT tile (0xFF: none)
+  unsigned char item_stage[kMaxItems], item_mt[kMaxItems], item_flags[kMaxItems], item_wstage[kMaxItems], item_wmt[kMaxItems];
+  unsigned short item_nmma[kMaxItems], item_first[kMaxItems];   // MMAs of the item / its first entry in the descriptor table
+  unsigned char item_dep[kMaxItems][8];                         // per producer stage: last M tile the item needs (0xFF: none)
+  uint32_t tab_off, hdr_off;                                    // byte offsets of the descriptor table / item headers
+  int n_entries;
+  int slot_w, n_slots, n_groups;
   uint32_t x_bytes, w_bytes, bias_off_b, bar_off;
   __nv_bfloat16* dst; int dCtot, dC0, st256;
   float* nchw; int nCtot, nC0, nC;
+  int prof;     // LY_CHAIN_PROF=1: CTA 0 prints where each role spent its cycles
 };
 
 __device__ __forceinline__ uint32_t lds32x4(uint32_t addr, uint32_t* v) {
@@ -86,6 +95,23 @@ __device__ __forceinline__ uint32_t lds32x4(uint32_t addr, uint32_t* v) {
 }
 __device__ __forceinline__ void sts32x4(uint32_t addr, const uint32_t* v) {
   asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]) : "memory");
+}
+
+// The MMAs of one source block of one item: all taps x k-steps as straight-line code.  A descriptor is (constant high
+// word | 14-bit address field): moving to the next tap / k-step is an integer add on the low word.  (A generic
+// loop with run-time bounds spent ~130 cycles of dependent integer work per MMA in the single issuing thread.)
+template <int TAPS, int KS>
+__device__ __forceinline__ void issue_block(uint32_t d_tmem, uint32_t a_hi, uint32_t a0, uint32_t rowb16, uint32_t pwr16, uint32_t b_hi,
+                                            uint32_t b0, uint32_t bstep, uint32_t idesc, uint32_t acc0) {
+#pragma unroll
+  for (int tap = 0; tap < TAPS; ++tap) {
+    const uint32_t alo = a0 + (uint32_t)(tap / 3) * pwr16 + (uint32_t)(tap % 3) * rowb16;
+    const uint32_t blo = b0 + (uint32_t)tap * bstep;
+#pragma unroll
+    for (int kk = 0; kk < KS; ++kk)
+      umma_bf16(d_tmem, ((uint64_t)a_hi << 32) | (uint64_t)(alo + 2 * kk), ((uint64_t)b_hi << 32) | (uint64_t)(blo + 2 * kk), idesc,
+                (tap | kk) != 0 ? 1u : acc0);
+  }
 }
 
 __global__ void __launch_bounds__(kThreads, 1) chain_tc_kernel(const __grid_constant__ Params p) {
@@ -130,6 +156,31 @@ __global__ void __launch_bounds__(kThreads, 1) chain_tc_kernel(const __grid_cons
           tma_load_2d(base + S.w_off + (uint32_t)(tap * S.n_src + b) * S.w_tile, &p.tmW[s], b_wfull, tap * ctot + b * kc, 0);
     }
   }
+  // Descriptor table: the (A, B) shared-memory descriptors of every MMA of the item list.  They do not depend on the
+  // tile, so the single issuing thread only streams 16-byte entries instead of chasing parameter-bank loads
+  // (measured: ~400 cycles of dependent constant loads per item and source block in the generic loop).
+  uint4* tab = reinterpret_cast<uint4*>(gen + p.tab_off);
+  uint4* hdr = reinterpret_cast<uint4*>(gen + p.hdr_off);
+  for (int i = 0; i < p.n_items; ++i) {
+    const StageP& S = p.st[p.item_stage[i]];
+    const int mt = p.item_mt[i], taps = S.k * S.k, per_blk = taps * S.ksteps, n = p.item_nmma[i];
+    for (int idx = threadIdx.x; idx < n; idx += kThreads) {
+      const int b = idx / per_blk, rem = idx - b * per_blk, tap = rem / S.ksteps, kk = rem - tap * S.ksteps;
+      const int R = S.src_region[b];
+      const uint32_t rowb16 = (uint32_t)p.region_rowb[R] >> 4;
+      const uint32_t trow = S.k == 3 ? (uint32_t)((tap / 3) * p.PW + (tap % 3)) : 0u;
+      const uint32_t alo = (((base + p.region_off[R]) >> 4) + ((uint32_t)(mt * 128 + S.src_rows[b]) + trow) * rowb16 + (uint32_t)S.src_a16[b] + 2u * kk) | (1u << 16);
+      const uint32_t blo = (((base + S.w_off + (uint32_t)(tap * S.n_src + b) * S.w_tile) >> 4) + 2u * kk) | (1u << 16);
+      tab[p.item_first[i] + idx] = make_uint4(alo, p.region_hi[R], blo, S.b_hi);
+    }
+    if (threadIdx.x == 0) {
+      const unsigned char* d = p.item_dep[i];
+      hdr[2 * i] = make_uint4((uint32_t)p.item_stage[i] | ((uint32_t)mt << 8) | ((uint32_t)p.item_flags[i] << 16), (uint32_t)n | ((uint32_t)p.item_first[i] << 16),
+                              S.idesc, 0u);
+      hdr[2 * i + 1] = make_uint4((uint32_t)d[0] | ((uint32_t)d[1] << 8) | ((uint32_t)d[2] << 16) | ((uint32_t)d[3] << 24),
+                                  (uint32_t)d[4] | ((uint32_t)d[5] << 8) | ((uint32_t)d[6] << 16) | ((uint32_t)d[7] << 24), 0u, 0u);
+    }
+  }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -160,74 +211,107 @@ __global__ void __launch_bounds__(kThreads, 1) chain_tc_kernel(const __grid_cons
     if (elect_one()) {
       mbar_wait(b_wfull, 0);
       tc_fence_after();
-      uint32_t gi = 0, itp = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        mbar_wait(b_xfull, itp);
-        tc_fence_after();
+      uint32_t gi = 0;
+      long long t_x = 0, t_done = 0, t_slot = 0, t_issue = 0, t_start = clock64();
+      const int n_tiles = (p.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // tiles of this CTA
+      int x_tile = -1;                       // local tile whose input frame has been waited for
+      for (int it = p.early ? -1 : 0; it < n_tiles; ++it) {
         int waited[kMaxSt];
 #pragma unroll
         for (int s = 0; s < kMaxSt; ++s) waited[s] = 0;
+        // wait until stage `prod` of local tile `it` has written its rows up to last_row
         auto need_rows = [&](int prod, int last_row) {
-          if (prod < 0) return;
+          if (prod < 0 || it < 0) return;
           int need = last_row >> 7;
           if (need > p.st[prod].n_mt - 1) need = p.st[prod].n_mt - 1;
           while (waited[prod] <= need) {
-            mbar_wait(done(prod, waited[prod]), itp);
+            mbar_wait(done(prod, waited[prod]), (uint32_t)it & 1u);
             ++waited[prod];
           }
         };
         for (int i = 0; i < p.n_items; ++i) {
-          const int s = p.item_stage[i], mt = p.item_mt[i];
-          const StageP& S = p.st[s];
-          const int last = mt * 128 + 127;
-          for (int b = 0; b < S.n_src; ++b) need_rows(S.src_prod[b], last + S.reads_halo + S.src_rows[b]);
-          need_rows(S.res_prod, last + S.res_rows);
+          const uint4 h0 = hdr[2 * i], h1 = hdr[2 * i + 1];
+          const int fl = (int)((h0.x >> 16) & 0xFFu);
+          const int t = it + (fl & 1);
+          if (t < 0 || t >= n_tiles) continue;
+          long long t1 = clock64();
+          if ((fl & 2) && x_tile != t) {
+            mbar_wait(b_xfull, (uint32_t)t & 1u);
+            x_tile = t;
+            t_x += clock64() - t1;
+            t1 = clock64();
+          }
+          if (it >= 0) {
+#pragma unroll
+            for (int s = 0; s < kMaxSt; ++s) {
+              const uint32_t need = ((s < 4 ? h1.x : h1.y) >> (8 * (s & 3))) & 0xFFu;
+              if (need != 0xFFu)
+                while (waited[s] <= (int)need) {
+                  mbar_wait(done(s, waited[s]), (uint32_t)it & 1u);
+                  ++waited[s];
+                }
+            }
+          }
+          tc_fence_after();
+          long long t2 = clock64();
+          t_done += t2 - t1;
           const uint32_t slot = gi % (uint32_t)p.n_slots, use = gi / (uint32_t)p.n_slots;
           ++gi;
           mbar_wait(tempty(slot), (use & 1u) ^ 1u);
           tc_fence_after();
+          long long t3 = clock64();
+          t_slot += t3 - t2;
           const uint32_t d_tmem = tmem_base + slot * (uint32_t)p.slot_w;
-          uint32_t acc = 0;
-          const int taps = S.k * S.k;
-          for (int b = 0; b < S.n_src; ++b) {
-            const int R = S.src_region[b];
-            const uint32_t rowb16 = (uint32_t)p.region_rowb[R] >> 4;
-            const uint32_t a0 = ((base + p.region_off[R]) >> 4) + (uint32_t)(mt * 128 + S.src_rows[b]) * rowb16 + (uint32_t)S.src_a16[b];
-            const uint32_t a_hi = p.region_hi[R];
-            for (int tap = 0; tap < taps; ++tap) {
-              const uint32_t trow = S.k == 3 ? (uint32_t)((tap / 3) * p.PW + (tap % 3)) : 0u;
-              const uint32_t alo = (a0 + trow * rowb16) | (1u << 16);
-              const uint32_t blo = ((base + S.w_off + (uint32_t)(tap * S.n_src + b) * S.w_tile) >> 4) | (1u << 16);
-              for (int kk = 0; kk < S.ksteps; ++kk) {
-                umma_bf16(d_tmem, ((uint64_t)a_hi << 32) | (uint64_t)(alo + 2 * kk), ((uint64_t)S.b_hi << 32) | (uint64_t)(blo + 2 * kk),
-                          S.idesc, acc);
-                acc = 1u;
-              }
-            }
+          const uint32_t idesc = h0.z;
+          const int n = (int)(h0.y & 0xFFFFu);
+          const uint4* e = tab + (h0.y >> 16);
+          int m = 0;
+          for (; m + 4 <= n; m += 4) {
+            const uint4 d0 = e[m], d1 = e[m + 1], d2 = e[m + 2], d3 = e[m + 3];
+            umma_bf16(d_tmem, ((uint64_t)d0.y << 32) | d0.x, ((uint64_t)d0.w << 32) | d0.z, idesc, m != 0 ? 1u : 0u);
+            umma_bf16(d_tmem, ((uint64_t)d1.y << 32) | d1.x, ((uint64_t)d1.w << 32) | d1.z, idesc, 1u);
+            umma_bf16(d_tmem, ((uint64_t)d2.y << 32) | d2.x, ((uint64_t)d2.w << 32) | d2.z, idesc, 1u);
+            umma_bf16(d_tmem, ((uint64_t)d3.y << 32) | d3.x, ((uint64_t)d3.w << 32) | d3.z, idesc, 1u);
+          }
+          for (; m < n; ++m) {
+            const uint4 d0 = e[m];
+            umma_bf16(d_tmem, ((uint64_t)d0.y << 32) | d0.x, ((uint64_t)d0.w << 32) | d0.z, idesc, m != 0 ? 1u : 0u);
           }
           umma_commit(tfull(slot));
-          if (i == p.x_last_item) umma_commit(b_xempty);    // the input frame may be overwritten by the next tile's
+          if (fl & 4) umma_commit(b_xempty);    // the input frame may be overwritten by the next tile's
+          t_issue += clock64() - t3;
         }
-        // every region row written in this tile has been consumed (or at least produced) before the next tile
-        // starts overwriting: wait for the M tiles nobody asked for, which also keeps the barrier phases in step
+        // every region row written for tile `it` has been consumed (or at least produced) before later tiles
+        // overwrite it: wait for the M tiles nobody asked for, which also keeps the barrier phases in step
         for (int s = 0; s < p.n_stages; ++s)
           if (p.st[s].dst_region >= 0) need_rows(s, p.st[s].n_mt * 128 - 1);
-        itp ^= 1u;
       }
+      if (p.prof && blockIdx.x == 0)
+        printf("[chain prof] mma: tiles %d total %lld  wait_x %lld wait_done %lld wait_slot %lld issue %lld (cycles)\n", n_tiles,
+               clock64() - t_start, t_x, t_done, t_slot, t_issue);
     }
   } else {
     // ============================== epilogue (4 groups x 4 warps) ==============
     const int q = warp & 3, group = (warp - 2) >> 2;
     const uint32_t row_in = (uint32_t)(q * 32 + lane);
-    uint32_t gi = 0, itp = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      const int b = tile / tiles_img, t2 = tile - b * tiles_img;
-      const int yt = t2 / p.tiles_x, xt = t2 - yt * p.tiles_x;
-      const int y00 = yt * p.TH - p.halo, x00 = xt * p.TW - p.halo;
+    uint32_t gi = 0;
+    long long e_wait = 0, e_work = 0, e_start = clock64();
+    const int n_tiles = (p.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    for (int it = p.early ? -1 : 0; it < n_tiles; ++it) {
       for (int i = 0; i < p.n_items; ++i) {
+        const int t = it + (p.item_flags[i] & 1);
+        if (t < 0 || t >= n_tiles) continue;
         const uint32_t slot = gi % (uint32_t)p.n_slots, use = gi / (uint32_t)p.n_slots;
+        // items go to the groups by their GLOBAL sequence number: n_slots is a multiple of the group count, so every
+        // use of an accumulator slot is drained by the same group and its parity waits see every phase in turn
+        const bool mine_item = (int)(gi % (uint32_t)p.n_groups) == group;
         ++gi;
-        if ((i & 3) != group) continue;
+        if (!mine_item) continue;
+        const uint32_t itp = (uint32_t)t & 1u;
+        const int tile = (int)blockIdx.x + t * (int)gridDim.x;
+        const int b = tile / tiles_img, t2 = tile - b * tiles_img;
+        const int yt = t2 / p.tiles_x, xt = t2 - yt * p.tiles_x;
+        const int y00 = yt * p.TH - p.halo, x00 = xt * p.TW - p.halo;
         const int s = p.item_stage[i], mt = p.item_mt[i];
         const StageP& S = p.st[s];
         const uint32_t r = (uint32_t)mt * 128u + row_in;
@@ -267,7 +351,10 @@ __global__ void __launch_bounds__(kThreads, 1) chain_tc_kernel(const __grid_cons
         const float pre = S.act ? 0.5f : 1.0f;
         const float* bias = s_bias + S.bias_off;
         const int nch = S.cout >> 4;
+        const long long w0 = clock64();
         mbar_wait(tfull(slot), use & 1u);
+        const long long w1 = clock64();
+        e_wait += w1 - w0;
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + slot * (uint32_t)p.slot_w;
         uint32_t nxt[16];
@@ -334,9 +421,11 @@ __global__ void __launch_bounds__(kThreads, 1) chain_tc_kernel(const __grid_cons
           __syncwarp();
           if (lane == 0) mbar_arrive(done(s, mt));
         }
+        e_work += clock64() - w1;
       }
-      itp ^= 1u;
     }
+    if (p.prof && blockIdx.x == 0 && lane == 0 && q == 0)
+      printf("[chain prof] epilogue group %d: total %lld wait_tfull %lld work %lld\n", group, clock64() - e_start, e_wait, e_work);
   }
 
   tc_fence_before();
@@ -365,7 +454,7 @@ struct Layout {
   int rows[kMaxReg];
   uint32_t region_off[kMaxReg];
   uint32_t w_off[kMaxSt], w_tile[kMaxSt];
-  uint32_t bias_off_b, bar_off, total;
+  uint32_t bias_off_b, bar_off, tab_off, hdr_off, total;
   int items;
   double cost;
 };
@@ -482,6 +571,7 @@ int32_t chain_tc_prepare(const ly_op& op, ChainState** out) {
   p.halo = halo;
   p.slot_w = max_cout <= 64 ? 64 : (max_cout <= 128 ? 128 : 256);
   p.n_slots = std::min(kMaxSlots, 512 / p.slot_w);
+  p.n_groups = std::min(4, p.n_slots);
   for (int r = 0; r < ch.n_regions; ++r) {
     p.region_rowb[r] = rowb[r];
     const int swz = rowb[r] == 128 ? 2 : (rowb[r] == 64 ? 4 : 6);
@@ -522,7 +612,12 @@ int32_t chain_tc_prepare(const ly_op& op, ChainState** out) {
       off += L.w_tile[s] * (uint32_t)(cs.k * cs.k * cs.n_src);
     }
     L.bias_off_b = off; off += ((uint32_t)bias_total * 4 + 15u) / 16u * 16u;
-    L.bar_off = off; off += 8u * kNumBars;
+    L.bar_off = off; off += (8u * kNumBars + 15u) / 16u * 16u;
+    int entries = 0;
+    for (int s = 0; s < ch.n_stages; ++s) entries += L.n_mt[s] * ch.st[s].k * ch.st[s].k * ch.st[s].n_src * (ch.st[s].src[0].c / 16);
+    if (entries > kMaxEntries) return false;
+    L.tab_off = off; off += 16u * (uint32_t)entries;
+    L.hdr_off = off; off += 32u * (uint32_t)L.items;
     L.total = off + 1024u;
     if (L.total > kSmemMax) return false;
     const long long tiles = (long long)((W + TW - 1) / TW) * ((H + TH - 1) / TH);
@@ -531,8 +626,8 @@ int32_t chain_tc_prepare(const ly_op& op, ChainState** out) {
   };
   Layout best; best.cost = 1e300; bool found = false;
   const int force_tw = env_i("LY_CHAIN_TW", 0), force_th = env_i("LY_CHAIN_TH", 0);
-  for (int TW = 4; TW <= std::min(W, 128); TW += 2)
-    for (int TH = 2; TH <= std::min(H, 128); ++TH) {
+  for (int TW = 2; TW <= std::min(W + 1, 128); TW += 2)
+    for (int TH = 1; TH <= std::min(H, 128); ++TH) {
       if (force_tw && (TW != force_tw || TH != force_th)) continue;
       Layout L;
       if (layout(TW, TH, L) && L.cost < best.cost) { best = L; found = true; }
@@ -545,7 +640,6 @@ int32_t chain_tc_prepare(const ly_op& op, ChainState** out) {
   if (total > 0x7FFFFFFF) { delete st; set_error("chain: too many tiles"); return LY_E_ARG; }
   p.total_tiles = (int)total;
   p.mg_pw = (uint32_t)((1ull << 32) / (uint32_t)L.PW + 1);
-  p.n_items = 0;
   for (int s = 0; s < ch.n_stages; ++s) {
     StageP& S = p.st[s];
     S.n_mt = L.n_mt[s];
@@ -553,12 +647,91 @@ int32_t chain_tc_prepare(const ly_op& op, ChainState** out) {
     for (int b = 0; b < S.n_src; ++b) S.src_rows[b] = src_sh[s][b] * (L.PW + 1);
     S.res_rows = res_sh[s] * (L.PW + 1);
     S.w_off = L.w_off[s]; S.w_tile = L.w_tile[s];
-    for (int m = 0; m < S.n_mt; ++m) {
-      p.item_stage[p.n_items] = (unsigned char)s; p.item_mt[p.n_items] = (unsigned char)m;
-      if (s == x_last_stage) p.x_last_item = p.n_items;
-      ++p.n_items;
-    }
     p.w_bytes += (uint32_t)(S.k * S.k * S.n_src) * (uint32_t)(S.cout * S.ksteps * 16 * 2);
+  }
+  // ---- item schedule.  A stage that reads only the input frame ("early") does not depend on anything of its own
+  // tile, so its M tiles are hoisted into the tail of the PREVIOUS tile's item list: each one right after the last
+  // item of that tile whose MMAs read the rows it is going to overwrite.  The stage boundary bubble (issuer waiting
+  // for the epilogue of the first stage) then overlaps the previous tile's last stage.
+  bool is_early[kMaxSt];
+  bool reads_in[kMaxSt];
+  int n_early = 0;
+  for (int s = 0; s < ch.n_stages; ++s) {
+    reads_in[s] = false; is_early[s] = ch.st[s].dst.region >= 0 && ch.st[s].res.region < 0;
+    for (int b = 0; b < ch.st[s].n_src; ++b) {
+      if (ch.st[s].src[b].region < ch.n_in) reads_in[s] = true; else is_early[s] = false;
+    }
+    n_early += is_early[s];
+  }
+  bool early_mode = env_i("LY_CHAIN_EARLY", 1) != 0 && n_early == 1 && is_early[0];
+  for (int s = 1; s < ch.n_stages; ++s)
+    if (reads_in[s]) early_mode = false;      // a later stage still needs the input frame of its own tile
+  struct Item { int s, m, fl, ws, wm; };
+  Item items[kMaxItems];
+  int n_it = 0;
+  for (int s = early_mode ? 1 : 0; s < ch.n_stages; ++s)
+    for (int m = 0; m < p.st[s].n_mt; ++m) items[n_it++] = Item{s, m, reads_in[s] ? 2 : 0, 0xFF, 0};
+  if (early_mode) {
+    const StageP& E = p.st[0];
+    int prev_pos = -1, res_readers = 0;
+    for (int c = 1; c < ch.n_stages; ++c) res_readers += (p.st[c].res_region == E.dst_region && p.st[c].res_prod == 0);
+    if (res_readers > 1) early_mode = false;
+    for (int j = 0; early_mode && j < E.n_mt; ++j) {
+      const int lo = j * 128, hi = j * 128 + 127;
+      int pos = prev_pos, ws = 0xFF, wm = 0;
+      for (int q = 0; q < n_it; ++q) {
+        if (items[q].fl & 1) continue;
+        const StageP& C = p.st[items[q].s];
+        for (int b = 0; b < C.n_src; ++b) {
+          if (C.src_region[b] != E.dst_region || C.src_prod[b] != 0) continue;
+          const int rlo = items[q].m * 128 + C.src_rows[b], rhi = rlo + 127 + C.reads_halo;
+          if (rlo <= hi && rhi >= lo) pos = std::max(pos, q);
+        }
+        if (C.res_region == E.dst_region && C.res_prod == 0) {
+          const int rlo = items[q].m * 128 + C.res_rows, rhi = rlo + 127;
+          if (rlo <= hi && rhi >= lo) { ws = items[q].s; wm = std::max(wm, items[q].m); }
+        }
+      }
+      // insert after position `pos`
+      for (int q = n_it; q > pos + 1; --q) items[q] = items[q - 1];
+      items[pos + 1] = Item{0, j, 1 | 2, ws, wm};
+      ++n_it;
+      prev_pos = pos + 1;
+    }
+  }
+  if (!early_mode) {   // (re)build the plain stage-major list
+    n_it = 0;
+    for (int s = 0; s < ch.n_stages; ++s)
+      for (int m = 0; m < p.st[s].n_mt; ++m) items[n_it++] = Item{s, m, reads_in[s] ? 2 : 0, 0xFF, 0};
+  }
+  int last_x = -1;
+  for (int q = 0; q < n_it; ++q)
+    if (items[q].fl & 2) last_x = q;
+  items[last_x].fl |= 4;
+  p.n_items = n_it; p.early = early_mode ? 1 : 0;
+  p.tab_off = L.tab_off; p.hdr_off = L.hdr_off; p.n_entries = 0;
+  for (int q = 0; q < n_it; ++q) {
+    const StageP& S = p.st[items[q].s];
+    p.item_stage[q] = (unsigned char)items[q].s; p.item_mt[q] = (unsigned char)items[q].m; p.item_flags[q] = (unsigned char)items[q].fl;
+    p.item_wstage[q] = (unsigned char)items[q].ws; p.item_wmt[q] = (unsigned char)items[q].wm;
+    p.item_nmma[q] = (unsigned short)(S.k * S.k * S.n_src * S.ksteps);
+    p.item_first[q] = (unsigned short)p.n_entries;
+    p.n_entries += p.item_nmma[q];
+    // producer M tiles this item has to wait for (tile `it` of the issuer's loop): sources and shortcut of a late
+    // item; for an early item the shortcut readers of the region it overwrites
+    unsigned char* dep = p.item_dep[q];
+    for (int s = 0; s < 8; ++s) dep[s] = 0xFF;
+    auto need = [&](int prod, int last_row) {
+      if (prod < 0) return;
+      const int m = std::min(p.st[prod].n_mt - 1, last_row >> 7);
+      dep[prod] = dep[prod] == 0xFF ? (unsigned char)m : (unsigned char)std::max<int>(dep[prod], m);
+    };
+    const int last = items[q].m * 128 + 127;
+    if (!(items[q].fl & 1)) {
+      for (int b = 0; b < S.n_src; ++b) need(S.src_prod[b], last + S.reads_halo + S.src_rows[b]);
+      need(S.res_prod, last + S.res_rows);
+    }
+    if (items[q].ws != 0xFF) need(items[q].ws, items[q].wm * 128 + 127);
   }
   for (int r = 0; r < ch.n_regions; ++r) p.region_off[r] = L.region_off[r];
   p.bias_off_b = L.bias_off_b; p.bar_off = L.bar_off;
@@ -596,9 +769,15 @@ int32_t chain_tc_prepare(const ly_op& op, ChainState** out) {
   p.st256 = op.dst.ptr && op.dst.ctot % 16 == 0 && op.dst.c0 % 16 == 0 && reinterpret_cast<uintptr_t>(op.dst.ptr) % 32 == 0;
   p.nchw = op.nchw; p.nCtot = op.nchw_ctot; p.nC0 = op.nchw_c0; p.nC = op.nchw_c;
   st->grid = std::min(p.total_tiles, sm_count());
+  p.prof = env_i("LY_CHAIN_PROF", 0);
   if (env_i("LY_CHAIN_DEBUG", 0))
     fprintf(stderr, "[chain] %dx%d B %d stages %d halo %d: tile %dx%d frame %dx%d tiles %d items %d smem %zu slots %d x %d\n", H, W, op.B,
             ch.n_stages, halo, p.TW, p.TH, p.PW, p.FH, p.total_tiles, p.n_items, st->smem, p.n_slots, p.slot_w);
+  if (env_i("LY_CHAIN_DEBUG", 0) > 1) {
+    fprintf(stderr, "[chain] items (early %d):", p.early);
+    for (int q = 0; q < p.n_items; ++q) fprintf(stderr, " %s%d.%d", (p.item_flags[q] & 1) ? "+" : "", p.item_stage[q], p.item_mt[q]);
+    fprintf(stderr, "\n");
+  }
   cudaError_t e = cudaFuncSetAttribute(chain_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax);
   if (e != cudaSuccess) { delete st; set_error("chain: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e)); return LY_E_CUDA; }
   *out = st;

@@ -18,7 +18,7 @@ from . import _native as N
 from .plan import Op, PlanBuilder, View
 
 _KIND = {"stem": N.OP_STEM, "conv": N.OP_CONV, "dw": N.OP_DW, "dwpw": N.OP_DWPW, "pool": N.OP_POOL, "up": N.OP_UP,
-         "attn": N.OP_ATTN, "export": N.OP_EXPORT, "import": N.OP_IMPORT}
+         "attn": N.OP_ATTN, "export": N.OP_EXPORT, "import": N.OP_IMPORT, "chain": N.OP_CHAIN}
 
 
 def _view(v: Optional[View], base: int) -> N.LyView:
@@ -80,6 +80,7 @@ class Engine:
         base, wbase, bbase = ws.data_ptr(), self._w.data_ptr(), self._b.data_ptr()
         esz = pb.esize
         dt = N.LY_BF16 if self.dtype == "bf16" else N.LY_F32
+        chains = []     # ctypes ly_chain structs: must outlive ly_plan_create (which copies them)
         for i, op in enumerate(pb.ops):
             o = arr[i]
             o.kind, o.dtype, o.B = _KIND[op.kind], dt, B
@@ -106,12 +107,32 @@ class Engine:
                 name, level, c0, c, ctot = op.nchw
                 o.nchw_ctot, o.nchw_c0, o.nchw_c = ctot, c0, c
                 o.ext_slot = in_slots[(name, level)] if op.kind == "import" else slots[(name, level)]
+            if op.kind == "chain":
+                chains.append(self._chain_struct(op, wbase, bbase, esz))
+                o.chain = C.pointer(chains[-1])
         handle = C.c_void_p()
         with torch.cuda.device(self.device):
             N.check(self.lib.ly_plan_create(arr, len(pb.ops), C.byref(handle)), "ly_plan_create")
         comp = Compiled(pb, B, ws, handle, out_keys, len(pb.ops), in_keys)
         self._plans[key] = comp
         return comp
+
+    @staticmethod
+    def _chain_struct(op: Op, wbase: int, bbase: int, esz: int) -> "N.LyChain":
+        ex = op.extra
+        ch = N.LyChain()
+        ch.n_regions, ch.n_in, ch.n_stages = len(ex["regions"]), ex["n_in"], len(ex["stages"])
+        for i, c in enumerate(ex["regions"]):
+            ch.region_c[i] = c
+        for i, st in enumerate(ex["stages"]):
+            s = ch.st[i]
+            s.k, s.act, s.cout, s.n_src = st["k"], int(st["act"]), st["cout"], len(st["src"])
+            for j, blk in enumerate(st["src"]):
+                s.src[j] = N.LyChainBlk(*blk)
+            s.dst = N.LyChainBlk(*(st["dst"] if st["dst"] is not None else (-1, 0, 0)))
+            s.res = N.LyChainBlk(*(st["res"] if st["res"] is not None else (-1, 0, 0)))
+            s.w, s.bias = wbase + esz * st["w_off"], bbase + 4 * st["b_off"]
+        return ch
 
     # ------------------------------------------------------------------ run
     def _launch(self, comp: Compiled, x: Optional[torch.Tensor], outs: Dict[Tuple[str, int], torch.Tensor], img0: int,
@@ -181,7 +202,11 @@ class Engine:
                 es = comp.pb.esize
                 for i, op in enumerate(comp.pb.ops):
                     flops = byts = 0
-                    if op.kind in ("conv", "dwpw"):
+                    if op.kind == "chain":
+                        hw_ = op.src.H * op.src.W
+                        flops = sum(2 * n * hw_ * st["cout"] * st["cin"] * st["k"] ** 2 for st in op.extra["stages"])
+                        byts = n * hw_ * (op.src.c * es + op.cout * (es if op.dst is not None else 4))
+                    elif op.kind in ("conv", "dwpw"):
                         Ho, Wo = op.src.H // op.stride, op.src.W // op.stride
                         flops = 2 * n * Ho * Wo * op.cout * op.cin * op.k * op.k
                         byts = n * (op.src.H * op.src.W * op.src.c * es + Ho * Wo * op.extra["cpad"] * (es if op.dst is not None else 4)

@@ -124,6 +124,8 @@ class C2f(nn.Module):
         """``upcat=(low, skip)``: the block's input is cat[upsample2x(low), skip] (top-down neck);
         cv1 is then applied without materialising either (PlanBuilder.upcat_conv)."""
         c = self.c
+        if upcat is None and self._chain_ok(pb, src):
+            return self._emit_chain(pb, src, dst)
         cat = pb.buffer(src.H, src.W, (2 + self.n) * c)
         if upcat is not None:
             w, b = self.cv1.folded()
@@ -134,6 +136,30 @@ class C2f(nn.Module):
         for i, m in enumerate(self.m):
             y = m.emit(pb, y, cat.view((2 + i) * c, c))
         return self.cv2.emit(pb, cat.view(), dst)
+
+
+    def _chain_ok(self, pb, src) -> bool:
+        """One Bottleneck, narrow enough for all four weight sets to stay resident in shared memory (56 c^2 bytes):
+        the block's thin intermediates (cv1 output, the two 3x3 results, the concat) then never reach HBM."""
+        c = self.c
+        return (pb.chain_fusable() and self.n == 1 and isinstance(self.m[0], Bottleneck) and c in (16, 32)
+                and src.c == self.cv1.conv.in_channels and src.c in (16, 32, 64) and self.cv2.conv.out_channels % 16 == 0)
+
+    def _emit_chain(self, pb, src, dst):
+        """layers.py:129-173 as ONE launch.  Regions: 0 = x, 1 = cv1(x) = [y1 | y2], 2 = the Bottleneck's 3x3
+        results (the second overwrites the first in place)."""
+        c, m = self.c, self.m[0]
+        w1, b1 = self.cv1.folded()
+        wa, ba = m.cv1.folded()
+        wb, bb = m.cv2.folded()
+        w2, b2 = self.cv2.folded()
+        stages = [
+            dict(k=1, act=True, w=w1, b=b1, src=[(0, 0, src.c)], dst=(1, 0, 2 * c)),
+            dict(k=3, act=True, w=wa, b=ba, src=[(1, c, c)], dst=(2, 0, c)),
+            dict(k=3, act=True, w=wb, b=bb, src=[(2, 0, c)], dst=(2, 0, c), res=(1, c, c) if m.add else None),
+            dict(k=1, act=True, w=w2, b=b2, src=[(1, 0, c), (1, c, c), (2, 0, c)]),
+        ]
+        return pb.chain(src, [src.c, 2 * c, c], 1, stages, dst=dst)
 
 
 class SPPF(nn.Module):
@@ -361,10 +387,17 @@ class Detect(nn.Module):
             else:
                 firsts = [reg[i][0].emit(pb, f) for _, reg, _ in branches]
             for (out_name, reg, cls), r in zip(branches, firsts):
-                r = reg[i][1].emit(pb, r)
                 fin = reg[i][2]
-                pb.conv(r, fin.weight.detach().double().cpu(), fin.bias.detach().double().cpu(), k=1, stride=1,
-                        act=False, nchw=(out_name, i, 0, 4 * self.reg_max, self.no))
+                wf, bf = fin.weight.detach().double().cpu(), fin.bias.detach().double().cpu()
+                if pb.chain_fusable() and r.c in (16, 32, 64) and r.c == c2 and (4 * self.reg_max) % 16 == 0:
+                    # 3x3 -> 1x1 tail of the regression stack as one launch (the 3x3 result stays in shared memory)
+                    wm, bm = reg[i][1].folded()
+                    pb.chain(r, [c2, c2], 1, [dict(k=3, act=True, w=wm, b=bm, src=[(0, 0, c2)], dst=(1, 0, c2)),
+                                              dict(k=1, act=False, w=wf, b=bf, src=[(1, 0, c2)])],
+                             nchw=(out_name, i, 0, 4 * self.reg_max, self.no))
+                else:
+                    r = reg[i][1].emit(pb, r)
+                    pb.conv(r, wf, bf, k=1, stride=1, act=False, nchw=(out_name, i, 0, 4 * self.reg_max, self.no))
                 c = emit_dw_pw(pb, cls[i][0][0], cls[i][0][1], f)
                 c = emit_dw_pw(pb, cls[i][1][0], cls[i][1][1], c)
                 fin = cls[i][2]

@@ -252,6 +252,40 @@ class PlanBuilder:
                            extra=dict(cpad=cpad, pre_w_off=self._add_w(dwp), pre_b_off=self._add_b(dw_b), pre_act=dw_act)))
         return dst
 
+    def chain_fusable(self) -> bool:
+        """LY_OP_CHAIN (csrc/chain_tc.cu) is a bf16 tensor-core kernel.  Opt-in (LEANYOLO_FUSE_CHAIN=1): measured on
+        yolov10s at batch 256 the fused C2f block runs at 2.35 ms against 1.40 ms layer by layer (its N = 32 MMAs
+        issue at ~67 cycles each and the per-stage epilogues of a tile serialise), see DESIGN.md."""
+        import os
+        return self.tensor_core and os.environ.get("LEANYOLO_FUSE_CHAIN", "0") == "1"
+
+    def chain(self, src: View, regions: Sequence[int], n_in: int, stages: Sequence[dict], *, dst: Optional[View] = None,
+              nchw: Optional[Tuple[str, int, int, int, int]] = None) -> Optional[View]:
+        """A chain of dense conv stages executed per spatial tile with every intermediate in shared memory
+        (``LY_OP_CHAIN``, include/leanyolo_b200.h).  ``regions``: channels of each shared-memory region (the first
+        ``n_in`` are the 64-channel blocks of ``src``); ``stages``: dicts {k, act, w [cout,cin,k,k], b [cout],
+        src [(region, c0, c)], dst (region, c0, c) | None, res (region, c0, c) | None}; the last stage writes
+        ``dst`` (NHWC slice) or the public NCHW tensor ``nchw``."""
+        assert self.dtype == "bf16" and sum(regions[:n_in]) == src.c and 1 <= len(stages) <= 6 and len(regions) <= 8
+        packed = []
+        for st in stages:
+            w, b, k = st["w"], st["b"], st["k"]
+            cout, cin = w.shape[0], w.shape[1]
+            assert cout % CH_ALIGN == 0 and cin == sum(c for _, _, c in st["src"]) and w.shape[2] == w.shape[3] == k
+            packed.append(dict(k=k, act=bool(st["act"]), cout=cout, cin=cin, src=list(st["src"]), dst=st.get("dst"), res=st.get("res"),
+                               w_off=self._add_w(w.permute(0, 2, 3, 1).contiguous()), b_off=self._add_b(b)))
+        cout = packed[-1]["cout"]
+        if nchw is None:
+            if dst is None:
+                dst = self.buffer(src.H, src.W, cout).view()
+            assert dst.c == cout and (dst.H, dst.W) == (src.H, src.W)
+        else:
+            name, level, c0, c, ctot = nchw
+            self.outputs[(name, level)] = (ctot, src.H, src.W)
+        self.ops.append(Op("chain", src=src, dst=dst, k=1, stride=1, cin=src.c, cout=cout, nchw=nchw,
+                           extra=dict(regions=list(regions), n_in=n_in, stages=packed, cpad=cout)))
+        return dst
+
     def sppf_pool(self, cat: Buf, c: int) -> None:
         """cat[..., c:4c] <- three chained 5x5/s1/p2 max-pools of cat[..., 0:c] (windows 5, 9, 13)."""
         assert cat.C == 4 * c and c % 8 == 0
@@ -290,6 +324,8 @@ class PlanBuilder:
             if op.kind in ("conv", "dwpw"):
                 Ho, Wo = op.src.H // op.stride, op.src.W // op.stride
                 f += 2 * Ho * Wo * op.cout * op.cin * op.k * op.k
+            elif op.kind == "chain":
+                f += sum(2 * op.src.H * op.src.W * st["cout"] * st["cin"] * st["k"] ** 2 for st in op.extra["stages"])
             elif op.kind == "stem":
                 f += 2 * op.dst.H * op.dst.W * op.cout * 27
         return f

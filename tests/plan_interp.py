@@ -56,6 +56,19 @@ def run_plan(pb: PlanBuilder, x: torch.Tensor, quant=None):
             if op.nchw is not None:
                 name, level, c0, c, _ = op.nchw
                 outs[(name, level)][:, c0:c0 + c] = y[..., :c].permute(0, 3, 1, 2)
+        elif op.kind == "chain":
+            stages = []
+            for st in op.extra["stages"]:
+                n = st["cout"] * st["k"] * st["k"] * st["cin"]
+                stages.append(dict(k=st["k"], act=st["act"], cout=st["cout"], src=st["src"], dst=st["dst"], res=st["res"],
+                                   w=w_blob[st["w_off"]:st["w_off"] + n].view(st["cout"], st["k"], st["k"], st["cin"]),
+                                   b=b_blob[st["b_off"]:st["b_off"] + st["cout"]]))
+            y = run_chain(op.extra["regions"], op.extra["n_in"], stages, rd(op.src), quant=q)
+            if op.dst is not None:
+                wr(op.dst, y)
+            if op.nchw is not None:
+                name, level, c0, c, _ = op.nchw
+                outs[(name, level)][:, c0:c0 + c] = y[..., :c].permute(0, 3, 1, 2)
         elif op.kind == "dwpw":
             c, cp = op.src.c, op.extra["cpad"]
             dww = w_blob[op.extra["pre_w_off"]:op.extra["pre_w_off"] + 9 * c].view(3, 3, c).permute(2, 0, 1).unsqueeze(1)

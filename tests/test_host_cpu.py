@@ -208,7 +208,7 @@ def test_shared_library_exports_every_declared_symbol():
     for sym in declared:
         assert hasattr(lib, sym), sym
     assert N.lib().ly_abi_version() == N.ABI_VERSION
-    assert ctypes.sizeof(N.LyView) == 32 and ctypes.sizeof(N.LyOp) == 264
+    assert ctypes.sizeof(N.LyView) == 32 and ctypes.sizeof(N.LyOp) == 272 and ctypes.sizeof(N.LyChain) == 672
 
 
 # ------------------------------------------------------------------ lowering vs oracle
@@ -230,7 +230,10 @@ def test_lowering_matches_oracle_fp32(name):
             assert float((outs[(br, i)] - ref[br][i]).abs().max() / ref[br][i].abs().max()) < 1e-4, (br, i)
 
 
-def test_lowering_bf16_storage_emulation_within_tolerance():
+@pytest.mark.parametrize("chain", ["0", "1"])
+def test_lowering_bf16_storage_emulation_within_tolerance(chain, monkeypatch):
+    """chain=1: the C2f block and the regression tails lowered to LY_OP_CHAIN (opt-in fused chains)."""
+    monkeypatch.setenv("LEANYOLO_FUSE_CHAIN", chain)
     m = get_model("yolov10s", weights=None, class_names=NAMES)
     sd = synth_state_dict(m.state_dict(), seed=1, gain=1.25)
     m.load_state_dict(sd)
@@ -238,6 +241,7 @@ def test_lowering_bf16_storage_emulation_within_tolerance():
     ref = O.forward(sd, x)
     pb = PlanBuilder(1, 128, 128, "bf16")
     m.emit(pb)
+    assert any(op.kind == "chain" for op in pb.ops) == (chain == "1")
     outs = run_plan(pb, x, quant=lambda t: t.to(torch.bfloat16).float())
     for i in range(3):
         r = ref["one2one"][i]
@@ -274,6 +278,18 @@ def test_plan_is_pure_views_no_copy_ops_and_counts_flops():
     # launch; RepVGGDW pairs merged: 24 dw -> 22, 12 of them inside the fused launches
     # the two upsample+concat+1x1 of the top-down neck are 2 convs each (half-resolution part + skip part), no upsample op
     assert kinds == {"stem": 1, "conv": 73, "dw": 10, "dwpw": 12, "pool": 1, "attn": 1}
+    # opt-in fused chains (LY_OP_CHAIN): the 160x160 C2f block (4 convs) and the 3x3 -> 1x1 tails of the six regression stacks (2 each)
+    os.environ["LEANYOLO_FUSE_CHAIN"] = "1"
+    try:
+        pbc = PlanBuilder(1, 640, 640, "bf16")
+        m.emit(pbc)
+    finally:
+        del os.environ["LEANYOLO_FUSE_CHAIN"]
+    kc = {}
+    for op in pbc.ops:
+        kc[op.kind] = kc.get(op.kind, 0) + 1
+    assert kc == {"stem": 1, "conv": 57, "chain": 7, "dw": 10, "dwpw": 12, "pool": 1, "attn": 1}
+    assert abs(pbc.dense_flops() - pb.dense_flops()) < 1e-6 * pb.dense_flops()
     # the reference does 24.625 dense GFLOP / image; applying the upsampled half of the
     # two neck 1x1 convs at half resolution removes 0.629 of them
     assert abs(pb.dense_flops() / 1e9 - 23.996) < 0.01
