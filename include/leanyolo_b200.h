@@ -200,6 +200,21 @@ LY_API int32_t ly_decode_nms(const ly_levels* lv, float conf_thresh, float iou_t
                       int32_t classwise, float* out, int32_t* out_count, int32_t* out_anchor,
                       void* scratch, int64_t scratch_bytes, void* stream);
 
+/* Replaces the decode of `YOLOv10ONNXExport.forward` (models/yolov10/export.py:97-198): fixed-shape detections
+ * out `[B, kmax, 6]` + num_dets `[B]` (int32).
+ *   nms == 0 (export.py:126-144): top-k anchors by best class score, scores below `conf` masked, argmax class, boxes
+ *            clamped to [0,img_w] x [0,img_h]; kmax = min(max_det, A); rows past num_dets hold the lowest-index masked
+ *            anchors (the reference leaves the tie order of torch.topk there).
+ *   nms != 0 (export.py:145-198): the `pre_topk` best (anchor, class) pairs, boxes offset per (image, class) group in fp32
+ *            exactly like the reference (`img0` = global index of image 0 of this batch enters that arithmetic), ONE
+ *            torchvision-style greedy NMS (unclamped areas, no epsilon, fp32 overlap > double threshold), first
+ *            kmax = min(max_det, pre_topk, A*nc) survivors, rows below `conf` zeroed.
+ * max_det, pre_topk <= 1024.                                                                                     */
+LY_API int64_t ly_decode_export_scratch_bytes(const ly_levels* lv, int32_t max_det, int32_t pre_topk);
+LY_API int32_t ly_decode_export(const ly_levels* lv, float conf, int32_t max_det, int32_t nms, double iou_thresh, int32_t pre_topk,
+                                int32_t img_h, int32_t img_w, int32_t img0, float* out, int32_t* num_dets, void* scratch,
+                                int64_t scratch_bytes, void* stream);
+
 /* Replaces `leanyolo.utils.box_ops.nms` on explicit inputs: boxes `[B,N,4]`
  * xyxy fp32, scores `[B,N]`, labels `[B,N]` int32 (may be NULL when
  * classwise=0), n_valid `[B]` int32 (may be NULL = N).  keep `[B,max_keep]`

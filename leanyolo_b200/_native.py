@@ -82,6 +82,9 @@ PROTOTYPES = {
                                    C.c_void_p, C.c_int64, C.c_void_p]),
     "ly_decode_nms": (C.c_int32, [C.POINTER(LyLevels), C.c_float, C.c_float, C.c_int32, C.c_int32, C.c_void_p,
                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "ly_decode_export_scratch_bytes": (C.c_int64, [C.POINTER(LyLevels), C.c_int32, C.c_int32]),
+    "ly_decode_export": (C.c_int32, [C.POINTER(LyLevels), C.c_float, C.c_int32, C.c_int32, C.c_double, C.c_int32, C.c_int32, C.c_int32,
+                                     C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "ly_letterbox_u8": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "ly_unletterbox": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "ly_nms_scratch_bytes": (C.c_int64, [C.c_int32, C.c_int32]),

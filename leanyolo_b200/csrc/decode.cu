@@ -273,6 +273,20 @@ __device__ __forceinline__ bool iou_gt(const float4& a, float area_a, const floa
   return iou > thr;
 }
 
+// torchvision.ops.nms (CPU kernel nms_kernel_impl, what export.py:182 calls): areas are NOT clamped, no epsilon
+__device__ __forceinline__ float box_area_tv(const float4& a) { return __fmul_rn(__fsub_rn(a.z, a.x), __fsub_rn(a.w, a.y)); }
+__device__ __forceinline__ bool iou_gt_tv(const float4& a, float area_a, const float4& b, float area_b, float thr) {
+  const float w = fmaxf(0.f, __fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x)));
+  const float h = fmaxf(0.f, __fsub_rn(fminf(a.w, b.w), fmaxf(a.y, b.y)));
+  const float inter = __fmul_rn(w, h);
+  const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_a, area_b), inter));
+  return ovr > thr;     // thr = the largest float <= the double threshold (the reference compares in double)
+}
+template <bool TV>
+__device__ __forceinline__ bool iou_gt_m(const float4& a, float area_a, const float4& b, float area_b, float thr) {
+  return TV ? iou_gt_tv(a, area_a, b, area_b, thr) : iou_gt(a, area_a, b, area_b, thr);
+}
+
 struct NmsSmem {
   float4 kbox[TOPK_MAX];
   float karea[TOPK_MAX];
@@ -289,6 +303,7 @@ struct NmsSmem {
 // boxes [B,N,4], scores [B,N], labels [B,N] or null.  A candidate is valid when
 // (n_valid ? i < n_valid[b] : true) && (use_conf ? score > conf : true).
 // sort_g: per-image global scratch of npad u64 (used when the keys do not fit in smem).
+template <bool TV>
 __global__ void __launch_bounds__(NT)
 nms_kernel(const float* __restrict__ boxes, const float* __restrict__ scores, const int* __restrict__ labels,
            const int* __restrict__ n_valid, int N, int npad, int use_conf, float conf, float thr, int max_keep,
@@ -331,7 +346,7 @@ nms_kernel(const float* __restrict__ boxes, const float* __restrict__ scores, co
         const float4 v = bx[idx];
         S.cidx[i] = idx;
         S.cbox[i] = v;
-        S.carea[i] = box_area_rn(v);
+        S.carea[i] = TV ? box_area_tv(v) : box_area_rn(v);
         S.clabel[i] = lb ? lb[idx] : 0;
       }
     }
@@ -349,7 +364,7 @@ nms_kernel(const float* __restrict__ boxes, const float* __restrict__ scores, co
         const int lv = S.clabel[i];
         bool hit = false;
         for (int j = lane; j < nk && !hit; j += 32)
-          hit = (!classwise || S.klabel[j] == lv) && iou_gt(S.kbox[j], S.karea[j], v, av, thr);
+          hit = (!classwise || S.klabel[j] == lv) && iou_gt_m<TV>(S.kbox[j], S.karea[j], v, av, thr);
         if (__any_sync(0xFFFFFFFFu, hit) && lane == 0) atomicAnd(&S.alive[i >> 5], ~(1u << (i & 31)));
       }
     }
@@ -364,7 +379,7 @@ nms_kernel(const float* __restrict__ boxes, const float* __restrict__ scores, co
         const int jend = min(32, m - wj * 32);
         for (int jj = 0; jj < jend; ++jj) {
           const int j = wj * 32 + jj;
-          if (j > i && (!classwise || S.clabel[j] == lv) && iou_gt(v, av, S.cbox[j], S.carea[j], thr)) bits |= 1u << jj;
+          if (j > i && (!classwise || S.clabel[j] == lv) && iou_gt_m<TV>(v, av, S.cbox[j], S.carea[j], thr)) bits |= 1u << jj;
         }
       }
       S.mask[i][wj] = bits;
@@ -421,6 +436,148 @@ nms_kernel(const float* __restrict__ boxes, const float* __restrict__ scores, co
   }
 }
 
+// ------------------------------------------------------------------------ export-style outputs
+// export.py:126-144 (nms = False): top-k anchors by best class score with everything below `conf` masked to -1,
+// argmax class, boxes clamped to the image, num_dets = #(score >= conf).  One CTA per image.
+__global__ void __launch_bounds__(NT_TOPK, 3)
+export_topk_kernel(int A, int k, float conf, float img_w, float img_h, const float* __restrict__ boxes, const float* __restrict__ best,
+                   const int* __restrict__ label, float* __restrict__ out, int* __restrict__ num) {
+  __shared__ unsigned long long sortbuf[TOPK_MAX];
+  __shared__ unsigned hist[256];
+  __shared__ unsigned bcast[2];
+  __shared__ int cnt, nvalid;
+  const int b = blockIdx.x;
+  const int P = next_pow2(k);
+  const float* bestb = best + (long long)b * A;
+  auto key = [&](int i) -> unsigned long long {
+    const float v = bestb[i];
+    return ((unsigned long long)orderable(v >= conf ? v : -1.0f) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)i);
+  };
+  const unsigned long long thr = block_kth_largest(key, A, k, hist, bcast);
+  if (threadIdx.x == 0) { cnt = 0; nvalid = 0; }
+  for (int i = threadIdx.x; i < P; i += blockDim.x) sortbuf[i] = 0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < A; i += blockDim.x) {
+    const unsigned long long kk = key(i);
+    if (kk >= thr) sortbuf[atomicAdd(&cnt, 1)] = kk;
+  }
+  __syncthreads();
+  block_bitonic_desc(sortbuf, P);
+  for (int r = threadIdx.x; r < k; r += blockDim.x) {
+    const int g = (int)(0xFFFFFFFFu - (unsigned)(sortbuf[r] & 0xFFFFFFFFull));
+    const float4 bx = reinterpret_cast<const float4*>(boxes)[(long long)b * A + g];
+    const float sc = fmaxf(bestb[g], 0.f);
+    float* o = out + ((long long)b * k + r) * 6;
+    o[0] = fminf(fmaxf(bx.x, 0.f), img_w); o[1] = fminf(fmaxf(bx.y, 0.f), img_h);
+    o[2] = fminf(fmaxf(bx.z, 0.f), img_w); o[3] = fminf(fmaxf(bx.w, 0.f), img_h);
+    o[4] = sc;
+    o[5] = (float)label[(long long)b * A + g];
+    if (sc >= conf) atomicAdd(&nvalid, 1);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) num[b] = nvalid;
+}
+
+// export.py:148-176: the k2 best (anchor, class) pairs of an image, score-descending with the canonical tie rule
+// (score desc, flat index anchor*nc + class asc), and their boxes offset per (image, class) group in fp32.
+// The pairs of the flat top-k all belong to the k1 = min(k2, A) best anchors by best class score (each of those
+// anchors contributes a pair that precedes any pair of an anchor outside the set), so the selection is two-stage
+// like topk_kernel: anchors first, then k1*nc pair scores.
+__global__ void __launch_bounds__(NT_TOPK, 3)
+export_pairs_kernel(Levels lv, int k1, int k2, int img0, float group_off, const float* __restrict__ boxes,
+                    const float* __restrict__ best, float* s2, float* __restrict__ cand_box, float* __restrict__ cand_off,
+                    float* __restrict__ cand_score, int* __restrict__ cand_cls) {
+  __shared__ unsigned long long sortbuf[TOPK_MAX];
+  __shared__ int anchors[TOPK_MAX];
+  __shared__ unsigned hist[256];
+  __shared__ unsigned bcast[2];
+  __shared__ int cnt;
+  const int b = blockIdx.x;
+  const int A = lv.A, nc = lv.nc;
+  const float* bestb = best + (long long)b * A;
+  auto key1 = [&](int i) -> unsigned long long {
+    return ((unsigned long long)orderable(bestb[i]) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)i);
+  };
+  unsigned long long thr = block_kth_largest(key1, A, k1, hist, bcast);
+  if (threadIdx.x == 0) cnt = 0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < A; i += blockDim.x)
+    if (key1(i) >= thr) anchors[atomicAdd(&cnt, 1)] = i;     // any order: stage 2 keys carry the flat index
+  __syncthreads();
+  float* s2b = s2 + (long long)b * k1 * nc;
+  const int creg = 4 * lv.reg_max;
+  for (int i = threadIdx.x; i < k1 * nc; i += blockDim.x) {
+    const int r = i / nc, c = i - r * nc;
+    const int g = anchors[r];
+    const int l = level_of(lv, g);
+    const int HW = lv.H[l] * lv.W[l];
+    s2b[i] = sigmoid_precise(lv.p[l][((long long)b * (creg + nc) + creg + c) * HW + (g - lv.off[l])]);
+  }
+  __syncthreads();
+  auto key2 = [&](int i) -> unsigned long long {
+    const int r = i / nc, c = i - r * nc;
+    return ((unsigned long long)orderable(s2b[i]) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)(anchors[r] * nc + c));
+  };
+  thr = block_kth_largest(key2, k1 * nc, k2, hist, bcast);
+  const int P = next_pow2(k2);
+  if (threadIdx.x == 0) cnt = 0;
+  for (int i = threadIdx.x; i < P; i += blockDim.x) sortbuf[i] = 0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < k1 * nc; i += blockDim.x) {
+    const unsigned long long kk = key2(i);
+    if (kk >= thr) sortbuf[atomicAdd(&cnt, 1)] = kk;
+  }
+  __syncthreads();
+  block_bitonic_desc(sortbuf, P);
+  for (int r = threadIdx.x; r < k2; r += blockDim.x) {
+    const unsigned flat = 0xFFFFFFFFu - (unsigned)(sortbuf[r] & 0xFFFFFFFFull);
+    const int g = (int)(flat / (unsigned)nc), c = (int)(flat - (unsigned)g * (unsigned)nc);
+    const float4 bx = reinterpret_cast<const float4*>(boxes)[(long long)b * A + g];
+    const long long o = (long long)b * k2 + r;
+    // export.py:165-170: group_id = img * C + cls; off = group_id * (10 * max(H, W)); every step rounded to fp32
+    const float gid = __fadd_rn(__fmul_rn((float)(img0 + b), (float)nc), (float)c);
+    const float off = __fmul_rn(gid, group_off);
+    reinterpret_cast<float4*>(cand_box)[o] = bx;
+    reinterpret_cast<float4*>(cand_off)[o] = make_float4(__fadd_rn(bx.x, off), __fadd_rn(bx.y, off), __fadd_rn(bx.z, off), __fadd_rn(bx.w, off));
+    // the score is recomputed from the key's bits (exactly the value that was sorted)
+    const unsigned u = (unsigned)(sortbuf[r] >> 32);
+    cand_score[o] = __uint_as_float((u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u);
+    cand_cls[o] = c;
+  }
+}
+
+// export.py:184-198: the first max_det survivors (already score-descending), zeroed below `conf`
+__global__ void export_finish_kernel(int k2, int kmax, float conf, float img_w, float img_h, const float* __restrict__ cand_box,
+                                     const float* __restrict__ cand_score, const int* __restrict__ cand_cls,
+                                     const int* __restrict__ keep, const int* __restrict__ keep_count, float* __restrict__ out,
+                                     int* __restrict__ num) {
+  const int b = blockIdx.x;
+  __shared__ int nvalid;
+  if (threadIdx.x == 0) nvalid = 0;
+  __syncthreads();
+  const int kept = keep_count[b];
+  for (int r = threadIdx.x; r < kmax; r += blockDim.x) {
+    float* o = out + ((long long)b * kmax + r) * 6;
+    bool ok = false;
+    if (r < kept) {
+      const int idx = keep[(long long)b * kmax + r];
+      const float sc = cand_score[(long long)b * k2 + idx];
+      if (sc >= conf) {
+        const float4 bx = reinterpret_cast<const float4*>(cand_box)[(long long)b * k2 + idx];
+        o[0] = fminf(fmaxf(bx.x, 0.f), img_w); o[1] = fminf(fmaxf(bx.y, 0.f), img_h);
+        o[2] = fminf(fmaxf(bx.z, 0.f), img_w); o[3] = fminf(fmaxf(bx.w, 0.f), img_h);
+        o[4] = sc;
+        o[5] = (float)cand_cls[(long long)b * k2 + idx];
+        ok = true;
+        atomicAdd(&nvalid, 1);
+      }
+    }
+    if (!ok) o[0] = o[1] = o[2] = o[3] = o[4] = o[5] = 0.f;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) num[b] = nvalid;
+}
+
 int32_t make_levels(const ly_levels* in, Levels& lv) {
   LY_CHECK_ARG(in && in->n_levels >= 1 && in->n_levels <= 4, "decode: n_levels must be 1..4");
   LY_CHECK_ARG(in->B >= 1 && in->nc >= 1 && in->reg_max >= 1, "decode: bad B/nc/reg_max");
@@ -468,18 +625,20 @@ constexpr int kSmemSortMaxKeys = 16384;  // 128 KB of keys next to ~65 KB of NMS
 
 int32_t run_nms(const float* boxes, const float* scores, const int* labels, const int* n_valid, int B, int N,
                 int use_conf, float conf, float thr, int max_keep, int classwise, unsigned long long* sort_g,
-                int* keep, int* keep_count, float* out_rows, cudaStream_t st) {
+                int* keep, int* keep_count, float* out_rows, cudaStream_t st, bool tv = false) {
   LY_CHECK_ARG(max_keep >= 1 && max_keep <= TOPK_MAX, "nms: max_keep must be in 1..%d", TOPK_MAX);
   const int npad = pow2_ge(N);
   const int in_smem = npad <= kSmemSortMaxKeys;
   const size_t smem = ((sizeof(NmsSmem) + 15) / 16) * 16 + (in_smem ? (size_t)npad * 8 : 0);
-  static bool attr_set = false;
-  if (!attr_set) {
-    LY_CUDA(cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
-  nms_kernel<<<B, NT, smem, st>>>(boxes, scores, labels, n_valid, N, npad, use_conf, conf, thr, max_keep, classwise,
-                                  in_smem, sort_g, keep, keep_count, out_rows);
+  // (the attribute is per device: set it on every call, it is cheap)
+  LY_CUDA(cudaFuncSetAttribute(nms_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  LY_CUDA(cudaFuncSetAttribute(nms_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  if (tv)
+    nms_kernel<true><<<B, NT, smem, st>>>(boxes, scores, labels, n_valid, N, npad, use_conf, conf, thr, max_keep, classwise,
+                                          in_smem, sort_g, keep, keep_count, out_rows);
+  else
+    nms_kernel<false><<<B, NT, smem, st>>>(boxes, scores, labels, n_valid, N, npad, use_conf, conf, thr, max_keep, classwise,
+                                           in_smem, sort_g, keep, keep_count, out_rows);
   return post_launch("nms");
 }
 
@@ -550,4 +709,72 @@ extern "C" int32_t ly_nms(const float* boxes, const float* scores, const int32_t
   LY_CHECK_ARG(scratch_bytes >= ly_nms_scratch_bytes(B, N), "nms: scratch too small");
   return run_nms(boxes, scores, labels, n_valid, B, N, 0, 0.f, iou_thresh, max_keep, classwise,
                  (unsigned long long*)scratch, keep, keep_count, nullptr, (cudaStream_t)stream);
+}
+
+// ---- export-style fixed-shape outputs --------------------------------------
+namespace ly { namespace {
+struct ExportScratch {
+  Scratch d; float* cand_box; float* cand_off; float* cand_score; int* cand_cls; long long total;
+};
+ExportScratch carve_export(void* base, int B, int A, int nc, int max_det, int pre_topk) {
+  ExportScratch e;
+  const int k1 = pre_topk < A ? pre_topk : A;
+  e.d = carve(base, B, A, nc, k1 > max_det ? k1 : max_det);
+  long long o = e.d.total;
+  auto take = [&](long long bytes) { long long r = o; o += rup256(bytes); return (char*)base + r; };
+  e.cand_box = (float*)take((long long)B * pre_topk * 16);
+  e.cand_off = (float*)take((long long)B * pre_topk * 16);
+  e.cand_score = (float*)take((long long)B * pre_topk * 4);
+  e.cand_cls = (int*)take((long long)B * pre_topk * 4);
+  e.total = o;
+  return e;
+}
+} }  // namespace ly::
+
+extern "C" int64_t ly_decode_export_scratch_bytes(const ly_levels* in, int32_t max_det, int32_t pre_topk) {
+  Levels lv;
+  if (make_levels(in, lv) != LY_OK || max_det < 1 || pre_topk < 1) return -1;
+  return carve_export(nullptr, lv.B, lv.A, lv.nc, max_det, pre_topk).total;
+}
+
+extern "C" int32_t ly_decode_export(const ly_levels* in, float conf, int32_t max_det, int32_t nms, double iou_thresh, int32_t pre_topk,
+                                    int32_t img_h, int32_t img_w, int32_t img0, float* out, int32_t* num_dets, void* scratch,
+                                    int64_t scratch_bytes, void* stream) {
+  Levels lv;
+  int32_t rc = make_levels(in, lv);
+  if (rc != LY_OK) return rc;
+  LY_CHECK_ARG(!lv.direct, "decode_export: DFL layout only");
+  LY_CHECK_ARG(out && num_dets && scratch, "decode_export: null pointer");
+  LY_CHECK_ARG(max_det >= 1 && max_det <= TOPK_MAX && pre_topk >= 1 && pre_topk <= TOPK_MAX, "decode_export: max_det and pre_topk must be in 1..%d", TOPK_MAX);
+  LY_CHECK_ARG(img_h > 0 && img_w > 0 && img0 >= 0, "decode_export: bad image size / index");
+  ExportScratch e = carve_export(scratch, lv.B, lv.A, lv.nc, max_det, pre_topk);
+  LY_CHECK_ARG(scratch_bytes >= e.total, "decode_export: scratch too small (%lld < %lld)", (long long)scratch_bytes, e.total);
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 g1((lv.A + 255) / 256, lv.B);
+  if (lv.reg_max == 16) dfl_kernel<true, 16><<<g1, 256, 0, st>>>(lv, e.d.boxes, e.d.best, e.d.label);
+  else dfl_kernel<true, 0><<<g1, 256, 0, st>>>(lv, e.d.boxes, e.d.best, e.d.label);
+  rc = post_launch("dfl_decode");
+  if (rc != LY_OK) return rc;
+  if (!nms) {
+    const int k = max_det < lv.A ? max_det : lv.A;
+    export_topk_kernel<<<lv.B, NT_TOPK, 0, st>>>(lv.A, k, conf, (float)img_w, (float)img_h, e.d.boxes, e.d.best, e.d.label, out, num_dets);
+    return post_launch("export_topk");
+  }
+  const long long pairs = (long long)lv.A * lv.nc;
+  const int k2 = pairs < pre_topk ? (int)pairs : pre_topk;
+  const int k1 = k2 < lv.A ? k2 : lv.A;
+  const int kmax = max_det < k2 ? max_det : k2;
+  const float group_off = (float)((img_h > img_w ? img_h : img_w) * 10.0);
+  export_pairs_kernel<<<lv.B, NT_TOPK, 0, st>>>(lv, k1, k2, img0, group_off, e.d.boxes, e.d.best, e.d.s2, e.cand_box, e.cand_off,
+                                                e.cand_score, e.cand_cls);
+  rc = post_launch("export_pairs");
+  if (rc != LY_OK) return rc;
+  // torchvision compares the fp32 overlap with the DOUBLE threshold: ovr > thr_d  <=>  ovr > (largest float <= thr_d)
+  float thr_f = (float)iou_thresh;
+  if ((double)thr_f > iou_thresh) thr_f = nextafterf(thr_f, -INFINITY);
+  rc = run_nms(e.cand_off, e.cand_score, nullptr, nullptr, lv.B, k2, 0, 0.f, thr_f, kmax, 0, e.d.sortbuf, e.d.keep, e.d.count, nullptr, st, true);
+  if (rc != LY_OK) return rc;
+  export_finish_kernel<<<lv.B, 256, 0, st>>>(k2, kmax, conf, (float)img_w, (float)img_h, e.cand_box, e.cand_score, e.cand_cls, e.d.keep,
+                                             e.d.count, out, num_dets);
+  return post_launch("export_finish");
 }

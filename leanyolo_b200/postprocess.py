@@ -19,7 +19,8 @@ MAX_DET_LIMIT = 1024  # per-CTA sort buffers in decode.cu
 
 
 def _levels(preds: Sequence[torch.Tensor], num_classes: int, strides: Sequence[int], img_size=None, nms_path=False):
-    assert len(preds) == len(strides), "preds and strides length mismatch"
+    if len(preds) != len(strides):
+        raise ValueError("preds and strides length mismatch")
     if len(preds) > 4:
         raise ValueError("at most 4 pyramid levels are supported")
     p0 = preds[0]
@@ -30,10 +31,11 @@ def _levels(preds: Sequence[torch.Tensor], num_classes: int, strides: Sequence[i
     b, c = p0.shape[0], p0.shape[1]
     direct = bool(nms_path and c == 4 + num_classes)
     reg_max = 1 if direct else (c - num_classes) // 4
-    if not direct:
-        assert 4 * reg_max + num_classes == c, "Invalid channel layout for v10 head"
+    if not direct and 4 * reg_max + num_classes != c:
+        raise ValueError("Invalid channel layout for v10 head")
     for i, (p, s) in enumerate(zip(preds, strides)):
-        assert p.shape[0] == b and p.shape[1] == c and p.device == p0.device
+        if p.shape[0] != b or p.shape[1] != c or p.device != p0.device:
+            raise ValueError("head tensors must share batch size, channel count and device")
         q = p.detach()
         if q.dtype != torch.float32 or not q.is_contiguous():
             q = q.float().contiguous()
@@ -91,6 +93,34 @@ def decode_v10_official_topk(
 
 
 @torch.no_grad()
+def export_decode(preds: Sequence[torch.Tensor], *, num_classes: int, strides: Sequence[int] = (8, 16, 32), imgsz=640,
+                  max_dets: int = 300, conf: float = 0.25, nms: bool = False, iou: float = 0.45, pre_topk: int = 1000,
+                  img0: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
+    """The decode of the reference's ONNX wrapper (``YOLOv10ONNXExport.forward``, models/yolov10/export.py:97-198) on
+    the GPU: fixed-shape ``detections [B, k, 6]`` and ``num_dets [B]`` (int64).  ``nms=False``: top-k anchors by best
+    class score with the confidence mask and the clamp to the image; ``nms=True``: class-wise NMS over the
+    ``pre_topk`` best (anchor, class) pairs, bit-compatible with the reference's class-offset + torchvision NMS
+    (``img0`` = global index of the first image, which enters the reference's fp32 offset arithmetic when a batch
+    is sharded).  ``imgsz``: int (square, like the reference) or (H, W).  max_dets, pre_topk <= 1024."""
+    if not 1 <= max_dets <= MAX_DET_LIMIT or not 1 <= pre_topk <= MAX_DET_LIMIT:
+        raise ValueError(f"max_dets and pre_topk must be in 1..{MAX_DET_LIMIT}")
+    ih, iw = (int(imgsz), int(imgsz)) if isinstance(imgsz, (int, float)) else (int(imgsz[0]), int(imgsz[1]))
+    lib = N.lib()
+    lv, keep, A = _levels(preds, num_classes, strides)
+    dev = keep[0].device
+    k = min(max_dets, A) if not nms else min(max_dets, pre_topk, A * int(num_classes))
+    with torch.cuda.device(dev):
+        nbytes = lib.ly_decode_export_scratch_bytes(C.byref(lv), max_dets, pre_topk)
+        scratch = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        out = torch.empty((lv.B, k, 6), dtype=torch.float32, device=dev)
+        num = torch.empty((lv.B,), dtype=torch.int32, device=dev)
+        N.check(lib.ly_decode_export(C.byref(lv), float(conf), max_dets, int(bool(nms)), float(iou), pre_topk, ih, iw, int(img0),
+                                     out.data_ptr(), num.data_ptr(), scratch.data_ptr(), nbytes, _stream(dev)), "ly_decode_export")
+        scratch.record_stream(torch.cuda.current_stream(dev))
+    return out, num.to(torch.int64)
+
+
+@torch.no_grad()
 def nms_raw(preds: Sequence[torch.Tensor], *, num_classes: int, strides: Sequence[int] = (8, 16, 32),
             conf_thresh: float = 0.25, iou_thresh: float = 0.45, max_det: int = 300,
             img_size: Optional[Tuple[int, int]] = None, classwise: bool = False):
@@ -140,7 +170,9 @@ def nms(boxes: torch.Tensor, scores: torch.Tensor, iou_thresh: float, *, labels:
         max_keep: Optional[int] = None) -> torch.Tensor:
     """Drop-in for ``leanyolo.utils.box_ops.nms`` on CUDA tensors: keep indices
     (int64) into the input order, score-descending.  ``labels`` switches to
-    class-wise suppression.  ``max_keep`` (<= 1024) truncates; None keeps up to 1024."""
+    class-wise suppression.  ``max_keep`` (<= 1024) truncates.  The kernel keeps at most 1024 boxes (its kept set lives
+    in shared memory): with ``max_keep=None`` a result that reaches that cap raises instead of silently truncating
+    what the reference would return in full."""
     if not boxes.is_cuda:
         raise RuntimeError("leanyolo_b200 nms runs on CUDA only (no CPU fallback)")
     n = boxes.shape[0]
@@ -161,4 +193,7 @@ def nms(boxes: torch.Tensor, scores: torch.Tensor, iou_thresh: float, *, labels:
                            float(iou_thresh), mk, int(l is not None), keep.data_ptr(), cnt.data_ptr(),
                            scratch.data_ptr(), nbytes, _stream(dev)), "ly_nms")
         k = int(cnt.item())
+    if max_keep is None and k >= MAX_DET_LIMIT and n > MAX_DET_LIMIT:
+        raise RuntimeError(f"nms: {MAX_DET_LIMIT} or more boxes survive; leanyolo_b200 keeps at most {MAX_DET_LIMIT} "
+                           "(pass max_keep to truncate explicitly)")
     return keep[0, :k].to(torch.long)

@@ -16,6 +16,8 @@ Fixtures
                              640x640 pyramid, nc=80) + reg_max=1 / max_det edge cases
   decode_nms.pt              reference decode_v10_predictions (two threshold settings)
   nms.pt                     reference box_ops.nms keep indices on seeded boxes
+  decode_export.pt           reference YOLOv10ONNXExport.forward (export.py:126-198: top-k with conf mask + clamp, and the
+                             class-wise pre-top-k NMS through the real torchvision.ops.nms) on seeded head logits
 """
 from __future__ import annotations
 
@@ -116,9 +118,45 @@ def main() -> None:
     keep = {str(thr): ref_nms(boxes, scores, thr) for thr in (0.3, 0.5, 0.7)}
     torch.save({"seed": 31, "n": n, "keep": keep}, os.path.join(OUT, "nms.pt"))
     print("nms keep sizes", {k: int(v.numel()) for k, v in keep.items()})
+    # ---- export-style fixed-shape outputs (export.py:126-198), through the reference's own wrapper.  The wrapper
+    # calls self.model(images): a stub with the reference's V10Detect head hands it the seeded logits.
+    from leanyolo.models.yolov10.export import YOLOv10ONNXExport
+    from leanyolo.models.yolov10.head import V10Detect
+
+    class Stub(torch.nn.Module):
+        def __init__(self, preds, nc):
+            super().__init__()
+            self.head = V10Detect(nc=nc, ch=(16, 16, 16), reg_max=16)
+            self.preds = preds
+
+        def forward(self, x):
+            return self.preds
+
+    exp_cases = {}
+    for tag, seed, mean, kw in (("topk_default", 41, -3.0, dict(nms=False, conf=0.25, max_dets=300)),
+                                ("topk_lowconf", 42, -2.0, dict(nms=False, conf=0.05, max_dets=100)),
+                                ("nms_default", 43, -3.0, dict(nms=True, conf=0.25, iou=0.45, max_dets=300, pre_topk=1000)),
+                                ("nms_stress", 44, -1.0, dict(nms=True, conf=0.001, iou=0.7, max_dets=300, pre_topk=1000)),
+                                ("nms_small_k", 45, -2.0, dict(nms=True, conf=0.1, iou=0.5, max_dets=50, pre_topk=200)),
+                                ("topk_sparse", 46, -6.5, dict(nms=False, conf=0.25, max_dets=300)),
+                                ("nms_sparse", 46, -6.5, dict(nms=True, conf=0.25, iou=0.45, max_dets=300, pre_topk=1000)),
+                                ("topk_none", 47, -12.0, dict(nms=False, conf=0.25, max_dets=300)),
+                                ("nms_none", 47, -12.0, dict(nms=True, conf=0.25, iou=0.45, max_dets=300, pre_topk=1000))):
+        lg = synth_head_logits(3, 80, hw, seed=seed, cls_mean=mean)
+        wrap = YOLOv10ONNXExport(Stub(lg, 80), imgsz=640, **kw)
+        det, num = wrap(torch.zeros(3, 3, 640, 640))
+        exp_cases[tag] = dict(seed=seed, cls_mean=mean, kw=kw, det=det.clone(), num=num.clone())
+        print("export", tag, tuple(det.shape), num.tolist())
+    torch.save({"hw": hw, "nc": 80, "B": 3, "cases": exp_cases}, os.path.join(OUT, "decode_export.pt"))
     total = sum(os.path.getsize(os.path.join(OUT, f)) for f in os.listdir(OUT))
     print(f"golden dir: {total / 1e6:.2f} MB")
 
 
 if __name__ == "__main__":
-    main()
+    if "--only-export" in sys.argv:      # regenerate decode_export.pt alone (the other fixtures are unchanged)
+        _src = open(__file__).read()
+        _body = _src[_src.index("    # ---- export-style fixed-shape outputs"):_src.index("    total = sum(")]
+        hw = [(80, 80), (40, 40), (20, 20)]
+        exec(compile("if True:\n" + _body, __file__, "exec"))
+    else:
+        main()

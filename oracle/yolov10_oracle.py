@@ -371,6 +371,92 @@ def nms_classwise(boxes, scores, labels, iou_thresh: float, max_keep: int | None
     return order[torch.tensor(keep, dtype=torch.long)]
 
 
+def nms_torchvision(boxes: torch.Tensor, scores: torch.Tensor, iou_thresh: float) -> torch.Tensor:
+    """``torchvision.ops.nms`` restated (third-party dependency of export.py:30-33,182; torchvision is not under the
+    reference tree, unpinned in requirements.txt, 0.26.0 in this image; CPU kernel ``nms_kernel_impl``): areas
+    ``(x2-x1)*(y2-y1)`` WITHOUT clamping, candidates visited by a stable descending sort of the scores,
+    ``ovr = inter / (area_i + area_j - inter)`` in fp32 (no epsilon) and ``ovr > thr`` with the threshold held
+    as a double.  Returns kept indices in visiting order."""
+    n = boxes.shape[0]
+    if n == 0:
+        return torch.zeros((0,), dtype=torch.long)
+    order = torch.sort(scores, descending=True, stable=True)[1]
+    b = boxes[order]
+    area = (b[:, 2] - b[:, 0]) * (b[:, 3] - b[:, 1])
+    alive = torch.ones(n, dtype=torch.bool)
+    keep: List[int] = []
+    for i in range(n):
+        if not alive[i]:
+            continue
+        keep.append(i)
+        if i + 1 < n:
+            w = (torch.min(b[i, 2], b[i + 1:, 2]) - torch.max(b[i, 0], b[i + 1:, 0])).clamp(min=0)
+            h = (torch.min(b[i, 3], b[i + 1:, 3]) - torch.max(b[i, 1], b[i + 1:, 1])).clamp(min=0)
+            inter = w * h
+            ovr = inter / (area[i] + area[i + 1:] - inter)
+            alive[i + 1:] &= ~(ovr.double() > float(iou_thresh))
+    return order[torch.tensor(keep, dtype=torch.long)]
+
+
+@torch.no_grad()
+def decode_export(preds: Sequence[torch.Tensor], *, num_classes: int, strides: Sequence[int] = (8, 16, 32),
+                  imgsz: int = 640, max_dets: int = 300, conf: float = 0.25, nms: bool = False, iou: float = 0.45,
+                  pre_topk: int = 1000, img0: int = 0):
+    """``YOLOv10ONNXExport.forward`` after the model call (export.py:97-198): fixed-shape detections
+    ``[B, k, 6]`` + ``num_dets [B]`` (int64).
+
+    nms=False (:126-144): top-k anchors by best class score (scores below ``conf`` masked to -1), argmax class,
+    boxes clamped to the image, ``num_dets = #(score >= conf)``; rows past ``num_dets`` are whatever anchors the
+    tie order of ``torch.topk`` at -1 picks (canonical rule here: index ascending).
+    nms=True (:145-198): the ``pre_topk`` best (anchor, class) pairs, boxes offset by ``(image*C + class) * 10*imgsz``
+    IN FP32 (the rounding of that addition is part of the reference's result), ONE torchvision NMS over all
+    images, then the first ``max_dets`` survivors per image; entries below ``conf`` are zeroed.  ``img0`` = global
+    index of image 0 of this batch (the offset arithmetic depends on it)."""
+    boxes, scores = _dfl_boxes_scores(preds, num_classes, strides)
+    B, A, C = scores.shape
+    H = W = float(imgsz)
+    lo = torch.tensor(0.0)
+
+    def clamp_boxes(bx):
+        bx = bx.clone()
+        bx[..., 0].clamp_(0, W); bx[..., 2].clamp_(0, W); bx[..., 1].clamp_(0, H); bx[..., 3].clamp_(0, H)
+        return bx
+
+    conf_t = torch.tensor(conf, dtype=boxes.dtype)
+    if not nms:
+        best, cls = scores.max(dim=2)
+        masked = torch.where(best >= conf_t, best, torch.full_like(best, -1.0))
+        k = min(max_dets, A)
+        _, idx = topk_canonical(masked, k)
+        sel_b = clamp_boxes(boxes.gather(1, idx[..., None].expand(B, k, 4)))
+        sel_s = best.gather(1, idx).clamp(min=0.0)
+        sel_c = cls.gather(1, idx).to(boxes.dtype)
+        return torch.cat((sel_b, sel_s[..., None], sel_c[..., None]), -1), (sel_s >= conf_t).sum(1).to(torch.int64)
+    flat = scores.reshape(B, A * C)
+    k_pre = min(pre_topk, A * C)
+    vals, pidx = topk_canonical(flat, k_pre)
+    anc, cls = pidx // C, pidx % C
+    cand = boxes.gather(1, anc[..., None].expand(B, k_pre, 4))
+    img = (torch.arange(B) + img0).view(B, 1).to(boxes.dtype)
+    off = ((img * float(C) + cls.to(boxes.dtype)) * float(max(H, W) * 10.0)).unsqueeze(-1)
+    cand_off = cand + off                                        # fp32 addition: rounds the coordinates
+    keep = nms_torchvision(cand_off.reshape(B * k_pre, 4), vals.reshape(B * k_pre), iou)
+    kmax = min(max_dets, k_pre)
+    det = torch.zeros(B, kmax, 6)
+    num = torch.zeros(B, dtype=torch.int64)
+    cand_c = clamp_boxes(cand)
+    for b in range(B):
+        kb = keep[(keep >= b * k_pre) & (keep < (b + 1) * k_pre)] - b * k_pre      # already score-descending
+        kb = kb[:kmax]
+        kb = kb[vals[b, kb] >= conf_t]
+        n = kb.numel()
+        det[b, :n, :4] = cand_c[b, kb]
+        det[b, :n, 4] = vals[b, kb]
+        det[b, :n, 5] = cls[b, kb].to(boxes.dtype)
+        num[b] = n
+    return det, num
+
+
 @torch.no_grad()
 def decode_forward(sd: SD, x: torch.Tensor, *, max_det: int = 300):
     """``model.decode_forward(model(x))`` (yolov10s.py:124-144): top-k on one2one."""

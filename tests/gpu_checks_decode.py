@@ -133,3 +133,49 @@ def check_decode_nms_direct():
                                   iou_thresh=0.5, max_det=5, img_size=(64, 64))
     assert d[0][0].shape[0] >= 1 and d[1][0].shape[0] == 0
     return {}
+
+
+# ------------------------------------------------------------------ export-style outputs (export.py:126-198)
+def _compare_export(det, num, rdet, rnum, nms):
+    det, num = det.cpu(), num.cpu()
+    assert det.shape == rdet.shape, (det.shape, rdet.shape)
+    assert torch.equal(num.to(torch.int64), rnum.to(torch.int64)), (num.tolist(), rnum.tolist())
+    frac = 1.0
+    for b in range(det.shape[0]):
+        n = int(rnum[b])
+        o, r = det[b, :n], rdet[b, :n]
+        assert torch.allclose(o[:, 4], r[:, 4], atol=2e-6, rtol=0), "scores differ"
+        if n > 2:
+            solid = _solid_rows(r[:, 4])
+            frac = min(frac, float(solid.float().mean()))
+            assert torch.equal(o[solid, 5], r[solid, 5]), "class indices differ on tie-free rows"
+            assert torch.allclose(o[solid, :4], r[solid, :4], atol=2e-3, rtol=1e-5), "boxes differ"
+        if nms and n < det.shape[1]:
+            assert float(det[b, n:].abs().max()) == 0.0, "rows past num_dets must be zero"
+    return frac
+
+
+def check_export_golden():
+    """CUDA export decode against outputs of the reference's own YOLOv10ONNXExport (real torchvision NMS)."""
+    g = torch.load(os.path.join(G, "decode_export.pt"))
+    worst = 1.0
+    for tag, c in g["cases"].items():
+        lg = [t.to(DEV) for t in synth_head_logits(g["B"], g["nc"], g["hw"], seed=c["seed"], cls_mean=c["cls_mean"])]
+        kw = c["kw"]
+        det, num = PP.export_decode(lg, num_classes=g["nc"], imgsz=640, max_dets=kw["max_dets"], conf=kw["conf"], nms=kw["nms"],
+                                    iou=kw.get("iou", 0.45), pre_topk=kw.get("pre_topk", 1000))
+        worst = min(worst, _compare_export(det, num, c["det"], c["num"], kw["nms"]))
+    return {"solid_fraction": worst}
+
+
+def check_export_vs_oracle(B=3, seed=51, nms=True, conf=0.2, iou=0.6, max_dets=120, pre_topk=700, img0=37, hw=None, nc=80,
+                           cls_mean=-2.5, strides=(8, 16, 32), imgsz=640):
+    """... and against the oracle, incl. a non-zero first-image index (the reference's fp32 class-offset arithmetic
+    depends on the global image index) and small pyramids where A < pre_topk."""
+    hw = hw or HW640
+    lg = synth_head_logits(B, nc, hw, seed=seed, cls_mean=cls_mean)
+    rdet, rnum = O.decode_export(lg, num_classes=nc, strides=strides, imgsz=imgsz, max_dets=max_dets, conf=conf, nms=nms, iou=iou,
+                                 pre_topk=pre_topk, img0=img0)
+    det, num = PP.export_decode([t.to(DEV) for t in lg], num_classes=nc, strides=strides, imgsz=imgsz, max_dets=max_dets, conf=conf,
+                                nms=nms, iou=iou, pre_topk=pre_topk, img0=img0)
+    return {"solid_fraction": _compare_export(det, num, rdet, rnum, nms), "num": num.tolist()}

@@ -20,7 +20,8 @@ def _errs(a, b):
     return float((a - b).abs().max() / b.abs().max().clamp(min=1e-12)), float((a - b).norm() / b.norm().clamp(min=1e-12))
 
 
-def build(name, seed=1, gain=1.25, precision="bf16", conv_impl=None, nc=80):
+def build(name, seed=1, gain=1.25, precision="bf16", conv_impl=None, nc=80, chain=False):
+    os.environ["LEANYOLO_FUSE_CHAIN"] = "1" if chain else "0"     # opt-in fused conv chains (LY_OP_CHAIN)
     if conv_impl:
         os.environ["LEANYOLO_CONV_IMPL"] = conv_impl
     else:
@@ -33,10 +34,10 @@ def build(name, seed=1, gain=1.25, precision="bf16", conv_impl=None, nc=80):
     return m, sd
 
 
-def check_model(name="yolov10s", precision="bf16", hw=64, B=2, conv_impl=None, seed=1):
+def check_model(name="yolov10s", precision="bf16", hw=64, B=2, conv_impl=None, seed=1, chain=False):
     """bf16: raw head outputs and the c3..p5 taps within 2e-2 (max-abs / max|ref| and rel-L2);
     fp32 check mode: within 1e-4 (north_star tolerances)."""
-    m, sd = build(name, seed=seed, precision=precision, conv_impl=conv_impl)
+    m, sd = build(name, seed=seed, precision=precision, conv_impl=conv_impl, chain=chain)
     x = synth_images(B, hw, hw, seed=seed + 10)
     taps = {}
     ref = O.forward(sd, x, taps=taps)

@@ -300,3 +300,16 @@ def test_plan_is_pure_views_no_copy_ops_and_counts_flops():
     finally:
         del os.environ["LEANYOLO_FUSE_UPCAT"]
     assert abs(pb2.dense_flops() / 1e9 - 24.625) < 0.01 and sum(op.kind == "up" for op in pb2.ops) == 2
+
+
+def test_export_wrapper_surface_matches_reference():
+    """leanyolo_b200.export mirrors leanyolo/models/yolov10/export.py:34-94,201-221 (constructor arguments, validation)."""
+    from leanyolo_b200.export import YOLOv10ONNXExport, build_export_wrapper
+    m = get_model("yolov10n", weights=None, class_names=NAMES)
+    w = build_export_wrapper(m, imgsz=320, max_dets=50, conf=0.1, decode="nms", iou=0.5, pre_topk=200)
+    assert isinstance(w, YOLOv10ONNXExport) and w.nms and (w.imgsz, w.max_dets, w.pre_topk) == (320, 50, 200)
+    assert (w.num_classes, w.reg_max, w.strides) == (80, 16, (8, 16, 32)) and not w.model.training
+    with pytest.raises(ValueError, match="V10Detect"):
+        YOLOv10ONNXExport(torch.nn.Linear(2, 2))
+    with pytest.raises(RuntimeError, match="CUDA"):        # no CPU fallback
+        w(torch.zeros(1, 3, 64, 64))

@@ -174,3 +174,41 @@ def test_classwise_nms_only_suppresses_equal_labels():
     labels = torch.tensor([0, 1, 0])
     assert O.nms(boxes, scores, 0.5).tolist() == [0]
     assert O.nms_classwise(boxes, scores, labels, 0.5).tolist() == [0, 1]
+
+
+# ------------------------------------------------------------------ export-style outputs (export.py:126-198)
+def _export_rows_match(det, num, rdet, rnum, gap_ulps=16.0):
+    """num_dets equal; valid rows: scores equal to 2e-6, and rows whose score is separated from both neighbours
+    (torch.topk tie order is unspecified) equal in box (1e-3 px) and class.  nms=True zeroes the invalid rows
+    (checked); nms=False leaves whatever the -1 ties pick there (not compared)."""
+    assert torch.equal(num.to(torch.int64), rnum.to(torch.int64)), (num.tolist(), rnum.tolist())
+    for b in range(det.shape[0]):
+        n = int(rnum[b])
+        o, r = det[b, :n], rdet[b, :n]
+        assert torch.allclose(o[:, 4], r[:, 4], atol=2e-6, rtol=0)
+        s = r[:, 4].double()
+        if n > 2:
+            ulp = torch.finfo(torch.float32).eps * s.abs()
+            sep = torch.ones(n, dtype=torch.bool)
+            sep[1:] &= (s[:-1] - s[1:]) > gap_ulps * ulp[1:]
+            sep[:-1] &= (s[:-1] - s[1:]) > gap_ulps * ulp[:-1]
+            assert sep.float().mean() > 0.5
+            assert torch.allclose(o[sep][:, :4], r[sep][:, :4], atol=1e-3, rtol=0)
+            assert torch.equal(o[sep][:, 5], r[sep][:, 5])
+
+
+@pytest.mark.parametrize("tag", ["topk_default", "topk_lowconf", "nms_default", "nms_stress", "nms_small_k", "topk_sparse",
+                                 "nms_sparse", "topk_none", "nms_none"])
+def test_export_decode_matches_reference_golden(tag):
+    """Pins decode_export (incl. the restated torchvision NMS and the fp32 class-offset arithmetic) to outputs of the
+    reference's own YOLOv10ONNXExport wrapper running the real torchvision.ops.nms (oracle/make_golden.py)."""
+    g = torch.load(os.path.join(G, "decode_export.pt"))
+    c = g["cases"][tag]
+    lg = synth_head_logits(g["B"], g["nc"], g["hw"], seed=c["seed"], cls_mean=c["cls_mean"])
+    det, num = O.decode_export(lg, num_classes=g["nc"], imgsz=640, **c["kw"])
+    assert det.shape == c["det"].shape
+    _export_rows_match(det, num, c["det"], c["num"])
+    if c["kw"]["nms"]:
+        for b in range(det.shape[0]):
+            assert float(det[b, int(num[b]):].abs().max()) == 0.0 if int(num[b]) < det.shape[1] else True
+            assert float(c["det"][b, int(num[b]):].abs().max()) == 0.0 if int(num[b]) < det.shape[1] else True

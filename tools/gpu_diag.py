@@ -132,6 +132,15 @@ def registry():
     add("decode_nms_stress", D.check_decode_nms, conf=0.001, iou=0.7, cls_mean=-2.0, seed=22)
     add("decode_nms_empty", D.check_decode_nms, conf=0.25, iou=0.45, cls_mean=-12.0, seed=23)
     add("decode_nms_direct", D.check_decode_nms_direct)
+    # export-style fixed-shape outputs + the class-wise pre-top-k NMS (export.py:126-198), pinned to the reference's wrapper
+    add("export_golden", D.check_export_golden)
+    add("export_nms_vs_oracle_img0", D.check_export_vs_oracle)
+    add("export_nms_big_offset", D.check_export_vs_oracle, B=2, seed=52, img0=5000, iou=0.45, conf=0.05)
+    add("export_topk_vs_oracle", D.check_export_vs_oracle, nms=False, seed=53, conf=0.3, max_dets=200, cls_mean=-5.0)
+    add("export_nms_small_pyramid", D.check_export_vs_oracle, B=2, seed=54, hw=[(6, 8), (3, 4)], nc=5, strides=(8, 16), imgsz=64,
+        pre_topk=1000, max_dets=300, conf=0.01, cls_mean=-1.0)
+    add("export_topk_small_pyramid", D.check_export_vs_oracle, B=2, seed=55, nms=False, hw=[(6, 8), (3, 4)], nc=5, strides=(8, 16),
+        imgsz=64, max_dets=300, conf=0.2, cls_mean=-1.0)
     # whole model
     for name in ("yolov10n", "yolov10s"):
         add(f"model_{name}_f32", M.check_model, name=name, precision="fp32", hw=64, B=2)
@@ -141,6 +150,9 @@ def registry():
         add(f"model_{name}_bf16", M.check_model, name=name, precision="bf16", hw=64, B=2)
         add(f"model_{name}_f32", M.check_model, name=name, precision="fp32", hw=64, B=1)
     add("model_s_bf16_320", M.check_model, name="yolov10s", precision="bf16", hw=320, B=2)
+    add("model_s_bf16_chain_64", M.check_model, name="yolov10s", precision="bf16", hw=64, B=2, chain=True)
+    add("model_s_bf16_chain_320", M.check_model, name="yolov10s", precision="bf16", hw=320, B=2, chain=True)
+    add("model_n_bf16_chain_160", M.check_model, name="yolov10n", precision="bf16", hw=160, B=3, chain=True)
     add("model_s_golden", M.check_model_golden, name="yolov10s")
     add("model_s_subbatch_graph", M.check_subbatch_and_graph, name="yolov10s")
     add("model_s_decode_e2e", M.check_decode_e2e, name="yolov10s")
