@@ -22,12 +22,14 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
-int sm_count() {
-  static int n = 0;
+int sm_count() {   // of the CURRENT device (cached per device)
+  static std::atomic<int> cache[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  int n = cache[dev & 63].load(std::memory_order_relaxed);
   if (n == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
-      n = 148;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cache[dev & 63].store(n, std::memory_order_relaxed);
   }
   return n;
 }
@@ -41,18 +43,26 @@ bool pdl_enabled() {
   return on == 1;
 }
 
-static int32_t check_arch() {
-  static int ok = -1;
-  if (ok < 0) {
-    int dev = 0, major = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) {
+static int32_t check_arch() {   // of the CURRENT device (cached per device: 0 unknown, 1 ok, 2 wrong architecture)
+  static std::atomic<int> cache[64];
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) {
+    set_error("no CUDA device available (leanyolo_b200 has no CPU fallback)");
+    return LY_E_CUDA;
+  }
+  int st = cache[dev & 63].load(std::memory_order_relaxed);
+  if (st == 0) {
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) {
       set_error("no CUDA device available (leanyolo_b200 has no CPU fallback)");
       return LY_E_CUDA;
     }
-    ok = (major == 10) ? 1 : 0;
-    if (!ok) set_error("device compute capability %d.x is not sm_100 (this library is built for sm_100a only)", major);
+    st = (major == 10) ? 1 : 2;
+    cache[dev & 63].store(st, std::memory_order_relaxed);
   }
-  if (!ok) return LY_E_ARCH;
+  if (st != 1) {
+    set_error("device %d is not compute capability 10.x (this library is built for sm_100a only)", dev);
+    return LY_E_ARCH;
+  }
   return LY_OK;
 }
 

@@ -84,6 +84,14 @@ void chain_tc_free(ChainState* st);
 bool chain_tc_supported(const ly_op& op);
 
 int sm_count();
+// true exactly once per (flag, current device): per-device one-time setup such as cudaFuncSetAttribute (the
+// Python API allows models on several GPUs of one process; a process-wide flag would skip the second device)
+inline bool first_on_device(std::atomic<unsigned long long>& devs) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return true;
+  const unsigned long long bit = 1ull << (dev & 63);
+  return (devs.fetch_or(bit, std::memory_order_acq_rel) & bit) == 0;
+}
 
 // Tile traversal direction of the op being prepared / launched (set by the plan executor: ops
 // alternate).  A layer that walks its tiles in the opposite order to its producer starts on the

@@ -1004,12 +1004,11 @@ int32_t conv_tc_prepare(const ly_op& op, ConvTcState** out) {
     fprintf(stderr, "[conv_tc] k%d s%d %dx%d cin %d cout %d B %d: mode %d pair %d bn %d tiles_n %d kc %d a_stages %d (%d B) b_res %d b_stages %d res_slot %d "
             "band R %d mt %d bands %d units %d smem %zu\n", op.k, op.stride, op.src.H, op.src.W, Cin, Cout, op.B, p.halo, p.pair, bn, p.tiles_n, p.kc,
             p.a_stages, p.a_stage, p.b_resident, p.b_stages, p.res_slot, p.band_r, p.band_mt, p.bands, p.total_tiles, st->smem);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static std::atomic<unsigned long long> attr_devs{0};   // per DEVICE: the attribute does not carry over to another GPU
+  if (first_on_device(attr_devs)) {
     cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          227 * 1024 - (int)sizeof(float) * kMaxCout - 1024 /* static smem: s_bias */);
     if (e != cudaSuccess) { delete st; set_error("conv_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e)); return LY_E_CUDA; }
-    attr_set = true;
   }
   *out = st;
   return LY_OK;

@@ -257,10 +257,9 @@ int32_t launch_cfg(const ly_op& op, cudaStream_t st) {
     if (r != CUDA_SUCCESS) { set_error("dw_tma: cuTensorMapEncodeTiled failed with %d", (int)r); return LY_E_CUDA; }
   }
   const size_t smem = (size_t)p.stages * p.stage_bytes + 128;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static std::atomic<unsigned long long> attr_devs{0};   // per DEVICE: the attribute does not carry over to another GPU
+  if (first_on_device(attr_devs)) {
     LY_CUDA(cudaFuncSetAttribute(dw_tma_kernel<K, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
   }
   const int sms = sm_count();
   int grid = ctas_per_sm * sms;
@@ -473,10 +472,9 @@ int32_t launch_strip(const ly_op& op, cudaStream_t st) {
     if (r != CUDA_SUCCESS) { set_error("dw_tma: cuTensorMapEncodeTiled failed with %d", (int)r); return LY_E_CUDA; }
   }
   const size_t smem = (size_t)p.stages * p.stage_bytes + 128;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static std::atomic<unsigned long long> attr_devs{0};   // per DEVICE: the attribute does not carry over to another GPU
+  if (first_on_device(attr_devs)) {
     LY_CUDA(cudaFuncSetAttribute(dw_strip_kernel<K, S, CBV, TW_T, TH_T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
   }
   const int sms = sm_count();
   // three CTAs per SM when they fit: more loads in flight, epilogue of one overlaps compute of the other
@@ -703,10 +701,9 @@ int32_t launch_dw7(const ly_op& op, cudaStream_t st) {
                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("dw7: cuTensorMapEncodeTiled failed with %d", (int)r); return LY_E_CUDA; }
   }
-  static bool attr_set = false;
-  if (!attr_set) {
+  static std::atomic<unsigned long long> attr_devs{0};   // per DEVICE: the attribute does not carry over to another GPU
+  if (first_on_device(attr_devs)) {
     LY_CUDA(cudaFuncSetAttribute(dw7_kernel<PH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
   }
   // every CTA owns one channel block: the grid is a multiple of the channel-block count
   const int sms = sm_count();

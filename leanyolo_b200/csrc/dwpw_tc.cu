@@ -465,11 +465,10 @@ int32_t dwpw_prepare(const ly_op& op, DwPwState** out) {
   p.nchw = op.nchw; p.nCtot = op.nchw_ctot; p.nC0 = op.nchw_c0; p.nC = op.nchw_c;
   const int sms = sm_count();
   st->grid = p.total_tiles < sms ? p.total_tiles : sms;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static std::atomic<unsigned long long> attr_devs{0};   // per DEVICE: the attribute does not carry over to another GPU
+  if (first_on_device(attr_devs)) {
     cudaError_t e = cudaFuncSetAttribute(dwpw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
     if (e != cudaSuccess) { delete st; set_error("dwpw: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e)); return LY_E_CUDA; }
-    attr_set = true;
   }
   *out = st;
   return LY_OK;

@@ -631,10 +631,9 @@ static int32_t run_pool(const ly_op& op, cudaStream_t s) {
   while (cbv > 1 && (nvec % cbv != 0 || (size_t)2 * op.src.H * op.src.W * cbv * 16 > (size_t)plane_kb * 1024)) cbv >>= 1;
   const size_t smem = (size_t)2 * op.src.H * op.src.W * cbv * 16;
   LY_CHECK_ARG(smem <= 200 * 1024, "pool: feature map %dx%d too large for the shared-memory plane", op.src.H, op.src.W);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static std::atomic<unsigned long long> attr_devs{0};   // per DEVICE: the attribute does not carry over to another GPU
+  if (first_on_device(attr_devs)) {
     LY_CUDA(cudaFuncSetAttribute(pool_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
   }
   dim3 grid(nvec / cbv, op.B);
   launch_k(pool_kernel<T>, grid, dim3(256), smem, s, (T*)op.src.ptr, op.src.H, op.src.W, op.src.ctot, op.src.c0, op.src.c, cbv);

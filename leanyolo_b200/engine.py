@@ -42,7 +42,7 @@ class Engine:
     """One per (model, dtype).  ``emit`` fills a PlanBuilder for a batch of ``B`` images."""
 
     def __init__(self, emit: Callable[[PlanBuilder], None], device: torch.device, dtype: str = "bf16",
-                 conv_impl: Optional[str] = None):
+                 conv_impl: Optional[str] = None, pack_cache=None):
         if device.type != "cuda":
             raise RuntimeError("leanyolo_b200 runs on CUDA (sm_100a) only; there is no CPU path")
         self.emit, self.device, self.dtype = emit, device, dtype
@@ -54,23 +54,49 @@ class Engine:
             N.check(self.lib.ly_device_check(C.byref(sms)), "ly_device_check")
         self.sm_count = sms.value
         self._plans: Dict[Tuple[int, int, int, bool], Compiled] = {}
+        self._workspaces: Dict[Tuple[int, int, int], torch.Tensor] = {}   # shared by the fp32- and uint8-input plans of a shape
         self._w: Optional[torch.Tensor] = None
         self._b: Optional[torch.Tensor] = None
         self._graphs: Dict[Tuple, Tuple[torch.cuda.CUDAGraph, torch.Tensor, Dict]] = {}
+        self.pack_cache = pack_cache       # weights.PackCache or None
+        self.pack_seconds = 0.0            # host time spent producing the packed parameters (fold + pack, or cache load)
 
     # ------------------------------------------------------------------ build
     def compile(self, B: int, H: int, W: int, in_u8: bool = False) -> Compiled:
         key = (B, H, W, in_u8)
         if key in self._plans:
             return self._plans[key]
-        pb = PlanBuilder(B, H, W, self.dtype, tensor_core=self.impl != N.IMPL_SIMT)
-        self.emit(pb)
-        w, b = pb.finalize_params()
-        if self._w is None:
-            self._w, self._b = w.to(self.device), b.to(self.device)
-        else:
-            assert self._w.numel() == w.numel() and self._b.numel() == b.numel(), "parameter packing is shape dependent"
-        ws = torch.empty(max(pb.ws_bytes, 1024), dtype=torch.uint8, device=self.device)
+        import time
+        tc = self.impl != N.IMPL_SIMT
+        pb = None
+        t0 = time.perf_counter()
+        if self._w is None and self.pack_cache is not None:
+            # packed blobs of an earlier process, stored next to the checkpoint (keyed by its sha256 and this lowering)
+            dry = PlanBuilder(B, H, W, self.dtype, tensor_core=tc, dry=True)
+            self.emit(dry)
+            blobs = self.pack_cache.load(dry.signature())
+            if blobs is not None and blobs[0].numel() == dry._w_len and blobs[1].numel() == dry._b_len:
+                self._w, self._b = blobs[0].to(self.device), blobs[1].to(self.device)
+                pb = dry
+        if pb is None:
+            # parameters are packed ONCE per engine: later shapes lower dry (offsets only, no fp64 folding)
+            pb = PlanBuilder(B, H, W, self.dtype, tensor_core=tc, dry=self._w is not None)
+            self.emit(pb)
+            if self._w is None:
+                w, b = pb.finalize_params()
+                self._w, self._b = w.to(self.device), b.to(self.device)
+                if self.pack_cache is not None:
+                    self.pack_cache.save(pb.signature(), w, b)
+            elif self._w.numel() != pb._w_len or self._b.numel() != pb._b_len:
+                raise RuntimeError("parameter packing must not depend on the input shape")
+        if not self._plans:
+            self.pack_seconds = time.perf_counter() - t0
+        pb.assign_offsets(reuse=os.environ.get("LEANYOLO_WS_REUSE", "1") != "0")
+        # the two stem variants (fp32 / uint8 image) differ in one op's flag only: same buffer layout, one workspace
+        ws = self._workspaces.get((B, H, W))
+        if ws is None or ws.numel() < pb.ws_bytes:
+            ws = torch.empty(max(pb.ws_bytes, 1024), dtype=torch.uint8, device=self.device)
+            self._workspaces[(B, H, W)] = ws
         # external pointer table of a run: [image | named NCHW inputs ... | NCHW outputs ...]
         in_keys = list(pb.inputs.keys())
         out_keys = sorted(pb.outputs.keys())
@@ -147,21 +173,22 @@ class Engine:
         stream = torch.cuda.current_stream(self.device).cuda_stream
         N.check(self.lib.ly_plan_run(comp.handle, ext, len(ext), img0, C.c_void_p(stream)), "ly_plan_run")
 
-    def alloc_outputs(self, B: int, H: int, W: int, sub: int) -> Dict[Tuple[str, int], torch.Tensor]:
-        comp = self.compile(sub, H, W)
+    def alloc_outputs(self, B: int, H: int, W: int, sub: int, in_u8: bool = False) -> Dict[Tuple[str, int], torch.Tensor]:
+        comp = self.compile(sub, H, W, in_u8)      # (the plan this run uses anyway: no second plan for the shapes)
         return {k: torch.empty((B, c, h, w), dtype=torch.float32, device=self.device)
                 for k, (c, h, w) in comp.pb.outputs.items()}
 
     def run(self, x: torch.Tensor, sub_batch: Optional[int] = None,
             outs: Optional[Dict[Tuple[str, int], torch.Tensor]] = None) -> Dict[Tuple[str, int], torch.Tensor]:
         """x: [B,3,H,W] fp32 or uint8, contiguous, on the engine's device.  Returns {(name, level): NCHW fp32}."""
-        assert x.is_cuda and x.dtype in (torch.float32, torch.uint8) and x.is_contiguous() and x.dim() == 4 and x.shape[1] == 3
+        if not (x.is_cuda and x.dtype in (torch.float32, torch.uint8) and x.is_contiguous() and x.dim() == 4 and x.shape[1] == 3):
+            raise ValueError("expected a contiguous CUDA tensor [B,3,H,W] of dtype float32 or uint8")
         u8 = x.dtype == torch.uint8
         B, _, H, W = x.shape
         sub = min(B, sub_batch) if sub_batch else B
         with torch.cuda.device(self.device):
             if outs is None:
-                outs = self.alloc_outputs(B, H, W, sub)
+                outs = self.alloc_outputs(B, H, W, sub, u8)
             for img0 in range(0, B, sub):
                 n = min(sub, B - img0)
                 self._launch(self.compile(n, H, W, u8), x, outs, img0)
@@ -173,7 +200,8 @@ class Engine:
         ts = list(ins.values()) + ([x] if x is not None else [])
         B = ts[0].shape[0]
         for t in ins.values():
-            assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.shape[0] == B
+            if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.shape[0] == B):
+                raise ValueError("sub-module inputs must be contiguous CUDA float32 tensors with the same batch size")
         with torch.cuda.device(self.device):
             comp = self.compile(B, H, W, False)
             outs = {k: torch.empty((B, c, h, w), dtype=torch.float32, device=self.device) for k, (c, h, w) in comp.pb.outputs.items()}
@@ -243,6 +271,10 @@ class Engine:
         for comp in self._plans.values():
             self.lib.ly_plan_destroy(comp.handle)
         self._plans.clear()
+        self._workspaces.clear()
+
+    def __deepcopy__(self, memo):
+        raise TypeError("Engine owns native plan handles and device memory and cannot be copied; build a new one")
 
     def __del__(self):
         try:

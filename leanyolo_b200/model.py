@@ -48,10 +48,24 @@ class YOLOv10(nn.Module):
         self.sub_batch: Optional[int] = int(sb) if sb else None
         self._engines: Dict[tuple, Engine] = {}
         self._eval_branches: Dict[str, List[torch.Tensor]] = {}
+        self._weights_source = None      # (path, sha256) of the checkpoint the parameters came from (registry.get_model)
         # the sub-modules are callable like the reference's (model.backbone(x), model.neck(c3, c4, c5),
         # model.head(feats), head.forward_feat(feats, cv2, cv3)): they run their slice of the plan through this model
         for m in (self.backbone, self.neck, self.head):
             object.__setattr__(m, "_root", weakref.ref(self))
+
+    def __deepcopy__(self, memo):
+        """``copy.deepcopy(model)`` (EMA / clone patterns): parameters and buffers are copied, compiled engines are NOT
+        (they own native plan handles and device workspaces and are rebuilt on first use), and the sub-modules of the
+        copy dispatch to the copy."""
+        import copy
+        new = self.__class__.__new__(self.__class__)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            new.__dict__[k] = {} if k in ("_engines", "_eval_branches") else copy.deepcopy(v, memo)
+        for m in (new.backbone, new.neck, new.head):
+            object.__setattr__(m, "_root", weakref.ref(new))
+        return new
 
     # ---- class tables kept for callers that introspect them (yolov10s.py:62-65)
     @property
@@ -70,7 +84,7 @@ class YOLOv10(nn.Module):
     def emit(self, pb, taps: bool = False) -> None:
         """Lower the whole eval forward (both head branches) into ``pb``."""
         bb, nk, hd = self.backbone, self.neck, self.head
-        w0, b0 = bb.cv0.folded()
+        w0, b0 = bb.cv0.folded(pb)
         x = pb.stem(w0, b0, self.input_subtract.flatten().tolist(), self.input_divide.flatten().tolist())
         cats = nk.concat_buffers(pb, pb.H // 8, pb.W // 8)
         c3w, c4w, c5w, h13, h16, h19, _ = nk.widths
@@ -90,7 +104,7 @@ class YOLOv10(nn.Module):
         h8, w8 = pb.H // 8, pb.W // 8
         if part == "backbone":
             # the reference's backbone takes the already-normalised image (yolov10s.py:107-114)
-            w0, b0 = bb.cv0.folded()
+            w0, b0 = bb.cv0.folded(pb)
             x = pb.stem(w0, b0, [0.0, 0.0, 0.0], [1.0, 1.0, 1.0])
             for name, v, c in zip(("c3", "c4", "c5"), bb.emit(pb, x), bb.out_c):
                 pb.export_nchw(v, name, c)
@@ -123,11 +137,14 @@ class YOLOv10(nn.Module):
         xin = x.detach().to(torch.float32).contiguous() if x is not None else None
         return self._engines[key].run_named(named, hw[0], hw[1], xin)
 
-    def invalidate(self) -> None:
-        """Drop packed weights / plans (call after mutating parameters in place)."""
+    def invalidate(self, params_changed: bool = True) -> None:
+        """Drop packed weights / plans (call after mutating parameters in place).  ``params_changed`` also forgets
+        which checkpoint the parameters came from (the on-disk pack cache is keyed by it)."""
         for e in self._engines.values():
             e.close()
         self._engines.clear()
+        if params_changed:
+            self._weights_source = None
 
     def load_state_dict(self, *args, **kwargs):
         ret = super().load_state_dict(*args, **kwargs)
@@ -136,14 +153,26 @@ class YOLOv10(nn.Module):
 
     def _apply(self, fn, *args, **kwargs):
         ret = super()._apply(fn, *args, **kwargs)
-        self.invalidate()
+        self.invalidate(params_changed=False)     # a device move keeps the values (a dtype change is caught in _pack_cache)
         return ret
+
+    def _pack_cache(self, prec: str):
+        """weights.PackCache for this model's checkpoint, or None (random init, mutated or non-fp32 parameters,
+        LEANYOLO_PACK_CACHE=0)."""
+        src = getattr(self, "_weights_source", None)
+        if src is None or os.environ.get("LEANYOLO_PACK_CACHE", "1") == "0":
+            return None
+        if any(p.dtype != torch.float32 for p in self.parameters()):
+            return None
+        from .weights import PackCache
+        return PackCache(src[0], src[1], f"{self.variant.name}.{prec}.nc{len(self.class_names)}")
 
     def engine(self, device: torch.device, taps: bool = False) -> Engine:
         prec = "f32" if self.precision in ("fp32", "f32", "float32") else "bf16"
         key = (str(device), prec, taps)
         if key not in self._engines:
-            self._engines[key] = Engine(lambda pb: self.emit(pb, taps), device, prec)
+            self._engines[key] = Engine(lambda pb: self.emit(pb, taps), device, prec,
+                                        pack_cache=None if taps else self._pack_cache(prec))
         return self._engines[key]
 
     # ------------------------------------------------------------------ reference surface

@@ -23,6 +23,7 @@ from typing import List, Optional, Sequence
 import torch
 import torch.nn as nn
 
+from .plan import ShapeOnly
 from .variants import REG_MAX, Variant
 
 BN_EPS = 1e-3  # layers.py:84 (not torch's 1e-5 default)
@@ -37,15 +38,19 @@ class ConvBN(nn.Module):
         self.bn = nn.BatchNorm2d(cout, eps=BN_EPS, momentum=0.03)
         self.k, self.s, self.g, self.act = k, s, g, act
 
-    def folded(self):
-        """BN folded into the conv (fp64): w' = w*gamma/sqrt(var+eps), b' = beta - mean*gamma/sqrt(var+eps)."""
+    def folded(self, pb=None):
+        """BN folded into the conv (fp64): w' = w*gamma/sqrt(var+eps), b' = beta - mean*gamma/sqrt(var+eps).
+        With a dry PlanBuilder (packed parameters already exist: later shapes of the same model, or the on-disk
+        pack cache) only the SHAPES are produced (``plan.ShapeOnly``): no fp64 arithmetic, no copies."""
+        if pb is not None and pb.dry:
+            return ShapeOnly(self.conv.weight.shape), ShapeOnly(self.conv.weight.shape[:1])
         w = self.conv.weight.detach().double().cpu()
         bn = self.bn
         scale = bn.weight.detach().double().cpu() / torch.sqrt(bn.running_var.detach().double().cpu() + BN_EPS)
         return w * scale.view(-1, 1, 1, 1), bn.bias.detach().double().cpu() - bn.running_mean.detach().double().cpu() * scale
 
     def emit(self, pb, src, dst=None, res=None):
-        w, b = self.folded()
+        w, b = self.folded(pb)
         if self.g == 1:
             return pb.conv(src, w, b, k=self.k, stride=self.s, act=self.act, dst=dst, res=res)
         assert self.g == self.conv.in_channels == self.conv.out_channels, "only depthwise groups"
@@ -56,8 +61,8 @@ def emit_dw_pw(pb, dw: "ConvBN", pw: "ConvBN", src, dst=None):
     """dw3x3 (+SiLU) followed by a 1x1: one fused launch when the tensor-core kernel takes the
     pair (bf16, stride 1, C % 64 == 0, Cout <= 256), otherwise the two separate ops."""
     if dw.g > 1 and pw.g == 1 and pw.k == 1 and pw.s == 1 and pb.dwpw_fusable(src, dw.conv.in_channels, pw.conv.out_channels, dw.k, dw.s):
-        dw_w, dw_b = dw.folded()
-        pw_w, pw_b = pw.folded()
+        dw_w, dw_b = dw.folded(pb)
+        pw_w, pw_b = pw.folded(pb)
         return pb.dwpw(src, dw_w, dw_b, pw_w, pw_b, dw_act=dw.act, act=pw.act, dst=dst)
     return pw.emit(pb, dw.emit(pb, src), dst)
 
@@ -82,8 +87,8 @@ class RepVGGDW(nn.Module):
         self.conv1 = ConvBN(c, c, 3, g=c, act=False)
 
     def emit(self, pb, src, dst=None, res=None):
-        w7, b7 = self.conv.folded()
-        w3, b3 = self.conv1.folded()
+        w7, b7 = self.conv.folded(pb)
+        w3, b3 = self.conv1.folded(pb)
         w = w7.clone()
         w[:, :, 2:5, 2:5] += w3
         return pb.dwconv(src, w, b7 + b3, k=7, stride=1, act=True, dst=dst, res=res)
@@ -128,7 +133,7 @@ class C2f(nn.Module):
             return self._emit_chain(pb, src, dst)
         cat = pb.buffer(src.H, src.W, (2 + self.n) * c)
         if upcat is not None:
-            w, b = self.cv1.folded()
+            w, b = self.cv1.folded(pb)
             pb.upcat_conv(upcat[0], upcat[1], w, b, act=self.cv1.act, dst=cat.view(0, 2 * c))
         else:
             self.cv1.emit(pb, src, cat.view(0, 2 * c))
@@ -149,10 +154,10 @@ class C2f(nn.Module):
         """layers.py:129-173 as ONE launch.  Regions: 0 = x, 1 = cv1(x) = [y1 | y2], 2 = the Bottleneck's 3x3
         results (the second overwrites the first in place)."""
         c, m = self.c, self.m[0]
-        w1, b1 = self.cv1.folded()
-        wa, ba = m.cv1.folded()
-        wb, bb = m.cv2.folded()
-        w2, b2 = self.cv2.folded()
+        w1, b1 = self.cv1.folded(pb)
+        wa, ba = m.cv1.folded(pb)
+        wb, bb = m.cv2.folded(pb)
+        w2, b2 = self.cv2.folded(pb)
         stages = [
             dict(k=1, act=True, w=w1, b=b1, src=[(0, 0, src.c)], dst=(1, 0, 2 * c)),
             dict(k=3, act=True, w=wa, b=ba, src=[(1, c, c)], dst=(2, 0, c)),
@@ -198,7 +203,7 @@ class Attention(nn.Module):
         for part, width, padw in ((0, kd, kdp), (kd, kd, kdp), (2 * kd, hd, hd)):
             for h in range(nh):
                 perm += [h * per + part + j for j in range(width)] + [-1] * (padw - width)
-        w, bias = self.qkv.folded()
+        w, bias = self.qkv.folded(pb)
         qkv = pb.conv(b, w, bias, k=1, stride=1, act=False, out_perm=perm)
         att = pb.attention(qkv, nh=nh, kdp=kdp, hd=hd, scale=float(kd) ** -0.5)
         xa = self.pe.emit(pb, qkv.sub(2 * nh * kdp, nh * hd), res=att)
@@ -379,19 +384,19 @@ class Detect(nn.Module):
         input, twice the MMA width); each branch then continues from its channel slice."""
         branches = (("one2many", self.cv2, self.cv3), ("one2one", self.one2one_cv2, self.one2one_cv3))
         for i, f in enumerate(feats):
-            folded = [reg[i][0].folded() for _, reg, _ in branches]
+            folded = [reg[i][0].folded(pb) for _, reg, _ in branches]
             c2 = folded[0][0].shape[0]
             if c2 % 16 == 0:
-                r01 = pb.conv(f, torch.cat([w for w, _ in folded]), torch.cat([b for _, b in folded]), k=3, stride=1, act=True)
+                r01 = pb.conv(f, pb.cat0([w for w, _ in folded]), pb.cat0([b for _, b in folded]), k=3, stride=1, act=True)
                 firsts = [r01.sub(j * c2, c2) for j in range(len(branches))]
             else:
                 firsts = [reg[i][0].emit(pb, f) for _, reg, _ in branches]
             for (out_name, reg, cls), r in zip(branches, firsts):
                 fin = reg[i][2]
-                wf, bf = fin.weight.detach().double().cpu(), fin.bias.detach().double().cpu()
+                wf, bf = pb.param(fin.weight), pb.param(fin.bias)
                 if pb.chain_fusable() and r.c in (16, 32, 64) and r.c == c2 and (4 * self.reg_max) % 16 == 0:
                     # 3x3 -> 1x1 tail of the regression stack as one launch (the 3x3 result stays in shared memory)
-                    wm, bm = reg[i][1].folded()
+                    wm, bm = reg[i][1].folded(pb)
                     pb.chain(r, [c2, c2], 1, [dict(k=3, act=True, w=wm, b=bm, src=[(0, 0, c2)], dst=(1, 0, c2)),
                                               dict(k=1, act=False, w=wf, b=bf, src=[(1, 0, c2)])],
                              nchw=(out_name, i, 0, 4 * self.reg_max, self.no))
@@ -401,5 +406,5 @@ class Detect(nn.Module):
                 c = emit_dw_pw(pb, cls[i][0][0], cls[i][0][1], f)
                 c = emit_dw_pw(pb, cls[i][1][0], cls[i][1][1], c)
                 fin = cls[i][2]
-                pb.conv(c, fin.weight.detach().double().cpu(), fin.bias.detach().double().cpu(), k=1, stride=1,
+                pb.conv(c, pb.param(fin.weight), pb.param(fin.bias), k=1, stride=1,
                         act=False, nchw=(out_name, i, 4 * self.reg_max, self.nc, self.no))

@@ -30,6 +30,46 @@ def _rup(x: int, a: int) -> int:
     return (x + a - 1) // a * a
 
 
+class ShapeOnly:
+    """Stand-in for a weight tensor in a DRY lowering (``PlanBuilder(dry=True)``): it carries the shape through
+    the few manipulations the emitters apply (slicing, clone, add) and ignores the arithmetic.  (The meta device
+    would do, but its first in-place op or cat imports seconds of symbolic-shape machinery.)"""
+    __slots__ = ("shape",)
+
+    def __init__(self, shape):
+        self.shape = tuple(int(v) for v in shape)
+
+    def numel(self) -> int:
+        n = 1
+        for v in self.shape:
+            n *= v
+        return n
+
+    def __getitem__(self, idx):
+        idx = idx if isinstance(idx, tuple) else (idx,)
+        shape = []
+        for d, n in enumerate(self.shape):
+            if d < len(idx):
+                i = idx[d]
+                if isinstance(i, slice):
+                    shape.append(len(range(*i.indices(n))))
+                # an int index drops the dimension
+            else:
+                shape.append(n)
+        return ShapeOnly(shape)
+
+    def __setitem__(self, idx, value):
+        pass
+
+    def clone(self):
+        return ShapeOnly(self.shape)
+
+    def __add__(self, other):
+        return self
+
+    __radd__ = __iadd__ = __add__
+
+
 @dataclass
 class Buf:
     id: int
@@ -82,8 +122,11 @@ class Op:
 
 
 class PlanBuilder:
-    def __init__(self, B: int, H: int, W: int, dtype: str = "bf16", tensor_core: bool = True):
+    def __init__(self, B: int, H: int, W: int, dtype: str = "bf16", tensor_core: bool = True, dry: bool = False):
+        """``dry``: lower the op list and the parameter OFFSETS only; weights are shape-only meta tensors (see
+        ``ConvBN.folded``), nothing is folded, copied or stored.  Used when the packed blobs already exist."""
         assert dtype in ("bf16", "f32")
+        self.dry = dry
         # False: bring-up / bisecting mode (every conv on the CUDA-core kernel): no tensor-core-only fusions
         self.tensor_core = tensor_core and dtype == "bf16"
         assert H % 32 == 0 and W % 32 == 0, "input H, W must be multiples of 32 (neck concat, SURVEY App. C.10)"
@@ -107,20 +150,115 @@ class PlanBuilder:
         self.bufs.append(b)
         return b
 
+    def assign_offsets(self, reuse: bool = True) -> int:
+        """Place the buffers in the workspace.  The op list is linear and kernels of one forward run in stream
+        order, so a buffer only needs memory from the first op that touches it to the last one: buffers with
+        disjoint lifetimes share bytes (first-fit over a free list of address ranges, processed in order of first
+        use).  Without reuse yolov10s needs 74.8 MB per image at 640x640 and yolov10x 317 MB (19 GB / 81 GB at batch
+        256); with it roughly a third of that.  Returns the workspace size in bytes."""
+        first, last = {}, {}
+        for i, op in enumerate(self.ops):
+            for v in (op.src, op.dst, op.res, op.extra.get("up")):
+                if v is not None:
+                    first.setdefault(v.buf.id, i)
+                    last[v.buf.id] = i
+        size = {b.id: _rup(self.B * b.H * b.W * b.C * self.esize, BUF_ALIGN) for b in self.bufs}
+        if not reuse:
+            off = 0
+            for b in self.bufs:
+                b.offset = off
+                off += size[b.id]
+            self.ws_bytes = off
+            return off
+        order = sorted((b for b in self.bufs if b.id in first), key=lambda b: (first[b.id], b.id))
+        free: List[Tuple[int, int]] = []          # (offset, bytes), sorted by offset, coalesced
+        live: List[Tuple[int, int, int]] = []     # (last use, offset, bytes)
+        top = 0
+
+        def release(off: int, n: int) -> None:
+            free.append((off, n))
+            free.sort()
+            merged: List[Tuple[int, int]] = []
+            for o, m in free:
+                if merged and merged[-1][0] + merged[-1][1] == o:
+                    merged[-1] = (merged[-1][0], merged[-1][1] + m)
+                else:
+                    merged.append((o, m))
+            free[:] = merged
+
+        for b in order:
+            t = first[b.id]
+            for item in [x for x in live if x[0] < t]:
+                live.remove(item)
+                release(item[1], item[2])
+            need = size[b.id]
+            slot = next((i for i, (o, m) in enumerate(free) if m >= need), None)
+            if slot is None:
+                if free and free[-1][0] + free[-1][1] == top:      # grow the free tail instead of leaving a hole
+                    o, m = free.pop()
+                    b.offset = o
+                    top = o + need
+                else:
+                    b.offset = top
+                    top += need
+            else:
+                o, m = free.pop(slot)
+                b.offset = o
+                if m > need:
+                    release(o + need, m - need)
+            live.append((last[b.id], b.offset, need))
+        for b in self.bufs:                       # never referenced by an op: park at 0 (no bytes needed)
+            if b.id not in first:
+                b.offset = 0
+        self.ws_bytes = max(top, BUF_ALIGN)
+        return self.ws_bytes
+
     # ---------------------------------------------------------------- params
-    def _add_w(self, w: torch.Tensor) -> int:
+    def param(self, t: torch.Tensor) -> torch.Tensor:
+        """A raw (un-foldable) parameter as fp64 on the CPU; shape only when dry."""
+        if self.dry:
+            return ShapeOnly(t.shape)
+        return t.detach().double().cpu()
+
+    def cat0(self, ts: Sequence[torch.Tensor]) -> torch.Tensor:
+        """torch.cat along dim 0 (shape only when dry: the first torch.cat on the meta device costs seconds of lazy imports)."""
+        if self.dry:
+            return ShapeOnly((sum(t.shape[0] for t in ts),) + tuple(ts[0].shape[1:]))
+        return torch.cat(list(ts))
+
+    def _add_w(self, w) -> int:
+        """w: tensor, or (dry) the element count."""
         off = self._w_len
-        pad = (-w.numel()) % 64          # keep every weight block 128-byte aligned (TMA base address)
-        self._w.append(torch.cat([w.reshape(-1).double(), torch.zeros(pad, dtype=torch.float64)]))
-        self._w_len += w.numel() + pad
+        n = w if isinstance(w, int) else w.numel()
+        pad = (-n) % 64          # keep every weight block 128-byte aligned (TMA base address)
+        if not self.dry:
+            self._w.append(torch.cat([w.reshape(-1).double(), torch.zeros(pad, dtype=torch.float64)]))
+        self._w_len += n + pad
         return off
 
-    def _add_b(self, b: torch.Tensor) -> int:
+    def _add_b(self, b) -> int:
         off = self._b_len
-        pad = (-b.numel()) % 4
-        self._b.append(torch.cat([b.reshape(-1).double(), torch.zeros(pad, dtype=torch.float64)]))
-        self._b_len += b.numel() + pad
+        n = b if isinstance(b, int) else b.numel()
+        pad = (-n) % 4
+        if not self.dry:
+            self._b.append(torch.cat([b.reshape(-1).double(), torch.zeros(pad, dtype=torch.float64)]))
+        self._b_len += n + pad
         return off
+
+    def signature(self) -> str:
+        """Identifies the parameter packing (op kinds, shapes, blob offsets): a cached blob is only valid for the
+        lowering that produced it (fusion switches and package versions change the layout)."""
+        import hashlib
+        h = hashlib.sha256()
+        h.update(f"{self.dtype}|{self.tensor_core}|{self._w_len}|{self._b_len}".encode())
+        for op in self.ops:
+            h.update(f"{op.kind},{op.w_off},{op.b_off},{op.k},{op.stride},{op.cin},{op.cout},{int(op.act)}".encode())
+            for key in ("pre_w_off", "pre_b_off"):
+                if key in op.extra:
+                    h.update(f",{op.extra[key]}".encode())
+            for st in op.extra.get("stages", ()):
+                h.update(f",{st['w_off']},{st['b_off']},{st['k']},{st['cout']},{st['cin']}".encode())
+        return h.hexdigest()
 
     def finalize_params(self) -> Tuple[torch.Tensor, torch.Tensor]:
         wdt = torch.bfloat16 if self.dtype == "bf16" else torch.float32
@@ -136,10 +274,13 @@ class PlanBuilder:
         cout, cin = w.shape[0], w.shape[1]
         assert cin == 3 and w.shape[2:] == (3, 3)
         dst = self.buffer(self.H // 2, self.W // 2, cout).view()
-        wp = torch.zeros(dst.c, 27, dtype=torch.float64)
-        wp[:cout] = w.permute(0, 2, 3, 1).reshape(cout, 27)      # [co][ky][kx][ci]
-        bp = torch.zeros(dst.c, dtype=torch.float64)
-        bp[:cout] = b
+        if self.dry:
+            wp, bp = dst.c * 27, dst.c
+        else:
+            wp = torch.zeros(dst.c, 27, dtype=torch.float64)
+            wp[:cout] = w.permute(0, 2, 3, 1).reshape(cout, 27)      # [co][ky][kx][ci]
+            bp = torch.zeros(dst.c, dtype=torch.float64)
+            bp[:cout] = b
         op = Op("stem", dst=dst, k=3, stride=2, act=True, cin=3, cout=cout,
                 extra=dict(sub=[float(v) for v in sub], div=[float(v) for v in div]))
         # stem weights are consumed by CUDA cores in fp32 regardless of the storage dtype
@@ -155,12 +296,16 @@ class PlanBuilder:
         assert w.shape[2] == w.shape[3] == k and k in (1, 3) and stride in (1, 2)
         assert cin <= src.c < cin + CH_ALIGN, (cin, src.c)
         if out_perm is not None:
-            wn = torch.zeros(len(out_perm), *w.shape[1:], dtype=torch.float64)
-            bn = torch.zeros(len(out_perm), dtype=torch.float64)
-            idx = torch.tensor(out_perm)
-            m = idx >= 0
-            wn[m], bn[m] = w[idx[m]], b[idx[m]]
-            w, b, cout = wn, bn, len(out_perm)
+            if self.dry:
+                w, b = ShapeOnly((len(out_perm),) + tuple(w.shape[1:])), ShapeOnly((len(out_perm),))
+            else:
+                wn = torch.zeros(len(out_perm), *w.shape[1:], dtype=torch.float64)
+                bn = torch.zeros(len(out_perm), dtype=torch.float64)
+                idx = torch.tensor(out_perm)
+                m = idx >= 0
+                wn[m], bn[m] = w[idx[m]], b[idx[m]]
+                w, b = wn, bn
+            cout = len(out_perm)
         cpad = _rup(cout, CH_ALIGN)
         Ho, Wo = src.H // stride, src.W // stride
         if nchw is None:
@@ -170,10 +315,13 @@ class PlanBuilder:
         else:
             name, level, c0, c, ctot = nchw
             self.outputs[(name, level)] = (ctot, Ho, Wo)
-        wp = torch.zeros(cpad, k, k, src.c, dtype=torch.float64)
-        wp[:cout, :, :, :cin] = w.permute(0, 2, 3, 1)
-        bp = torch.zeros(cpad, dtype=torch.float64)
-        bp[:cout] = b
+        if self.dry:
+            wp, bp = cpad * k * k * src.c, cpad
+        else:
+            wp = torch.zeros(cpad, k, k, src.c, dtype=torch.float64)
+            wp[:cout, :, :, :cin] = w.permute(0, 2, 3, 1)
+            bp = torch.zeros(cpad, dtype=torch.float64)
+            bp[:cout] = b
         if res is not None:
             assert res.c == cpad and (res.H, res.W) == (Ho, Wo)
         extra = dict(cpad=cpad)
@@ -196,7 +344,7 @@ class PlanBuilder:
         conv over ``skip`` (neck.py:116-121; cat order [up, skip])."""
         c_low = w.shape[1] - skip.c
         assert c_low == low.c and w.shape[2:] == (1, 1) and (2 * low.H, 2 * low.W) == (skip.H, skip.W)
-        t = self.conv(low, w[:, :c_low], torch.zeros_like(b), k=1, stride=1, act=False)
+        t = self.conv(low, w[:, :c_low], b if self.dry else torch.zeros_like(b), k=1, stride=1, act=False)
         return self.conv(skip, w[:, c_low:], b, k=1, stride=1, act=act, dst=dst, up=t)
 
     def dwconv(self, src: View, w: torch.Tensor, b: torch.Tensor, *, k: int, stride: int, act: bool,
@@ -208,10 +356,13 @@ class PlanBuilder:
         if dst is None:
             dst = self.buffer(Ho, Wo, c).view()
         assert dst.c == src.c and (dst.H, dst.W) == (Ho, Wo)
-        wp = torch.zeros(k * k, src.c, dtype=torch.float64)
-        wp[:, :c] = w.reshape(c, k * k).t()
-        bp = torch.zeros(src.c, dtype=torch.float64)
-        bp[:c] = b
+        if self.dry:
+            wp, bp = k * k * src.c, src.c
+        else:
+            wp = torch.zeros(k * k, src.c, dtype=torch.float64)
+            wp[:, :c] = w.reshape(c, k * k).t()
+            bp = torch.zeros(src.c, dtype=torch.float64)
+            bp[:c] = b
         if res is not None:
             assert res.c == dst.c and (res.H, res.W) == (Ho, Wo)
         self.ops.append(Op("dw", src=src, dst=dst, res=res, w_off=self._add_w(wp), b_off=self._add_b(bp),
@@ -242,11 +393,14 @@ class PlanBuilder:
         else:
             name, level, c0, cc, ctot = nchw
             self.outputs[(name, level)] = (ctot, src.H, src.W)
-        dwp = dw_w.reshape(c, 9).t().contiguous()                      # [9][C]
-        wp = torch.zeros(cpad, 1, 1, src.c, dtype=torch.float64)
-        wp[:cout, :, :, :cin] = pw_w.permute(0, 2, 3, 1)
-        bp = torch.zeros(cpad, dtype=torch.float64)
-        bp[:cout] = pw_b
+        if self.dry:
+            dwp, wp, bp, dw_b = 9 * c, cpad * src.c, cpad, c
+        else:
+            dwp = dw_w.reshape(c, 9).t().contiguous()                      # [9][C]
+            wp = torch.zeros(cpad, 1, 1, src.c, dtype=torch.float64)
+            wp[:cout, :, :, :cin] = pw_w.permute(0, 2, 3, 1)
+            bp = torch.zeros(cpad, dtype=torch.float64)
+            bp[:cout] = pw_b
         self.ops.append(Op("dwpw", src=src, dst=dst, w_off=self._add_w(wp), b_off=self._add_b(bp), k=1, stride=1, act=act,
                            cin=cin, cout=cout, nchw=nchw,
                            extra=dict(cpad=cpad, pre_w_off=self._add_w(dwp), pre_b_off=self._add_b(dw_b), pre_act=dw_act)))
@@ -273,7 +427,8 @@ class PlanBuilder:
             cout, cin = w.shape[0], w.shape[1]
             assert cout % CH_ALIGN == 0 and cin == sum(c for _, _, c in st["src"]) and w.shape[2] == w.shape[3] == k
             packed.append(dict(k=k, act=bool(st["act"]), cout=cout, cin=cin, src=list(st["src"]), dst=st.get("dst"), res=st.get("res"),
-                               w_off=self._add_w(w.permute(0, 2, 3, 1).contiguous()), b_off=self._add_b(b)))
+                               w_off=self._add_w(w.numel() if self.dry else w.permute(0, 2, 3, 1).contiguous()),
+                               b_off=self._add_b(b.numel() if self.dry else b)))
         cout = packed[-1]["cout"]
         if nchw is None:
             if dst is None:

@@ -119,8 +119,10 @@ def unletterbox_dets(dets: torch.Tensor, meta: torch.Tensor) -> torch.Tensor:
     """In place: xyxy columns of ``dets [B,K,>=4]`` fp32 back to original-image coordinates (box_ops.py:96-124)."""
     if not dets.is_cuda or not meta.is_cuda:
         raise RuntimeError("leanyolo_b200 unletterbox runs on CUDA tensors only (no CPU fallback)")
-    assert dets.dtype == torch.float32 and dets.dim() == 3 and dets.shape[2] >= 4 and dets.is_contiguous()
-    assert meta.dtype == torch.float32 and meta.shape == (dets.shape[0], 6) and meta.is_contiguous()
+    if not (dets.dtype == torch.float32 and dets.dim() == 3 and dets.shape[2] >= 4 and dets.is_contiguous()):
+        raise ValueError("dets must be a contiguous float32 tensor [B, K, >=4]")
+    if not (meta.dtype == torch.float32 and tuple(meta.shape) == (dets.shape[0], 6) and meta.is_contiguous()):
+        raise ValueError("meta must be a contiguous float32 tensor [B, 6]")
     if dets.shape[1] == 0:
         return dets
     with torch.cuda.device(dets.device):

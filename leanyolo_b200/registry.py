@@ -14,7 +14,7 @@ import torch
 import torch.nn as nn
 
 from .model import MODEL_CLASSES
-from .weights import (YOLOv10Weights, adapt_state_dict_for_lean, extract_state_dict,
+from .weights import (YOLOv10Weights, adapt_state_dict_for_lean, extract_state_dict, file_sha256,
                       remap_official_yolov10_to_lean)
 
 
@@ -57,6 +57,7 @@ def get_model(
     if isinstance(weights, str) and os.path.isfile(weights):
         try:
             _load_local_pt_into_model(weights, model)
+            _note_source(model, weights)
         except Exception as e:
             raise ValueError(f"Failed to load local weights '{weights}': {e}. "
                              "Provide a state_dict compatible with this library version.")
@@ -96,8 +97,19 @@ def _load_local_pt_into_model(path: str, model: nn.Module) -> None:
         raise RuntimeError("state_dict keys mismatch for this model version")
 
 
+def _note_source(model: nn.Module, path: Optional[str]) -> None:
+    """Remember which file the parameters came from: the pre-packed weight cache (weights.PackCache) is keyed by its
+    sha256.  Best effort: an unreadable file just means no cache."""
+    try:
+        if path and os.path.isfile(path):
+            model._weights_source = (os.path.abspath(path), file_sha256(path))
+    except OSError:
+        pass
+
+
 def _load_official_pretrained_into_model(model_name: str, model: nn.Module) -> None:
-    loaded = YOLOv10Weights().get(model_name, "PRETRAINED_COCO").get_state_dict(progress=True)
+    entry = YOLOv10Weights().get(model_name, "PRETRAINED_COCO")
+    loaded = entry.get_state_dict(progress=True)
     mapped = remap_official_yolov10_to_lean(loaded, model)
     state = mapped if mapped else adapt_state_dict_for_lean(loaded)
     missing, unexpected = model.load_state_dict(state, strict=False)
@@ -115,3 +127,5 @@ def _load_official_pretrained_into_model(model_name: str, model: nn.Module) -> N
         warnings.warn(f"Unexpected keys when loading weights: {sorted(unexpected)[:10]}...", RuntimeWarning)
     if missing:
         warnings.warn(f"Missing keys when loading weights: {sorted(missing)[:10]}...", RuntimeWarning)
+    else:
+        _note_source(model, entry.resolved_path)

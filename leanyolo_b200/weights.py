@@ -90,6 +90,7 @@ class WeightsEntry:
     filename: Optional[str] = None
     metadata: Optional[Dict[str, Any]] = None
     sha256: Optional[str] = None
+    resolved_path: Optional[str] = None
 
     def _target_filename(self) -> str:
         if self.filename:
@@ -103,11 +104,15 @@ class WeightsEntry:
 
     def get_state_dict(self, *, progress: bool = True, map_location="cpu", local_path: Optional[str] = None,
                        cache_dir: Optional[str] = None, verify_hash: bool = True):
+        """Resolution order of the reference (utils/weights.py:140-207).  ``self.resolved_path`` records the file
+        that was read (the pre-packed weight cache is keyed by its sha256)."""
         if local_path is not None:
+            self.resolved_path = local_path
             return safe_load(local_path, map_location)
         fname = self._target_filename()
         env_dir = os.environ.get("LEANYOLO_WEIGHTS_DIR")
         if env_dir and os.path.exists(os.path.join(env_dir, fname)):
+            self.resolved_path = os.path.join(env_dir, fname)
             return safe_load(os.path.join(env_dir, fname), map_location)
         cache_dir = cache_dir or self._default_cache_dir()
         os.makedirs(cache_dir, exist_ok=True)
@@ -121,6 +126,7 @@ class WeightsEntry:
             except FileNotFoundError:
                 return False
 
+        self.resolved_path = path
         if os.path.exists(path) and ok(path):
             return safe_load(path, map_location)
         if not self.url:
@@ -297,3 +303,58 @@ def remap_official_yolov10_to_lean(loaded, dst_model: torch.nn.Module) -> Dict[s
                 out[stem + "bn.running_mean"] = torch.zeros_like(dst[stem + "bn.running_mean"])
                 out[stem + "bn.running_var"] = torch.ones_like(dst[stem + "bn.running_var"])
     return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# Pre-packed weight cache: the BN-folded, re-parameterised, re-ordered, padded parameter blobs
+# (bf16 / fp32 weights + fp32 biases) that the plan consumes, serialised next to the checkpoint and keyed by the
+# checkpoint's sha256, so that a later ``get_model(..., weights=...)`` + first forward skips remap-independent work
+# (fp64 folding and packing) and only uploads.  Reference counterpart of the key: utils/weights.py:140-207 (the
+# sha256-verified cache of the .pt itself).
+PACK_FORMAT = 1     # bump when the packing in plan.py / modules.py changes meaning
+
+
+def file_sha256(path: str) -> str:
+    return _sha256(path)
+
+
+class PackCache:
+    """One cache file per (checkpoint sha256, tag); ``tag`` names the variant, precision and class count."""
+
+    def __init__(self, weights_path: str, sha256: str, tag: str):
+        self.weights_path, self.sha256, self.tag = os.path.abspath(weights_path), sha256, tag
+        self.hit = False
+
+    def _candidates(self):
+        base = os.path.basename(self.weights_path)
+        name = f"{base}.{self.sha256[:16]}.{self.tag}.lypack"
+        yield os.path.join(os.path.dirname(self.weights_path), name)
+        yield os.path.join(os.environ.get("LEANYOLO_CACHE_DIR", os.path.join(os.path.expanduser("~"), ".cache", "leanyolo")), name)
+
+    def load(self, signature: str):
+        """(w, b) CPU tensors, or None when there is no valid cache for this lowering."""
+        for path in self._candidates():
+            if not os.path.isfile(path):
+                continue
+            try:
+                d = torch.load(path, map_location="cpu", weights_only=True)
+                if (d.get("format") == PACK_FORMAT and d.get("sha256") == self.sha256 and d.get("signature") == signature
+                        and isinstance(d.get("w"), torch.Tensor) and isinstance(d.get("b"), torch.Tensor)):
+                    self.hit = True
+                    return d["w"], d["b"]
+            except Exception:
+                continue
+        return None
+
+    def save(self, signature: str, w: torch.Tensor, b: torch.Tensor) -> Optional[str]:
+        payload = {"format": PACK_FORMAT, "sha256": self.sha256, "signature": signature, "tag": self.tag, "w": w.cpu(), "b": b.cpu()}
+        for path in self._candidates():
+            try:
+                os.makedirs(os.path.dirname(path), exist_ok=True)
+                with tempfile.NamedTemporaryFile(delete=False, dir=os.path.dirname(path)) as tmp:
+                    torch.save(payload, tmp)
+                os.replace(tmp.name, path)
+                return path
+            except OSError:
+                continue
+        return None

@@ -261,3 +261,43 @@ def check_fullsize_properties(name="yolov10s", B=256, hw=640, seed=11):
             worst = max(worst, float(iou.max()))
     assert worst <= 0.45 + 1e-6, f"two kept boxes overlap with IoU {worst:.4f} > 0.45"
     return {"max_kept_iou": worst, "mean_kept": float(cnt.float().mean())}
+
+
+def check_pack_cache(name="yolov10s"):
+    """the second ``get_model(weights=file).to('cuda')`` + first forward takes the packed blobs
+    from the cache next to the checkpoint (no fp64 fold) and gives bit-identical head tensors; timed."""
+    import tempfile
+    import time
+    with tempfile.TemporaryDirectory() as d:
+        ck = os.path.join(d, f"{name}.pt")
+        m0 = get_model(name, weights=None, class_names=NAMES)
+        torch.save(synth_state_dict(m0.state_dict(), seed=7, gain=1.25), ck)
+        x = synth_images(2, 128, 128, seed=8).to(DEV)
+        outs, secs, hits = [], [], []
+        for _ in range(2):
+            m = get_model(name, weights=ck, class_names=NAMES).to(DEV).eval()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            y = [t.clone() for t in m(x)]
+            torch.cuda.synchronize()
+            secs.append(time.perf_counter() - t0)
+            eng = m.engine(torch.device(DEV, torch.cuda.current_device()))
+            hits.append(bool(eng.pack_cache is not None and eng.pack_cache.hit))
+            outs.append(y)
+            packs = eng.pack_seconds
+        assert hits == [False, True], hits
+        assert any(f.endswith(".lypack") for f in os.listdir(d)), os.listdir(d)
+        for a, b in zip(*outs):
+            assert torch.equal(a, b), "cached pack gives different head tensors"
+        # a second shape on the warm engine lowers dry (no folding): must match a cold engine bit for bit
+        x2 = synth_images(1, 64, 96, seed=9).to(DEV)
+        y_warm = [t.clone() for t in m(x2)]
+        os.environ["LEANYOLO_PACK_CACHE"] = "0"
+        try:
+            mc = get_model(name, weights=ck, class_names=NAMES).to(DEV).eval()
+            y_cold = mc(x2)
+        finally:
+            os.environ.pop("LEANYOLO_PACK_CACHE")
+        for a, b in zip(y_warm, y_cold):
+            assert torch.equal(a, b)
+    return {"first_forward_s_cold": round(secs[0], 3), "first_forward_s_cached": round(secs[1], 3), "pack_seconds_cached": round(packs, 4)}

@@ -6,7 +6,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from leanyolo_b200.dist import gather_detections, shard_range
+from leanyolo_b200.dist import ShardedDetector, gather_detections, shard_range
 
 
 def _free_port():
@@ -27,7 +27,20 @@ def _worker(rank, world, port, n_images, q):
     lo, hi = shard_range(n_images, rank, world)
     got = gather_detections(full[lo:hi].clone(), n_images)      # partition known
     got2 = gather_detections(full[lo:hi].clone())               # sizes exchanged
-    q.put((rank, bool(torch.equal(got, full)), bool(torch.equal(got2, full)), (lo, hi)))
+    # the overlapped form (ring of pre-allocated gather buffers, tickets): even shards
+    even = _fake_dets(2 * world)
+    sd = ShardedDetector(model=None, group=None, depth=2)
+    t0 = sd.submit_detections(even[2 * rank:2 * rank + 2].clone())
+    t1 = sd.submit_detections(even[2 * rank:2 * rank + 2].clone() + 1.0)
+    ok3 = bool(torch.equal(sd.collect(t0), even)) and bool(torch.equal(sd.collect(t1), even + 1.0))
+    t2 = sd.submit_detections(even[2 * rank:2 * rank + 2].clone() + 2.0)
+    try:
+        sd.collect(t0)
+        ok3 = False            # ticket 0 was overwritten by ticket 2 (depth 2): must raise
+    except RuntimeError:
+        pass
+    ok3 = ok3 and bool(torch.equal(sd.collect(t2), even + 2.0))
+    q.put((rank, bool(torch.equal(got, full)), bool(torch.equal(got2, full)) and ok3, (lo, hi)))
     dist.destroy_process_group()
 
 

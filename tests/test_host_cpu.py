@@ -313,3 +313,68 @@ def test_export_wrapper_surface_matches_reference():
         YOLOv10ONNXExport(torch.nn.Linear(2, 2))
     with pytest.raises(RuntimeError, match="CUDA"):        # no CPU fallback
         w(torch.zeros(1, 3, 64, 64))
+
+
+@pytest.mark.parametrize("name", ["yolov10n", "yolov10s", "yolov10x"])
+def test_workspace_reuse_never_overlaps_live_buffers(name):
+    """PlanBuilder.assign_offsets: buffers whose lifetimes (first..last op touching them) intersect must not share
+    bytes; the reused layout is several times smaller than one-buffer-one-range."""
+    m = get_model(name, weights=None, class_names=NAMES)
+    pb = PlanBuilder(2, 320, 320, "bf16")
+    m.emit(pb, taps=True)
+    flat = pb.assign_offsets(reuse=False)
+    packed = pb.assign_offsets(reuse=True)
+    assert packed * 3 < flat
+    first, last = {}, {}
+    for i, op in enumerate(pb.ops):
+        for v in (op.src, op.dst, op.res, op.extra.get("up")):
+            if v is not None:
+                first.setdefault(v.buf.id, i)
+                last[v.buf.id] = i
+    bufs = [b for b in pb.bufs if b.id in first]
+    size = {b.id: pb.B * b.H * b.W * b.C * pb.esize for b in bufs}
+    for i, x in enumerate(bufs):
+        assert x.offset % 1024 == 0 and x.offset + size[x.id] <= packed
+        for y in bufs[i + 1:]:
+            if first[x.id] <= last[y.id] and first[y.id] <= last[x.id]:
+                assert x.offset + size[x.id] <= y.offset or y.offset + size[y.id] <= x.offset, (x.id, y.id)
+
+
+def test_pack_cache_roundtrip_and_keying(tmp_path):
+    """weights.PackCache: blobs are stored next to the checkpoint, keyed by the checkpoint's
+    sha256 + the lowering's signature; a different signature or a changed checkpoint is a miss."""
+    from leanyolo_b200.weights import PackCache, file_sha256
+    m = get_model("yolov10n", weights=None, class_names=NAMES)
+    ck = tmp_path / "w.pt"
+    torch.save(synth_state_dict(m.state_dict(), seed=3), ck)
+    m2 = get_model("yolov10n", weights=str(ck), class_names=NAMES)
+    assert m2._weights_source == (str(ck), file_sha256(str(ck)))
+    pb = PlanBuilder(1, 64, 64, "bf16")
+    m2.emit(pb)
+    w, b = pb.finalize_params()
+    dry = PlanBuilder(2, 128, 96, "bf16", dry=True)          # another shape, no folding: same packing
+    m2.emit(dry)
+    assert dry.signature() == pb.signature() and (dry._w_len, dry._b_len) == (w.numel(), b.numel()) and not dry._w
+    pc = m2._pack_cache("bf16")
+    assert pc is not None and pc.load(pb.signature()) is None
+    path = pc.save(pb.signature(), w, b)
+    assert path is not None and os.path.dirname(path) == str(tmp_path)
+    got = m2._pack_cache("bf16").load(pb.signature())
+    assert got is not None and torch.equal(got[0], w) and torch.equal(got[1], b)
+    assert pc.load("0" * 64) is None                          # other lowering (fusion switches, package version)
+    assert m2._pack_cache("f32").load(pb.signature()) is None  # other precision: other file
+    m2.load_state_dict(m.state_dict())                        # parameters replaced: the checkpoint key is forgotten
+    assert m2._weights_source is None and m2._pack_cache("bf16") is None
+    m3 = get_model("yolov10n", weights=str(ck), class_names=NAMES).half()
+    assert m3._pack_cache("bf16") is None                     # values changed by the cast
+
+
+def test_deepcopy_rebinds_submodules_and_drops_engines():
+    import copy
+    m = get_model("yolov10n", weights=None, class_names=NAMES)
+    m._engines[("x",)] = object()
+    c = copy.deepcopy(m)
+    assert c._engines == {} and c.backbone._root() is c and c.head._root() is c and m.backbone._root() is m
+    assert c.backbone.cv0.conv.weight is not m.backbone.cv0.conv.weight
+    assert all(torch.equal(a, b) for a, b in zip(c.state_dict().values(), m.state_dict().values()))
+    m._engines.clear()

@@ -156,6 +156,8 @@ def registry():
     add("model_s_golden", M.check_model_golden, name="yolov10s")
     add("model_s_subbatch_graph", M.check_subbatch_and_graph, name="yolov10s")
     add("model_s_decode_e2e", M.check_decode_e2e, name="yolov10s")
+    add("model_s_pack_cache", M.check_pack_cache, name="yolov10s")
+    add("model_x_pack_cache", M.check_pack_cache, name="yolov10x")
     # the reference's component surface: backbone / neck / head / forward_feat callables
     add("submodules_s_bf16", M.check_submodules, name="yolov10s", precision="bf16")
     add("submodules_s_f32", M.check_submodules, name="yolov10s", precision="fp32")
