@@ -48,19 +48,13 @@ __device__ __forceinline__ int level_of(const Levels& lv, int g) {
 // reference's argmax over the sigmoid VALUES (first maximum wins, ties included): LABEL = true.
 // RM = 16: the standard reg_max with the 16 bin loads of a side issued together (fully unrolled);
 // RM = 0: any reg_max, rolled loops.
-template <bool LABEL, int RM>
-__global__ void __launch_bounds__(256)
-dfl_kernel(Levels lv, float* __restrict__ boxes, float* __restrict__ best, int* __restrict__ label) {
-  const int g = blockIdx.x * blockDim.x + threadIdx.x;
-  const int b = blockIdx.y;
-  if (g >= lv.A) return;
-  const int l = level_of(lv, g);
-  const int a = g - lv.off[l];
+// xyxy box of anchor (level l, cell a) of image b: DFL softmax-expectation + anchor decode (postprocess.py:217-235,
+// utils/tal.py:10-46), or the legacy direct-offset layout (postprocess.py:70-92).  p = &pred[b][0][a].
+template <int RM>
+__device__ __forceinline__ float4 decode_box(const Levels& lv, int l, int a, const float* p) {
   const int HW = lv.H[l] * lv.W[l];
   const int y = a / lv.W[l], x = a - y * lv.W[l];
   const float s = (float)lv.stride[l];
-  const int creg = lv.direct ? 4 : 4 * lv.reg_max;
-  const float* p = lv.p[l] + (long long)b * (creg + lv.nc) * HW + a;
   float x1, y1, x2, y2;
   if (lv.direct) {
     // postprocess.py:70-92: sigmoid centre offsets on the integer grid, exp sizes
@@ -103,6 +97,22 @@ dfl_kernel(Levels lv, float* __restrict__ boxes, float* __restrict__ best, int* 
     const float ax = (float)x + 0.5f, ay = (float)y + 0.5f;
     x1 = (ax - d[0]) * s; y1 = (ay - d[1]) * s; x2 = (ax + d[2]) * s; y2 = (ay + d[3]) * s;
   }
+  return make_float4(x1, y1, x2, y2);
+}
+
+template <bool LABEL, int RM>
+__global__ void __launch_bounds__(256)
+dfl_kernel(Levels lv, float* __restrict__ boxes, float* __restrict__ best, int* __restrict__ label) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (g >= lv.A) return;
+  const int l = level_of(lv, g);
+  const int a = g - lv.off[l];
+  const int HW = lv.H[l] * lv.W[l];
+  const int creg = lv.direct ? 4 : 4 * lv.reg_max;
+  const float* p = lv.p[l] + (long long)b * (creg + lv.nc) * HW + a;
+  const float4 bx = decode_box<RM>(lv, l, a, p);
+  const float x1 = bx.x, y1 = bx.y, x2 = bx.z, y2 = bx.w;
   const float* c = p + (long long)creg * HW;
   float bs = -1.f;
   int bl = 0;
@@ -121,6 +131,30 @@ dfl_kernel(Levels lv, float* __restrict__ boxes, float* __restrict__ best, int* 
   reinterpret_cast<float4*>(boxes)[o] = make_float4(x1, y1, x2, y2);
   best[o] = bs;
   if (LABEL) label[o] = bl;
+}
+
+// Top-k path: only the best class score of every anchor is needed up front (sigmoid is monotonic: sigmoid(max
+// logit)); the box of an anchor is decoded later, for the k selected anchors only (topk_kernel).  Reads the class
+// logits once (nc * 4 B per anchor) instead of the whole head tensor.
+__global__ void __launch_bounds__(256) best_kernel(Levels lv, float* __restrict__ best) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (g >= lv.A) return;
+  const int l = level_of(lv, g);
+  const int a = g - lv.off[l];
+  const int HW = lv.H[l] * lv.W[l];
+  const int creg = 4 * lv.reg_max;
+  const float* c = lv.p[l] + ((long long)b * (creg + lv.nc) + creg) * HW + a;
+  float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+  int i = 0;
+  for (; i + 4 <= lv.nc; i += 4) {     // four independent loads in flight per step
+    m0 = fmaxf(m0, __ldg(c + (long long)i * HW));
+    m1 = fmaxf(m1, __ldg(c + (long long)(i + 1) * HW));
+    m2 = fmaxf(m2, __ldg(c + (long long)(i + 2) * HW));
+    m3 = fmaxf(m3, __ldg(c + (long long)(i + 3) * HW));
+  }
+  for (; i < lv.nc; ++i) m0 = fmaxf(m0, __ldg(c + (long long)i * HW));
+  best[(long long)b * lv.A + g] = sigmoid_precise(fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
 }
 
 // ------------------------------------------------------------------- block-wide primitives
@@ -190,8 +224,9 @@ __device__ __forceinline__ int next_pow2(int v) {
 }
 
 // ----------------------------------------------------------------------------------- top-k
+template <int RM>
 __global__ void __launch_bounds__(NT_TOPK, 3)
-topk_kernel(Levels lv, int k, const float* __restrict__ boxes, const float* __restrict__ best, float* s2,
+topk_kernel(Levels lv, int k, const float* __restrict__ best, float* s2,
             float* __restrict__ out, int* __restrict__ out_anchor, int* __restrict__ out_cls) {
   __shared__ unsigned long long sortbuf[TOPK_MAX];
   __shared__ int anchors[TOPK_MAX];
@@ -249,7 +284,8 @@ topk_kernel(Levels lv, int k, const float* __restrict__ boxes, const float* __re
     const int flat = (int)(0xFFFFFFFFu - (unsigned)(sortbuf[r] & 0xFFFFFFFFull));
     const int rel = flat / nc, c = flat - rel * nc;
     const int g = anchors[rel];
-    const float4 bx = reinterpret_cast<const float4*>(boxes)[(long long)b * A + g];
+    const int l = level_of(lv, g);
+    const float4 bx = decode_box<RM>(lv, l, g - lv.off[l], lv.p[l] + (long long)b * (creg + nc) * (lv.H[l] * lv.W[l]) + (g - lv.off[l]));
     float* o = out + ((long long)b * k + r) * 6;
     o[0] = bx.x; o[1] = bx.y; o[2] = bx.z; o[3] = bx.w;
     o[4] = s2b[flat];
@@ -667,11 +703,11 @@ extern "C" int32_t ly_decode_topk(const ly_levels* in, int32_t max_det, float* o
   cudaStream_t st = (cudaStream_t)stream;
   const int k = max_det < lv.A ? max_det : lv.A;
   dim3 g1((lv.A + 255) / 256, lv.B);
-  if (lv.reg_max == 16) dfl_kernel<false, 16><<<g1, 256, 0, st>>>(lv, s.boxes, s.best, s.label);
-  else dfl_kernel<false, 0><<<g1, 256, 0, st>>>(lv, s.boxes, s.best, s.label);
-  rc = post_launch("dfl_decode");
+  best_kernel<<<g1, 256, 0, st>>>(lv, s.best);
+  rc = post_launch("best_score");
   if (rc != LY_OK) return rc;
-  topk_kernel<<<lv.B, NT_TOPK, 0, st>>>(lv, k, s.boxes, s.best, s.s2, out, out_anchor, out_cls);
+  if (lv.reg_max == 16) topk_kernel<16><<<lv.B, NT_TOPK, 0, st>>>(lv, k, s.best, s.s2, out, out_anchor, out_cls);
+  else topk_kernel<0><<<lv.B, NT_TOPK, 0, st>>>(lv, k, s.best, s.s2, out, out_anchor, out_cls);
   return post_launch("topk");
 }
 

@@ -81,8 +81,8 @@ class YOLOv10(nn.Module):
         return dict(self.variant.reps)
 
     # ------------------------------------------------------------------ lowering
-    def emit(self, pb, taps: bool = False) -> None:
-        """Lower the whole eval forward (both head branches) into ``pb``."""
+    def emit(self, pb, taps: bool = False, head_only: Optional[str] = None) -> None:
+        """Lower the whole eval forward (both head branches, or just ``head_only``) into ``pb``."""
         bb, nk, hd = self.backbone, self.neck, self.head
         w0, b0 = bb.cv0.folded(pb)
         x = pb.stem(w0, b0, self.input_subtract.flatten().tolist(), self.input_divide.flatten().tolist())
@@ -95,7 +95,7 @@ class YOLOv10(nn.Module):
             for name, v, c in (("c3", c3, c3w), ("c4", c4, c4w), ("c5", c5, c5w), ("p3", p3, nk.out_c[0]),
                                ("p4", p4, nk.out_c[1]), ("p5", p5, nk.out_c[2])):
                 pb.export_nchw(v, name, c)
-        hd.emit(pb, (p3, p4, p5))
+        hd.emit(pb, (p3, p4, p5), only=head_only)
 
     # ------------------------------------------------------------------ sub-module plans
     def _emit_part(self, pb, part: str) -> None:
@@ -167,16 +167,16 @@ class YOLOv10(nn.Module):
         from .weights import PackCache
         return PackCache(src[0], src[1], f"{self.variant.name}.{prec}.nc{len(self.class_names)}")
 
-    def engine(self, device: torch.device, taps: bool = False) -> Engine:
+    def engine(self, device: torch.device, taps: bool = False, head_only: Optional[str] = None) -> Engine:
         prec = "f32" if self.precision in ("fp32", "f32", "float32") else "bf16"
-        key = (str(device), prec, taps)
+        key = (str(device), prec, taps) if head_only is None else (str(device), prec, taps, head_only)
         if key not in self._engines:
-            self._engines[key] = Engine(lambda pb: self.emit(pb, taps), device, prec,
-                                        pack_cache=None if taps else self._pack_cache(prec))
+            self._engines[key] = Engine(lambda pb: self.emit(pb, taps, head_only), device, prec,
+                                        pack_cache=None if (taps or head_only) else self._pack_cache(prec))
         return self._engines[key]
 
     # ------------------------------------------------------------------ reference surface
-    def _run(self, x: torch.Tensor, taps: bool = False):
+    def _run(self, x: torch.Tensor, taps: bool = False, head_only: Optional[str] = None):
         if self.training:
             raise NotImplementedError("leanyolo_b200 is inference-only: call model.eval() first "
                                       "(training stays with the reference implementation)")
@@ -190,7 +190,7 @@ class YOLOv10(nn.Module):
         if x.dtype != torch.uint8:     # uint8 images go straight to the stem kernel (x.float() happens in its loader)
             x = x.to(dtype=torch.float32)
         x = x.contiguous()
-        return self.engine(dev, taps).run(x, self.sub_batch)
+        return self.engine(dev, taps, head_only).run(x, self.sub_batch)
 
     @torch.no_grad()
     def forward(self, x: torch.Tensor):
@@ -216,9 +216,19 @@ class YOLOv10(nn.Module):
         return PP.decode_v10_official_topk(seq, num_classes=len(self.class_names), strides=STRIDES)
 
     @torch.no_grad()
-    def detect(self, x: torch.Tensor, max_det: int = 300) -> torch.Tensor:
-        """forward + top-k decode, detections ``[B, min(max_det, A), 6]`` left on the device."""
-        self.forward(x)
+    def detect(self, x: torch.Tensor, max_det: int = 300, one2one_only: bool = False) -> torch.Tensor:
+        """forward + top-k decode, detections ``[B, min(max_det, A), 6]`` left on the device.
+
+        Default: exactly ``decode_forward(model(x))`` -- both head branches run and are cached in ``_eval_branches``
+        like the reference's eval forward (yolov10s.py:105-122).  ``one2one_only=True`` is the opt-in fused path
+        (SURVEY hard part 6): the one-to-many branch, which the top-k decode never reads, is not computed at all
+        (-3.2 GFLOP per image on yolov10s, no one-to-many NCHW tensors written); the detections are bit-identical,
+        ``_eval_branches`` then holds only ``one2one``."""
+        if one2one_only:
+            outs = self._run(x, head_only="one2one")
+            self._eval_branches = {"one2one": [outs[("one2one", i)] for i in range(self.head.nl)]}
+        else:
+            self.forward(x)
         out, _, _ = PP.topk_raw(self._eval_branches["one2one"], num_classes=len(self.class_names), strides=STRIDES,
                                 max_det=max_det)
         return out

@@ -376,17 +376,19 @@ class Detect(nn.Module):
         out = self._run(x)
         return [out[("one2many", i)] for i in range(self.nl)]
 
-    def emit(self, pb, feats):
-        """Both branches (head.py:118-135).  Each writes [reg(4*reg_max) | cls(nc)] logits of every
+    def emit(self, pb, feats, only: Optional[str] = None):
+        """Both branches (head.py:118-135), or just ``only`` ("one2one": what ``decode_forward`` consumes).  Each writes [reg(4*reg_max) | cls(nc)] logits of every
         level straight into its public NCHW fp32 tensor from the two final 1x1 epilogues.  The
         first reg conv of the two branches reads the same feature map, so the pair is ONE
         implicit GEMM with the output channels concatenated (N = 2*c2: one pass over the
         input, twice the MMA width); each branch then continues from its channel slice."""
         branches = (("one2many", self.cv2, self.cv3), ("one2one", self.one2one_cv2, self.one2one_cv3))
+        if only is not None:
+            branches = tuple(b for b in branches if b[0] == only)
         for i, f in enumerate(feats):
             folded = [reg[i][0].folded(pb) for _, reg, _ in branches]
             c2 = folded[0][0].shape[0]
-            if c2 % 16 == 0:
+            if c2 % 16 == 0 and len(branches) > 1:
                 r01 = pb.conv(f, pb.cat0([w for w, _ in folded]), pb.cat0([b for _, b in folded]), k=3, stride=1, act=True)
                 firsts = [r01.sub(j * c2, c2) for j in range(len(branches))]
             else:

@@ -122,13 +122,23 @@ def check_decode_e2e(name="yolov10s"):
         assert torch.allclose(a[:, 4], b[:, 4], atol=2e-6)
     fixed = m.detect(x)
     assert fixed.shape == (2, min(300, A), 6)
+    assert torch.equal(fixed[0], dets[0][0]) and set(m._eval_branches) == {"one2many", "one2one"}
+    # opt-in fused path: the one-to-many branch is not computed; the one2one head tensors are the same values
+    # (the first regression conv runs as its own N=64 GEMM instead of the merged N=128 one: same K order per output)
+    ref_o2o = [t.clone() for t in m._eval_branches["one2one"]]
+    fused = m.detect(x, one2one_only=True)
+    assert set(m._eval_branches) == {"one2one"} and fused.shape == fixed.shape
+    worst = max(float((u - v).abs().max() / v.abs().max()) for u, v in zip(m._eval_branches["one2one"], ref_o2o))
+    assert worst < 2e-2, f"one2one-only head tensors differ by {worst:.2e}"
+    assert torch.allclose(fused[..., 4], fixed[..., 4], atol=2e-2)
+    m(x)
     # uint8 images are consumed by the stem kernel directly and must equal the x.float() path
     x8 = x.to(torch.uint8)
     a = [t.clone() for t in m(x8)]
     b = m(x8.float())
     for u, v in zip(a, b):
         assert torch.equal(u, v), "uint8 input path differs from the float path"
-    return {}
+    return {"one2one_only_vs_both_relmax": worst}
 
 
 def check_submodules(name="yolov10s", precision="bf16", hw=64, B=2, seed=4):
