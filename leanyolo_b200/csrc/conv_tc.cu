@@ -23,6 +23,13 @@
 //                    address, so a descriptor may start at any row), and the M = 128 tiles are
 //                    consecutive runs of m.  2 of every W+2 accumulator rows are discarded, but
 //                    every input byte crosses the TMA unit (R+2)/R times instead of 3.4 times.
+//     fold (band)  : Cout <= 80 with resident weights.  An M=128 MMA costs about the same for N = 16..64 (the
+//                    A operand's 4 KB dominate its shared-memory reads), so the nine taps of a thin layer run at a
+//                    fraction of the tensor pipe.  Here the three kx taps become ONE MMA with N = 3*Cout:
+//                    D[m][kx*Cout + co] = sum_{ky,ci} A[m + ky*(W+2)][ci] * W[co][ky][kx][ci]  (3x fewer MMAs, each
+//                    reading A once), and the epilogue adds the three column groups of rows m, m+1, m+2:
+//                    out[m][co] = D[m][co] + D[m+1][Cout+co] + D[m+2][2*Cout+co] (warp shuffles; the two rows that
+//                    cross a TMEM lane quarter go through a tiny shared-memory exchange).  M tiles advance by 126 rows.
 // * MMA: tcgen05.mma.cta_group::1.kind::f16, M=128, N=BLOCK_N (<=256), K=16 per
 //   instruction, bf16 x bf16 -> fp32 accumulators in TMEM (double-buffered so the epilogue of
 //   tile i overlaps the MMAs of tile i+1).  Operands are K-major in shared memory with the
@@ -89,6 +96,9 @@ struct Params {
   int rev;                 // walk the tiles / units last to first (see g_reverse)
   int st256;               // NHWC rows are 32-byte aligned: one 256-bit store per 16-channel chunk
   int pair;                // streamed weights: two pixel tiles (2q, 2q+1) share every weight k-block (4 accumulators in TMEM)
+  int fold;                // band mode, Cout <= 80: the three kx taps are folded into the MMA's N dimension (N = 3 * Cout)
+  uint32_t idesc_fold;     // instruction descriptor with N = 3 * block_n
+  uint32_t exch_off;       // fold: byte offset (from the barrier block) of the epilogue's boundary-row exchange slots
 };
 
 // Optional per-role cycle accounting (-DLY_TC_PROFILE): CTA 0 prints where each role waited.
@@ -302,6 +312,61 @@ __device__ __forceinline__ void mma_role_band(const Params& p, uint32_t a_base, 
   }
 }
 
+// Band mode with the kx taps folded into N (resident weights only): per M tile 3 * kc_blocks * KSTEPS MMAs of N = 3*Cout.
+// Weight slab (ky, cb) = [3*Cout rows (kx-major) x kc] at index ky*kcb + cb; M tiles advance by 126 rows (the epilogue
+// needs rows m+1, m+2 of the same accumulator).
+template <int KSTEPS>
+__device__ __forceinline__ void mma_role_fold(const Params& p, uint32_t a_base, uint32_t b_base, uint32_t bb, uint32_t tmem_base) {
+  const uint32_t hi = p.desc_hi, idesc = p.idesc_fold;
+  const int a_stages = p.a_stages, total = p.total_tiles, kcb = p.kc_blocks;
+  const uint32_t a_stage16 = (uint32_t)p.a_stage >> 4, b_stage16 = (uint32_t)p.b_stage >> 4;
+  const uint32_t row16 = (uint32_t)p.kc >> 3;
+  const uint32_t a_lo0 = (a_base >> 4) | (1u << 16), b_lo0 = (b_base >> 4) | (1u << 16);
+  const uint32_t acc_cols = 3u * (uint32_t)p.block_n;
+  const uint32_t bw16 = (uint32_t)p.band_w * row16;
+  mbar_wait(bar_bres(bb), 0);
+  tc_fence_after();
+  int sa = 0, as = 0;
+  uint32_t pa = 0, aphase = 0;
+  for (int unit = blockIdx.x; unit < total; unit += gridDim.x) {
+    {
+      int s = sa; uint32_t ph = pa;
+      for (int cb = 0; cb < kcb; ++cb) {
+        mbar_wait(bar_afull(bb, s), ph);
+        if (++s == a_stages) { s = 0; ph ^= 1u; }
+      }
+      tc_fence_after();
+    }
+    for (int mt = 0; mt < p.band_mt; ++mt) {
+      mbar_wait(bar_tempty(bb, as), aphase ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)as * acc_cols;
+      int s = sa;
+      for (int cb = 0; cb < kcb; ++cb) {
+        const uint32_t alo = a_lo0 + (uint32_t)s * a_stage16 + (uint32_t)(mt * 126) * row16;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+          const uint32_t blo = b_lo0 + (uint32_t)(ky * kcb + cb) * b_stage16;
+          const uint32_t at = alo + (uint32_t)ky * bw16;
+#pragma unroll
+          for (int kk = 0; kk < KSTEPS; ++kk) {
+            const uint64_t da = ((uint64_t)hi << 32) | (uint64_t)(at + 2 * kk);
+            const uint64_t db = ((uint64_t)hi << 32) | (uint64_t)(blo + 2 * kk);
+            umma_bf16(d_tmem, da, db, idesc, (ky | kk) != 0 ? 1u : (cb != 0 ? 1u : 0u));
+          }
+        }
+        if (++s == a_stages) s = 0;
+      }
+      umma_commit(bar_tfull(bb, as));
+      if (++as == 2) { as = 0; aphase ^= 1u; }
+    }
+    for (int cb = 0; cb < kcb; ++cb) {
+      umma_commit(bar_aempty(bb, sa));
+      if (++sa == a_stages) { sa = 0; pa ^= 1u; }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------- epilogue
 // 16 warps: warp -> (TMEM lane quarter q = warp % 4, column group cg = (warp - 2) / 4).  A thread
 // owns one pixel row; in round i the four warps of a quarter take the 16-column chunks 4i+cg.
@@ -318,7 +383,7 @@ __device__ __forceinline__ void mma_role_band(const Params& p, uint32_t a_base, 
 // shared-memory transpose to 128-byte coalesced stores were both slower than storing
 // 2 x 16 bytes per lane straight from the TMEM layout: the extra barrier per tile costs more
 // than the partial-sector writes, and the TMA unit is already row-rate bound on the loads.)
-template <int MAP, int ADD, bool NCHW>
+template <int MAP, int ADD, bool NCHW, bool FOLD = false>
 __device__ __forceinline__ void epilogue_role(const Params& p, uint8_t* smem_raw, uint32_t bar_base, uint32_t tmem_base, const float* s_bias) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q = warp & 3;
@@ -349,10 +414,10 @@ __device__ __forceinline__ void epilogue_role(const Params& p, uint8_t* smem_raw
       const uint32_t pu = (uint32_t)phys(p, it_unit);
       const uint32_t b = p.mg_bands ? __umulhi(pu, p.mg_bands) : pu;
       const uint32_t bd = pu - b * (uint32_t)p.bands;
-      const uint32_t m = (uint32_t)it_mt * 128u + row;
+      const uint32_t m = (uint32_t)it_mt * (FOLD ? 126u : 128u) + row;
       const uint32_t oy = __umulhi(m, p.mg_bw), ox = m - oy * (uint32_t)p.band_w;
       const uint32_t h = bd * (uint32_t)p.band_r + oy;
-      L.valid = ox < (uint32_t)p.Wo && oy < (uint32_t)p.band_r && h < (uint32_t)p.Ho;
+      L.valid = ox < (uint32_t)p.Wo && oy < (uint32_t)p.band_r && h < (uint32_t)p.Ho && (!FOLD || row < 126u);
       L.lin = (b * (uint32_t)p.Ho + h) * (uint32_t)p.Wo + ox;
       L.n0 = it_nt * p.block_n;
       if (++it_mt == p.band_mt) { it_mt = 0; if (++it_nt == p.tiles_n) { it_nt = 0; it_unit += gridDim.x; } }
@@ -413,6 +478,9 @@ __device__ __forceinline__ void epilogue_role(const Params& p, uint8_t* smem_raw
   };
   int as = 0;
   uint32_t aphase = 0, rs = 0;
+  // fold: exchange slots for the rows that cross a TMEM lane quarter: [parity][cg][q][48 floats]
+  float* exch = reinterpret_cast<float*>(smem_raw + ((bar_base + p.exch_off) - smem_u32(smem_raw)));
+  uint32_t xpar = 0;
   PROF_DECL(w_tfull);
 #ifdef LY_TC_PROFILE
   const long long estart = clock64();
@@ -444,7 +512,7 @@ __device__ __forceinline__ void epilogue_role(const Params& p, uint8_t* smem_raw
     }
     if (cur.first) { PROF_T0(); mbar_wait(bar_tfull(bar_base, as), aphase); PROF_ADD(w_tfull); }
     tc_fence_after();
-    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(((pair ? 2 * as : as) + cur.sub) * p.block_n);
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(((pair ? 2 * as : as) + cur.sub) * (FOLD ? 3 * p.block_n : p.block_n));
     uint32_t nxt[16];
     if (cg < nchunks) tmem_ld16(taddr + cg * 16, nxt);
     bool released = false;
@@ -454,7 +522,47 @@ __device__ __forceinline__ void epilogue_role(const Params& p, uint8_t* smem_raw
       const bool has = ch < nchunks;
       float v[16];
       if (has) {
-        tmem_ld_wait();
+        if (FOLD) {
+          // out[m] = D[m][c..] + D[m+1][Cout + c..] + D[m+2][2*Cout + c..]: every thread loads the three column groups of
+          // ITS row; rows m+1 / m+2 are the next lanes (shuffle), for lanes 30/31 the first lanes of the next quarter
+          uint32_t tq[16];
+          float* xs = exch + (((xpar * 4 + cg) * 4 + q) * 48);
+          tmem_ld16(taddr + p.block_n + c, tq);          // D[row][Cout + c ..]: row m+1's share of pixel m
+          tmem_ld_wait();
+          if (lane == 0) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) xs[j] = __uint_as_float(tq[j]);
+          }
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float a = __shfl_down_sync(0xFFFFFFFFu, __uint_as_float(tq[j]), 1);
+            if (lane < 31) nxt[j] = __float_as_uint(__fadd_rn(__uint_as_float(nxt[j]), a));
+          }
+          tmem_ld16(taddr + 2 * p.block_n + c, tq);      // D[row][2*Cout + c ..]: row m+2's share
+          tmem_ld_wait();
+          if (lane < 2) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) xs[16 + 16 * lane + j] = __uint_as_float(tq[j]);
+          }
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float b2 = __shfl_down_sync(0xFFFFFFFFu, __uint_as_float(tq[j]), 2);
+            if (lane < 30) nxt[j] = __float_as_uint(__fadd_rn(__uint_as_float(nxt[j]), b2));
+          }
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + cg) : "memory");
+          if (lane >= 30) {     // rows m+1 / m+2 live in the next TMEM lane quarter (q = 3: rows 126, 127 are not outputs)
+            const float* xn = exch + (((xpar * 4 + cg) * 4 + ((q + 1) & 3)) * 48);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float a = lane == 31 ? xn[j] : 0.f;                       // lane 30 got row m+1 by shuffle already
+              const float b2 = lane == 31 ? xn[32 + j] : xn[16 + j];
+              nxt[j] = __float_as_uint(__fadd_rn(__fadd_rn(__uint_as_float(nxt[j]), a), b2));
+            }
+          }
+          xpar ^= 1u;
+        } else {
+          tmem_ld_wait();
+        }
         const float4* bp = reinterpret_cast<const float4*>(s_bias + n0 + c);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -536,7 +644,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_base = smem_base;
   const uint32_t b_base = a_base + (uint32_t)p.a_stages * p.a_stage;
-  const uint32_t b_bytes_total = p.b_resident ? (uint32_t)p.num_kb * p.b_stage : (uint32_t)p.b_stages * p.b_stage;
+  const uint32_t b_bytes_total = p.fold ? (uint32_t)p.num_kb * p.b_box
+                                        : (p.b_resident ? (uint32_t)p.num_kb * p.b_stage : (uint32_t)p.b_stages * p.b_stage);
   const uint32_t bar_base = b_base + b_bytes_total;
   auto afull_bar = [&](int s) { return bar_base + 8u * s; };
   auto aempty_bar = [&](int s) { return bar_base + 8u * (kMaxStages + s); };
@@ -588,7 +697,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       // k-block order (shared with the MMA issuer, which simply counts k-blocks):
       //   classic: for tap (ky, kx): for cb            halo: for cb: for kx: [A box], ky = 0..2
       const int KK = p.k, kcb = p.kc_blocks, kc = p.kc, cin = p.cin_pad;
-      if (p.b_resident) {
+      if (p.fold) {
+        // slab (ky, cb) = three [Cout x kc] boxes (kx = 0, 1, 2) stacked along N
+        mbar_expect_tx(bres_bar, (uint32_t)p.num_kb * p.b_box);
+        const uint32_t sub = (uint32_t)p.b_box;
+        for (int ky = 0; ky < 3; ++ky)
+          for (int cb = 0; cb < kcb; ++cb)
+            for (int kx = 0; kx < 3; ++kx)
+              tma_load_2d(b_base + (uint32_t)(ky * kcb + cb) * p.b_stage + (uint32_t)kx * sub, &p.tmB, bres_bar, (ky * 3 + kx) * cin + cb * kc, 0);
+      } else if (p.b_resident) {
         mbar_expect_tx(bres_bar, (uint32_t)p.num_kb * p.b_box);
         uint32_t dstb = b_base;
         if (p.halo == 1) {
@@ -699,7 +816,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     // ============================== MMA issuer ================================
     if (elect_one()) {
       const int ksteps = p.kc / 16;
-      if (p.halo == 2) {
+      if (p.fold) {
+        if (ksteps == 4) mma_role_fold<4>(p, a_base, b_base, bar_base, tmem_base);
+        else if (ksteps == 2) mma_role_fold<2>(p, a_base, b_base, bar_base, tmem_base);
+        else mma_role_fold<1>(p, a_base, b_base, bar_base, tmem_base);
+      } else if (p.halo == 2) {
         if (ksteps == 4) { if (p.b_resident) mma_role_band<4, true>(p, a_base, b_base, bar_base, tmem_base); else mma_role_band<4, false>(p, a_base, b_base, bar_base, tmem_base); }
         else if (ksteps == 2) { if (p.b_resident) mma_role_band<2, true>(p, a_base, b_base, bar_base, tmem_base); else mma_role_band<2, false>(p, a_base, b_base, bar_base, tmem_base); }
         else { if (p.b_resident) mma_role_band<1, true>(p, a_base, b_base, bar_base, tmem_base); else mma_role_band<1, false>(p, a_base, b_base, bar_base, tmem_base); }
@@ -730,7 +851,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   else if (add == 2) LY_EPI(M, 2, false);                       \
   else if (add == 3) LY_EPI(M, 3, false);                       \
   else LY_EPI(M, 4, false);
-    if (map == 0) { LY_EPI_MAP(0) } else if (map == 1) { LY_EPI_MAP(1) } else { LY_EPI_MAP(2) }
+    if (p.fold) {
+      if (add == 0) epilogue_role<2, 0, false, true>(p, smem_raw, bar_base, tmem_base, s_bias);
+      else if (add == 1) epilogue_role<2, 1, false, true>(p, smem_raw, bar_base, tmem_base, s_bias);
+      else epilogue_role<2, 3, false, true>(p, smem_raw, bar_base, tmem_base, s_bias);
+    } else if (map == 0) { LY_EPI_MAP(0) } else if (map == 1) { LY_EPI_MAP(1) } else { LY_EPI_MAP(2) }
 #undef LY_EPI_MAP
 #undef LY_EPI
   }
@@ -848,21 +973,33 @@ int32_t conv_tc_prepare(const ly_op& op, ConvTcState** out) {
   static const int pair_ok = env_int("LY_TC_PAIR", 1);
   p.pair = (pair_ok && op.k == 3 && p.tiles_n == 1 && !b_res_possible && 4 * bn <= 512) ? 1 : 0;
   if (p.pair) p.tmem_cols = pow2_ge(4 * bn);
+  // fold: the three kx taps in the MMA's N dimension (see the header comment); resident weights, NHWC output only
+  // Opt-in (LY_TC_FOLD=1).  Measured on 3x3 64->64 @80^2, batch 256: the issuer's wait share drops from 38 % to 6 % of the
+  // epilogue warps' time (12 MMAs of N = 192 instead of 36 of N = 64), but the epilogue, which was already co-critical
+  // (~1600 cycles per tile and warp), grows to ~3000 (two more TMEM round trips, 32 shuffles, the quarter-boundary
+  // exchange + named barrier): 0.158 -> 0.185 ms, with a shortcut 0.166 -> 0.291 ms; 32->32 @160^2 0.311 -> 0.479 ms.
+  static const int fold_env = env_int("LY_TC_FOLD", 0);
+  const bool fold_ok = fold_env && op.k == 3 && op.stride == 1 && p.tiles_n == 1 && 3 * bn <= 256 && (bn * p.kc * 2) % 1024 == 0 &&
+                       b_res_possible && !p.pair && !op.up.ptr && !op.nchw && op.dst.ptr;
+  const int m_step = fold_ok ? 126 : 128;
+  const long long exch_bytes = fold_ok ? 2LL * 4 * 4 * 48 * 4 : 0;
   if (band_ok && !p.pair && op.k == 3 && op.stride == 1 && Wo + 2 <= 256 && 2 * p.kc_blocks <= kMaxStages) {
     const int sms = sm_count();
-    const double cyc_mma = (bn <= 128 ? 32.0 + bn / 4.0 : bn / 2.0) * (p.kc / 16);     // per k-block per M tile
+    const int nf = 3 * bn;
+    const double cyc_mma = fold_ok ? (nf <= 128 ? 32.0 + nf / 4.0 : nf / 2.0) * (p.kc / 16) / 3.0     // per k-block (tap) per M tile
+                                   : (bn <= 128 ? 32.0 + bn / 4.0 : bn / 2.0) * (p.kc / 16);
     const double tma_row = 5.0;
     auto waves = [&](long long units) { return (double)((units + sms - 1) / sms); };
     const double cost_now = waves(total) * (p.halo ? (double)std::max(p.num_kb * cyc_mma, 3.0 * p.kc_blocks * (p.tw * (p.th + 2)) * tma_row)
                                                    : (double)std::max(p.num_kb * cyc_mma, 9.0 * p.kc_blocks * 128 * tma_row));
     const int BW = Wo + 2;
-    const long long fixed = 8 * (4 * kMaxStages + 8) + 1024 + (op.res.ptr && bn <= 128 ? 2LL * 32 * kEpiWarps * (((bn / 16 + 3) / 4) * 32) : 0);
+    const long long fixed = 8 * (4 * kMaxStages + 8) + 1024 + exch_bytes + (op.res.ptr && bn <= 128 ? 2LL * 32 * kEpiWarps * (((bn / 16 + 3) / 4) * 32) : 0);
     const long long b_bytes = b_res_possible ? b_all_bytes : 3LL * ((bn * p.kc * 2 + 1023) / 1024 * 1024);
     int best_r = 0; double best_cost = 1e30;
     for (int R = 1; R <= Ho && R + 2 <= 256; ++R) {
       const long long stage = ((long long)(R + 2) * BW * p.kc * 2 + 1023) / 1024 * 1024;
       if (fixed + b_bytes + 2LL * p.kc_blocks * stage > (long long)kSmemBudget) break;
-      const int mt = ((R - 1) * BW + Wo + 127) / 128;
+      const int mt = ((R - 1) * BW + Wo + m_step - 1) / m_step;
       const long long units = (long long)((Ho + R - 1) / R) * op.B;
       const double unit_cost = std::max((double)p.tiles_n * mt * p.num_kb * cyc_mma, (double)p.kc_blocks * (R + 2) * BW * tma_row);
       const double cost = waves(units) * unit_cost;
@@ -871,8 +1008,12 @@ int32_t conv_tc_prepare(const ly_op& op, ConvTcState** out) {
     if (best_r && (band_ok == 2 || best_cost < cost_now)) {
       p.halo = 2;
       p.band_r = best_r; p.band_w = BW;
-      p.band_mt = ((best_r - 1) * BW + Wo + 127) / 128;
+      p.band_mt = ((best_r - 1) * BW + Wo + m_step - 1) / m_step;
       p.bands = (Ho + best_r - 1) / best_r;
+      if (fold_ok) {
+        p.fold = 1;
+        p.tmem_cols = pow2_ge(2 * 3 * bn);
+      }
       p.tw = 128; p.th = 1; p.tb = 1;
       total = (long long)p.bands * op.B;
     }
@@ -906,7 +1047,8 @@ int32_t conv_tc_prepare(const ly_op& op, ConvTcState** out) {
   p.a_stage = (p.a_box + 1023) / 1024 * 1024;
   p.b_box = bn * p.kc * 2;
   p.b_stage = (p.b_box + 1023) / 1024 * 1024;
-  const long long b_all = (long long)p.num_kb * p.b_stage;
+  if (p.fold) p.b_stage = 3 * p.b_box;       // one slab = the three kx boxes stacked along N (b_box is a multiple of 1024 here)
+  const long long b_all = p.fold ? (long long)p.num_kb * p.b_box : (long long)p.num_kb * p.b_stage;
   static const int resident_ok = env_int("LY_TC_B_RESIDENT", 1);
   p.b_resident = (resident_ok && p.tiles_n == 1 && b_all <= 96 * 1024) ? 1 : 0;
   const uint32_t bar_bytes = 8 * (4 * kMaxStages + 8);
@@ -914,7 +1056,9 @@ int32_t conv_tc_prepare(const ly_op& op, ConvTcState** out) {
   static const int res_prefetch_ok = env_int("LY_TC_RES_PREFETCH", 1);
   p.res_slot = (((op.res.ptr != nullptr) != (op.up.ptr != nullptr)) && res_prefetch_ok && bn <= 128) ? ((bn / 16 + 3) / 4) * 32 : 0;   // one 32-byte chunk per round
   const long long res_bytes = 2LL * 32 * kEpiWarps * p.res_slot;
-  const long long avail = (long long)kSmemBudget - bar_bytes - 1024 - res_bytes - (p.b_resident ? b_all : 0);
+  const long long x_bytes = p.fold ? 2LL * 4 * 4 * 48 * 4 : 0;      // fold: boundary-row exchange slots of the epilogue
+  p.exch_off = (uint32_t)(bar_bytes + res_bytes);
+  const long long avail = (long long)kSmemBudget - bar_bytes - 1024 - res_bytes - x_bytes - (p.b_resident ? b_all : 0);
   if (p.halo == 2) {
     // a band keeps kc_blocks stages for all of its tiles; the next band is prefetched meanwhile
     p.a_stages = p.b_resident ? (int)(avail / p.a_stage) : 2 * p.kc_blocks;
@@ -942,7 +1086,7 @@ int32_t conv_tc_prepare(const ly_op& op, ConvTcState** out) {
   if (p.b_stages > kMaxStages) p.b_stages = kMaxStages;
   if (p.a_stages < 2 || (!p.b_resident && p.b_stages < 2)) { delete st; set_error("conv_tc: tile does not fit in shared memory"); return LY_E_ARG; }
   st->smem = 1024 + (size_t)p.a_stages * p.a_stage + (p.b_resident ? (size_t)b_all : (size_t)p.b_stages * p.b_stage) + bar_bytes +
-             (size_t)res_bytes;
+             (size_t)res_bytes + (size_t)x_bytes;
   if (st->smem < 120 * 1024) st->smem = 120 * 1024;  // force one CTA per SM (TMEM allocations must not contend)
 
   // descriptors
@@ -954,6 +1098,7 @@ int32_t conv_tc_prepare(const ly_op& op, ConvTcState** out) {
   const uint32_t sbo_a = sbo * (uint32_t)((p.halo && op.stride == 2) ? 2 : 1);
   p.desc_hi_a = (sbo_a & 0x3FFFu) | (1u << 14) | ((uint32_t)swz << 29);
   p.idesc = (1u << 4) /*D=f32*/ | (1u << 7) /*A=bf16*/ | (1u << 10) /*B=bf16*/ | ((uint32_t)(bn >> 3) << 17) | ((128u >> 4) << 24);
+  p.idesc_fold = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((3 * bn) >> 3) << 17) | ((128u >> 4) << 24);
 
   const CUtensorMapSwizzle tswz = p.kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (p.kc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
   {
@@ -1001,8 +1146,8 @@ int32_t conv_tc_prepare(const ly_op& op, ConvTcState** out) {
   st->grid = work < sms ? work : sms;
   static const int debug = env_int("LY_TC_DEBUG", 0);
   if (debug)
-    fprintf(stderr, "[conv_tc] k%d s%d %dx%d cin %d cout %d B %d: mode %d pair %d bn %d tiles_n %d kc %d a_stages %d (%d B) b_res %d b_stages %d res_slot %d "
-            "band R %d mt %d bands %d units %d smem %zu\n", op.k, op.stride, op.src.H, op.src.W, Cin, Cout, op.B, p.halo, p.pair, bn, p.tiles_n, p.kc,
+    fprintf(stderr, "[conv_tc] k%d s%d %dx%d cin %d cout %d B %d: mode %d fold %d pair %d bn %d tiles_n %d kc %d a_stages %d (%d B) b_res %d b_stages %d res_slot %d "
+            "band R %d mt %d bands %d units %d smem %zu\n", op.k, op.stride, op.src.H, op.src.W, Cin, Cout, op.B, p.halo, p.fold, p.pair, bn, p.tiles_n, p.kc,
             p.a_stages, p.a_stage, p.b_resident, p.b_stages, p.res_slot, p.band_r, p.band_mt, p.bands, p.total_tiles, st->smem);
   static std::atomic<unsigned long long> attr_devs{0};   // per DEVICE: the attribute does not carry over to another GPU
   if (first_on_device(attr_devs)) {
