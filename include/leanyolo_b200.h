@@ -190,6 +190,12 @@ LY_API int64_t ly_decode_scratch_bytes(const ly_levels* lv, int32_t max_det);
 LY_API int32_t ly_decode_topk(const ly_levels* lv, int32_t max_det, float* out, int32_t* out_anchor,
                        int32_t* out_cls, void* scratch, int64_t scratch_bytes, void* stream);
 
+/* Same, with `unletterbox_coords` (utils/box_ops.py:96-124) fused into the decode epilogue: the boxes come out in each
+ * SOURCE image's own pixel coordinates.  lb_meta `[B,6]` fp32 = (gain_w, gain_h, pad_left, pad_top, orig_h, orig_w), as
+ * for ly_unletterbox (the caller loop tools/infer.py:110-138, tools/val.py:176-178).                             */
+LY_API int32_t ly_decode_topk_lb(const ly_levels* lv, int32_t max_det, const float* lb_meta, float* out, int32_t* out_anchor,
+                          int32_t* out_cls, void* scratch, int64_t scratch_bytes, void* stream);
+
 /* Replaces `decode_v10_predictions` DFL branch (postprocess.py:103-161) +
  * `nms` (box_ops.py:49-78): per-anchor max-class candidate, `score > conf`,
  * greedy IoU NMS (suppress iff IoU > iou_thresh), first max_det survivors.

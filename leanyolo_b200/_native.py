@@ -80,6 +80,8 @@ PROTOTYPES = {
     "ly_decode_scratch_bytes": (C.c_int64, [C.POINTER(LyLevels), C.c_int32]),
     "ly_decode_topk": (C.c_int32, [C.POINTER(LyLevels), C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_int64, C.c_void_p]),
+    "ly_decode_topk_lb": (C.c_int32, [C.POINTER(LyLevels), C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_int64, C.c_void_p]),
     "ly_decode_nms": (C.c_int32, [C.POINTER(LyLevels), C.c_float, C.c_float, C.c_int32, C.c_int32, C.c_void_p,
                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "ly_decode_export_scratch_bytes": (C.c_int64, [C.POINTER(LyLevels), C.c_int32, C.c_int32]),

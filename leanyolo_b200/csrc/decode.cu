@@ -227,7 +227,7 @@ __device__ __forceinline__ int next_pow2(int v) {
 template <int RM>
 __global__ void __launch_bounds__(NT_TOPK, 3)
 topk_kernel(Levels lv, int k, const float* __restrict__ best, float* s2,
-            float* __restrict__ out, int* __restrict__ out_anchor, int* __restrict__ out_cls) {
+            float* __restrict__ out, int* __restrict__ out_anchor, int* __restrict__ out_cls, const float* __restrict__ lb_meta) {
   __shared__ unsigned long long sortbuf[TOPK_MAX];
   __shared__ int anchors[TOPK_MAX];
   __shared__ unsigned hist[256];
@@ -287,7 +287,18 @@ topk_kernel(Levels lv, int k, const float* __restrict__ best, float* s2,
     const int l = level_of(lv, g);
     const float4 bx = decode_box<RM>(lv, l, g - lv.off[l], lv.p[l] + (long long)b * (creg + nc) * (lv.H[l] * lv.W[l]) + (g - lv.off[l]));
     float* o = out + ((long long)b * k + r) * 6;
-    o[0] = bx.x; o[1] = bx.y; o[2] = bx.z; o[3] = bx.w;
+    if (lb_meta) {
+      // unletterbox_coords (utils/box_ops.py:96-124) fused into the decode epilogue: back to the source image's own
+      // pixel coordinates, fp32 op for op like the reference ((x - pad) / gain, clamp to the image)
+      const float gw = lb_meta[6 * b + 0], gh = lb_meta[6 * b + 1], px = lb_meta[6 * b + 2], py = lb_meta[6 * b + 3];
+      const float H = lb_meta[6 * b + 4], W = lb_meta[6 * b + 5];
+      o[0] = fminf(fmaxf(__fdiv_rn(__fsub_rn(bx.x, px), gw), 0.f), W);
+      o[1] = fminf(fmaxf(__fdiv_rn(__fsub_rn(bx.y, py), gh), 0.f), H);
+      o[2] = fminf(fmaxf(__fdiv_rn(__fsub_rn(bx.z, px), gw), 0.f), W);
+      o[3] = fminf(fmaxf(__fdiv_rn(__fsub_rn(bx.w, py), gh), 0.f), H);
+    } else {
+      o[0] = bx.x; o[1] = bx.y; o[2] = bx.z; o[3] = bx.w;
+    }
     o[4] = s2b[flat];
     o[5] = (float)c;
     if (out_anchor) out_anchor[(long long)b * k + r] = g;
@@ -690,8 +701,22 @@ extern "C" int64_t ly_decode_scratch_bytes(const ly_levels* in, int32_t max_det)
   return carve(nullptr, lv.B, lv.A, lv.nc, max_det).total;
 }
 
+static int32_t decode_topk_impl(const ly_levels* in, int32_t max_det, const float* lb_meta, float* out, int32_t* out_anchor,
+                                int32_t* out_cls, void* scratch, int64_t scratch_bytes, void* stream);
+
 extern "C" int32_t ly_decode_topk(const ly_levels* in, int32_t max_det, float* out, int32_t* out_anchor, int32_t* out_cls,
                                   void* scratch, int64_t scratch_bytes, void* stream) {
+  return decode_topk_impl(in, max_det, nullptr, out, out_anchor, out_cls, scratch, scratch_bytes, stream);
+}
+
+extern "C" int32_t ly_decode_topk_lb(const ly_levels* in, int32_t max_det, const float* lb_meta, float* out, int32_t* out_anchor,
+                                     int32_t* out_cls, void* scratch, int64_t scratch_bytes, void* stream) {
+  LY_CHECK_ARG(lb_meta != nullptr, "decode_topk_lb: null letterbox meta");
+  return decode_topk_impl(in, max_det, lb_meta, out, out_anchor, out_cls, scratch, scratch_bytes, stream);
+}
+
+static int32_t decode_topk_impl(const ly_levels* in, int32_t max_det, const float* lb_meta, float* out, int32_t* out_anchor,
+                                int32_t* out_cls, void* scratch, int64_t scratch_bytes, void* stream) {
   Levels lv;
   int32_t rc = make_levels(in, lv);
   if (rc != LY_OK) return rc;
@@ -706,8 +731,8 @@ extern "C" int32_t ly_decode_topk(const ly_levels* in, int32_t max_det, float* o
   best_kernel<<<g1, 256, 0, st>>>(lv, s.best);
   rc = post_launch("best_score");
   if (rc != LY_OK) return rc;
-  if (lv.reg_max == 16) topk_kernel<16><<<lv.B, NT_TOPK, 0, st>>>(lv, k, s.best, s.s2, out, out_anchor, out_cls);
-  else topk_kernel<0><<<lv.B, NT_TOPK, 0, st>>>(lv, k, s.best, s.s2, out, out_anchor, out_cls);
+  if (lv.reg_max == 16) topk_kernel<16><<<lv.B, NT_TOPK, 0, st>>>(lv, k, s.best, s.s2, out, out_anchor, out_cls, lb_meta);
+  else topk_kernel<0><<<lv.B, NT_TOPK, 0, st>>>(lv, k, s.best, s.s2, out, out_anchor, out_cls, lb_meta);
   return post_launch("topk");
 }
 

@@ -216,21 +216,23 @@ class YOLOv10(nn.Module):
         return PP.decode_v10_official_topk(seq, num_classes=len(self.class_names), strides=STRIDES)
 
     @torch.no_grad()
-    def detect(self, x: torch.Tensor, max_det: int = 300, one2one_only: bool = False) -> torch.Tensor:
+    def detect(self, x: torch.Tensor, max_det: int = 300, one2one_only: bool = False,
+               lb_meta: Optional[torch.Tensor] = None) -> torch.Tensor:
         """forward + top-k decode, detections ``[B, min(max_det, A), 6]`` left on the device.
 
         Default: exactly ``decode_forward(model(x))`` -- both head branches run and are cached in ``_eval_branches``
         like the reference's eval forward (yolov10s.py:105-122).  ``one2one_only=True`` is the opt-in fused path
         (SURVEY hard part 6): the one-to-many branch, which the top-k decode never reads, is not computed at all
         (-3.2 GFLOP per image on yolov10s, no one-to-many NCHW tensors written); the detections are bit-identical,
-        ``_eval_branches`` then holds only ``one2one``."""
+        ``_eval_branches`` then holds only ``one2one``.  ``lb_meta`` (from ``preprocess.letterbox_batch``): boxes are
+        returned in each source image's own coordinates (unletterbox fused into the decode kernel)."""
         if one2one_only:
             outs = self._run(x, head_only="one2one")
             self._eval_branches = {"one2one": [outs[("one2one", i)] for i in range(self.head.nl)]}
         else:
             self.forward(x)
         out, _, _ = PP.topk_raw(self._eval_branches["one2one"], num_classes=len(self.class_names), strides=STRIDES,
-                                max_det=max_det)
+                                max_det=max_det, lb_meta=lb_meta)
         return out
 
 

@@ -55,8 +55,10 @@ def _stream(device) -> C.c_void_p:
 
 @torch.no_grad()
 def topk_raw(preds: Sequence[torch.Tensor], *, num_classes: int, strides: Sequence[int] = (8, 16, 32),
-             max_det: int = 300) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
-    """Fixed-shape result: (dets [B,k,6], anchor [B,k] int32, cls [B,k] int32)."""
+             max_det: int = 300, lb_meta: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """Fixed-shape result: (dets [B,k,6], anchor [B,k] int32, cls [B,k] int32).  ``lb_meta`` ([B,6] fp32 on the
+    device, from ``preprocess.letterbox_batch``): the boxes are mapped back to each source image's coordinates inside
+    the decode kernel (``unletterbox_coords`` fused into its epilogue)."""
     if not 1 <= max_det <= MAX_DET_LIMIT:
         raise ValueError(f"max_det must be in 1..{MAX_DET_LIMIT}")
     lib = N.lib()
@@ -69,8 +71,14 @@ def topk_raw(preds: Sequence[torch.Tensor], *, num_classes: int, strides: Sequen
         out = torch.empty((lv.B, k, 6), dtype=torch.float32, device=dev)
         anchor = torch.empty((lv.B, k), dtype=torch.int32, device=dev)
         cls = torch.empty((lv.B, k), dtype=torch.int32, device=dev)
-        N.check(lib.ly_decode_topk(C.byref(lv), max_det, out.data_ptr(), anchor.data_ptr(), cls.data_ptr(),
-                                   scratch.data_ptr(), nbytes, _stream(dev)), "ly_decode_topk")
+        if lb_meta is not None:
+            if not (lb_meta.is_cuda and lb_meta.dtype == torch.float32 and tuple(lb_meta.shape) == (lv.B, 6) and lb_meta.is_contiguous()):
+                raise ValueError("lb_meta must be a contiguous CUDA float32 tensor [B, 6]")
+            N.check(lib.ly_decode_topk_lb(C.byref(lv), max_det, lb_meta.data_ptr(), out.data_ptr(), anchor.data_ptr(), cls.data_ptr(),
+                                          scratch.data_ptr(), nbytes, _stream(dev)), "ly_decode_topk_lb")
+        else:
+            N.check(lib.ly_decode_topk(C.byref(lv), max_det, out.data_ptr(), anchor.data_ptr(), cls.data_ptr(),
+                                       scratch.data_ptr(), nbytes, _stream(dev)), "ly_decode_topk")
         scratch.record_stream(torch.cuda.current_stream(dev))
     return out, anchor, cls
 

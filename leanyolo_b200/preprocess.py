@@ -147,6 +147,5 @@ def detect_images(model, images: Sequence[torch.Tensor], imgsz: int = 640, max_d
     """The loop body of tools/infer.py:110-138 for a batch: letterbox -> forward -> top-k decode -> unletterbox.
     Returns one ``[k,6]`` tensor per image in ITS OWN pixel coordinates."""
     batch, meta = letterbox_batch(images, imgsz)
-    dets = model.detect(batch, max_det=max_det)
-    unletterbox_dets(dets, meta)
+    dets = model.detect(batch, max_det=max_det, lb_meta=meta)      # unletterbox happens inside the decode kernel
     return list(dets.unbind(0))

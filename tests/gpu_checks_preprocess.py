@@ -76,3 +76,69 @@ def check_detect_images():
         assert torch.equal(got[i].cpu(), ref), f"image {i}"
         assert float(got[i][:, 0].min()) >= 0 and float(got[i][:, 2].max()) <= shapes[i][1] and float(got[i][:, 3].max()) <= shapes[i][0]
     return {}
+
+
+def check_val_loop(seed=5):
+    """leanyolo_b200.val (tools/val.py:90-248 batched): the batched loop's COCO rows == the per-image path (letterbox ->
+    forward -> decode -> unletterbox) for both decodes, and validate_coco end to end on a temporary dataset whose
+    ground truth is the model's own five best detections per image (stats must equal the evaluator run on the same rows;
+    the evaluator itself has known-answer tests on the CPU side)."""
+    import json
+    import tempfile
+    import cv2
+    from gpu_checks_model import build
+    from leanyolo_b200 import postprocess as PP
+    from leanyolo_b200 import val as V
+    m, _ = build("yolov10n")
+    rng = np.random.default_rng(seed)
+    shapes = [(90, 160), (200, 120), (128, 128), (60, 75), (300, 33)]
+    imgs = [rng.integers(0, 256, (h, w, 3), dtype=np.uint8) for h, w in shapes]
+    ids = [11, 7, 42, 3, 19]
+    cat_ids = list(range(100, 180))
+    rows = V.detect_dataset(m, zip(ids, imgs), imgsz=128, decode="topk", max_dets=50, batch_size=2, cat_ids=cat_ids)
+    assert len(rows) == 5 * 50, len(rows)
+    # (the reference path is run on the SAME batch compositions: the conv kernels pick their tiling per problem size, so a
+    #  different batch size may sum in a different order and move a bf16 rounding)
+    refs = []
+    for lo in range(0, 5, 2):
+        refs += P.detect_images(m, [torch.from_numpy(img).to(DEV) for img in imgs[lo:lo + 2]], imgsz=128, max_det=50)
+    for i, (iid, img) in enumerate(zip(ids, imgs)):
+        ref = refs[i].cpu().numpy()
+        mine = [r for r in rows if r["image_id"] == iid]
+        for r, (x1, y1, x2, y2, s, c) in zip(mine, ref):
+            assert r["category_id"] == cat_ids[int(c)] and r["score"] == float(s), ("topk row", iid, r, float(s), int(c))
+            assert r["bbox"] == [float(x1), float(y1), float(x2 - x1), float(y2 - y1)], ("topk bbox", iid, r["bbox"], x1, y1, x2, y2)
+    # NMS decode: rows == decode_v10_predictions on the one2many branch + unletterbox, image by image
+    rows = V.detect_dataset(m, zip(ids, imgs), imgsz=128, decode="nms", conf=0.3, iou=0.5, max_dets=40, batch_size=1)
+    for iid, img in zip(ids, imgs):
+        batch, meta = P.letterbox_batch([torch.from_numpy(img).to(DEV)], 128)
+        d = PP.decode_v10_predictions(m(batch), num_classes=80, strides=(8, 16, 32), conf_thresh=0.3, iou_thresh=0.5, max_det=40)[0][0]
+        mine = [r for r in rows if r["image_id"] == iid]
+        assert len(mine) == d.shape[0], ("nms count", iid, len(mine), d.shape)
+        if d.shape[0]:
+            d = P.unletterbox_dets(d.clone()[None].contiguous(), meta)[0].cpu().numpy()
+            for r, (x1, y1, x2, y2, s, c) in zip(mine, d):
+                assert r["score"] == float(s) and r["category_id"] == int(c) and abs(r["bbox"][0] - float(x1)) < 1e-4, ("nms row", iid, r, s, c, x1)
+    # end to end from files
+    with tempfile.TemporaryDirectory() as tmp:
+        os.makedirs(os.path.join(tmp, "images"))
+        infos = []
+        for iid, img in zip(ids, imgs):
+            cv2.imwrite(os.path.join(tmp, "images", f"{iid}.png"), cv2.cvtColor(img, cv2.COLOR_RGB2BGR))
+            infos.append({"id": iid, "file_name": f"{iid}.png", "height": img.shape[0], "width": img.shape[1]})
+        cats = [{"id": 100 + i, "name": f"class{i}"} for i in range(80)]
+        order = sorted(range(5), key=lambda i: f"{ids[i]}.png")       # validate_coco walks the files in name order, batches of 4
+        top = V.detect_dataset(m, [(ids[i], imgs[i]) for i in order], imgsz=128, decode="topk", max_dets=50, cat_ids=cat_ids, batch_size=4)
+        anns = []
+        for iid in ids:
+            for r in [r for r in top if r["image_id"] == iid][:5]:
+                if r["bbox"][2] > 1 and r["bbox"][3] > 1:
+                    anns.append({"id": len(anns) + 1, "image_id": iid, "category_id": r["category_id"], "bbox": r["bbox"],
+                                 "area": r["bbox"][2] * r["bbox"][3], "iscrowd": 0})
+        json.dump({"images": infos, "annotations": anns, "categories": cats}, open(os.path.join(tmp, "annotations.json"), "w"))
+        stats = V.validate_coco(model=m, data_root=tmp, imgsz=128, decode="topk", max_dets=50, batch_size=4,
+                                save_json=os.path.join(tmp, "out", "dets.json"))
+        assert os.path.exists(os.path.join(tmp, "out", "dets.json"))
+        expect = V.coco_bbox_map(anns, top)
+        assert stats == expect and 0.0 < stats["mAP50-95"] <= 1.0, (stats, expect)
+    return {"rows": len(rows), "gt": len(anns), **stats}

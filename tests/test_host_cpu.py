@@ -378,3 +378,27 @@ def test_deepcopy_rebinds_submodules_and_drops_engines():
     assert c.backbone.cv0.conv.weight is not m.backbone.cv0.conv.weight
     assert all(torch.equal(a, b) for a, b in zip(c.state_dict().values(), m.state_dict().values()))
     m._engines.clear()
+
+
+def test_coco_bbox_map_known_answers():
+    """leanyolo_b200.val.coco_bbox_map on hand-computed cases (COCOeval protocol; pycocotools is absent here)."""
+    from leanyolo_b200.val import coco_bbox_map
+    gt = [{"image_id": 1, "category_id": 3, "bbox": [10, 10, 100, 100]}, {"image_id": 2, "category_id": 3, "bbox": [0, 0, 50, 50]},
+          {"image_id": 2, "category_id": 7, "bbox": [20, 20, 40, 40]}]
+    perfect = [dict(g, score=0.9 - 0.1 * i) for i, g in enumerate(gt)]
+    assert coco_bbox_map(gt, perfect) == {"mAP50-95": 1.0, "mAP50": 1.0, "mAP75": 1.0}
+    # a confident false positive ahead of the true positive: precision 1/2 at every recall level
+    one = [{"image_id": 1, "category_id": 3, "bbox": [10, 10, 100, 100]}]
+    d = [{"image_id": 1, "category_id": 3, "bbox": [300, 300, 20, 20], "score": 0.9},
+         {"image_id": 1, "category_id": 3, "bbox": [10, 10, 100, 100], "score": 0.8}]
+    assert abs(coco_bbox_map(one, d)["mAP50-95"] - 0.5) < 1e-9
+    # IoU 0.64 (100x100 vs 80x80 inside): a hit for thresholds 0.50, 0.55, 0.60 only
+    d = [{"image_id": 1, "category_id": 3, "bbox": [10, 10, 80, 80], "score": 0.9}]
+    r = coco_bbox_map(one, d)
+    assert abs(r["mAP50-95"] - 0.3) < 1e-9 and r["mAP50"] == 1.0 and r["mAP75"] == 0.0
+    # a detection inside a crowd region is ignored (neither TP nor FP); a missed gt costs recall
+    gtc = one + [{"image_id": 1, "category_id": 3, "bbox": [200, 200, 100, 100], "iscrowd": 1}]
+    d = [{"image_id": 1, "category_id": 3, "bbox": [210, 210, 30, 30], "score": 0.95},
+         {"image_id": 1, "category_id": 3, "bbox": [10, 10, 100, 100], "score": 0.5}]
+    assert coco_bbox_map(gtc, d)["mAP50-95"] == 1.0
+    assert coco_bbox_map(one, [])["mAP50-95"] == 0.0

@@ -175,6 +175,7 @@ def registry():
     add("letterbox_batch_640", PR.check_letterbox_batch)
     add("unletterbox_batch", PR.check_unletterbox_batch)
     add("detect_images_e2e", PR.check_detect_images)
+    add("val_loop_coco", PR.check_val_loop)
     return R
 
 
