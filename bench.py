@@ -309,7 +309,7 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         fused = {"value": round(world * B * fsteps / (float(t.item()) / 1e3), 1), "unit": "images/s", "ms_per_step": round(float(t.item()) / fsteps, 3),
                  "note": "model.detect(x, one2one_only=True): one-to-many head branch not computed (not the reference's eval forward; "
-                         "detections equal the headline path's); per-GPU detections left on the device, no gather"}
+                         "same detections up to fp32 summation order); per-GPU detections left on the device, no gather"}
         model(x)      # restore both cached branches for the decode timing below
 
     if rank != 0:

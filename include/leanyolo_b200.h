@@ -63,6 +63,9 @@ enum {
   LY_IMPL_AUTO = 0,   /* bf16: tcgen05/TMEM/TMA implicit GEMM; f32: CUDA-core check kernel */
   LY_IMPL_SIMT = 1,   /* force the CUDA-core tiled kernel (bring-up / bisecting only)      */
   LY_STEM_IN_U8 = 2,  /* STEM only: the external image tensor is uint8 NCHW instead of fp32 */
+  LY_STEM_IN_LB = 3,  /* STEM only (bf16): the external "image" is a DEVICE array of ly_lb_desc[B]; the loader samples the
+                         letterboxed pixels (utils/letterbox.py:9-91: cv2 bilinear resize + border) straight from the
+                         source images, so the letterboxed batch never exists in HBM.  Border colour = (nh, kdp, hd). */
 };
 
 /* A channel slice [c0, c0+c) of an NHWC buffer whose pixel pitch is `ctot` elements. */

@@ -14,7 +14,7 @@ ABI_VERSION = 4
 LY_BF16, LY_F32 = 0, 1
 OP_STEM, OP_CONV, OP_DW, OP_POOL, OP_UP, OP_ATTN, OP_EXPORT, OP_IMPORT, OP_DWPW, OP_CHAIN = 1, 2, 3, 4, 5, 6, 7, 8, 9, 10
 CHAIN_MAX_STAGES, CHAIN_MAX_BLOCKS, CHAIN_MAX_REGIONS = 6, 4, 8
-IMPL_AUTO, IMPL_SIMT, STEM_IN_U8 = 0, 1, 2
+IMPL_AUTO, IMPL_SIMT, STEM_IN_U8, STEM_IN_LB = 0, 1, 2, 3
 
 
 class LyView(C.Structure):
@@ -59,7 +59,7 @@ class LyLevels(C.Structure):
     ]
 
 
-class LyLbDesc(C.Structure):      # mirrors `ly_lb_desc` (32 bytes)
+class LyLbDesc(C.Structure):      # mirrors `ly_lb_desc` (40 bytes)
     _fields_ = [("src", C.c_void_p), ("src_pitch", C.c_int64), ("src_h", C.c_int32), ("src_w", C.c_int32),
                 ("new_h", C.c_int32), ("new_w", C.c_int32), ("top", C.c_int32), ("left", C.c_int32)]
 

@@ -190,11 +190,12 @@ static int32_t plan_run_impl(ly_plan* pl, float* const* ext, int32_t n_ext, int3
       LY_CHECK_ARG(ext && op.ext_slot < n_ext && ext[op.ext_slot], "ly_plan_run: op %d needs ext[%d]", (int)i, op.ext_slot);
       // offset by img0 whole images of the external NCHW tensor
       long long per_img;
-      if (op.kind == LY_OP_STEM) per_img = 3LL * (2 * op.dst.H) * (2 * op.dst.W);
+      if (op.kind == LY_OP_STEM && op.impl == LY_STEM_IN_LB) per_img = (long long)sizeof(ly_lb_desc);
+      else if (op.kind == LY_OP_STEM) per_img = 3LL * (2 * op.dst.H) * (2 * op.dst.W);
       else if (op.kind == LY_OP_IMPORT) per_img = (long long)op.nchw_ctot * op.dst.H * op.dst.W;
       else if (op.kind == LY_OP_EXPORT) per_img = (long long)op.nchw_ctot * op.src.H * op.src.W;
       else per_img = (long long)op.nchw_ctot * (op.src.H / op.stride) * (op.src.W / op.stride);
-      const long long esz = (op.kind == LY_OP_STEM && op.impl == LY_STEM_IN_U8) ? 1 : 4;
+      const long long esz = (op.kind == LY_OP_STEM && (op.impl == LY_STEM_IN_U8 || op.impl == LY_STEM_IN_LB)) ? 1 : 4;
       nchw = reinterpret_cast<float*>(reinterpret_cast<char*>(ext[op.ext_slot]) + (long long)img0 * per_img * esz);
     }
     int32_t rc;

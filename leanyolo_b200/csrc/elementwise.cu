@@ -5,6 +5,8 @@
 #include <type_traits>
 #include <stdlib.h>
 #include "common.cuh"
+#include "preprocess.cuh"
+#include <type_traits>
 
 namespace ly {
 
@@ -175,7 +177,7 @@ template <typename TIn, int NT>
 __global__ void __launch_bounds__(SM_THREADS, 4)
 stem_mma_kernel(const TIn* __restrict__ x, int H, int W, __nv_bfloat16* __restrict__ dst, int dCtot, int dC0,
                 const float* __restrict__ w, const float* __restrict__ bias,
-                float s0, float s1, float s2, float d0, float d1, float d2) {
+                float s0, float s1, float s2, float d0, float d1, float d2, int fr, int fg, int fb) {
   constexpr int CP = NT * 8;                           // padded output channels
   __shared__ __align__(16) __nv_bfloat16 tile[3 * SM_IH * SM_IWP];
   __shared__ __align__(16) __nv_bfloat16 wsm[CP * 32];
@@ -192,6 +194,55 @@ stem_mma_kernel(const TIn* __restrict__ x, int H, int W, __nv_bfloat16* __restri
     const int co = 2 * NT * (j >> 1) + 2 * nt + (j & 1);      // channel behind mma column (nt, j)
     wsm[i] = __float2bfloat16_rn(wi >= 0 ? 0.5f * w[co * 27 + wi] : 0.f);
   }
+  if constexpr (std::is_same<TIn, ly_lb_desc>::value) {
+    // Fused letterbox (utils/letterbox.py:9-91): `x` is the per-image descriptor array; every element of the staged tile
+    // is sampled straight from the SOURCE image (cv2's fixed-point bilinear / 2x area / copy, border colour outside the
+    // resized picture), so the letterboxed uint8 batch never exists in HBM.  The axis coefficient tables of the tile
+    // (IEEE double arithmetic, OpenCV's order) are built once per CTA, not per pixel.
+    constexpr int NCOL = 2 * SM_TW + 1;
+    __shared__ AxisCoef cx[NCOL], cy[SM_IH];
+    const ly_lb_desc d = x[b];
+    const int mode = lb_mode(d);
+    const int hi0 = 2 * ho0 - 1, wi0 = 2 * wo0 - 1;
+    if (mode == 2) {
+      for (int i = tid; i < NCOL + SM_IH; i += SM_THREADS) {
+        if (i < NCOL) {
+          const int rx = wi0 + i - d.left;
+          if (rx >= 0 && rx < d.new_w) cx[i] = axis_coef(rx, d.new_w, d.src_w, true);
+        } else {
+          const int ry = hi0 + (i - NCOL) - d.top;
+          if (ry >= 0 && ry < d.new_h) cy[i - NCOL] = axis_coef(ry, d.new_h, d.src_h, false);
+        }
+      }
+      __syncthreads();
+    }
+    for (int i = tid; i < SM_IH * NCOL; i += SM_THREADS) {
+      const int r = i / NCOL, col = i - r * NCOL;
+      const int hi = hi0 + r, wi = wi0 + col;
+      float f0 = 0.f, f1 = 0.f, f2 = 0.f;            // zero padding of the conv is applied AFTER the normalisation
+      if (hi >= 0 && hi < H && wi >= 0 && wi < W) {
+        int v[3] = {fr, fg, fb};
+        const int rx = wi - d.left, ry = hi - d.top;
+        if (rx >= 0 && rx < d.new_w && ry >= 0 && ry < d.new_h) {
+          if (mode == 0) {
+            const uint8_t* p = d.src + ry * d.src_pitch + 3 * rx;
+            v[0] = p[0]; v[1] = p[1]; v[2] = p[2];
+          } else if (mode == 1) {
+            const uint8_t* p0 = d.src + (2 * ry) * d.src_pitch + 6 * rx;
+            const uint8_t* p1 = p0 + d.src_pitch;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) v[c] = (p0[c] + p0[3 + c] + p1[c] + p1[3 + c] + 2) >> 2;
+          } else {
+            lb_bilinear(d, cx[col], cy[r], v);
+          }
+        }
+        f0 = ((float)v[0] - s0) * r0; f1 = ((float)v[1] - s1) * r1; f2 = ((float)v[2] - s2) * r2;
+      }
+      tile[(0 * SM_IH + r) * SM_IWP + col] = __float2bfloat16_rn(f0);
+      tile[(1 * SM_IH + r) * SM_IWP + col] = __float2bfloat16_rn(f1);
+      tile[(2 * SM_IH + r) * SM_IWP + col] = __float2bfloat16_rn(f2);
+    }
+  } else
   {
     // aligned 4-element vectors: vector v of a line covers input columns 2*wo0 - 4 + 4v .. +3;
     // tile column 0 is input column 2*wo0 - 1 (the last element of vector 0)
@@ -557,17 +608,17 @@ int32_t launch_stem(const ly_op& op, cudaStream_t s) {
   launch_k(stem_kernel<T, TIN>, grid, dim3(ST_THREADS), smem, s, (const TIN*)op.nchw, H, W, (T*)op.dst.ptr, op.dst.ctot, op.dst.c0, \
                                                      Cpad, (const float*)op.w, op.bias, op.sub[0], op.sub[1], op.sub[2], \
                                                      op.div[0], op.div[1], op.div[2])
-  const bool u8 = op.impl == LY_STEM_IN_U8;
+  const bool u8 = op.impl == LY_STEM_IN_U8, lb = op.impl == LY_STEM_IN_LB;
   if (op.dtype == LY_BF16 && Cpad % 8 == 0 && Cpad <= 80 && W % 4 == 0 && op.dst.ctot % 8 == 0 && op.dst.c0 % 8 == 0 &&
       reinterpret_cast<uintptr_t>(op.nchw) % 16 == 0 && reinterpret_cast<uintptr_t>(op.dst.ptr) % 16 == 0) {
     dim3 g2((op.dst.W + SM_TW - 1) / SM_TW, (op.dst.H + SM_TH - 1) / SM_TH, op.B);
 #define LY_STEM_MMA(TIN, NT)                                                                                          \
   launch_k(stem_mma_kernel<TIN, NT>, g2, dim3(SM_THREADS), 0, s, (const TIN*)op.nchw, H, W, (__nv_bfloat16*)op.dst.ptr, op.dst.ctot, \
                                                      op.dst.c0, (const float*)op.w, op.bias, op.sub[0], op.sub[1],    \
-                                                     op.sub[2], op.div[0], op.div[1], op.div[2])
+                                                     op.sub[2], op.div[0], op.div[1], op.div[2], op.nh, op.kdp, op.hd)
 #define LY_STEM_NT(NT)                                                 \
   case NT:                                                             \
-    if (u8) LY_STEM_MMA(uint8_t, NT); else LY_STEM_MMA(float, NT);     \
+    if (lb) LY_STEM_MMA(ly_lb_desc, NT); else if (u8) LY_STEM_MMA(uint8_t, NT); else LY_STEM_MMA(float, NT);     \
     return post_launch("stem_mma");
     switch (Cpad / 8) {
       LY_STEM_NT(2) LY_STEM_NT(4) LY_STEM_NT(6) LY_STEM_NT(8) LY_STEM_NT(10)
@@ -576,6 +627,7 @@ int32_t launch_stem(const ly_op& op, cudaStream_t s) {
 #undef LY_STEM_NT
 #undef LY_STEM_MMA
   }
+  LY_CHECK_ARG(!lb, "stem: the fused letterbox loader needs the bf16 tensor-core stem (Cout_pad in {16,32,48,64,80}, W %% 4 == 0)");
   if (op.dtype == LY_F32) {
     LY_CHECK_ARG(aligned16<float>(op.dst), "stem: dst not 16-byte aligned");
     if (u8) LY_STEM(float, uint8_t); else LY_STEM(float, float);

@@ -12,64 +12,19 @@
 //
 // Both are pure bandwidth work: one thread per output pixel (3 channels) / per box.
 #include "common.cuh"
+#include "preprocess.cuh"
 
 namespace ly {
 
 namespace {
-
-// one axis of cv::resize's coefficient table
-struct AxisCoef { int s; int c0, c1; };
-
-__device__ __forceinline__ AxisCoef axis_coef(int d, int dst, int src, bool clamp_fraction) {
-  const double scale = __drcp_rn(__ddiv_rn((double)dst, (double)src));       // 1 / (dst / src)
-  const float f0 = (float)__dadd_rn(__dmul_rn((double)d + 0.5, scale), -0.5);
-  int s = (int)floorf(f0);
-  float f = __fsub_rn(f0, (float)s);
-  if (clamp_fraction) {
-    if (s < 0) { s = 0; f = 0.f; }
-    if (s >= src - 1) { s = src - 1; f = 0.f; }
-  }
-  AxisCoef a;
-  a.s = s;
-  a.c0 = __float2int_rn(__fmul_rn(__fsub_rn(1.0f, f), 2048.0f));
-  a.c1 = __float2int_rn(__fmul_rn(f, 2048.0f));
-  return a;
-}
 
 __global__ void __launch_bounds__(256) letterbox_kernel(const ly_lb_desc* __restrict__ descs, uint8_t* __restrict__ dst, int dst_h,
                                                         int dst_w, int chw, int fr, int fg, int fb) {
   const ly_lb_desc d = descs[blockIdx.z];
   const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
   if (x >= dst_w || y >= dst_h) return;
-  int v[3] = {fr, fg, fb};
-  const int rx = x - d.left, ry = y - d.top;
-  if (rx >= 0 && rx < d.new_w && ry >= 0 && ry < d.new_h) {
-    const uint8_t* src = d.src;
-    const long long pitch = d.src_pitch;
-    if (d.new_w == d.src_w && d.new_h == d.src_h) {
-      const uint8_t* p = src + ry * pitch + 3 * rx;
-      v[0] = p[0]; v[1] = p[1]; v[2] = p[2];
-    } else if (d.src_w == 2 * d.new_w && d.src_h == 2 * d.new_h) {
-      // INTER_LINEAR with an exact 2x decimation is INTER_AREA in cv::resize
-      const uint8_t* p0 = src + (2 * ry) * pitch + 6 * rx;
-      const uint8_t* p1 = p0 + pitch;
-#pragma unroll
-      for (int c = 0; c < 3; ++c) v[c] = (p0[c] + p0[3 + c] + p1[c] + p1[3 + c] + 2) >> 2;
-    } else {
-      const AxisCoef ax = axis_coef(rx, d.new_w, d.src_w, true);
-      const AxisCoef ay = axis_coef(ry, d.new_h, d.src_h, false);
-      const int x0 = ax.s, x1 = min(ax.s + 1, d.src_w - 1);
-      const int y0 = min(max(ay.s, 0), d.src_h - 1), y1 = min(max(ay.s + 1, 0), d.src_h - 1);
-      const uint8_t* r0 = src + y0 * pitch;
-      const uint8_t* r1 = src + y1 * pitch;
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        const int S0 = r0[3 * x0 + c] * ax.c0 + r0[3 * x1 + c] * ax.c1;
-        const int S1 = r1[3 * x0 + c] * ax.c0 + r1[3 * x1 + c] * ax.c1;
-        v[c] = (((ay.c0 * (S0 >> 4)) >> 16) + ((ay.c1 * (S1 >> 4)) >> 16) + 2) >> 2;
-      }
-    }
-  }
+  int v[3];
+  lb_sample(d, x, y, fr, fg, fb, v);
   uint8_t* o = dst + (size_t)blockIdx.z * 3 * dst_h * dst_w;
   if (chw) {
     const size_t plane = (size_t)dst_h * dst_w, at = (size_t)y * dst_w + x;

@@ -118,7 +118,10 @@ class Engine:
                 for j in range(3):
                     o.sub[j], o.div[j] = op.extra["sub"][j], op.extra["div"][j]
                 o.ext_slot = 0
-                if in_u8:
+                if in_u8 == "lb":     # fused letterbox: ext[0] is the device array of ly_lb_desc, border colour in nh/kdp/hd
+                    o.impl = N.STEM_IN_LB
+                    o.nh, o.kdp, o.hd = 114, 114, 114
+                elif in_u8:
                     o.impl = N.STEM_IN_U8
             elif op.w_off >= 0:
                 o.w, o.bias = wbase + esz * op.w_off, bbase + 4 * op.b_off
@@ -192,6 +195,21 @@ class Engine:
             for img0 in range(0, B, sub):
                 n = min(sub, B - img0)
                 self._launch(self.compile(n, H, W, u8), x, outs, img0)
+        return outs
+
+    def run_lb(self, descs: torch.Tensor, B: int, H: int, W: int, sub_batch: Optional[int] = None) -> Dict[Tuple[str, int], torch.Tensor]:
+        """Forward of B images given as letterbox descriptors (``ly_lb_desc[B]`` on the device, see
+        ``preprocess.letterbox_descs``): the stem kernel samples the letterboxed H x W pixels from the source images."""
+        rec = C.sizeof(N.LyLbDesc)
+        if not (descs.is_cuda and descs.dtype == torch.uint8 and descs.is_contiguous() and descs.numel() == rec * B):
+            raise ValueError(f"descs must be a contiguous CUDA uint8 tensor of B ly_lb_desc records ({rec} bytes each)")
+        if self.dtype != "bf16":
+            raise RuntimeError("the fused letterbox loader exists for the bf16 path only")
+        sub = min(B, sub_batch) if sub_batch else B
+        with torch.cuda.device(self.device):
+            outs = self.alloc_outputs(B, H, W, sub, "lb")
+            for img0 in range(0, B, sub):
+                self._launch(self.compile(min(sub, B - img0), H, W, "lb"), descs, outs, img0)
         return outs
 
     def run_named(self, ins: Dict[Tuple[str, int], torch.Tensor], H: int, W: int,

@@ -193,6 +193,28 @@ class YOLOv10(nn.Module):
         return self.engine(dev, taps, head_only).run(x, self.sub_batch)
 
     @torch.no_grad()
+    def detect_letterboxed(self, descs: torch.Tensor, n_images: int, hw, meta: Optional[torch.Tensor] = None, max_det: int = 300,
+                           one2one_only: bool = False) -> torch.Tensor:
+        """forward + top-k decode of ``n_images`` SOURCE images of any sizes described by ``descs``
+        (``preprocess.letterbox_descs``): the letterbox (utils/letterbox.py:9-91) runs inside the stem kernel's loader
+        and, with ``meta``, the unletterbox (utils/box_ops.py:96-124) inside the decode kernel -- the letterboxed batch
+        never exists in memory.  bf16 path only."""
+        if self.training:
+            raise NotImplementedError("leanyolo_b200 is inference-only: call model.eval() first")
+        dev = self.input_subtract.device
+        if dev.type != "cuda":
+            raise RuntimeError("leanyolo_b200 runs on CUDA (sm_100a) only; there is no CPU fallback")
+        H, W = (int(hw), int(hw)) if isinstance(hw, int) else (int(hw[0]), int(hw[1]))
+        if H % 32 or W % 32:
+            raise ValueError("the letterbox target must be a multiple of 32")
+        outs = self.engine(dev, False, "one2one" if one2one_only else None).run_lb(descs, n_images, H, W, self.sub_batch)
+        keys = ("one2one",) if one2one_only else ("one2many", "one2one")
+        self._eval_branches = {k: [outs[(k, i)] for i in range(self.head.nl)] for k in keys}
+        out, _, _ = PP.topk_raw(self._eval_branches["one2one"], num_classes=len(self.class_names), strides=STRIDES,
+                                max_det=max_det, lb_meta=meta)
+        return out
+
+    @torch.no_grad()
     def forward(self, x: torch.Tensor):
         outs = self._run(x)
         self._eval_branches = {k: [outs[(k, i)] for i in range(self.head.nl)] for k in ("one2many", "one2one")}
@@ -223,8 +245,10 @@ class YOLOv10(nn.Module):
         Default: exactly ``decode_forward(model(x))`` -- both head branches run and are cached in ``_eval_branches``
         like the reference's eval forward (yolov10s.py:105-122).  ``one2one_only=True`` is the opt-in fused path
         (SURVEY hard part 6): the one-to-many branch, which the top-k decode never reads, is not computed at all
-        (-3.2 GFLOP per image on yolov10s, no one-to-many NCHW tensors written); the detections are bit-identical,
-        ``_eval_branches`` then holds only ``one2one``.  ``lb_meta`` (from ``preprocess.letterbox_batch``): boxes are
+        (-3.2 GFLOP per image on yolov10s, no one-to-many NCHW tensors written).  Same arithmetic per output; the first
+        regression conv runs as its own N = c2 GEMM instead of the merged two-branch one, so its fp32 summation order
+        (hence a bf16 rounding here and there) may differ: detections agree to ~1e-2 px / 1e-4 in score, bit for bit
+        when both lower to the same conv mode.  ``_eval_branches`` then holds only ``one2one``.  ``lb_meta`` (from ``preprocess.letterbox_batch``): boxes are
         returned in each source image's own coordinates (unletterbox fused into the decode kernel)."""
         if one2one_only:
             outs = self._run(x, head_only="one2one")

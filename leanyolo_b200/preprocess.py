@@ -46,6 +46,48 @@ def letterbox_params(orig_h: int, orig_w: int, new_shape=640, auto: bool = False
     return new_w, new_h, left, top, right, bottom, float(gain_w), float(gain_h)
 
 
+def letterbox_params_batch(hs, ws, new_shape=640, scale_fill: bool = False, scaleup: bool = True):
+    """``letterbox_params`` for a whole batch at once (numpy, no Python loop over images): arrays
+    (new_w, new_h, left, top, gain_w, gain_h).  Python's round() and numpy's rint() both round half to even."""
+    import numpy as np
+    hs, ws = np.asarray(hs, dtype=np.float64), np.asarray(ws, dtype=np.float64)
+    tgt_h, tgt_w = (new_shape, new_shape) if isinstance(new_shape, int) else (int(new_shape[0]), int(new_shape[1]))
+    if scale_fill:
+        gw, gh = tgt_w / np.maximum(ws, 1), tgt_h / np.maximum(hs, 1)
+        new_w, new_h = np.full(ws.shape, tgt_w, dtype=np.int64), np.full(hs.shape, tgt_h, dtype=np.int64)
+        pad_w, pad_h = np.zeros_like(ws), np.zeros_like(hs)
+    else:
+        r = np.minimum(tgt_w / np.maximum(ws, 1), tgt_h / np.maximum(hs, 1))
+        if not scaleup:
+            r = np.minimum(r, 1.0)
+        new_w, new_h = np.rint(ws * r).astype(np.int64), np.rint(hs * r).astype(np.int64)
+        gw = gh = r
+        pad_w, pad_h = (tgt_w - new_w).astype(np.float64), (tgt_h - new_h).astype(np.float64)
+    left, top = np.rint(pad_w / 2.0).astype(np.int64), np.rint(pad_h / 2.0).astype(np.int64)
+    return new_w, new_h, left, top, gw, gh
+
+
+def letterbox_descs(images: Sequence[torch.Tensor], new_shape=640, scale_fill: bool = False, scaleup: bool = True):
+    """Descriptors for the fused path (``model.detect_letterboxed``): (descs uint8 on the device = ly_lb_desc[B],
+    meta [B,6] fp32 on the device).  One host->device copy each; the geometry is vectorised."""
+    import numpy as np
+    if len(images) == 0:
+        raise ValueError("empty batch")
+    for img in images:
+        _check_img(img)
+    dev = images[0].device
+    hs = np.array([img.shape[0] for img in images], dtype=np.int64)
+    ws = np.array([img.shape[1] for img in images], dtype=np.int64)
+    new_w, new_h, left, top, gw, gh = letterbox_params_batch(hs, ws, new_shape, scale_fill, scaleup)
+    a = np.zeros(len(images), dtype=np.dtype([("src", "<u8"), ("pitch", "<i8"), ("sh", "<i4"), ("sw", "<i4"), ("nh", "<i4"),
+                                              ("nw", "<i4"), ("top", "<i4"), ("left", "<i4")]))
+    a["src"] = [img.data_ptr() for img in images]
+    a["pitch"] = [img.stride(0) for img in images]
+    a["sh"], a["sw"], a["nh"], a["nw"], a["top"], a["left"] = hs, ws, new_h, new_w, top, left
+    meta = np.stack([gw, gh, left, top, hs, ws], 1).astype(np.float32)
+    return torch.from_numpy(a.view(np.uint8).copy()).to(dev), torch.from_numpy(meta).to(dev)
+
+
 def _check_img(img: torch.Tensor) -> None:
     if not isinstance(img, torch.Tensor) or not img.is_cuda:
         raise RuntimeError("leanyolo_b200 letterbox runs on CUDA tensors only (no CPU fallback)")
@@ -146,6 +188,20 @@ def unletterbox_coords(boxes: torch.Tensor, gain: Tuple[float, float], pad: Tupl
 def detect_images(model, images: Sequence[torch.Tensor], imgsz: int = 640, max_det: int = 300) -> List[torch.Tensor]:
     """The loop body of tools/infer.py:110-138 for a batch: letterbox -> forward -> top-k decode -> unletterbox.
     Returns one ``[k,6]`` tensor per image in ITS OWN pixel coordinates."""
+    if getattr(model, "precision", "bf16") == "bf16" and _fused_ok(model):
+        # letterbox inside the stem loader, unletterbox inside the decode kernel: no letterboxed batch in memory
+        descs, meta = letterbox_descs(images, imgsz)
+        dets = model.detect_letterboxed(descs, len(images), imgsz, meta, max_det=max_det)
+        for img in images:                     # the source images must outlive the asynchronous forward
+            img.record_stream(torch.cuda.current_stream(img.device))
+        return list(dets.unbind(0))
     batch, meta = letterbox_batch(images, imgsz)
     dets = model.detect(batch, max_det=max_det, lb_meta=meta)      # unletterbox happens inside the decode kernel
     return list(dets.unbind(0))
+
+
+def _fused_ok(model) -> bool:
+    """The fused letterbox loader lives in the tensor-core stem kernel: bf16, first conv <= 80 channels."""
+    import os
+    return (os.environ.get("LEANYOLO_FUSE_LETTERBOX", "1") != "0" and os.environ.get("LEANYOLO_CONV_IMPL", "auto") != "simt"
+            and model.backbone.cv0.conv.out_channels <= 80)

@@ -123,8 +123,8 @@ def check_decode_e2e(name="yolov10s"):
     fixed = m.detect(x)
     assert fixed.shape == (2, min(300, A), 6)
     assert torch.equal(fixed[0], dets[0][0]) and set(m._eval_branches) == {"one2many", "one2one"}
-    # opt-in fused path: the one-to-many branch is not computed; the one2one head tensors are the same values
-    # (the first regression conv runs as its own N=64 GEMM instead of the merged N=128 one: same K order per output)
+    # opt-in fused path: the one-to-many branch is not computed; the one2one head tensors are the same values up to the
+    # fp32 summation order of the first regression conv (its own N=64 GEMM instead of the merged N=128 one)
     ref_o2o = [t.clone() for t in m._eval_branches["one2one"]]
     fused = m.detect(x, one2one_only=True)
     assert set(m._eval_branches) == {"one2one"} and fused.shape == fixed.shape

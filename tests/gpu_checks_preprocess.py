@@ -142,3 +142,37 @@ def check_val_loop(seed=5):
         expect = V.coco_bbox_map(anns, top)
         assert stats == expect and 0.0 < stats["mAP50-95"] <= 1.0, (stats, expect)
     return {"rows": len(rows), "gt": len(anns), **stats}
+
+
+def check_fused_letterbox(seed=9):
+    """Letterbox fused into the stem loader (LY_STEM_IN_LB) == letterbox kernel -> uint8 batch -> stem, bit for bit, on the
+    reference-golden source images (down/up-scale, exact 2x decimation, plain copy, 1-pixel-high) and random sizes; with
+    the unletterbox fused into the decode kernel the detections equal the two-step pipeline's too."""
+    from gpu_checks_model import build
+    m, _ = build("yolov10n")
+    gold = torch.load(os.path.join(G, "letterbox.pt"), weights_only=False)
+    rng = np.random.default_rng(seed)
+    imgs = [g["img"] for g in gold] + [torch.from_numpy(rng.integers(0, 256, (h, w, 3), dtype=np.uint8))
+                                       for h, w in ((256, 320), (64, 80), (128, 160), (37, 411), (500, 20))]
+    imgs = [i.to(DEV).contiguous() for i in imgs]
+    n_modes = set()
+    for tgt, kw in (((128, 160), {}), (96, {"scaleup": False}), ((64, 96), {"scale_fill": True})):
+        batch, meta = P.letterbox_batch(imgs, tgt, **kw)
+        two = m.detect(batch, max_det=100, lb_meta=meta)
+        ref = [t.clone() for t in m._eval_branches["one2one"]] + [t.clone() for t in m._eval_branches["one2many"]]
+        descs, meta2 = P.letterbox_descs(imgs, tgt, **kw)
+        assert torch.equal(meta, meta2), "descriptor meta differs from letterbox_batch's"
+        one = m.detect_letterboxed(descs, len(imgs), tgt, meta2, max_det=100)
+        got = list(m._eval_branches["one2one"]) + list(m._eval_branches["one2many"])
+        for a, b in zip(got, ref):
+            assert torch.equal(a, b), f"fused letterbox head tensors differ (target {tgt}, {kw})"
+        assert torch.equal(one, two), f"detections differ (target {tgt}): max abs {float((one - two).abs().max())}"
+        fused_o2o = m.detect_letterboxed(descs, len(imgs), tgt, meta2, max_det=100, one2one_only=True)
+        two_o2o = m.detect(batch, max_det=100, lb_meta=meta, one2one_only=True)     # same engine, two-step letterbox
+        assert torch.equal(fused_o2o, two_o2o), f"one2one-only fused detections differ (target {tgt}): max abs {float((fused_o2o - two_o2o).abs().max())}"
+        d = np.frombuffer(descs.cpu().numpy().tobytes(), dtype=np.dtype([("src", "<u8"), ("pitch", "<i8"), ("sh", "<i4"), ("sw", "<i4"),
+                                                                         ("nh", "<i4"), ("nw", "<i4"), ("top", "<i4"), ("left", "<i4")]))
+        for r in d:
+            n_modes.add(0 if (r["nw"] == r["sw"] and r["nh"] == r["sh"]) else (1 if (r["sw"] == 2 * r["nw"] and r["sh"] == 2 * r["nh"]) else 2))
+    assert n_modes == {0, 1, 2}, f"resize classes exercised: {n_modes}"
+    return {"images": len(imgs)}

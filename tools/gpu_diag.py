@@ -176,6 +176,7 @@ def registry():
     add("unletterbox_batch", PR.check_unletterbox_batch)
     add("detect_images_e2e", PR.check_detect_images)
     add("val_loop_coco", PR.check_val_loop)
+    add("letterbox_fused_stem", PR.check_fused_letterbox)
     return R
 
 
