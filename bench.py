@@ -348,6 +348,21 @@ def main():
     dec_bytes = sum(t.numel() * 4 for t in branch) + B * 300 * 6 * 4
     by_kind["decode"] = {"ms": round(dec_ms, 3), "bytes": dec_bytes, "flops": 0, "launches": 2,
                          "gbs": round(dec_bytes / (dec_ms / 1e3) / 1e9, 1)}
+    if a.decode == "nms":
+        # the NMS decode (DFL + per-anchor best class + candidate select/sort + greedy IoU suppression) timed alone on the cached
+        # one2many branch; algorithmic bytes = the head tensors once + the fixed-shape output (the kernel itself is bound by its
+        # shared-memory sort, not by HBM: profiles/r2_ncu_nms_kernel_config3_full.txt)
+        o2m = model._eval_branches["one2many"]
+        for _ in range(2):
+            PP.nms_raw(o2m, num_classes=len(names), strides=STRIDES, conf_thresh=a.conf, iou_thresh=a.iou, max_det=300)
+        e0.record()
+        for _ in range(5):
+            PP.nms_raw(o2m, num_classes=len(names), strides=STRIDES, conf_thresh=a.conf, iou_thresh=a.iou, max_det=300)
+        e1.record()
+        torch.cuda.synchronize()
+        nms_ms = e0.elapsed_time(e1) / 5
+        nms_bytes = sum(t.numel() * 4 for t in o2m) + B * 300 * 6 * 4
+        by_kind["nms"] = {"ms": round(nms_ms, 3), "bytes": nms_bytes, "flops": 0, "launches": 2, "gbs": round(nms_bytes / (nms_ms / 1e3) / 1e9, 1)}
     if a.profile_out:
         os.makedirs(os.path.dirname(os.path.abspath(a.profile_out)), exist_ok=True)
         json.dump({"rows": rows, "by_kind": by_kind}, open(a.profile_out, "w"), indent=1)

@@ -23,6 +23,7 @@ namespace {
 
 constexpr int TOPK_MAX = 1024;   // max_det supported by the per-CTA sort buffers
 constexpr int NMS_CH = 512;      // candidates per NMS chunk
+constexpr int NMS_PRESEL = 2048; // candidates selected and sorted up front when more pass the threshold
 constexpr int NT = 1024;
 constexpr int NT_TOPK = 512;     // top-k: 3 CTAs per SM so that a batch of 256 images is one wave
 
@@ -366,13 +367,42 @@ nms_kernel(const float* __restrict__ boxes, const float* __restrict__ scores, co
   const int nv = n_valid ? min(n_valid[b], N) : N;
   unsigned long long* sb = sort_in_smem ? sort_s : sort_g + (long long)b * npad;
 
+  // Candidate keys, score-descending.  The greedy scan stops at max_keep survivors, so it almost never looks past the
+  // first few thousand candidates: when more than NMS_PRESEL pass the threshold (config 3: all 8400 anchors) only the
+  // NMS_PRESEL best are selected (radix select on the keys computed on the fly) and sorted; if they run out before
+  // max_keep boxes survive, the kernel falls back to the full sort and starts over (identical result either way).
+  // ncu on config 3 before this: 1.10 ms per launch, DRAM 0.4 %, L1 66 %: the 16384-key shared-memory bitonic sort.
+  auto key_of = [&](int i) -> unsigned long long {
+    const float s = sc[i];
+    if (use_conf && !(s > conf)) return 0ull;      // below any real key (a real key has a non-zero index part or score part)
+    return ((unsigned long long)orderable(s) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)i);
+  };
+  __shared__ unsigned hist_s[256];
+  __shared__ unsigned bcast_s[2];
+  int* keepb = keep + (long long)b * max_keep;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int WORDS = NMS_CH / 32;
+  for (int attempt = 0; attempt < 2; ++attempt) {
   if (threadIdx.x == 0) { S.n_cand = 0; S.n_kept = 0; S.done = 0; }
   __syncthreads();
-  // ---- compaction of valid candidates (order is irrelevant: the sort key carries the index)
+  int total_valid = 0;
+  {
+    int local = 0;
+    for (int i = threadIdx.x; i < nv; i += blockDim.x) local += key_of(i) != 0ull;
+    local = __reduce_add_sync(0xFFFFFFFFu, local);
+    if (lane == 0 && local) atomicAdd(&S.n_cand, local);
+    __syncthreads();
+    total_valid = S.n_cand;
+    __syncthreads();
+    if (threadIdx.x == 0) S.n_cand = 0;
+    __syncthreads();
+  }
+  const bool presel = attempt == 0 && total_valid > NMS_PRESEL;
+  unsigned long long thr_key = 1ull;               // keep every valid key
+  if (presel) thr_key = block_kth_largest(key_of, nv, NMS_PRESEL, hist_s, bcast_s);
   for (int i = threadIdx.x; i < nv; i += blockDim.x) {
-    const float s = sc[i];
-    if (!use_conf || s > conf)
-      sb[atomicAdd(&S.n_cand, 1)] = ((unsigned long long)orderable(s) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)i);
+    const unsigned long long kk = key_of(i);
+    if (kk >= thr_key && kk != 0ull) sb[atomicAdd(&S.n_cand, 1)] = kk;
   }
   __syncthreads();
   const int n = S.n_cand;
@@ -381,9 +411,6 @@ nms_kernel(const float* __restrict__ boxes, const float* __restrict__ scores, co
   __syncthreads();
   block_bitonic_desc(sb, P);
 
-  int* keepb = keep + (long long)b * max_keep;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr int WORDS = NMS_CH / 32;
 
   for (int c0 = 0; c0 < n; c0 += NMS_CH) {
     const int m = min(NMS_CH, n - c0);
@@ -462,6 +489,11 @@ nms_kernel(const float* __restrict__ boxes, const float* __restrict__ scores, co
     }
     __syncthreads();
     if (S.done) break;
+  }
+  __syncthreads();
+  // the preselected candidates ran out before max_keep boxes survived and there are more: full sort, start over
+  if (!(presel && S.n_kept < max_keep)) break;
+  __syncthreads();
   }
   __syncthreads();
   const int kept = S.n_kept;
@@ -678,8 +710,8 @@ int32_t run_nms(const float* boxes, const float* scores, const int* labels, cons
   const int in_smem = npad <= kSmemSortMaxKeys;
   const size_t smem = ((sizeof(NmsSmem) + 15) / 16) * 16 + (in_smem ? (size_t)npad * 8 : 0);
   // (the attribute is per device: set it on every call, it is cheap)
-  LY_CUDA(cudaFuncSetAttribute(nms_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  LY_CUDA(cudaFuncSetAttribute(nms_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  LY_CUDA(cudaFuncSetAttribute(nms_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
+  LY_CUDA(cudaFuncSetAttribute(nms_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
   if (tv)
     nms_kernel<true><<<B, NT, smem, st>>>(boxes, scores, labels, n_valid, N, npad, use_conf, conf, thr, max_keep, classwise,
                                           in_smem, sort_g, keep, keep_count, out_rows);
