@@ -165,6 +165,11 @@ __device__ __forceinline__ unsigned orderable(float f) {
 }
 
 // k-th largest of n DISTINCT 64-bit keys (k in [1,n]); key(i) may be called many times.
+// Keys are (orderable score << 32 | ~index).  Radix select, 8 bits per pass from the top; four keys per thread and
+// step are fetched before any of them is binned (the loads are independent: the passes were bound by the latency of one
+// dependent global load per step, ncu: topk_kernel 320 us at 0.4 IPC).  After the four SCORE passes the k-th key's
+// score is known; unless equal scores straddle the cut (the bucket holds more keys than are still wanted) every key
+// of that score qualifies and the four index passes are skipped: the returned threshold is (score << 32).
 template <typename KeyFn>
 __device__ unsigned long long block_kth_largest(KeyFn key, int n, int k, unsigned* hist, unsigned* bcast) {
   unsigned long long prefix = 0, mask = 0;
@@ -172,16 +177,22 @@ __device__ unsigned long long block_kth_largest(KeyFn key, int n, int k, unsigne
     const int shift = pass * 8;
     for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
     __syncthreads();
-    for (int i0 = 0; i0 < n; i0 += blockDim.x) {
-      const int i = i0 + threadIdx.x;
-      unsigned digit = 0xFFFFFFFFu;  // sentinel: not a candidate
-      if (i < n) {
-        const unsigned long long kk = key(i);
-        if ((kk & mask) == prefix) digit = (unsigned)(kk >> shift) & 255u;
+    for (int i0 = 0; i0 < n; i0 += 4 * blockDim.x) {
+      unsigned long long kk[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int i = i0 + j * blockDim.x + threadIdx.x;
+        kk[j] = i < n ? key(i) : 0ull;
       }
-      // warp-aggregated histogram: one shared atomic per distinct digit per warp
-      const unsigned peers = __match_any_sync(0xFFFFFFFFu, digit);
-      if (digit != 0xFFFFFFFFu && (__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&hist[digit], __popc(peers));
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int i = i0 + j * blockDim.x + threadIdx.x;
+        unsigned digit = 0xFFFFFFFFu;  // sentinel: not a candidate
+        if (i < n && (kk[j] & mask) == prefix) digit = (unsigned)(kk[j] >> shift) & 255u;
+        // warp-aggregated histogram: one shared atomic per distinct digit per warp
+        const unsigned peers = __match_any_sync(0xFFFFFFFFu, digit);
+        if (digit != 0xFFFFFFFFu && (__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&hist[digit], __popc(peers));
+      }
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -192,12 +203,15 @@ __device__ unsigned long long block_kth_largest(KeyFn key, int n, int k, unsigne
       }
       bcast[0] = d;
       bcast[1] = k - cum;
+      bcast[2] = hist[d];
     }
     __syncthreads();
     prefix |= (unsigned long long)bcast[0] << shift;
     mask |= 0xFFull << shift;
     k = bcast[1];
+    const bool whole_bucket = (int)bcast[2] == k;
     __syncthreads();
+    if (pass == 4 && whole_bucket) return prefix;      // no tie across the cut: every key of this score is wanted
   }
   return prefix;
 }
@@ -232,7 +246,7 @@ topk_kernel(Levels lv, int k, const float* __restrict__ best, float* s2,
   __shared__ unsigned long long sortbuf[TOPK_MAX];
   __shared__ int anchors[TOPK_MAX];
   __shared__ unsigned hist[256];
-  __shared__ unsigned bcast[2];
+  __shared__ unsigned bcast[3];
   __shared__ int cnt;
   const int b = blockIdx.x;
   const int A = lv.A, nc = lv.nc;
@@ -378,7 +392,7 @@ nms_kernel(const float* __restrict__ boxes, const float* __restrict__ scores, co
     return ((unsigned long long)orderable(s) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)i);
   };
   __shared__ unsigned hist_s[256];
-  __shared__ unsigned bcast_s[2];
+  __shared__ unsigned bcast_s[3];
   int* keepb = keep + (long long)b * max_keep;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int WORDS = NMS_CH / 32;
@@ -523,7 +537,7 @@ export_topk_kernel(int A, int k, float conf, float img_w, float img_h, const flo
                    const int* __restrict__ label, float* __restrict__ out, int* __restrict__ num) {
   __shared__ unsigned long long sortbuf[TOPK_MAX];
   __shared__ unsigned hist[256];
-  __shared__ unsigned bcast[2];
+  __shared__ unsigned bcast[3];
   __shared__ int cnt, nvalid;
   const int b = blockIdx.x;
   const int P = next_pow2(k);
@@ -569,7 +583,7 @@ export_pairs_kernel(Levels lv, int k1, int k2, int img0, float group_off, const 
   __shared__ unsigned long long sortbuf[TOPK_MAX];
   __shared__ int anchors[TOPK_MAX];
   __shared__ unsigned hist[256];
-  __shared__ unsigned bcast[2];
+  __shared__ unsigned bcast[3];
   __shared__ int cnt;
   const int b = blockIdx.x;
   const int A = lv.A, nc = lv.nc;
