@@ -236,10 +236,9 @@ __global__ void __launch_bounds__(kFThreads, 1) dwpw_kernel(const __grid_constan
 #pragma unroll
                 for (int kx = 0; kx < 3; ++kx)
 #pragma unroll
-                  for (int ox = 0; ox < 4; ++ox) {
-                    acc[oy][ox][0] = fmaf(in[ox + kx][0], wv[ky * 3 + kx][0], acc[oy][ox][0]);
-                    acc[oy][ox][1] = fmaf(in[ox + kx][1], wv[ky * 3 + kx][1], acc[oy][ox][1]);
-                  }
+                  for (int ox = 0; ox < 4; ++ox)     // the lane's two channels of one output pixel: one packed FFMA2
+                    ffma2(acc[oy][ox][0], acc[oy][ox][1], in[ox + kx][0], in[ox + kx][1], wv[ky * 3 + kx][0], wv[ky * 3 + kx][1],
+                          acc[oy][ox][0], acc[oy][ox][1]);
               }
             }
           }
@@ -256,7 +255,7 @@ __global__ void __launch_bounds__(kFThreads, 1) dwpw_kernel(const __grid_constan
 #pragma unroll
             for (int x = 0; x < 4; ++x) {
               float v0 = acc[y][x][0], v1 = acc[y][x][1];
-              if (p.pre_act) { v0 = silu_from_half(v0); v1 = silu_from_half(v1); }
+              if (p.pre_act) silu2_from_half(v0, v1);
               const __nv_bfloat162 h2 = __floats2bfloat162_rn(v0, v1);
               const uint32_t r = (uint32_t)((kPH * pyi + y) * p.tw + 4 * pxi + x);   // tile row = pixel index, x fastest
               const uint32_t addr = ab + r * 128u + ((((uint32_t)lane >> 2) ^ (r & 7u)) << 4) + ((uint32_t)lane & 3u) * 4u;

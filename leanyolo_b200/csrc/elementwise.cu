@@ -160,16 +160,22 @@ __device__ __forceinline__ void mma_bf16_16816(float* c, const uint32_t* a, uint
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+// Tile column t holds input column 2*wo0 - 4 + t: the 4-element vectors of the loader land on aligned 8-byte slots (one
+// st.shared per vector; with column 0 = input column 2*wo0 - 1 every vector took three narrow stores and the kernel was
+// bound by its shared-memory wavefronts, ncu: L1 81 % at 52 % DRAM).  Output pixel px, tap kx reads tile column
+// 2*px + 3 + kx, so the (kx = 1, kx = 2) pair of a tap row sits at an EVEN column: one aligned 32-bit load.
+// K slots: k < 18: (c, ky) = k >> 1 with kx = 1 + (k & 1); k = 18..26: the kx = 0 singles; 27..31: zero padding.
+__device__ __forceinline__ int stem_slot_kx(int k) { return k < 18 ? 1 + (k & 1) : 0; }
 // element offset of K slot k inside the staged tile, relative to the pixel's (2*py, 2*px) corner
 __device__ __forceinline__ int stem_slot_off(int k) {
-  if (k >= 27) return 0;
-  const int j = k < 18 ? (k >> 1) : k - 18, kx = k < 18 ? (k & 1) : 2;
-  return ((j / 3) * SM_IH + (j % 3)) * SM_IWP + kx;
+  if (k >= 27) return 4;
+  const int j = k < 18 ? (k >> 1) : k - 18, kx = stem_slot_kx(k);
+  return ((j / 3) * SM_IH + (j % 3)) * SM_IWP + kx + 3;
 }
 // index of K slot k inside the packed [27] weight row ([ky][kx][c]); -1 = zero padding
 __device__ __forceinline__ int stem_slot_w(int k) {
   if (k >= 27) return -1;
-  const int j = k < 18 ? (k >> 1) : k - 18, kx = k < 18 ? (k & 1) : 2;
+  const int j = k < 18 ? (k >> 1) : k - 18, kx = stem_slot_kx(k);
   return ((j % 3) * 3 + kx) * 3 + (j / 3);
 }
 
@@ -238,9 +244,9 @@ stem_mma_kernel(const TIn* __restrict__ x, int H, int W, __nv_bfloat16* __restri
         }
         f0 = ((float)v[0] - s0) * r0; f1 = ((float)v[1] - s1) * r1; f2 = ((float)v[2] - s2) * r2;
       }
-      tile[(0 * SM_IH + r) * SM_IWP + col] = __float2bfloat16_rn(f0);
-      tile[(1 * SM_IH + r) * SM_IWP + col] = __float2bfloat16_rn(f1);
-      tile[(2 * SM_IH + r) * SM_IWP + col] = __float2bfloat16_rn(f2);
+      tile[(0 * SM_IH + r) * SM_IWP + col + 3] = __float2bfloat16_rn(f0);     // tile column = input column - (2*wo0 - 4)
+      tile[(1 * SM_IH + r) * SM_IWP + col + 3] = __float2bfloat16_rn(f1);
+      tile[(2 * SM_IH + r) * SM_IWP + col + 3] = __float2bfloat16_rn(f2);
     }
   } else
   {
@@ -269,12 +275,9 @@ stem_mma_kernel(const TIn* __restrict__ x, int H, int W, __nv_bfloat16* __restri
       const float sc = c == 0 ? s0 : (c == 1 ? s1 : s2), rc = c == 0 ? r0 : (c == 1 ? r1 : r2);
       const float f0 = ok ? ((float)v[it].x - sc) * rc : 0.f, f1 = ok ? ((float)v[it].y - sc) * rc : 0.f;
       const float f2 = ok ? ((float)v[it].z - sc) * rc : 0.f, f3 = ok ? ((float)v[it].w - sc) * rc : 0.f;
-      __nv_bfloat16* tp = tile + line * SM_IWP + 4 * vi - 3;   // tile column of element .x
-      if (vi > 0) {
-        tp[0] = __float2bfloat16_rn(f0);
-        *reinterpret_cast<__nv_bfloat162*>(tp + 1) = __floats2bfloat162_rn(f1, f2);
-      }
-      tp[3] = __float2bfloat16_rn(f3);
+      const __nv_bfloat162 lo2 = __floats2bfloat162_rn(f0, f1), hi2 = __floats2bfloat162_rn(f2, f3);
+      *reinterpret_cast<uint2*>(tile + line * SM_IWP + 4 * vi) =
+          make_uint2(*reinterpret_cast<const uint32_t*>(&lo2), *reinterpret_cast<const uint32_t*>(&hi2));
     }
   }
   __syncthreads();
