@@ -82,7 +82,8 @@ struct Params {
   unsigned char item_dep[kMaxItems][8];                         // per producer stage: last M tile the item needs (0xFF: none)
   uint32_t tab_off, hdr_off;                                    // byte offsets of the descriptor table / item headers
   int n_entries;
-  int slot_w, n_slots, n_groups;
+  int slot_w, n_slots, n_groups, wpg;   // epilogue: n_groups groups of wpg warps (wpg = 4: one warp per TMEM lane quarter; 8: + a column split)
+  uint32_t ehdr_off;                    // per-item epilogue constants (3 x uint4), built in the prologue
   uint32_t x_bytes, w_bytes, bias_off_b, bar_off;
   __nv_bfloat16* dst; int dCtot, dC0, st256;
   float* nchw; int nCtot, nC0, nC;
@@ -141,10 +142,10 @@ __global__ void __launch_bounds__(kThreads, 1) chain_tc_kernel(const __grid_cons
     mbar_init(b_wfull, 1);
     for (int s = 0; s < kMaxSlots; ++s) {
       mbar_init(tfull(s), 1);
-      mbar_init(tempty(s), 4);
+      mbar_init(tempty(s), (uint32_t)p.wpg);
     }
     for (int s = 0; s < kMaxSt; ++s)
-      for (int m = 0; m < kMaxMt; ++m) mbar_init(done(s, m), 4);
+      for (int m = 0; m < kMaxMt; ++m) mbar_init(done(s, m), (uint32_t)p.wpg);
     fence_barrier_init();
     // the weights are parameters (never written by a kernel): request them before waiting for the producer
     mbar_expect_tx(b_wfull, p.w_bytes);
@@ -161,6 +162,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_tc_kernel(const __grid_cons
   // (measured: ~400 cycles of dependent constant loads per item and source block in the generic loop).
   uint4* tab = reinterpret_cast<uint4*>(gen + p.tab_off);
   uint4* hdr = reinterpret_cast<uint4*>(gen + p.hdr_off);
+  uint4* ehdr = reinterpret_cast<uint4*>(gen + p.ehdr_off);
   for (int i = 0; i < p.n_items; ++i) {
     const StageP& S = p.st[p.item_stage[i]];
     const int mt = p.item_mt[i], taps = S.k * S.k, per_blk = taps * S.ksteps, n = p.item_nmma[i];
@@ -179,6 +181,18 @@ __global__ void __launch_bounds__(kThreads, 1) chain_tc_kernel(const __grid_cons
                               S.idesc, 0u);
       hdr[2 * i + 1] = make_uint4((uint32_t)d[0] | ((uint32_t)d[1] << 8) | ((uint32_t)d[2] << 16) | ((uint32_t)d[3] << 24),
                                   (uint32_t)d[4] | ((uint32_t)d[5] << 8) | ((uint32_t)d[6] << 16) | ((uint32_t)d[7] << 24), 0u, 0u);
+      // epilogue constants of the item: everything the epilogue warps would otherwise chase through the parameter bank
+      const bool to_smem = S.dst_region >= 0, has_res = S.res_region >= 0;
+      const uint32_t drb = to_smem ? (uint32_t)p.region_rowb[S.dst_region] : 0u, rrb = has_res ? (uint32_t)p.region_rowb[S.res_region] : 0u;
+      int res_need = 0;
+      if (has_res) res_need = min(p.st[S.res_prod].n_mt - 1, (mt * 128 + 127 + S.res_rows) >> 7);
+      ehdr[3 * i] = make_uint4((uint32_t)p.item_flags[i] | ((uint32_t)mt << 8) | ((uint32_t)p.item_stage[i] << 16) | ((to_smem ? 1u : 0u) << 24) |
+                                   ((has_res ? 1u : 0u) << 25) | ((S.act ? 1u : 0u) << 26),
+                               to_smem ? base + p.region_off[S.dst_region] + (uint32_t)(mt * 128) * drb : 0u, drb | ((uint32_t)S.dst_c0 << 16),
+                               (uint32_t)(S.dst_shift * (p.PW + 1) + mt * 128));
+      ehdr[3 * i + 1] = make_uint4(has_res ? base + p.region_off[S.res_region] + (uint32_t)(mt * 128 + S.res_rows) * rrb : 0u, rrb | ((uint32_t)S.res_c0 << 16),
+                                   (uint32_t)(mt * 128 + S.res_rows), (uint32_t)(has_res ? S.res_prod : 0) | ((uint32_t)res_need << 8));
+      ehdr[3 * i + 2] = make_uint4((uint32_t)S.cout, S.bias_off, 0u, 0u);
     }
   }
   if (warp == 1) {
@@ -291,15 +305,20 @@ __global__ void __launch_bounds__(kThreads, 1) chain_tc_kernel(const __grid_cons
                clock64() - t_start, t_x, t_done, t_slot, t_issue);
     }
   } else {
-    // ============================== epilogue (4 groups x 4 warps) ==============
-    const int q = warp & 3, group = (warp - 2) >> 2;
+    // ============================== epilogue (n_groups groups of wpg warps) ==============
+    const int q = warp & 3;
+    const int ew = warp - 2;                                   // 0..15
+    const int group = ew / p.wpg, sub = (ew % p.wpg) >> 2;      // sub: column share of the warp inside its group (wpg = 8: 0 / 1)
+    const int nsub = p.wpg >> 2;
     const uint32_t row_in = (uint32_t)(q * 32 + lane);
     uint32_t gi = 0;
     long long e_wait = 0, e_work = 0, e_start = clock64();
     const int n_tiles = (p.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const uint32_t PW = (uint32_t)p.PW;
     for (int it = p.early ? -1 : 0; it < n_tiles; ++it) {
       for (int i = 0; i < p.n_items; ++i) {
-        const int t = it + (p.item_flags[i] & 1);
+        const uint4 e0 = ehdr[3 * i];
+        const int t = it + (int)(e0.x & 1u);
         if (t < 0 || t >= n_tiles) continue;
         const uint32_t slot = gi % (uint32_t)p.n_slots, use = gi / (uint32_t)p.n_slots;
         // items go to the groups by their GLOBAL sequence number: n_slots is a multiple of the group count, so every
@@ -307,34 +326,33 @@ __global__ void __launch_bounds__(kThreads, 1) chain_tc_kernel(const __grid_cons
         const bool mine_item = (int)(gi % (uint32_t)p.n_groups) == group;
         ++gi;
         if (!mine_item) continue;
+        const uint4 e1 = ehdr[3 * i + 1], e2 = ehdr[3 * i + 2];
         const uint32_t itp = (uint32_t)t & 1u;
         const int tile = (int)blockIdx.x + t * (int)gridDim.x;
         const int b = tile / tiles_img, t2 = tile - b * tiles_img;
         const int yt = t2 / p.tiles_x, xt = t2 - yt * p.tiles_x;
         const int y00 = yt * p.TH - p.halo, x00 = xt * p.TW - p.halo;
-        const int s = p.item_stage[i], mt = p.item_mt[i];
-        const StageP& S = p.st[s];
-        const uint32_t r = (uint32_t)mt * 128u + row_in;
-        const uint32_t qi = r + (uint32_t)(S.dst_shift * (p.PW + 1));
-        const uint32_t fy = __umulhi(qi, p.mg_pw), fx = qi - fy * (uint32_t)p.PW;
+        const int s = (int)((e0.x >> 16) & 0xFFu), mt = (int)((e0.x >> 8) & 0xFFu);
+        const bool to_smem = (e0.x >> 24) & 1u, has_res = (e0.x >> 25) & 1u, act = (e0.x >> 26) & 1u;
+        const uint32_t qi = e0.w + row_in;                       // frame pixel index of this thread's row
+        const uint32_t fy = __umulhi(qi, p.mg_pw), fx = qi - fy * PW;
         const int gy = y00 + (int)fy, gx = x00 + (int)fx;
         const bool in_img = (unsigned)gy < (unsigned)p.H && (unsigned)gx < (unsigned)p.W;
-        const bool to_smem = S.dst_region >= 0;
         // shared-memory destination / shortcut rows
         uint32_t d_row = 0, d_sw = 0, r_row = 0, r_sw = 0;
+        const uint32_t drb = e0.z & 0xFFFFu, dc0 = e0.z >> 16, rrb = e1.y & 0xFFFFu, rc0 = e1.y >> 16;
         if (to_smem) {
-          const uint32_t rb = (uint32_t)p.region_rowb[S.dst_region];
-          d_row = base + p.region_off[S.dst_region] + r * rb;
-          d_sw = ((r * rb) >> 7) & ((rb >> 4) - 1u);
+          const uint32_t off = ((uint32_t)mt * 128u + row_in) * drb;
+          d_row = e0.y + row_in * drb;
+          d_sw = (off >> 7) & ((drb >> 4) - 1u);
         }
-        if (S.res_region >= 0) {
-          const uint32_t rb = (uint32_t)p.region_rowb[S.res_region];
-          const uint32_t rr = r + (uint32_t)S.res_rows;
-          r_row = base + p.region_off[S.res_region] + rr * rb;
-          r_sw = ((rr * rb) >> 7) & ((rb >> 4) - 1u);
+        if (has_res) {
+          const uint32_t rr = e1.z + row_in;
+          r_row = e1.x + row_in * rrb;
+          r_sw = ((rr * rrb) >> 7) & ((rrb >> 4) - 1u);
           // the shortcut region was written by epilogue warps of an earlier stage: make sure those rows are there
-          const int need = min(p.st[S.res_prod].n_mt - 1, (int)((mt * 128 + 127 + S.res_rows) >> 7));
-          for (int m = 0; m <= need; ++m) mbar_wait(done(S.res_prod, m), itp);
+          const int rp = (int)(e1.w & 0xFFu), need = (int)(e1.w >> 8);
+          for (int m = 0; m <= need; ++m) mbar_wait(done(rp, m), itp);
         }
         // global destination (last stage): only the tile's own pixels
         __nv_bfloat16* drow = nullptr;
@@ -348,9 +366,12 @@ __global__ void __launch_bounds__(kThreads, 1) chain_tc_kernel(const __grid_cons
             else drow = p.dst + (size_t)lin * (uint32_t)p.dCtot + p.dC0;
           }
         }
-        const float pre = S.act ? 0.5f : 1.0f;
-        const float* bias = s_bias + S.bias_off;
-        const int nch = S.cout >> 4;
+        const float pre = act ? 0.5f : 1.0f;
+        const float* bias = s_bias + e2.y;
+        const int nch = (int)e2.x >> 4;
+        // column share of this warp: chunks [c_lo, c_hi)
+        const int per = (nch + nsub - 1) / nsub;
+        const int c_lo = min(sub * per, nch), c_hi = min(c_lo + per, nch);
         const long long w0 = clock64();
         mbar_wait(tfull(slot), use & 1u);
         const long long w1 = clock64();
@@ -358,8 +379,13 @@ __global__ void __launch_bounds__(kThreads, 1) chain_tc_kernel(const __grid_cons
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + slot * (uint32_t)p.slot_w;
         uint32_t nxt[16];
-        tmem_ld16(taddr, nxt);
-        for (int ch = 0; ch < nch; ++ch) {
+        if (c_lo < c_hi) tmem_ld16(taddr + 16 * c_lo, nxt);
+        else {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty(slot));
+        }
+        for (int ch = c_lo; ch < c_hi; ++ch) {
           const int c = ch * 16;
           float v[16];
           tmem_ld_wait();
@@ -370,20 +396,20 @@ __global__ void __launch_bounds__(kThreads, 1) chain_tc_kernel(const __grid_cons
             ffma2(v[4 * j + 0], v[4 * j + 1], __uint_as_float(nxt[4 * j + 0]), __uint_as_float(nxt[4 * j + 1]), pre, pre, bb.x, bb.y);
             ffma2(v[4 * j + 2], v[4 * j + 3], __uint_as_float(nxt[4 * j + 2]), __uint_as_float(nxt[4 * j + 3]), pre, pre, bb.z, bb.w);
           }
-          if (ch + 1 < nch) {
+          if (ch + 1 < c_hi) {
             tmem_ld16(taddr + c + 16, nxt);
           } else {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty(slot));
           }
-          if (S.act) {
+          if (act) {
 #pragma unroll
             for (int j = 0; j < 16; j += 2) silu2_from_half(v[j], v[j + 1]);
           }
-          if (S.res_region >= 0) {
+          if (has_res) {
             uint32_t rw[8];
-            const uint32_t j0 = (uint32_t)(S.res_c0 + c) >> 3;
+            const uint32_t j0 = (rc0 + (uint32_t)c) >> 3;
             lds32x4(r_row + ((j0 ^ r_sw) << 4), rw);
             lds32x4(r_row + (((j0 + 1u) ^ r_sw) << 4), rw + 4);
 #pragma unroll
@@ -399,7 +425,7 @@ __global__ void __launch_bounds__(kThreads, 1) chain_tc_kernel(const __grid_cons
               const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
               w[j] = in_img ? *reinterpret_cast<const uint32_t*>(&h) : 0u;
             }
-            const uint32_t j0 = (uint32_t)(S.dst_c0 + c) >> 3;
+            const uint32_t j0 = (dc0 + (uint32_t)c) >> 3;
             sts32x4(d_row + ((j0 ^ d_sw) << 4), w);
             sts32x4(d_row + (((j0 + 1u) ^ d_sw) << 4), w + 4);
           } else if (drow) {
@@ -454,7 +480,7 @@ struct Layout {
   int rows[kMaxReg];
   uint32_t region_off[kMaxReg];
   uint32_t w_off[kMaxSt], w_tile[kMaxSt];
-  uint32_t bias_off_b, bar_off, tab_off, hdr_off, total;
+  uint32_t bias_off_b, bar_off, tab_off, hdr_off, ehdr_off, total;
   int items;
   double cost;
 };
@@ -571,7 +597,8 @@ int32_t chain_tc_prepare(const ly_op& op, ChainState** out) {
   p.halo = halo;
   p.slot_w = max_cout <= 64 ? 64 : (max_cout <= 128 ? 128 : 256);
   p.n_slots = std::min(kMaxSlots, 512 / p.slot_w);
-  p.n_groups = std::min(4, p.n_slots);
+  p.wpg = env_i("LY_CHAIN_WPG", 8) == 4 ? 4 : 8;
+  p.n_groups = std::min(kEpiWarps / p.wpg, p.n_slots);
   for (int r = 0; r < ch.n_regions; ++r) {
     p.region_rowb[r] = rowb[r];
     const int swz = rowb[r] == 128 ? 2 : (rowb[r] == 64 ? 4 : 6);
@@ -618,6 +645,7 @@ int32_t chain_tc_prepare(const ly_op& op, ChainState** out) {
     if (entries > kMaxEntries) return false;
     L.tab_off = off; off += 16u * (uint32_t)entries;
     L.hdr_off = off; off += 32u * (uint32_t)L.items;
+    L.ehdr_off = off; off += 48u * (uint32_t)L.items;
     L.total = off + 1024u;
     if (L.total > kSmemMax) return false;
     const long long tiles = (long long)((W + TW - 1) / TW) * ((H + TH - 1) / TH);
@@ -709,7 +737,7 @@ int32_t chain_tc_prepare(const ly_op& op, ChainState** out) {
     if (items[q].fl & 2) last_x = q;
   items[last_x].fl |= 4;
   p.n_items = n_it; p.early = early_mode ? 1 : 0;
-  p.tab_off = L.tab_off; p.hdr_off = L.hdr_off; p.n_entries = 0;
+  p.tab_off = L.tab_off; p.hdr_off = L.hdr_off; p.ehdr_off = L.ehdr_off; p.n_entries = 0;
   for (int q = 0; q < n_it; ++q) {
     const StageP& S = p.st[items[q].s];
     p.item_stage[q] = (unsigned char)items[q].s; p.item_mt[q] = (unsigned char)items[q].m; p.item_flags[q] = (unsigned char)items[q].fl;

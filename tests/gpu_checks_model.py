@@ -26,7 +26,7 @@ def build(name, seed=1, gain=1.25, precision="bf16", conv_impl=None, nc=80, chai
         os.environ["LEANYOLO_CONV_IMPL"] = conv_impl
     else:
         os.environ.pop("LEANYOLO_CONV_IMPL", None)
-    m = get_model(name, weights=None, class_names=NAMES[:nc])
+    m = get_model(name, weights=None, class_names=[f"class{i}" for i in range(nc)])
     sd = synth_state_dict(m.state_dict(), seed=seed, gain=gain)
     m.load_state_dict(sd, strict=True)
     m = m.to(DEV).eval()
@@ -34,11 +34,13 @@ def build(name, seed=1, gain=1.25, precision="bf16", conv_impl=None, nc=80, chai
     return m, sd
 
 
-def check_model(name="yolov10s", precision="bf16", hw=64, B=2, conv_impl=None, seed=1, chain=False):
+def check_model(name="yolov10s", precision="bf16", hw=64, B=2, conv_impl=None, seed=1, chain=False, nc=80):
     """bf16: raw head outputs and the c3..p5 taps within 2e-2 (max-abs / max|ref| and rel-L2);
-    fp32 check mode: within 1e-4 (north_star tolerances)."""
-    m, sd = build(name, seed=seed, precision=precision, conv_impl=conv_impl, chain=chain)
-    x = synth_images(B, hw, hw, seed=seed + 10)
+    fp32 check mode: within 1e-4 (north_star tolerances).  ``hw``: int or (H, W) -- the reference takes any multiple of
+    32 per axis (letterbox(auto=True) gives e.g. 384x640); ``nc``: class count (head widths c3 = max(ch0, min(nc, 100)))."""
+    m, sd = build(name, seed=seed, precision=precision, conv_impl=conv_impl, chain=chain, nc=nc)
+    H, W = (hw, hw) if isinstance(hw, int) else hw
+    x = synth_images(B, H, W, seed=seed + 10)
     taps = {}
     ref = O.forward(sd, x, taps=taps)
     got = m.forward_with_taps(x.to(DEV))

@@ -153,6 +153,16 @@ def registry():
     add("model_s_bf16_chain_64", M.check_model, name="yolov10s", precision="bf16", hw=64, B=2, chain=True)
     add("model_s_bf16_chain_320", M.check_model, name="yolov10s", precision="bf16", hw=320, B=2, chain=True)
     add("model_n_bf16_chain_160", M.check_model, name="yolov10n", precision="bf16", hw=160, B=3, chain=True)
+    # non-square inputs (H != W, W < H, odd H/32 or W/32) and class counts that change the head widths / NCHW padding
+    add("model_s_bf16_384x640", M.check_model, name="yolov10s", precision="bf16", hw=(384, 640), B=2)
+    add("model_s_bf16_224x96", M.check_model, name="yolov10s", precision="bf16", hw=(224, 96), B=3)
+    add("model_n_f32_96x160", M.check_model, name="yolov10n", precision="fp32", hw=(96, 160), B=2)
+    add("model_m_bf16_160x96", M.check_model, name="yolov10m", precision="bf16", hw=(160, 96), B=2)
+    add("model_n_bf16_nc1", M.check_model, name="yolov10n", precision="bf16", hw=(64, 96), B=2, nc=1)
+    add("model_n_bf16_nc90", M.check_model, name="yolov10n", precision="bf16", hw=(96, 64), B=2, nc=90)
+    add("model_s_bf16_nc7", M.check_model, name="yolov10s", precision="bf16", hw=64, B=2, nc=7)
+    add("model_n_f32_nc90", M.check_model, name="yolov10n", precision="fp32", hw=64, B=1, nc=90)
+    add("model_s_f32_nc7", M.check_model, name="yolov10s", precision="fp32", hw=(64, 96), B=1, nc=7)
     add("model_s_golden", M.check_model_golden, name="yolov10s")
     add("model_s_subbatch_graph", M.check_subbatch_and_graph, name="yolov10s")
     add("model_s_decode_e2e", M.check_decode_e2e, name="yolov10s")
