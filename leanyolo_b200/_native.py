@@ -8,7 +8,10 @@ from __future__ import annotations
 import ctypes as C
 from pathlib import Path
 
-LIB_PATH = Path(__file__).resolve().parent / "_lib" / "libleanyolo_b200.so"
+import os
+
+# LEANYOLO_B200_LIB: load an experimental build (LY_BUILD_DIR=... python -m leanyolo_b200.build) instead of the in-tree one
+LIB_PATH = Path(os.environ.get("LEANYOLO_B200_LIB") or Path(__file__).resolve().parent / "_lib" / "libleanyolo_b200.so")
 
 ABI_VERSION = 4
 LY_BF16, LY_F32 = 0, 1

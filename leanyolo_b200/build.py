@@ -14,7 +14,7 @@ from pathlib import Path
 
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
-OUT_DIR = PKG / "_lib"
+OUT_DIR = Path(os.environ.get("LY_BUILD_DIR") or PKG / "_lib")   # LY_BUILD_DIR: side-by-side experimental builds
 LIB = OUT_DIR / "libleanyolo_b200.so"
 STAMP = OUT_DIR / "build.stamp"
 

@@ -61,6 +61,8 @@ constexpr int kEpiWarps = 16;    // 4 TMEM lane quarters x 4 column groups
 constexpr int kThreads = 64 + 32 * kEpiWarps;    // TMA warp + MMA warp + epilogue warps
 constexpr int kMaxCout = 1024;   // bias vector staged in shared memory
 constexpr int kMaxStages = 12;   // per ring
+constexpr int kMaxAcc = 8;       // TMEM accumulator stages (512 columns / N)
+constexpr int kBarSlots = 4 * kMaxStages + 2 * kMaxAcc + 4;   // 8-byte slots of the barrier block
 constexpr uint32_t kSmemBudget = 216 * 1024;
 
 struct Params {
@@ -100,7 +102,17 @@ struct Params {
   uint32_t idesc_fold;     // instruction descriptor with N = 3 * block_n
   uint32_t exch_off;       // fold: byte offset (from the barrier block) of the epilogue's boundary-row exchange slots
   int xpre;                // epilogue: cross-tile TMEM prefetch (LY_TC_XPRE=1, default off)
+  int acc;                 // TMEM accumulator stages (each block_n columns; pair: 2 * block_n, fold: 3 * block_n)
+  int epi_groups;          // 0: column-parallel epilogue; 4: tile groups of the tile-parallel epilogue (needs acc >= 4)
+  int exp;                 // -DLY_TC_EXP builds only (LY_TC_EXP=mask): 1 skip the MMAs, 2 skip the epilogue's work, 4 skip the TMA loads after the first pass
 };
+
+// Knock-out experiments (-DLY_TC_EXP): which role bounds a layer?  Results are garbage, only the time is meaningful.
+#ifdef LY_TC_EXP
+#define EXP_ON(p, bit) (((p).exp & (bit)) != 0)
+#else
+#define EXP_ON(p, bit) false
+#endif
 
 // Optional per-role cycle accounting (-DLY_TC_PROFILE): CTA 0 prints where each role waited.
 #ifdef LY_TC_PROFILE
@@ -119,8 +131,8 @@ __device__ __forceinline__ uint32_t bar_aempty(uint32_t bb, int s) { return bb +
 __device__ __forceinline__ uint32_t bar_bfull(uint32_t bb, int s) { return bb + 8u * (2 * kMaxStages + s); }
 __device__ __forceinline__ uint32_t bar_bempty(uint32_t bb, int s) { return bb + 8u * (3 * kMaxStages + s); }
 __device__ __forceinline__ uint32_t bar_tfull(uint32_t bb, int s) { return bb + 8u * (4 * kMaxStages + s); }
-__device__ __forceinline__ uint32_t bar_tempty(uint32_t bb, int s) { return bb + 8u * (4 * kMaxStages + 2 + s); }
-__device__ __forceinline__ uint32_t bar_bres(uint32_t bb) { return bb + 8u * (4 * kMaxStages + 4); }
+__device__ __forceinline__ uint32_t bar_tempty(uint32_t bb, int s) { return bb + 8u * (4 * kMaxStages + kMaxAcc + s); }
+__device__ __forceinline__ uint32_t bar_bres(uint32_t bb) { return bb + 8u * (4 * kMaxStages + 2 * kMaxAcc); }
 
 // tile index -> (n tile, brick) without integer division (magic multipliers from the host)
 __device__ __forceinline__ int phys(const Params& p, int t) { return p.rev ? p.total_tiles - 1 - t : t; }
@@ -143,18 +155,23 @@ __device__ __forceinline__ void mma_role(const Params& p, uint32_t a_base, uint3
   const uint32_t a_stage16 = (uint32_t)p.a_stage >> 4, b_stage16 = (uint32_t)p.b_stage >> 4, tap16 = (uint32_t)p.a_tap_stride >> 4;
   const uint32_t a_lo0 = (a_base >> 4) | (1u << 16), b_lo0 = (b_base >> 4) | (1u << 16);
   const uint32_t block_n = (uint32_t)p.block_n;
+  const int acc = p.acc;
   if (BRES) {
-    mbar_wait(bar_bres(bb), 0);
+    mbar_wait_spin(bar_bres(bb), 0);
     tc_fence_after();
   }
   int sa = 0, sb = 0, as = 0;
   uint32_t pa = 0, pb = 0, aphase = 0;
+  PROF_DECL(w_afull); PROF_DECL(w_tempty);
+#ifdef LY_TC_PROFILE
+  const long long istart = clock64();
+#endif
   for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
-    mbar_wait(bar_tempty(bb, as), aphase ^ 1u);
+    { PROF_T0(); mbar_wait_spin(bar_tempty(bb, as), aphase ^ 1u); PROF_ADD(w_tempty); }
     tc_fence_after();
     const uint32_t d_tmem = tmem_base + (uint32_t)as * block_n;
     for (int ka = 0; ka < num_ka; ++ka) {
-      mbar_wait(bar_afull(bb, sa), pa);
+      { PROF_T0(); mbar_wait_spin(bar_afull(bb, sa), pa); PROF_ADD(w_afull); }
       tc_fence_after();
       const uint32_t alo = a_lo0 + (uint32_t)sa * a_stage16;
 #pragma unroll
@@ -163,7 +180,7 @@ __device__ __forceinline__ void mma_role(const Params& p, uint32_t a_base, uint3
         if (BRES) {
           blo = b_lo0 + (uint32_t)(ka * TPA + tt) * b_stage16;
         } else {
-          mbar_wait(bar_bfull(bb, sb), pb);
+          mbar_wait_spin(bar_bfull(bb, sb), pb);
           tc_fence_after();
           blo = b_lo0 + (uint32_t)sb * b_stage16;
         }
@@ -171,7 +188,7 @@ __device__ __forceinline__ void mma_role(const Params& p, uint32_t a_base, uint3
         for (int kk = 0; kk < KSTEPS; ++kk) {
           const uint64_t da = ((uint64_t)hi_a << 32) | (uint64_t)(alo + tt * tap16 + 2 * kk);
           const uint64_t db = ((uint64_t)hi << 32) | (uint64_t)(blo + 2 * kk);
-          umma_bf16(d_tmem, da, db, idesc, (tt | kk) != 0 ? 1u : (ka != 0 ? 1u : 0u));
+          if (!EXP_ON(p, 1)) umma_bf16(d_tmem, da, db, idesc, (tt | kk) != 0 ? 1u : (ka != 0 ? 1u : 0u));
         }
         if (!BRES) {
           umma_commit(bar_bempty(bb, sb));
@@ -182,8 +199,11 @@ __device__ __forceinline__ void mma_role(const Params& p, uint32_t a_base, uint3
       if (++sa == a_stages) { sa = 0; pa ^= 1u; }
     }
     umma_commit(bar_tfull(bb, as));
-    if (++as == 2) { as = 0; aphase ^= 1u; }
+    if (++as == acc) { as = 0; aphase ^= 1u; }
   }
+#ifdef LY_TC_PROFILE
+  if (blockIdx.x == 0) printf("[tc prof] issuer: total %lld wait_afull %lld wait_tempty %lld\n", clock64() - istart, w_afull, w_tempty);
+#endif
 }
 
 // Pair mode issuer (streamed weights, one n tile, 4 * N <= 512 TMEM columns).  The 3x3 N = 128 layers stream
@@ -197,28 +217,29 @@ __device__ __forceinline__ void mma_role_pair(const Params& p, uint32_t a_base, 
   const uint32_t a_stage16 = (uint32_t)p.a_stage >> 4, b_stage16 = (uint32_t)p.b_stage >> 4, tap16 = (uint32_t)p.a_tap_stride >> 4;
   const uint32_t a_lo0 = (a_base >> 4) | (1u << 16), b_lo0 = (b_base >> 4) | (1u << 16);
   const uint32_t block_n = (uint32_t)p.block_n;
+  const int acc = p.acc;
   const int pairs = (total + 1) >> 1;
   int sa = 0, sb = 0, as = 0;
   uint32_t pa = 0, pb = 0, aphase = 0;
   for (int q = blockIdx.x; q < pairs; q += gridDim.x) {
     const bool two = 2 * q + 1 < total;
-    mbar_wait(bar_tempty(bb, as), aphase ^ 1u);
+    mbar_wait_spin(bar_tempty(bb, as), aphase ^ 1u);
     tc_fence_after();
     const uint32_t d0 = tmem_base + (uint32_t)(2 * as) * block_n, d1 = d0 + block_n;
     for (int ka = 0; ka < num_ka; ++ka) {
       const int s0 = sa;
-      mbar_wait(bar_afull(bb, s0), pa);
+      mbar_wait_spin(bar_afull(bb, s0), pa);
       if (++sa == a_stages) { sa = 0; pa ^= 1u; }
       const int s1 = sa;
       if (two) {
-        mbar_wait(bar_afull(bb, s1), pa);
+        mbar_wait_spin(bar_afull(bb, s1), pa);
         if (++sa == a_stages) { sa = 0; pa ^= 1u; }
       }
       tc_fence_after();
       const uint32_t alo0 = a_lo0 + (uint32_t)s0 * a_stage16, alo1 = a_lo0 + (uint32_t)s1 * a_stage16;
 #pragma unroll
       for (int tt = 0; tt < TPA; ++tt) {
-        mbar_wait(bar_bfull(bb, sb), pb);
+        mbar_wait_spin(bar_bfull(bb, sb), pb);
         tc_fence_after();
         const uint32_t blo = b_lo0 + (uint32_t)sb * b_stage16;
         const uint32_t acc = (tt != 0 || ka != 0) ? 1u : 0u;
@@ -241,7 +262,7 @@ __device__ __forceinline__ void mma_role_pair(const Params& p, uint32_t a_base, 
       if (two) umma_commit(bar_aempty(bb, s1));
     }
     umma_commit(bar_tfull(bb, as));
-    if (++as == 2) { as = 0; aphase ^= 1u; }
+    if (++as == acc) { as = 0; aphase ^= 1u; }
   }
 }
 
@@ -255,26 +276,36 @@ __device__ __forceinline__ void mma_role_band(const Params& p, uint32_t a_base, 
   const uint32_t row16 = (uint32_t)p.kc >> 3;                       // one pixel row of the tile, in 16-byte units
   const uint32_t a_lo0 = (a_base >> 4) | (1u << 16), b_lo0 = (b_base >> 4) | (1u << 16);
   const uint32_t block_n = (uint32_t)p.block_n;
+  const int acc = p.acc;
   const uint32_t bw16 = (uint32_t)p.band_w * row16;
   if (BRES) {
-    mbar_wait(bar_bres(bb), 0);
+    mbar_wait_spin(bar_bres(bb), 0);
     tc_fence_after();
   }
   int sa = 0, sb = 0, as = 0;
   uint32_t pa = 0, pb = 0, aphase = 0;
+  PROF_DECL(w_afull); PROF_DECL(w_tempty); PROF_DECL(t_issue); PROF_DECL(t_commit);
+#ifdef LY_TC_PROFILE
+  const long long istart = clock64();
+#endif
   for (int unit = blockIdx.x; unit < total; unit += gridDim.x) {
     {  // all channel blocks of this band have landed
+      PROF_T0();
       int s = sa; uint32_t ph = pa;
       for (int cb = 0; cb < kcb; ++cb) {
-        mbar_wait(bar_afull(bb, s), ph);
+        mbar_wait_spin(bar_afull(bb, s), ph);
         if (++s == a_stages) { s = 0; ph ^= 1u; }
       }
       tc_fence_after();
+      PROF_ADD(w_afull);
     }
     for (int nt = 0; nt < p.tiles_n; ++nt)
       for (int mt = 0; mt < p.band_mt; ++mt) {
-        mbar_wait(bar_tempty(bb, as), aphase ^ 1u);
+        { PROF_T0(); mbar_wait_spin(bar_tempty(bb, as), aphase ^ 1u); PROF_ADD(w_tempty); }
         tc_fence_after();
+#ifdef LY_TC_PROFILE
+        const long long ti0 = clock64();
+#endif
         const uint32_t d_tmem = tmem_base + (uint32_t)as * block_n;
         int s = sa;
         for (int cb = 0; cb < kcb; ++cb) {
@@ -285,7 +316,7 @@ __device__ __forceinline__ void mma_role_band(const Params& p, uint32_t a_base, 
             if (BRES) {
               blo = b_lo0 + (uint32_t)(tap * kcb + cb) * b_stage16;
             } else {
-              mbar_wait(bar_bfull(bb, sb), pb);
+              mbar_wait_spin(bar_bfull(bb, sb), pb);
               tc_fence_after();
               blo = b_lo0 + (uint32_t)sb * b_stage16;
             }
@@ -294,7 +325,7 @@ __device__ __forceinline__ void mma_role_band(const Params& p, uint32_t a_base, 
             for (int kk = 0; kk < KSTEPS; ++kk) {
               const uint64_t da = ((uint64_t)hi << 32) | (uint64_t)(at + 2 * kk);
               const uint64_t db = ((uint64_t)hi << 32) | (uint64_t)(blo + 2 * kk);
-              umma_bf16(d_tmem, da, db, idesc, (tap | kk) != 0 ? 1u : (cb != 0 ? 1u : 0u));
+              if (!EXP_ON(p, 1)) umma_bf16(d_tmem, da, db, idesc, (tap | kk) != 0 ? 1u : (cb != 0 ? 1u : 0u));
             }
             if (!BRES) {
               umma_commit(bar_bempty(bb, sb));
@@ -303,14 +334,24 @@ __device__ __forceinline__ void mma_role_band(const Params& p, uint32_t a_base, 
           }
           if (++s == a_stages) s = 0;
         }
+#ifdef LY_TC_PROFILE
+        const long long ti1 = clock64();
+        t_issue += ti1 - ti0;
+#endif
         umma_commit(bar_tfull(bb, as));
-        if (++as == 2) { as = 0; aphase ^= 1u; }
+#ifdef LY_TC_PROFILE
+        t_commit += clock64() - ti1;
+#endif
+        if (++as == acc) { as = 0; aphase ^= 1u; }
       }
     for (int cb = 0; cb < kcb; ++cb) {   // the band's tiles are free once everything issued so far has completed
       umma_commit(bar_aempty(bb, sa));
       if (++sa == a_stages) { sa = 0; pa ^= 1u; }
     }
   }
+#ifdef LY_TC_PROFILE
+  if (blockIdx.x == 0) printf("[tc prof] band issuer: total %lld wait_afull %lld wait_tempty %lld issue %lld commit %lld\n", clock64() - istart, w_afull, w_tempty, t_issue, t_commit);
+#endif
 }
 
 // Band mode with the kx taps folded into N (resident weights only): per M tile 3 * kc_blocks * KSTEPS MMAs of N = 3*Cout.
@@ -324,8 +365,9 @@ __device__ __forceinline__ void mma_role_fold(const Params& p, uint32_t a_base, 
   const uint32_t row16 = (uint32_t)p.kc >> 3;
   const uint32_t a_lo0 = (a_base >> 4) | (1u << 16), b_lo0 = (b_base >> 4) | (1u << 16);
   const uint32_t acc_cols = 3u * (uint32_t)p.block_n;
+  const int acc = p.acc;
   const uint32_t bw16 = (uint32_t)p.band_w * row16;
-  mbar_wait(bar_bres(bb), 0);
+  mbar_wait_spin(bar_bres(bb), 0);
   tc_fence_after();
   int sa = 0, as = 0;
   uint32_t pa = 0, aphase = 0;
@@ -333,13 +375,13 @@ __device__ __forceinline__ void mma_role_fold(const Params& p, uint32_t a_base, 
     {
       int s = sa; uint32_t ph = pa;
       for (int cb = 0; cb < kcb; ++cb) {
-        mbar_wait(bar_afull(bb, s), ph);
+        mbar_wait_spin(bar_afull(bb, s), ph);
         if (++s == a_stages) { s = 0; ph ^= 1u; }
       }
       tc_fence_after();
     }
     for (int mt = 0; mt < p.band_mt; ++mt) {
-      mbar_wait(bar_tempty(bb, as), aphase ^ 1u);
+      mbar_wait_spin(bar_tempty(bb, as), aphase ^ 1u);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)as * acc_cols;
       int s = sa;
@@ -359,7 +401,7 @@ __device__ __forceinline__ void mma_role_fold(const Params& p, uint32_t a_base, 
         if (++s == a_stages) s = 0;
       }
       umma_commit(bar_tfull(bb, as));
-      if (++as == 2) { as = 0; aphase ^= 1u; }
+      if (++as == acc) { as = 0; aphase ^= 1u; }
     }
     for (int cb = 0; cb < kcb; ++cb) {
       umma_commit(bar_aempty(bb, sa));
@@ -459,7 +501,7 @@ __device__ __forceinline__ void epilogue_role(const Params& p, uint8_t* smem_raw
   // Slot layout: piece-major ([stage][2*round + half][epilogue thread] x 16 bytes), so the 32 lanes of a
   // warp touch 32 consecutive 16-byte words: thread-major slots (64-byte stride per lane) cost a 4-way
   // bank conflict on every cp.async write and LDS.128 read (ncu: 11.8 M conflicts, 28 % short-scoreboard stalls).
-  const uint32_t r_base = bar_base + 8u * (4 * kMaxStages + 8);
+  const uint32_t r_base = bar_base + 8u * kBarSlots;
   const uint32_t rslot = r_base + (uint32_t)(threadIdx.x - 64) * 16u;
   constexpr uint32_t kPiece = 32u * kEpiWarps * 16u;                    // bytes between pieces
   const uint32_t rstage = (uint32_t)(32 * kEpiWarps) * p.res_slot;
@@ -478,6 +520,7 @@ __device__ __forceinline__ void epilogue_role(const Params& p, uint8_t* smem_raw
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
   int as = 0;
+  const int acc = p.acc;
   uint32_t aphase = 0, rs = 0;
   // fold: exchange slots for the rows that cross a TMEM lane quarter: [parity][cg][q][48 floats]
   float* exch = reinterpret_cast<float*>(smem_raw + ((bar_base + p.exch_off) - smem_u32(smem_raw)));
@@ -519,6 +562,17 @@ __device__ __forceinline__ void epilogue_role(const Params& p, uint8_t* smem_raw
     }
     if (cur.first && !tpre) { PROF_T0(); mbar_wait(bar_tfull(bar_base, as), aphase); PROF_ADD(w_tfull); }
     tc_fence_after();
+    if (EXP_ON(p, 2)) {
+      if (cur.last) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_tempty(bar_base, as));
+        if (++as == acc) { as = 0; aphase ^= 1u; }
+      }
+      rs ^= 1u;
+      cur = nxtloc;
+      continue;
+    }
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(((pair ? 2 * as : as) + cur.sub) * (FOLD ? 3 * p.block_n : p.block_n));
     if (cg < nchunks && !tpre) tmem_ld16(taddr + cg * 16, nxt);
     tpre = false;
@@ -587,8 +641,8 @@ __device__ __forceinline__ void epilogue_role(const Params& p, uint8_t* smem_raw
           if (lane == 0) mbar_arrive(bar_tempty(bar_base, as));
         }
         if (xpre && has && nxtloc.more && cg < nchunks) {
-          const int as2 = as ^ 1;
-          const uint32_t ph2 = as == 1 ? aphase ^ 1u : aphase;
+          const int as2 = as + 1 == acc ? 0 : as + 1;
+          const uint32_t ph2 = as2 == 0 ? aphase ^ 1u : aphase;
           if (mbar_test(bar_tfull(bar_base, as2), ph2)) {
             tc_fence_after();
             tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as2 * p.block_n) + cg * 16, nxt);
@@ -642,7 +696,7 @@ __device__ __forceinline__ void epilogue_role(const Params& p, uint8_t* smem_raw
         }
       }
     }
-    if (cur.last && ++as == 2) { as = 0; aphase ^= 1u; }
+    if (cur.last && ++as == acc) { as = 0; aphase ^= 1u; }
     rs ^= 1u;
     cur = nxtloc;
   }
@@ -650,6 +704,194 @@ __device__ __forceinline__ void epilogue_role(const Params& p, uint8_t* smem_raw
 #ifdef LY_TC_PROFILE
   if (blockIdx.x == 0 && lane == 0 && (warp == 2 || warp == 6))
     printf("[tc prof] epilogue warp %d: total %lld wait_tfull %lld\n", warp, clock64() - estart, w_tfull);
+#endif
+}
+
+// ------------------------------------------------------------------ tile-parallel epilogue
+// Knock-out runs (tools/exp_knockout.sh, -DLY_TC_EXP) and per-role cycle accounting (-DLY_TC_PROFILE) showed that the
+// column-parallel role above costs ~1400-1600 cycles per 128-pixel tile whether the tile has 32 or 64 columns: with
+// N <= 64 every warp handles ONE 16-column chunk per tile (N = 32: half of the warps have none), so the per-tile work
+// of a warp (item arithmetic, barrier wait, arrival, pointers: ~130 instructions) is paid 16 times per tile for ~45
+// instructions of real work each.  Here the 16 warps are G = 4 tile groups: a tile group owns every 4th tile of the
+// issue order and its four warps (one per TMEM lane quarter) walk ALL the chunks of their rows, so the per-tile overhead
+// is paid 4 times per tile and a thread's NHWC stores are consecutive 32-byte pieces of one pixel row.  Four tiles are in
+// flight in the epilogue, which the TMEM stages (p.acc >= 4, i.e. N <= 128) make possible.
+// The shortcut / half-resolution addend is read directly, one chunk ahead (the slots of the other role would need
+// nchunks x 32 bytes per thread).
+template <int MAP, int ADD, bool NCHW>
+__device__ __forceinline__ void epilogue_tiles(const Params& p, uint32_t bar_base, uint32_t tmem_base, const float* s_bias) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = warp & 3;
+  constexpr int G = 4, CS = 1, cs = 0;     // (N > 128 keeps the column-parallel role: its per-tile overhead is amortised over 4 rounds)
+  const int tg = (warp - 2) >> 2;          // tile group 0..3
+  const int nchunks = p.block_n >> 4;
+  const int acc = p.acc;
+  const uint32_t row = (uint32_t)(q * 32 + lane);
+  const bool act = p.act != 0;
+  const float pre = act ? 0.5f : 1.0f;
+  constexpr bool kUp = ADD == 4;
+  constexpr bool kRes = ADD == 3;
+  uint32_t dw = 0, dh = 0, db = 0;
+  if (MAP == 1) { dw = row % (uint32_t)p.tw; dh = (row / (uint32_t)p.tw) % (uint32_t)p.th; db = row / (uint32_t)(p.tw * p.th); }
+
+  // position in the issue order: (unit, n tile, M tile) in band mode, one tile per step otherwise
+  int it_unit = blockIdx.x, it_nt = 0, it_mt = 0;
+  auto advance = [&]() {
+    if (MAP == 2) {
+      if (++it_mt == p.band_mt) { it_mt = 0; if (++it_nt == p.tiles_n) { it_nt = 0; it_unit += gridDim.x; } }
+    } else {
+      it_unit += gridDim.x;
+    }
+  };
+  for (int i = 0; i < tg; ++i) advance();
+  int as = tg;
+  uint32_t aphase = 0;
+  PROF_DECL(w_tfull);
+#ifdef LY_TC_PROFILE
+  const long long estart = clock64();
+#endif
+  while (it_unit < p.total_tiles) {
+    // ---- locate this thread's pixel
+    bool valid;
+    uint32_t lin;
+    int n0;
+    if (MAP == 2) {
+      const uint32_t pu = (uint32_t)phys(p, it_unit);
+      const uint32_t b = p.mg_bands ? __umulhi(pu, p.mg_bands) : pu;
+      const uint32_t bd = pu - b * (uint32_t)p.bands;
+      const uint32_t m = (uint32_t)it_mt * 128u + row;
+      const uint32_t oy = __umulhi(m, p.mg_bw), ox = m - oy * (uint32_t)p.band_w;
+      const uint32_t h = bd * (uint32_t)p.band_r + oy;
+      valid = ox < (uint32_t)p.Wo && oy < (uint32_t)p.band_r && h < (uint32_t)p.Ho;
+      lin = (b * (uint32_t)p.Ho + h) * (uint32_t)p.Wo + ox;
+      n0 = it_nt * p.block_n;
+    } else if (MAP == 0) {
+      const uint32_t t = (uint32_t)phys(p, it_unit);
+      const uint32_t qn = p.mg_n ? __umulhi(t, p.mg_n) : t;
+      n0 = (int)(t - qn * (uint32_t)p.tiles_n) * p.block_n;
+      lin = qn * 128u + row;
+      valid = lin < (uint32_t)p.Wo;
+    } else {
+      int nt, wt, ht, bt;
+      split_tile(p, it_unit, nt, wt, ht, bt);
+      const uint32_t w = (uint32_t)(wt * p.tw) + dw, h = (uint32_t)(ht * p.th) + dh, b = (uint32_t)(bt * p.tb) + db;
+      valid = w < (uint32_t)p.Wo && h < (uint32_t)p.Ho && b < (uint32_t)p.Bo;
+      lin = (b * (uint32_t)p.Ho + h) * (uint32_t)p.Wo + w;
+      n0 = nt * p.block_n;
+    }
+    const __nv_bfloat16* arow = nullptr;
+    if (kRes && valid) arow = p.res + (size_t)lin * (uint32_t)p.rCtot + p.rC0 + n0;
+    if (kUp && valid) {
+      const uint32_t ub = lin / (uint32_t)p.hw_real, urem = lin - ub * (uint32_t)p.hw_real;
+      const uint32_t uh = urem / (uint32_t)p.Wreal, uw = urem - uh * (uint32_t)p.Wreal;
+      arow = p.up + (size_t)((ub * (uint32_t)p.uH + (uh >> 1)) * (uint32_t)p.uW + (uw >> 1)) * (uint32_t)p.uCtot + p.uC0 + n0;
+    }
+    __nv_bfloat16* drow = nullptr;
+    float* nrow = nullptr;
+    if (NCHW) {
+      if (valid) {
+        const uint32_t nb = lin / (uint32_t)p.hw_real;
+        nrow = p.nchw + (size_t)(nb * (uint32_t)p.nCtot + (uint32_t)(p.nC0 + n0)) * (uint32_t)p.hw_real + (lin - nb * (uint32_t)p.hw_real);
+      }
+    } else if (valid) {
+      drow = p.dst + (size_t)lin * (uint32_t)p.dCtot + p.dC0 + n0;
+    }
+    // the addend of the first chunk is requested before the accumulator wait
+    uint4 a0 = make_uint4(0, 0, 0, 0), a1 = a0;
+    if ((kRes || kUp) && arow && cs < nchunks) {
+      a0 = *reinterpret_cast<const uint4*>(arow + cs * 16);
+      a1 = *reinterpret_cast<const uint4*>(arow + cs * 16 + 8);
+    }
+    { PROF_T0(); mbar_wait(bar_tfull(bar_base, as), aphase); PROF_ADD(w_tfull); }
+    tc_fence_after();
+    if (EXP_ON(p, 2)) {
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty(bar_base, as));
+    } else {
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * p.block_n);
+    uint32_t nxt[16];
+    if (cs < nchunks) tmem_ld16(taddr + cs * 16, nxt);
+    else {   // (a column group without chunks: N < 16 * CS)
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty(bar_base, as));
+    }
+    for (int ch = cs; ch < nchunks; ch += CS) {
+      const int c = ch * 16;
+      float v[16];
+      tmem_ld_wait();
+      const float4* bp = reinterpret_cast<const float4*>(s_bias + n0 + c);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 bb = bp[j];
+        ffma2(v[4 * j + 0], v[4 * j + 1], __uint_as_float(nxt[4 * j + 0]), __uint_as_float(nxt[4 * j + 1]), pre, pre, bb.x, bb.y);
+        ffma2(v[4 * j + 2], v[4 * j + 3], __uint_as_float(nxt[4 * j + 2]), __uint_as_float(nxt[4 * j + 3]), pre, pre, bb.z, bb.w);
+      }
+      const uint4 r0 = a0, r1 = a1;
+      if (ch + CS < nchunks) {
+        tmem_ld16(taddr + c + 16 * CS, nxt);   // next chunk in flight during the activation / store of this one
+        if ((kRes || kUp) && arow) {
+          a0 = *reinterpret_cast<const uint4*>(arow + c + 16 * CS);
+          a1 = *reinterpret_cast<const uint4*>(arow + c + 16 * CS + 8);
+        }
+      } else {                                  // the last chunk of this warp sits in registers: release the stage
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_tempty(bar_base, as));
+      }
+      if (kRes || kUp) {
+        float rv[16];
+        const __nv_bfloat162* h0 = reinterpret_cast<const __nv_bfloat162*>(&r0);
+        const __nv_bfloat162* h1 = reinterpret_cast<const __nv_bfloat162*>(&r1);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f0 = __bfloat1622float2(h0[j]), f1 = __bfloat1622float2(h1[j]);
+          rv[2 * j] = f0.x; rv[2 * j + 1] = f0.y; rv[8 + 2 * j] = f1.x; rv[8 + 2 * j + 1] = f1.y;
+        }
+        if (kUp) {    // pre-activation addend (the low-resolution half of a folded upsample + concat + 1x1)
+#pragma unroll
+          for (int j = 0; j < 16; j += 2) ffma2(v[j], v[j + 1], rv[j], rv[j + 1], pre, pre, v[j], v[j + 1]);
+          if (act) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 2) silu2_from_half(v[j], v[j + 1]);
+          }
+        } else {      // shortcut: added after the activation
+          if (act) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 2) silu2_from_half(v[j], v[j + 1]);
+          }
+#pragma unroll
+          for (int j = 0; j < 16; j += 2) fadd2(v[j], v[j + 1], v[j], v[j + 1], rv[j], rv[j + 1]);
+        }
+      } else if (act) {
+#pragma unroll
+        for (int j = 0; j < 16; j += 2) silu2_from_half(v[j], v[j + 1]);
+      }
+      if (NCHW) {
+        if (nrow) {
+          float* np = nrow + (size_t)c * (uint32_t)p.hw_real;
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (n0 + c + j < p.nC) np[(size_t)j * (uint32_t)p.hw_real] = v[j];
+        }
+      } else if (drow) {
+        if (p.st256) {
+          store_bf16x16(drow + c, v);
+        } else {
+          store_vec<__nv_bfloat16>(drow + c, v);
+          store_vec<__nv_bfloat16>(drow + c + 8, v + 8);
+        }
+      }
+    }
+    }
+    for (int i = 0; i < G; ++i) advance();
+    as += G;
+    if (as >= acc) { as -= acc; aphase ^= 1u; }
+  }
+#ifdef LY_TC_PROFILE
+  if (blockIdx.x == 0 && lane == 0 && (warp == 2 || warp == 6))
+    printf("[tc prof] tile epilogue warp %d: total %lld wait_tfull %lld\n", warp, clock64() - estart, w_tfull);
 #endif
 }
 
@@ -668,9 +910,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   auto bfull_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + s); };
   auto bempty_bar = [&](int s) { return bar_base + 8u * (3 * kMaxStages + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (4 * kMaxStages + s); };
-  auto tempty_bar = [&](int s) { return bar_base + 8u * (4 * kMaxStages + 2 + s); };
-  const uint32_t bres_bar = bar_base + 8u * (4 * kMaxStages + 4);
-  const uint32_t tmem_slot = bar_base + 8u * (4 * kMaxStages + 5);
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (4 * kMaxStages + kMaxAcc + s); };
+  const uint32_t bres_bar = bar_base + 8u * (4 * kMaxStages + 2 * kMaxAcc);
+  const uint32_t tmem_slot = bar_base + 8u * (4 * kMaxStages + 2 * kMaxAcc + 1);
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -687,9 +929,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       mbar_init(bfull_bar(s), 1);
       mbar_init(bempty_bar(s), 1);
     }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < kMaxAcc; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), kEpiWarps);
+      mbar_init(tempty_bar(s), p.epi_groups ? kEpiWarps / p.epi_groups : kEpiWarps);
     }
     mbar_init(bres_bar, 1);
     fence_barrier_init();
@@ -742,10 +984,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 #endif
       const bool bres = p.b_resident != 0;
       const uint32_t a_box = (uint32_t)p.a_box, b_box = (uint32_t)p.b_box;
+      int exp_loaded = 0; (void)exp_loaded;
       auto load_a = [&](int c0, int w, int h, int b) {
         { PROF_T0(); mbar_wait(aempty_bar(sa), pa ^ 1u); PROF_ADD(w_aempty); }
-        mbar_expect_tx(afull_bar(sa), a_box);
-        tma_load_4d(a_base + sa * p.a_stage, &p.tmA, afull_bar(sa), c0, w, h, b);
+        if (EXP_ON(p, 4) && exp_loaded >= p.a_stages) {
+          mbar_arrive(afull_bar(sa));
+        } else {
+          ++exp_loaded;
+          mbar_expect_tx(afull_bar(sa), a_box);
+          tma_load_4d(a_base + sa * p.a_stage, &p.tmA, afull_bar(sa), c0, w, h, b);
+        }
         if (++sa == p.a_stages) { sa = 0; pa ^= 1u; }
       };
       auto load_b = [&](int kcol, int n0) {
@@ -867,6 +1115,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   else if (add == 2) LY_EPI(M, 2, false);                       \
   else if (add == 3) LY_EPI(M, 3, false);                       \
   else LY_EPI(M, 4, false);
+#define LY_EPT(M, A, N) epilogue_tiles<M, A, N>(p, bar_base, tmem_base, s_bias)
+#define LY_EPT_MAP(M)                                           \
+  if (p.nchw) LY_EPT(M, 0, true);                               \
+  else if (add == 0) LY_EPT(M, 0, false);                       \
+  else if (add == 3) LY_EPT(M, 3, false);                       \
+  else LY_EPT(M, 4, false);
+    if (p.epi_groups) {
+      if (map == 0) { LY_EPT_MAP(0) } else if (map == 1) { LY_EPT_MAP(1) } else { LY_EPT_MAP(2) }
+    } else
+#undef LY_EPT_MAP
     if (p.fold) {
       if (add == 0) epilogue_role<2, 0, false, true>(p, smem_raw, bar_base, tmem_base, s_bias);
       else if (add == 1) epilogue_role<2, 1, false, true>(p, smem_raw, bar_base, tmem_base, s_bias);
@@ -999,6 +1257,8 @@ int32_t conv_tc_prepare(const ly_op& op, ConvTcState** out) {
                        b_res_possible && !p.pair && !op.up.ptr && !op.nchw && op.dst.ptr;
   const int m_step = fold_ok ? 126 : 128;
   const long long exch_bytes = fold_ok ? 2LL * 4 * 4 * 48 * 4 : 0;
+  // (the tile-parallel epilogue reads the shortcut directly: no prefetch slots)
+  const bool will_ept = env_int("LY_TC_EPT", 1) && !p.pair && !fold_ok && std::min(512 / bn, env_int("LY_TC_ACC", kMaxAcc)) >= 4;
   if (band_ok && !p.pair && op.k == 3 && op.stride == 1 && Wo + 2 <= 256 && 2 * p.kc_blocks <= kMaxStages) {
     const int sms = sm_count();
     const int nf = 3 * bn;
@@ -1009,7 +1269,7 @@ int32_t conv_tc_prepare(const ly_op& op, ConvTcState** out) {
     const double cost_now = waves(total) * (p.halo ? (double)std::max(p.num_kb * cyc_mma, 3.0 * p.kc_blocks * (p.tw * (p.th + 2)) * tma_row)
                                                    : (double)std::max(p.num_kb * cyc_mma, 9.0 * p.kc_blocks * 128 * tma_row));
     const int BW = Wo + 2;
-    const long long fixed = 8 * (4 * kMaxStages + 8) + 1024 + exch_bytes + (op.res.ptr && bn <= 128 ? 2LL * 32 * kEpiWarps * (((bn / 16 + 3) / 4) * 32) : 0);
+    const long long fixed = 8 * kBarSlots + 1024 + exch_bytes + (op.res.ptr && bn <= 128 && !will_ept ? 2LL * 32 * kEpiWarps * (((bn / 16 + 3) / 4) * 32) : 0);
     const long long b_bytes = b_res_possible ? b_all_bytes : 3LL * ((bn * p.kc * 2 + 1023) / 1024 * 1024);
     int best_r = 0; double best_cost = 1e30;
     for (int R = 1; R <= Ho && R + 2 <= 256; ++R) {
@@ -1067,10 +1327,17 @@ int32_t conv_tc_prepare(const ly_op& op, ConvTcState** out) {
   const long long b_all = p.fold ? (long long)p.num_kb * p.b_box : (long long)p.num_kb * p.b_stage;
   static const int resident_ok = env_int("LY_TC_B_RESIDENT", 1);
   p.b_resident = (resident_ok && p.tiles_n == 1 && b_all <= 96 * 1024) ? 1 : 0;
-  const uint32_t bar_bytes = 8 * (4 * kMaxStages + 8);
+  const uint32_t bar_bytes = 8 * kBarSlots;
   // shortcut prefetch slots: 2 stages x 512 epilogue threads x (chunks per warp x 32 B); only while small
+  // tile-parallel epilogue (see epilogue_tiles): whenever the TMEM stages allow >= 2 tiles in flight
+  static const int ept_env = env_int("LY_TC_EPT", 1);
+  {
+    const int per = bn;   // (pair and fold keep the column-parallel role)
+    const int acc_max = std::min(512 / per, std::min(env_int("LY_TC_ACC", kMaxAcc), (int)kMaxAcc));
+    p.epi_groups = (ept_env && !p.pair && !p.fold && acc_max >= 4) ? 4 : 0;
+  }
   static const int res_prefetch_ok = env_int("LY_TC_RES_PREFETCH", 1);
-  p.res_slot = (((op.res.ptr != nullptr) != (op.up.ptr != nullptr)) && res_prefetch_ok && bn <= 128) ? ((bn / 16 + 3) / 4) * 32 : 0;   // one 32-byte chunk per round
+  p.res_slot = p.epi_groups ? 0 : (((op.res.ptr != nullptr) != (op.up.ptr != nullptr)) && res_prefetch_ok && bn <= 128) ? ((bn / 16 + 3) / 4) * 32 : 0;   // one 32-byte chunk per round
   const long long res_bytes = 2LL * 32 * kEpiWarps * p.res_slot;
   const long long x_bytes = p.fold ? 2LL * 4 * 4 * 48 * 4 : 0;      // fold: boundary-row exchange slots of the epilogue
   p.exch_off = (uint32_t)(bar_bytes + res_bytes);
@@ -1105,6 +1372,22 @@ int32_t conv_tc_prepare(const ly_op& op, ConvTcState** out) {
              (size_t)res_bytes + (size_t)x_bytes;
   if (st->smem < 120 * 1024) st->smem = 120 * 1024;  // force one CTA per SM (TMEM allocations must not contend)
 
+  // TMEM accumulator stages.  Knock-out runs (-DLY_TC_EXP) showed that with two stages the thin layers are bound by the
+  // issuer -> epilogue -> issuer round trip of an accumulator (commit, mbarrier wake-ups, 16 arrivals: ~1400 cycles), not
+  // by the MMAs or the epilogue's work: per tile max(T_mma, T_epi, (T_mma + T_epi + L) / stages).  All 512 columns are ours
+  // (one CTA per SM), so use as many stages as fit.
+  {
+    static const int acc_env = env_int("LY_TC_ACC", kMaxAcc);
+    const int per = p.fold ? 3 * bn : (p.pair ? 2 * bn : bn);
+    int acc = 512 / per;
+    if (acc > acc_env) acc = acc_env;
+    if (acc > kMaxAcc) acc = kMaxAcc;
+    if (acc < 2) acc = 2;
+    p.acc = acc;
+    p.tmem_cols = pow2_ge(acc * per);
+    if (p.tmem_cols > 512) { delete st; set_error("conv_tc: accumulators exceed TMEM"); return LY_E_ARG; }
+  }
+
   // descriptors
   const int swz = p.kc == 64 ? 2 : (p.kc == 32 ? 4 : 6);       // UMMA LayoutType: SW128 / SW64 / SW32
   const uint32_t sbo = (uint32_t)(8 * p.kc * 2) >> 4;          // 8-row group stride, 16-byte units
@@ -1117,6 +1400,8 @@ int32_t conv_tc_prepare(const ly_op& op, ConvTcState** out) {
   // (measured: neutral -- conv_tc total 9.45 vs 9.49 ms per step, step time within run-to-run noise; off by default)
   static const int xpre_env = env_int("LY_TC_XPRE", 0);
   p.xpre = xpre_env;
+  static const int exp_env = env_int("LY_TC_EXP", 0);
+  p.exp = exp_env;
   p.idesc_fold = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((3 * bn) >> 3) << 17) | ((128u >> 4) << 24);
 
   const CUtensorMapSwizzle tswz = p.kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (p.kc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);

@@ -50,6 +50,26 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     }
   }
 }
+// Spinning wait for a single latency-critical thread (the MMA issuer): no suspend, the thread re-polls at once.
+__device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity) {
+#ifdef LY_MBAR_SPIN_ISSUER
+  uint32_t done = 0;
+  for (uint32_t it = 0; it < (1u << 30); ++it) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) return;
+  }
+  printf("leanyolo_b200: mbarrier spin timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
+  __trap();
+#else
+  mbar_wait(bar, parity);
+#endif
+}
 // non-blocking: has the phase with this parity completed?
 __device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
   uint32_t done = 0;

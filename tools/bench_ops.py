@@ -34,7 +34,7 @@ def parse(spec):
     return kind, kw
 
 
-def run(spec, iters=5):
+def run(spec, iters=int(os.environ.get("LY_BENCH_ITERS", "5"))):
     kind, kw = parse(spec)
     B = kw.get("B", 256)
     hw = kw.get("hw", 80)
