@@ -16,6 +16,8 @@ Fixtures
                              640x640 pyramid, nc=80) + reg_max=1 / max_det edge cases
   decode_nms.pt              reference decode_v10_predictions (two threshold settings)
   nms.pt                     reference box_ops.nms keep indices on seeded boxes
+  forward640_yolov10s.pt     reference eval forward of yolov10s @640x640, batch 1 (the headline resolution): 2048 sampled
+                             positions + double-precision sum / abs-sum of each of the six head tensors
   decode_export.pt           reference YOLOv10ONNXExport.forward (export.py:126-198: top-k with conf mask + clamp, and the
                              class-wise pre-top-k NMS through the real torchvision.ops.nms) on seeded head logits
 """
@@ -152,11 +154,36 @@ def main() -> None:
     print(f"golden dir: {total / 1e6:.2f} MB")
 
 
+def make_640() -> None:
+    """One full-resolution reference fixture (round-1 verdict: the 64x64 fixtures pin the oracle, 640x640 parity rested
+    on the oracle alone).  The six head tensors are 8400 x 144 floats each: store seeded samples and checksums."""
+    name, sw, si = "yolov10s", 301, 302
+    model = ref_get_model(name, weights=None, class_names=NAMES).eval()
+    model.load_state_dict(synth_state_dict(model.state_dict(), seed=sw, gain=GAIN), strict=True)
+    x = synth_images(1, 640, 640, seed=si)
+    with torch.no_grad():
+        one2many = model(x)
+        one2one = model._eval_branches["one2one"]
+    g = torch.Generator().manual_seed(303)
+    out = {"seed_weights": sw, "seed_input": si, "gain": GAIN, "hw": 640, "n_samples": 2048, "seed_samples": 303}
+    for br, ts in (("one2many", one2many), ("one2one", one2one)):
+        for i, t in enumerate(ts):
+            idx = torch.randint(0, t.numel(), (2048,), generator=g)
+            out[f"{br}{i}"] = {"shape": list(t.shape), "idx": idx, "val": t.flatten()[idx].clone(),
+                               "sum": float(t.double().sum()), "abs_sum": float(t.double().abs().sum()),
+                               "abs_max": float(t.abs().max())}
+            print(name, 640, br, i, tuple(t.shape), out[f"{br}{i}"]["abs_sum"])
+    torch.save(out, os.path.join(OUT, "forward640_yolov10s.pt"))
+
+
 if __name__ == "__main__":
-    if "--only-export" in sys.argv:      # regenerate decode_export.pt alone (the other fixtures are unchanged)
+    if "--only-640" in sys.argv:
+        make_640()
+    elif "--only-export" in sys.argv:      # regenerate decode_export.pt alone (the other fixtures are unchanged)
         _src = open(__file__).read()
         _body = _src[_src.index("    # ---- export-style fixed-shape outputs"):_src.index("    total = sum(")]
         hw = [(80, 80), (40, 40), (20, 20)]
         exec(compile("if True:\n" + _body, __file__, "exec"))
     else:
         main()
+        make_640()

@@ -95,22 +95,51 @@ def _canon(d):
     return d[idx]
 
 
+def flip_count(a, b):
+    """Rows of `a` without a counterpart in `b` plus rows of `b` without one in `a` (counterpart: same label,
+    |score difference| <= 1e-5, box corners within 1e-2 px).  Both sides decode the same logits; the GPU's DFL
+    (CUDA expf) and torch's CPU softmax differ by ulps, so a greedy-NMS decision whose IoU sits within an ulp of
+    the threshold may flip, and one flip can change a few later rows."""
+    if a.numel() == 0 or b.numel() == 0:
+        return int(a.shape[0] + b.shape[0])
+    same = ((a[:, None, :4] - b[None, :, :4]).abs().amax(-1) < 1e-2) & ((a[:, None, 4] - b[None, :, 4]).abs() <= 1e-5) & \
+           (a[:, None, 5] == b[None, :, 5])
+    return int((~same.any(1)).sum() + (~same.any(0)).sum())
+
+
+def nms_on_oracle_candidates(logits, conf, iou, max_det, classwise=False):
+    """The exact half of the end-to-end claim: the oracle decodes the candidates (boxes, best score, label) and BOTH
+    sides run NMS on those identical tensors: keep-sets must be equal, element for element."""
+    boxes, scores = O._dfl_boxes_scores(logits, 80, (8, 16, 32))
+    best, label = scores.max(-1)
+    kept = 0
+    for i in range(boxes.shape[0]):
+        cand = torch.nonzero(best[i] > conf).flatten()
+        if cand.numel() == 0:
+            continue
+        bi, si, li = boxes[i, cand].contiguous(), best[i, cand].contiguous(), label[i, cand].contiguous()
+        ref = O.nms_classwise(bi, si, li, iou, max_det) if classwise else O.nms(bi, si, iou, max_det)[:max_det]
+        got = PP.nms(bi.to(DEV), si.to(DEV), iou, labels=li.to(DEV) if classwise else None, max_keep=max_det).cpu()
+        assert torch.equal(got, ref[:max_det]), f"image {i}: keep-set on identical candidates differs ({len(got)} vs {len(ref)})"
+        kept += int(got.numel())
+    return kept
+
+
 def check_decode_nms(conf, iou, cls_mean, seed, B=2, classwise=False):
     logits = synth_head_logits(B, 80, HW640, seed=seed, cls_mean=cls_mean)
+    kept_exact = nms_on_oracle_candidates(logits, conf, iou, 300, classwise)
     ref = O.decode_nms(logits, num_classes=80, conf_thresh=conf, iou_thresh=iou, max_det=300, classwise=classwise)
     got = PP.decode_v10_predictions([t.to(DEV) for t in logits], num_classes=80, conf_thresh=conf, iou_thresh=iou,
                                     max_det=300, classwise=classwise)
-    same = 0
+    rows = flips = 0
     for r, g_ in zip(ref, got):
         a, b = _canon(r[0]), _canon(g_[0].cpu())
         assert a.shape == b.shape, (a.shape, b.shape)
-        if a.numel():
-            # boxes are decoded on the GPU (ulp-level differences) so borderline IoU decisions may
-            # flip; demand identical detections for >= 99% of rows
-            close = ((a - b).abs().max(1)[0] < 1e-2).float().mean()
-            assert close >= 0.99, f"only {float(close):.3f} of rows match"
-            same += int(close * a.shape[0])
-    return {"rows": same}
+        rows += a.shape[0]
+        flips += flip_count(a, b)
+    # end to end the boxes are decoded on each side (ulp-level differences): report the flips, bound them at 1 %
+    assert flips <= max(2, rows // 100), f"{flips} of {rows} rows differ end to end"
+    return {"rows": rows, "flips_end_to_end": flips, "kept_exact_on_identical_candidates": kept_exact}
 
 
 def check_decode_nms_direct():

@@ -73,6 +73,28 @@ def check_model_golden(name="yolov10s"):
     return {"max_relmax": worst}
 
 
+def check_model_golden_640(precision="bf16"):
+    """The CUDA path against the REFERENCE's own yolov10s @640x640 outputs (tests/golden/forward640_yolov10s.pt: 2048
+    sampled positions + abs-sum checksum per head tensor): bf16 within 2e-2, fp32 check mode within 1e-4."""
+    g = torch.load(os.path.join(G, "forward640_yolov10s.pt"))
+    m, _ = build("yolov10s", seed=g["seed_weights"], gain=g["gain"], precision=precision)
+    x = synth_images(1, g["hw"], g["hw"], seed=g["seed_input"])
+    raw = m(x.to(DEV))
+    tol = 2e-2 if precision == "bf16" else 1e-4
+    worst = 0.0
+    for br, ts in (("one2many", raw), ("one2one", m._eval_branches["one2one"])):
+        for i in range(3):
+            ref = g[f"{br}{i}"]
+            t = ts[i].float().cpu()
+            assert list(t.shape) == ref["shape"]
+            err = float((t.flatten()[ref["idx"]] - ref["val"]).abs().max()) / ref["abs_max"]
+            worst = max(worst, err)
+            assert err < tol, f"{br}{i}: {err:.2e} vs the reference golden at 640x640"
+            csum = abs(float(t.double().abs().sum()) - ref["abs_sum"]) / ref["abs_sum"]
+            assert csum < tol, f"{br}{i}: abs-sum checksum off by {csum:.2e}"
+    return {"max_relmax": worst}
+
+
 def check_subbatch_and_graph(name="yolov10s"):
     """A plan built for a sub-batch swept over the batch, and the same forward replayed from a
     CUDA graph, must give bit-identical head tensors to the one-shot run."""
@@ -189,18 +211,18 @@ def check_config_nms(name="yolov10m", hw=640, B=2, conf=0.001, iou=0.7, max_det=
     raw = m(x)
     got = PP.decode_v10_predictions(raw, num_classes=80, strides=(8, 16, 32), conf_thresh=conf, iou_thresh=iou, max_det=max_det)
     ref = O.decode_nms([t.cpu() for t in raw], num_classes=80, strides=(8, 16, 32), conf_thresh=conf, iou_thresh=iou, max_det=max_det)
-    from gpu_checks_decode import _canon
-    n_tot = 0
+    from gpu_checks_decode import _canon, flip_count, nms_on_oracle_candidates
+    # exact half: NMS of the oracle-decoded candidates of the GPU's head tensors, identical inputs on both sides
+    kept_exact = nms_on_oracle_candidates([t.cpu() for t in raw], conf, iou, max_det)
+    n_tot = flips = 0
     for i in range(B):
         a, b = _canon(got[i][0].cpu()), _canon(ref[i][0])
         assert a.shape == b.shape, f"image {i}: kept {tuple(a.shape)} vs oracle {tuple(b.shape)}"
-        if a.numel():
-            # boxes are decoded on the GPU (ulp-level differences), so a borderline IoU decision may flip:
-            # identical detections for >= 99% of the rows (same bar as check_decode_nms)
-            close = ((a - b).abs().max(1)[0] < 1e-2).float().mean()
-            assert close >= 0.99, f"image {i}: only {float(close):.3f} of rows match"
+        flips += flip_count(b, a)
         n_tot += a.shape[0]
-    return {"kept": n_tot}
+    # end to end each side decodes its own boxes (ulp-level differences): flips are reported and bounded at 1 %
+    assert flips <= max(2, n_tot // 100), f"{flips} of {n_tot} rows differ end to end"
+    return {"kept": n_tot, "flips_end_to_end": flips, "kept_exact_on_identical_candidates": kept_exact}
 
 
 def check_config_large(name="yolov10l", hw=1280, B=1, seed=8):

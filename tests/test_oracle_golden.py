@@ -45,6 +45,24 @@ def test_forward_matches_reference_golden(name):
     assert torch.allclose(scores, g["dets_scores"], atol=1e-5)
 
 
+def test_forward_640_matches_reference_golden_samples():
+    """Headline resolution: the oracle against the reference's yolov10s @640x640 head tensors (2048 sampled positions
+    and the double-precision checksums of each of the six tensors; oracle/make_golden.py::make_640)."""
+    g = torch.load(os.path.join(G, "forward640_yolov10s.pt"))
+    model = get_model("yolov10s", weights=None, class_names=NAMES)
+    sd = synth_state_dict(model.state_dict(), seed=g["seed_weights"], gain=g["gain"])
+    x = synth_images(1, g["hw"], g["hw"], seed=g["seed_input"])
+    out = O.forward(sd, x)
+    for br in ("one2many", "one2one"):
+        for i in range(3):
+            ref = g[f"{br}{i}"]
+            t = out[br][i]
+            assert list(t.shape) == ref["shape"]
+            err = float((t.flatten()[ref["idx"]] - ref["val"]).abs().max()) / ref["abs_max"]
+            assert err < 1e-4, (br, i, err)
+            assert abs(float(t.double().abs().sum()) - ref["abs_sum"]) < 1e-4 * ref["abs_sum"], (br, i)
+
+
 def test_state_dict_keys_match_reference_order_and_shapes():
     ref = json.load(open(os.path.join(G, "state_keys.json")))
     for name in VARIANTS:

@@ -164,6 +164,8 @@ def registry():
     add("model_n_f32_nc90", M.check_model, name="yolov10n", precision="fp32", hw=64, B=1, nc=90)
     add("model_s_f32_nc7", M.check_model, name="yolov10s", precision="fp32", hw=(64, 96), B=1, nc=7)
     add("model_s_golden", M.check_model_golden, name="yolov10s")
+    add("model_s_golden_640_bf16", M.check_model_golden_640, precision="bf16")
+    add("model_s_golden_640_f32", M.check_model_golden_640, precision="fp32")
     add("model_s_subbatch_graph", M.check_subbatch_and_graph, name="yolov10s")
     add("model_s_decode_e2e", M.check_decode_e2e, name="yolov10s")
     add("model_s_pack_cache", M.check_pack_cache, name="yolov10s")
