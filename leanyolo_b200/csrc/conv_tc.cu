@@ -901,143 +901,6 @@ __device__ __forceinline__ void epilogue_tiles(const Params& p, uint32_t bar_bas
 #endif
 }
 
-// ---------------------------------------------------- fold (kx taps in N): tile-parallel epilogue
-// out[m][co] = D[m][co] + D[m+1][Cout + co] + D[m+2][2*Cout + co].  The 16 warps are G tile groups x (4 / G) column
-// groups (G = 4 needs 4 accumulator stages of 3*Cout columns: Cout <= 32; otherwise G = 2).  Rows m+1 / m+2 are the next
-// lanes of the same warp (shuffles); for lanes 30 / 31 they are lanes 0 / 1 of the NEXT TMEM lane quarter, i.e. of
-// another warp: every warp first exports those three rows (D1 of lane 0, D2 of lanes 0 and 1) of its own chunks to a
-// double-buffered shared-memory block, ONE named barrier per tile joins the four quarter warps, then the chunks are
-// combined, activated and stored.  (The earlier column-parallel version paid a barrier per chunk.)
-__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
-__device__ __forceinline__ void lds128(uint32_t addr, uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d) {
-  asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(addr) : "memory");
-}
-
-template <int ADD, int G>
-__device__ __forceinline__ void epilogue_fold_tiles(const Params& p, uint32_t bar_base, uint32_t tmem_base, const float* s_bias) {
-  constexpr int CS = 4 / G;
-  constexpr bool kRes = ADD == 3;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q = warp & 3;
-  const int wg = (warp - 2) >> 2;
-  const int tg = wg % G, cs = wg / G;
-  const int bn = p.block_n, nchunks = bn >> 4, acc = p.acc;
-  const uint32_t row = (uint32_t)(q * 32 + lane);
-  const bool act = p.act != 0;
-  const float pre = act ? 0.5f : 1.0f;
-  // exchange block (shared-space byte addresses): [buffer][wg][quarter][D1 lane 0 | D2 lane 0 | D2 lane 1][bn] floats
-  const uint32_t xq = 12u * (uint32_t)bn;                   // bytes one quarter exports
-  const uint32_t xbuf = 16u * xq;
-  uint32_t xmine = bar_base + p.exch_off + (uint32_t)(wg * 4 + q) * xq;              // this tile's buffer: toggles by xbuf
-  uint32_t xnext = bar_base + p.exch_off + (uint32_t)(wg * 4 + ((q + 1) & 3)) * xq;
-  const int src1 = (lane + 1) & 31, src2 = (lane + 2) & 31;
-
-  int it_unit = blockIdx.x, it_mt = 0;
-  auto advance = [&]() { if (++it_mt == p.band_mt) { it_mt = 0; it_unit += gridDim.x; } };
-  for (int i = 0; i < tg; ++i) advance();
-  int as = tg;
-  uint32_t aphase = 0, xtog = 0;
-  while (it_unit < p.total_tiles) {
-    const uint32_t pu = (uint32_t)phys(p, it_unit);
-    const uint32_t b = p.mg_bands ? __umulhi(pu, p.mg_bands) : pu;
-    const uint32_t bd = pu - b * (uint32_t)p.bands;
-    const uint32_t m = (uint32_t)it_mt * 126u + row;
-    const uint32_t oy = __umulhi(m, p.mg_bw), ox = m - oy * (uint32_t)p.band_w;
-    const uint32_t h = bd * (uint32_t)p.band_r + oy;
-    const bool valid = ox < (uint32_t)p.Wo && oy < (uint32_t)p.band_r && h < (uint32_t)p.Ho && row < 126u;
-    const uint32_t lin = (b * (uint32_t)p.Ho + h) * (uint32_t)p.Wo + ox;
-    const __nv_bfloat16* arow = (kRes && valid) ? p.res + (size_t)lin * (uint32_t)p.rCtot + p.rC0 : nullptr;
-    __nv_bfloat16* drow = valid ? p.dst + (size_t)lin * (uint32_t)p.dCtot + p.dC0 : nullptr;
-    mbar_wait(bar_tfull(bar_base, as), aphase);
-    tc_fence_after();
-    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 3 * bn);
-    uint32_t tq[16];
-    // ---- export the rows the previous quarter needs
-    for (int ch = cs; ch < nchunks; ch += CS) {
-      tmem_ld16(taddr + bn + ch * 16, tq);
-      tmem_ld_wait();
-      if (lane == 0) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) sts128(xmine + (uint32_t)(ch * 64 + j * 16), tq[4 * j], tq[4 * j + 1], tq[4 * j + 2], tq[4 * j + 3]);
-      }
-      tmem_ld16(taddr + 2 * bn + ch * 16, tq);
-      tmem_ld_wait();
-      if (lane < 2) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) sts128(xmine + (uint32_t)((1 + lane) * bn * 4 + ch * 64 + j * 16), tq[4 * j], tq[4 * j + 1], tq[4 * j + 2], tq[4 * j + 3]);
-      }
-    }
-    asm volatile("bar.sync %0, 128;" ::"r"(1 + wg) : "memory");
-    for (int ch = cs; ch < nchunks; ch += CS) {
-      const int c = ch * 16;
-      uint32_t d0[16];
-      float v[16];
-      // rows m+1 / m+2 by a ROTATING shuffle: lanes 0 (and 1) first replace their own D1 (D2) values, which no lane of
-      // this warp needs, by the rows the next quarter exported, so lanes 31 (30, 31) pick those up
-      tmem_ld16(taddr + c, d0);
-      tmem_ld16(taddr + bn + c, tq);
-      tmem_ld_wait();
-      if (lane == 0) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) lds128(xnext + (uint32_t)(c * 4 + j * 16), tq[4 * j], tq[4 * j + 1], tq[4 * j + 2], tq[4 * j + 3]);
-      }
-#pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] = __fadd_rn(__uint_as_float(d0[j]), __shfl_sync(0xFFFFFFFFu, __uint_as_float(tq[j]), src1));
-      tmem_ld16(taddr + 2 * bn + c, tq);
-      tmem_ld_wait();
-      if (ch + CS >= nchunks) {                 // every TMEM load of this warp for the tile has completed
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_tempty(bar_base, as));
-      }
-      if (lane < 2) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) lds128(xnext + (uint32_t)((1 + lane) * bn * 4 + c * 4 + j * 16), tq[4 * j], tq[4 * j + 1], tq[4 * j + 2], tq[4 * j + 3]);
-      }
-#pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] = __fadd_rn(v[j], __shfl_sync(0xFFFFFFFFu, __uint_as_float(tq[j]), src2));
-      const float4* bp = reinterpret_cast<const float4*>(s_bias + c);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float4 bb = bp[j];
-        ffma2(v[4 * j + 0], v[4 * j + 1], v[4 * j + 0], v[4 * j + 1], pre, pre, bb.x, bb.y);
-        ffma2(v[4 * j + 2], v[4 * j + 3], v[4 * j + 2], v[4 * j + 3], pre, pre, bb.z, bb.w);
-      }
-      if (act) {
-#pragma unroll
-        for (int j = 0; j < 16; j += 2) silu2_from_half(v[j], v[j + 1]);
-      }
-      if (kRes && arow) {
-        const uint4 r0 = *reinterpret_cast<const uint4*>(arow + c), r1 = *reinterpret_cast<const uint4*>(arow + c + 8);
-        const __nv_bfloat162* h0 = reinterpret_cast<const __nv_bfloat162*>(&r0);
-        const __nv_bfloat162* h1 = reinterpret_cast<const __nv_bfloat162*>(&r1);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float2 f0 = __bfloat1622float2(h0[j]), f1 = __bfloat1622float2(h1[j]);
-          fadd2(v[2 * j], v[2 * j + 1], v[2 * j], v[2 * j + 1], f0.x, f0.y);
-          fadd2(v[8 + 2 * j], v[8 + 2 * j + 1], v[8 + 2 * j], v[8 + 2 * j + 1], f1.x, f1.y);
-        }
-      }
-      if (drow) {
-        if (p.st256) {
-          store_bf16x16(drow + c, v);
-        } else {
-          store_vec<__nv_bfloat16>(drow + c, v);
-          store_vec<__nv_bfloat16>(drow + c + 8, v + 8);
-        }
-      }
-    }
-    xtog ^= 1u;                                  // the other exchange buffer for this warp's next tile
-    xmine = xtog ? xmine + xbuf : xmine - xbuf;
-    xnext = xtog ? xnext + xbuf : xnext - xbuf;
-    for (int i = 0; i < G; ++i) advance();
-    as += G;
-    if (as >= acc) { as -= acc; aphase ^= 1u; }
-  }
-}
-
 // ------------------------------------------------------------------------------- kernel
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -1264,10 +1127,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   else if (add == 0) LY_EPT(M, 0, false);                       \
   else if (add == 3) LY_EPT(M, 3, false);                       \
   else LY_EPT(M, 4, false);
-    if (p.fold == 2) {
-      if (p.epi_groups == 4) { if (add == 0) epilogue_fold_tiles<0, 4>(p, bar_base, tmem_base, s_bias); else epilogue_fold_tiles<3, 4>(p, bar_base, tmem_base, s_bias); }
-      else { if (add == 0) epilogue_fold_tiles<0, 2>(p, bar_base, tmem_base, s_bias); else epilogue_fold_tiles<3, 2>(p, bar_base, tmem_base, s_bias); }
-    } else if (p.epi_groups) {
+    if (p.epi_groups) {
       if (map == 0) { LY_EPT_MAP(0) } else if (map == 1) { LY_EPT_MAP(1) } else { LY_EPT_MAP(2) }
     } else
 #undef LY_EPT_MAP
@@ -1398,11 +1258,18 @@ int32_t conv_tc_prepare(const ly_op& op, ConvTcState** out) {
   // epilogue warps' time (12 MMAs of N = 192 instead of 36 of N = 64), but the epilogue, which was already co-critical
   // (~1600 cycles per tile and warp), grows to ~3000 (two more TMEM round trips, 32 shuffles, the quarter-boundary
   // exchange + named barrier): 0.158 -> 0.185 ms, with a shortcut 0.166 -> 0.291 ms; 32->32 @160^2 0.311 -> 0.479 ms.
+  // Round 2, second attempt (commit "fold with a tile-parallel shuffle epilogue", removed again): one exchange barrier per tile
+  // instead of one per chunk, rotating shuffles, all chunks of a row per warp: correct, 0.143 -> 0.170 ms.  ncu showed why no
+  // fold can win: the l1tex data pipe (one 128-byte wavefront per cycle) carries the MMAs' operand reads (A: 32 + B: N/4
+  // wavefronts per instruction: THAT is the ~50-cycle floor of an N <= 64 MMA) AND every shuffle / LDS / STS / global store of
+  // the epilogue; the fold removes 768 operand wavefronts per tile and adds 512 shuffles + ~300 exchange LDS/STS: 96 % busy.
+  // tcgen05.shift (tools/tmem_probe.cu: one instruction shifts 8 columns by one lane inside each 32-lane quarter, ~24 cycles
+  // each) would cost 24 shifts = as much tensor-pipe time as the fold saves, and cannot cross the quarter boundary either.
   static const int fold_env = env_int("LY_TC_FOLD", 0);
   const bool fold_ok = fold_env && op.k == 3 && op.stride == 1 && p.tiles_n == 1 && 3 * bn <= 256 && (bn * p.kc * 2) % 1024 == 0 &&
                        b_res_possible && !p.pair && !op.up.ptr && !op.nchw && op.dst.ptr;
   const int m_step = fold_ok ? 126 : 128;
-  const long long exch_bytes = fold_ok ? (fold_env == 2 ? 2LL * 16 * 3 * bn * 4 : 2LL * 4 * 4 * 48 * 4) : 0;
+  const long long exch_bytes = fold_ok ? 2LL * 4 * 4 * 48 * 4 : 0;
   // (the tile-parallel epilogue reads the shortcut directly: no prefetch slots)
   const bool will_ept = env_int("LY_TC_EPT", 1) && !p.pair && !fold_ok && std::min(512 / bn, env_int("LY_TC_ACC", kMaxAcc)) >= 4;
   if (band_ok && !p.pair && op.k == 3 && op.stride == 1 && Wo + 2 <= 256 && 2 * p.kc_blocks <= kMaxStages) {
@@ -1415,7 +1282,7 @@ int32_t conv_tc_prepare(const ly_op& op, ConvTcState** out) {
     const double cost_now = waves(total) * (p.halo ? (double)std::max(p.num_kb * cyc_mma, 3.0 * p.kc_blocks * (p.tw * (p.th + 2)) * tma_row)
                                                    : (double)std::max(p.num_kb * cyc_mma, 9.0 * p.kc_blocks * 128 * tma_row));
     const int BW = Wo + 2;
-    const long long fixed = 8 * kBarSlots + 1024 + exch_bytes + (op.res.ptr && bn <= 128 && !will_ept && !(fold_ok && fold_env == 2) ? 2LL * 32 * kEpiWarps * (((bn / 16 + 3) / 4) * 32) : 0);
+    const long long fixed = 8 * kBarSlots + 1024 + exch_bytes + (op.res.ptr && bn <= 128 && !will_ept ? 2LL * 32 * kEpiWarps * (((bn / 16 + 3) / 4) * 32) : 0);
     const long long b_bytes = b_res_possible ? b_all_bytes : 3LL * ((bn * p.kc * 2 + 1023) / 1024 * 1024);
     int best_r = 0; double best_cost = 1e30;
     for (int R = 1; R <= Ho && R + 2 <= 256; ++R) {
@@ -1433,7 +1300,7 @@ int32_t conv_tc_prepare(const ly_op& op, ConvTcState** out) {
       p.band_mt = ((best_r - 1) * BW + Wo + m_step - 1) / m_step;
       p.bands = (Ho + best_r - 1) / best_r;
       if (fold_ok) {
-        p.fold = fold_env == 2 ? 2 : 1;      // 2: tile-parallel epilogue with one exchange barrier per tile
+        p.fold = 1;
         p.tmem_cols = pow2_ge(2 * 3 * bn);
       }
       p.tw = 128; p.th = 1; p.tb = 1;
@@ -1481,12 +1348,11 @@ int32_t conv_tc_prepare(const ly_op& op, ConvTcState** out) {
     const int per = bn;   // (pair and fold keep the column-parallel role)
     const int acc_max = std::min(512 / per, std::min(env_int("LY_TC_ACC", kMaxAcc), (int)kMaxAcc));
     p.epi_groups = (ept_env && !p.fold && (p.pair ? env_int("LY_TC_EPT_PAIR", 1) != 0 : acc_max >= 4)) ? 4 : 0;   // (pair: 2 sets x 2 tiles)
-    if (p.fold == 2) p.epi_groups = std::min(512 / (3 * bn), std::min(env_int("LY_TC_ACC", kMaxAcc), (int)kMaxAcc)) >= 4 ? 4 : 2;
   }
   static const int res_prefetch_ok = env_int("LY_TC_RES_PREFETCH", 1);
   p.res_slot = p.epi_groups ? 0 : (((op.res.ptr != nullptr) != (op.up.ptr != nullptr)) && res_prefetch_ok && bn <= 128) ? ((bn / 16 + 3) / 4) * 32 : 0;   // one 32-byte chunk per round
   const long long res_bytes = 2LL * 32 * kEpiWarps * p.res_slot;
-  const long long x_bytes = p.fold == 2 ? 2LL * 16 * 3 * bn * 4 : (p.fold ? 2LL * 4 * 4 * 48 * 4 : 0);      // fold: boundary-row exchange slots of the epilogue
+  const long long x_bytes = p.fold ? 2LL * 4 * 4 * 48 * 4 : 0;      // fold: boundary-row exchange slots of the epilogue
   p.exch_off = (uint32_t)(bar_bytes + res_bytes);
   const long long avail = (long long)kSmemBudget - bar_bytes - 1024 - res_bytes - x_bytes - (p.b_resident ? b_all : 0);
   if (p.halo == 2) {
