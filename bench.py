@@ -276,6 +276,14 @@ def main():
     e2e_step(1)
     drain()
     torch.cuda.synchronize()
+    # the host -> device copy alone (no compute): tells whether the end-to-end number is bound by the host link
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0.record()
+    for i in range(3):
+        d_in[i % 2].copy_(h_in, non_blocking=True)
+    c1.record()
+    torch.cuda.synchronize()
+    h2d_ms = c0.elapsed_time(c1) / 3
     if world > 1:
         dist.barrier()
     e0.record()
@@ -397,7 +405,8 @@ def main():
                    "gather": "all_gather_into_tensor on a side stream, overlapped with the next forward (leanyolo_b200.dist.ShardedDetector)" if world > 1 else None},
         "clocks": clocks,
         "e2e": {"value": round(e2e_value, 1), "unit": "images/s", "h2d_bytes_per_step": B * 3 * S * S,
-                "d2h_bytes_per_step": B * 300 * 6 * 4, "note": "pinned uint8 NCHW host batch -> detections in pinned host memory"},
+                "d2h_bytes_per_step": B * 300 * 6 * 4, "h2d_ms_alone": round(h2d_ms, 3), "h2d_gbs_alone": round(B * 3 * S * S / h2d_ms / 1e6, 1),
+                "note": "pinned uint8 NCHW host batch -> detections in pinned host memory; the copy of batch i+1 overlaps the forward of batch i"},
         "gpu_launches": int(launches),
         "gather_check": gather_check,
         "fused_detect": fused,

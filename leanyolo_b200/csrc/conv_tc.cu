@@ -68,6 +68,7 @@ constexpr uint32_t kSmemBudget = 216 * 1024;
 struct Params {
   CUtensorMap tmA;
   CUtensorMap tmB;
+  CUtensorMap tmD;         // output tensor (TMA-store epilogue): box = 32 channels x the 32 pixels of one epilogue warp
   // tiling
   int tw, th, tb;
   int tiles_w, tiles_h, tiles_b, tiles_n, total_tiles;
@@ -104,6 +105,8 @@ struct Params {
   int xpre;                // epilogue: cross-tile TMEM prefetch (LY_TC_XPRE=1, default off)
   int acc;                 // TMEM accumulator stages (each block_n columns; pair: 2 * block_n, fold: 3 * block_n)
   int epi_groups;          // 0: column-parallel epilogue; 4: tile groups of the tile-parallel epilogue (needs acc >= 4)
+  int ts;                  // TMA-store epilogue: staging slots per epilogue warp (0 = direct stores)
+  uint32_t stg_off;        // byte offset (from the barrier block, 1024-aligned) of the staging slots: [warp][slot][32 rows x 64 B]
   int exp;                 // -DLY_TC_EXP builds only (LY_TC_EXP=mask): 1 skip the MMAs, 2 skip the epilogue's work, 4 skip the TMA loads after the first pass
 };
 
@@ -718,6 +721,18 @@ __device__ __forceinline__ void epilogue_role(const Params& p, uint8_t* smem_raw
 // flight in the epilogue, which the TMEM stages (p.acc >= 4, i.e. N <= 128) make possible.
 // The shortcut / half-resolution addend is read directly, one chunk ahead (the slots of the other role would need
 // nchunks x 32 bytes per thread).
+// TMA store of one staged [32 pixels x 32 channels] block (64-byte rows, SWIZZLE_64B).  ncu on the thin layers: a
+// `st.global.v8.b32` whose 32 lanes hit 32 different 128-byte lines costs ~49 wavefronts of the l1tex data pipe, the
+// same pipe that feeds the MMAs' shared-memory operands (A: 32 + B: N/4 wavefronts per instruction) and takes the TMA
+// writes: the NHWC stores were 25-35 % of that pipe's traffic in every conv kernel.  Staged through shared memory
+// (4 conflict-free STS.128 wavefronts per 512 bytes) and written by the TMA unit they cost ~1/3 of that, and the
+// tensor map's bounds clip the rows / channels that fall outside the tensor (no per-thread masks).
+__device__ __forceinline__ void tma_store_4d(uint32_t src, const CUtensorMap* tm, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(tm), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+
 template <int MAP, int ADD, bool NCHW>
 __device__ __forceinline__ void epilogue_tiles(const Params& p, uint32_t bar_base, uint32_t tmem_base, const float* s_bias) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -736,6 +751,10 @@ __device__ __forceinline__ void epilogue_tiles(const Params& p, uint32_t bar_bas
   constexpr bool kRes = ADD == 3;
   uint32_t dw = 0, dh = 0, db = 0;
   if (MAP == 1) { dw = row % (uint32_t)p.tw; dh = (row / (uint32_t)p.tw) % (uint32_t)p.th; db = row / (uint32_t)(p.tw * p.th); }
+  const int ts = (!NCHW && MAP != 2) ? p.ts : 0;                   // staging slots of this warp (0: direct stores)
+  const uint32_t stg = bar_base + p.stg_off + (uint32_t)(warp - 2) * (uint32_t)ts * 2048u + (uint32_t)lane * 64u;
+  const uint32_t sw = (uint32_t)((lane >> 1) & 3);                 // SWIZZLE_64B: 16-byte chunk index ^= (row / 2) % 4
+  uint32_t stg_cnt = 0;
 
   // position in the issue order: (unit, n tile, M tile) in band mode, one tile per step otherwise
   int it_unit = blockIdx.x, it_nt = 0, it_mt = 0;
@@ -760,6 +779,7 @@ __device__ __forceinline__ void epilogue_tiles(const Params& p, uint32_t bar_bas
     bool valid;
     uint32_t lin;
     int n0;
+    int tc1 = 0, tc2 = 0, tc3 = 0;      // TMA-store coordinates of this lane's pixel (lane 0: the origin of the warp's box)
     if (MAP == 2) {
       const uint32_t pu = (uint32_t)phys(p, it_unit);
       const uint32_t b = p.mg_bands ? __umulhi(pu, p.mg_bands) : pu;
@@ -776,6 +796,7 @@ __device__ __forceinline__ void epilogue_tiles(const Params& p, uint32_t bar_bas
       n0 = (int)(t - qn * (uint32_t)p.tiles_n) * p.block_n;
       lin = qn * 128u + row;
       valid = lin < (uint32_t)p.Wo;
+      tc1 = (int)lin;
     } else {
       int nt, wt, ht, bt;
       split_tile(p, pair ? 2 * it_unit + it_mt : it_unit, nt, wt, ht, bt);
@@ -783,6 +804,7 @@ __device__ __forceinline__ void epilogue_tiles(const Params& p, uint32_t bar_bas
       valid = w < (uint32_t)p.Wo && h < (uint32_t)p.Ho && b < (uint32_t)p.Bo;
       lin = (b * (uint32_t)p.Ho + h) * (uint32_t)p.Wo + w;
       n0 = nt * p.block_n;
+      tc1 = (int)w; tc2 = (int)h; tc3 = (int)b;
     }
     const __nv_bfloat16* arow = nullptr;
     if (kRes && valid) arow = p.res + (size_t)lin * (uint32_t)p.rCtot + p.rC0 + n0;
@@ -881,6 +903,30 @@ __device__ __forceinline__ void epilogue_tiles(const Params& p, uint32_t bar_bas
           for (int j = 0; j < 16; ++j)
             if (n0 + c + j < p.nC) np[(size_t)j * (uint32_t)p.hw_real] = v[j];
         }
+      } else if (ts) {
+        if ((ch & 1) == 0) {               // first chunk of a 32-channel group: the slot's previous store must have been read
+          if (lane == 0) {
+            if (ts > 1) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          }
+          __syncwarp();
+        }
+        const uint32_t slot = stg + (ts > 1 ? (stg_cnt & 1u) * 2048u : 0u);
+        uint32_t w8[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const __nv_bfloat162 hh = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+          w8[j] = *reinterpret_cast<const uint32_t*>(&hh);
+        }
+        const uint32_t k0 = (uint32_t)(ch & 1) * 2u;
+        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(slot + ((k0 ^ sw) << 4)), "r"(w8[0]), "r"(w8[1]), "r"(w8[2]), "r"(w8[3]) : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(slot + (((k0 + 1u) ^ sw) << 4)), "r"(w8[4]), "r"(w8[5]), "r"(w8[6]), "r"(w8[7]) : "memory");
+        if ((ch & 1) != 0 || ch + 1 >= nchunks) {
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) tma_store_4d(slot, &p.tmD, n0 + (ch & ~1) * 16, tc1, tc2, tc3);
+          ++stg_cnt;
+        }
       } else if (drow) {
         if (p.st256) {
           store_bf16x16(drow + c, v);
@@ -895,6 +941,7 @@ __device__ __forceinline__ void epilogue_tiles(const Params& p, uint32_t bar_bas
     as += G;
     if (as >= acc) { as -= acc; aphase ^= 1u; }
   }
+  if (ts && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all of this warp's stores have been written
 #ifdef LY_TC_PROFILE
   if (blockIdx.x == 0 && lane == 0 && (warp == 2 || warp == 6))
     printf("[tc prof] tile epilogue warp %d: total %lld wait_tfull %lld\n", warp, clock64() - estart, w_tfull);
@@ -929,6 +976,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmB) : "memory");
+    if (p.ts) asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmD) : "memory");
     for (int s = 0; s < kMaxStages; ++s) {
       mbar_init(afull_bar(s), 1);
       mbar_init(aempty_bar(s), 1);
@@ -1354,7 +1402,18 @@ int32_t conv_tc_prepare(const ly_op& op, ConvTcState** out) {
   const long long res_bytes = 2LL * 32 * kEpiWarps * p.res_slot;
   const long long x_bytes = p.fold ? 2LL * 4 * 4 * 48 * 4 : 0;      // fold: boundary-row exchange slots of the epilogue
   p.exch_off = (uint32_t)(bar_bytes + res_bytes);
-  const long long avail = (long long)kSmemBudget - bar_bytes - 1024 - res_bytes - x_bytes - (p.b_resident ? b_all : 0);
+  // TMA-store epilogue (tile-parallel role, flat / brick pixel mappings, NHWC output): 1 or 2 staging slots of 2 KB per warp
+  // Only when the weights are resident: with streamed weights the 64 KB of slots cost pipeline stages (measured: pair-mode
+  // 3x3 128->128 @40^2 0.111 -> 0.160 ms with two slots, neutral with one), with resident weights the A ring has room
+  // to spare (1x1 256->128 @80^2 0.217 -> 0.201 ms, 3x3/s2 32->64 @320^2 0.469 -> 0.406 ms, the upsample-folded 1x1
+  // 128->128 @80^2 0.230 -> 0.193 ms).  N tiles must be whole 32-channel groups (a partial group is clipped by the tensor
+  // map only at the END of the channel range, not at an N-tile boundary).
+  static const int ts_env = env_int("LY_TC_TMASTORE", 2);
+  p.ts = (ts_env && p.epi_groups == 4 && p.halo != 2 && op.dst.ptr && !op.nchw && bn % 32 == 0 && (p.b_resident || ts_env >= 3))
+             ? (ts_env == 1 ? 1 : 2) : 0;
+  p.stg_off = (uint32_t)((bar_bytes + res_bytes + x_bytes + 1023) / 1024 * 1024);
+  const long long stg_bytes = p.ts ? (long long)p.stg_off - (bar_bytes + res_bytes + x_bytes) + 32LL * kEpiWarps * 64 * p.ts : 0;
+  const long long avail = (long long)kSmemBudget - bar_bytes - 1024 - res_bytes - x_bytes - stg_bytes - (p.b_resident ? b_all : 0);
   if (p.halo == 2) {
     // a band keeps kc_blocks stages for all of its tiles; the next band is prefetched meanwhile
     p.a_stages = p.b_resident ? (int)(avail / p.a_stage) : 2 * p.kc_blocks;
@@ -1382,7 +1441,7 @@ int32_t conv_tc_prepare(const ly_op& op, ConvTcState** out) {
   if (p.b_stages > kMaxStages) p.b_stages = kMaxStages;
   if (p.a_stages < 2 || (!p.b_resident && p.b_stages < 2)) { delete st; set_error("conv_tc: tile does not fit in shared memory"); return LY_E_ARG; }
   st->smem = 1024 + (size_t)p.a_stages * p.a_stage + (p.b_resident ? (size_t)b_all : (size_t)p.b_stages * p.b_stage) + bar_bytes +
-             (size_t)res_bytes + (size_t)x_bytes;
+             (size_t)res_bytes + (size_t)x_bytes + (size_t)stg_bytes;
   if (st->smem < 120 * 1024) st->smem = 120 * 1024;  // force one CTA per SM (TMEM allocations must not contend)
 
   // TMEM accumulator stages.  Knock-out runs (-DLY_TC_EXP) showed that with two stages the thin layers are bound by the
@@ -1450,6 +1509,26 @@ int32_t conv_tc_prepare(const ly_op& op, ConvTcState** out) {
     if (r != CUDA_SUCCESS) { delete st; set_error("conv_tc: cuTensorMapEncodeTiled(B) failed with %d", (int)r); return LY_E_CUDA; }
   }
 
+  if (p.ts) {
+    // the 32 pixels of an epilogue warp (rows 32q .. 32q+31 of the tile) are an aligned sub-box of the pixel brick
+    cuuint64_t dims[4], strides[3];
+    cuuint32_t box[4] = {32, 32, 1, 1}, estr[4] = {1, 1, 1, 1};
+    const cuuint64_t pitch = (cuuint64_t)op.dst.ctot * 2;
+    if (flat) {
+      dims[0] = (cuuint64_t)Cout; dims[1] = (cuuint64_t)dimW; dims[2] = 1; dims[3] = 1;
+      strides[0] = pitch; strides[1] = pitch * dimW; strides[2] = strides[1];
+    } else {
+      dims[0] = (cuuint64_t)Cout; dims[1] = (cuuint64_t)Wo; dims[2] = (cuuint64_t)Ho; dims[3] = (cuuint64_t)op.B;
+      strides[0] = pitch; strides[1] = pitch * Wo; strides[2] = strides[1] * Ho;
+      if (p.tw >= 32) { box[1] = 32; box[2] = 1; box[3] = 1; }
+      else if (p.tw * p.th >= 32) { box[1] = p.tw; box[2] = 32 / p.tw; box[3] = 1; }
+      else { box[1] = p.tw; box[2] = p.th; box[3] = 32 / (p.tw * p.th); }
+    }
+    char* base = (char*)op.dst.ptr + (size_t)op.dst.c0 * 2;
+    CUresult r = encode(&p.tmD, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { delete st; set_error("conv_tc: cuTensorMapEncodeTiled(D) failed with %d", (int)r); return LY_E_CUDA; }
+  }
   p.dst = (__nv_bfloat16*)op.dst.ptr; p.dCtot = op.dst.ctot; p.dC0 = op.dst.c0;
   static const int st256_ok = env_int("LY_ST256", 1);
   p.st256 = st256_ok && op.dst.ptr && op.dst.ctot % 16 == 0 && op.dst.c0 % 16 == 0 && reinterpret_cast<uintptr_t>(op.dst.ptr) % 32 == 0;

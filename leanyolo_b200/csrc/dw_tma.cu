@@ -16,6 +16,7 @@
 #include <algorithm>
 #include "common.cuh"
 #include "tma.cuh"
+#include "tc.cuh"
 
 namespace ly {
 
@@ -398,7 +399,8 @@ __global__ void __launch_bounds__(kThreadsDw) dw_strip_kernel(const __grid_const
           const int d = ix - kx;
           if (d >= 0 && d % S == 0 && d / S < SL) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) acc[d / S][j] = fmaf(in[j], wv[kx][j], acc[d / S][j]);
+            for (int j = 0; j < 8; j += 2)      // packed FFMA2: half the issue slots of the FMA stream
+              ffma2(acc[d / S][j], acc[d / S][j + 1], in[j], in[j + 1], wv[kx][j], wv[kx][j + 1], acc[d / S][j], acc[d / S][j + 1]);
           }
         }
       }
@@ -495,6 +497,9 @@ int32_t launch_strip(const ly_op& op, cudaStream_t st) {
 //  * the loop runs over INPUT rows: a row of the halo patch is loaded and unpacked once and
 //    feeds every output row it touches;
 //  * all arithmetic is packed FFMA2 on the lane's two channels.
+// (Round 2: keeping the 49 taps in shared memory instead of registers, 72 instead of 154 registers and two CTAs = 20
+//  compute warps per SM, measured the same 0.207 ms: the kernel is not occupancy-bound; ncu: IPC 1.9 of 4, 109 M
+//  warp-instructions.  Removed again.)
 // ---------------------------------------------------------------------------------------
 constexpr int kDw7Warps = 10;
 
