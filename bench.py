@@ -254,6 +254,7 @@ def main():
 
     # double-buffered: the H2D copy of batch i+1 (copy stream) overlaps the forward of batch i
     copy_stream = torch.cuda.Stream(device=dev)
+    out_stream = torch.cuda.Stream(device=dev)     # device -> host read of the detections, off the compute stream
     d_in = [torch.empty_like(x_u8) for _ in range(2)]
     ev_copied = [torch.cuda.Event() for _ in range(2)]
     ev_consumed = [torch.cuda.Event() for _ in range(2)]
@@ -270,7 +271,10 @@ def main():
         main.wait_event(ev_copied[s])
         det = step(d_in[s])              # uint8 NCHW goes straight into the stem kernel
         ev_consumed[s].record(main)
-        h_out.copy_(det, non_blocking=True)
+        out_stream.wait_stream(main)
+        with torch.cuda.stream(out_stream):
+            h_out.copy_(det, non_blocking=True)
+        det.record_stream(out_stream)
 
     e2e_step(0)
     e2e_step(1)
@@ -290,6 +294,7 @@ def main():
     for i in range(e2e_steps):
         e2e_step(i)
     drain()
+    main.wait_stream(out_stream)          # the last detections have landed in host memory
     e1.record()
     torch.cuda.synchronize()
     t = torch.tensor([e0.elapsed_time(e1)], device=dev)

@@ -27,6 +27,15 @@
 // A tile is tw x R output pixels of one image; accumulator row m = oy*(tw+2)+ox, so 2 of every
 // tw+2 rows are discarded ((R-1)*(tw+2)+tw <= 128).
 //
+// (Round 2, two measured dead ends, both bit-correct and removed again:
+//  * a TMA-store epilogue -- the four quarter warps of a column half stage a 32-channel group of the tile compacted to
+//    tw x R pixels, one named barrier, one box store: 128->128 @80^2 0.259 vs 0.261 ms with two slots, 0.288 with one.
+//    Unlike the resident-weight 1x1 layers of conv_tc this kernel is not bound by its store wavefronts.
+//  * a hybrid depthwise stage -- the first ct taps computed by the 8 middle warps on the CUDA cores straight from the
+//    swizzled raw tile (fp32 weights in shared memory, FFMA2), the other 9 - ct as diagonal MMAs: 0.264 ms at ct = 0,
+//    0.328 / 0.354 / 0.385 / 0.445 / 0.465 ms at ct = 2 / 3 / 4 / 6 / 8: every tap moved costs ~280 cycles per k-block on
+//    two warps per scheduler, six times the 48 cycles of the four MMAs it replaces.)
+//
 // Reference semantics: leanyolo/models/yolov10/head.py:95-107 (v10Detect class branch),
 // layers.py:256-264 (CIB).
 #include <cuda.h>
