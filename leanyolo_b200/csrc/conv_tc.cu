@@ -105,6 +105,7 @@ struct Params {
   int xpre;                // epilogue: cross-tile TMEM prefetch (LY_TC_XPRE=1, default off)
   int acc;                 // TMEM accumulator stages (each block_n columns; pair: 2 * block_n, fold: 3 * block_n)
   int epi_groups;          // 0: column-parallel epilogue; 4: tile groups of the tile-parallel epilogue (needs acc >= 4)
+  int ld256;               // shortcut / addend rows are 32-byte aligned: one 256-bit load per 16-channel chunk
   int ts;                  // TMA-store epilogue: staging slots per epilogue warp (0 = direct stores)
   uint32_t stg_off;        // byte offset (from the barrier block, 1024-aligned) of the staging slots: [warp][slot][32 rows x 64 B]
   int exp;                 // -DLY_TC_EXP builds only (LY_TC_EXP=mask): 1 skip the MMAs, 2 skip the epilogue's work, 4 skip the TMA loads after the first pass
@@ -733,6 +734,19 @@ __device__ __forceinline__ void tma_store_4d(uint32_t src, const CUtensorMap* tm
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
 
+// 16 bf16 channels of the shortcut / addend row.  32 lanes x 32 bytes in 32 different lines: like the stores, one 256-bit
+// request per lane costs about half the l1tex wavefronts of two 128-bit ones (3x3 32->32 @160^2 with a shortcut spends as
+// many data-pipe wavefronts on these loads as on its MMA operands).
+__device__ __forceinline__ void ld_addend(const __nv_bfloat16* ptr, int wide, uint4& a0, uint4& a1) {
+  if (wide) {
+    asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(a0.x), "=r"(a0.y), "=r"(a0.z), "=r"(a0.w), "=r"(a1.x), "=r"(a1.y), "=r"(a1.z), "=r"(a1.w) : "l"(ptr) : "memory");
+  } else {
+    a0 = *reinterpret_cast<const uint4*>(ptr);
+    a1 = *reinterpret_cast<const uint4*>(ptr + 8);
+  }
+}
+
 template <int MAP, int ADD, bool NCHW>
 __device__ __forceinline__ void epilogue_tiles(const Params& p, uint32_t bar_base, uint32_t tmem_base, const float* s_bias) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -825,10 +839,7 @@ __device__ __forceinline__ void epilogue_tiles(const Params& p, uint32_t bar_bas
     }
     // the addend of the first chunk is requested before the accumulator wait
     uint4 a0 = make_uint4(0, 0, 0, 0), a1 = a0;
-    if ((kRes || kUp) && arow && cs < nchunks) {
-      a0 = *reinterpret_cast<const uint4*>(arow + cs * 16);
-      a1 = *reinterpret_cast<const uint4*>(arow + cs * 16 + 8);
-    }
+    if ((kRes || kUp) && arow && cs < nchunks) ld_addend(arow + cs * 16, p.ld256, a0, a1);
     const int bs = pair ? as >> 1 : as;          // barrier index of this accumulator
     { PROF_T0(); mbar_wait(bar_tfull(bar_base, bs), aphase); PROF_ADD(w_tfull); }
     tc_fence_after();
@@ -859,10 +870,7 @@ __device__ __forceinline__ void epilogue_tiles(const Params& p, uint32_t bar_bas
       const uint4 r0 = a0, r1 = a1;
       if (ch + CS < nchunks) {
         tmem_ld16(taddr + c + 16 * CS, nxt);   // next chunk in flight during the activation / store of this one
-        if ((kRes || kUp) && arow) {
-          a0 = *reinterpret_cast<const uint4*>(arow + c + 16 * CS);
-          a1 = *reinterpret_cast<const uint4*>(arow + c + 16 * CS + 8);
-        }
+        if ((kRes || kUp) && arow) ld_addend(arow + c + 16 * CS, p.ld256, a0, a1);
       } else {                                  // the last chunk of this warp sits in registers: release the stage
         tc_fence_before();
         __syncwarp();
@@ -1533,6 +1541,11 @@ int32_t conv_tc_prepare(const ly_op& op, ConvTcState** out) {
   static const int st256_ok = env_int("LY_ST256", 1);
   p.st256 = st256_ok && op.dst.ptr && op.dst.ctot % 16 == 0 && op.dst.c0 % 16 == 0 && reinterpret_cast<uintptr_t>(op.dst.ptr) % 32 == 0;
   p.res = (const __nv_bfloat16*)op.res.ptr; p.rCtot = op.res.ctot; p.rC0 = op.res.c0;
+  {
+    static const int ld256_ok = env_int("LY_LD256", 1);
+    const ly_view& av = op.res.ptr ? op.res : op.up;
+    p.ld256 = ld256_ok && av.ptr && av.ctot % 16 == 0 && av.c0 % 16 == 0 && reinterpret_cast<uintptr_t>(av.ptr) % 32 == 0;
+  }
   p.up = (const __nv_bfloat16*)op.up.ptr; p.uCtot = op.up.ctot; p.uC0 = op.up.c0; p.uH = op.up.H; p.uW = op.up.W; p.Wreal = Wo;
   p.bias = op.bias;
   p.nchw = op.nchw; p.nCtot = op.nchw_ctot; p.nC0 = op.nchw_c0; p.nC = op.nchw_c;
