@@ -380,13 +380,13 @@ def main():
         os.makedirs(os.path.dirname(os.path.abspath(a.profile_out)), exist_ok=True)
         json.dump({"rows": rows, "by_kind": by_kind}, open(a.profile_out, "w"), indent=1)
     traffic = None
-    tp = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    tp = os.path.join(ROOT, "profiles", "r2_traffic.json")
     if os.path.exists(tp) and a.model == "yolov10s" and B == 256 and S == 640:
         traffic = json.load(open(tp))["conv_tc_kernel"]["dram_bytes_per_launch"]   # ncu capture of this workload
     alg_bytes = sum(r["bytes"] for r in tc) / max(len(tc), 1)
     roofline = {"bound": "tensor", "kernel": "conv_tc_kernel", "achieved": round(achieved, 1), "peak": peaks["tf_sust"],
                 "unit": "TFLOP/s", "frac": round(achieved / peaks["tf_sust"], 4), "traffic": traffic,
-                "traffic_unit": "DRAM bytes per launch (ncu dram read+write, profiles/r1_final_ncu_launch_summary.txt)",
+                "traffic_unit": "DRAM bytes per launch (ncu dram read+write, profiles/r2_final_ncu_launch_summary.txt)",
                 "algorithmic_bytes_per_launch": int(alg_bytes),
                 "peak_source": peaks["src"] + " (bf16_tflops_sustained: kernel timed inside a long step)",
                 "launches_per_step": len(tc), "share_of_step": round(tc_ms / all_ms, 3) if all_ms else None,

@@ -722,11 +722,13 @@ __device__ __forceinline__ void epilogue_role(const Params& p, uint8_t* smem_raw
 // flight in the epilogue, which the TMEM stages (p.acc >= 4, i.e. N <= 128) make possible.
 // The shortcut / half-resolution addend is read directly, one chunk ahead (the slots of the other role would need
 // nchunks x 32 bytes per thread).
-// TMA store of one staged [32 pixels x 32 channels] block (64-byte rows, SWIZZLE_64B).  ncu on the thin layers: a
-// `st.global.v8.b32` whose 32 lanes hit 32 different 128-byte lines costs ~49 wavefronts of the l1tex data pipe, the
-// same pipe that feeds the MMAs' shared-memory operands (A: 32 + B: N/4 wavefronts per instruction) and takes the TMA
-// writes: the NHWC stores were 25-35 % of that pipe's traffic in every conv kernel.  Staged through shared memory
-// (4 conflict-free STS.128 wavefronts per 512 bytes) and written by the TMA unit they cost ~1/3 of that, and the
+// TMA store of one staged [32 pixels x 32 channels] block (64-byte rows, SWIZZLE_64B).  ncu on the thin layers
+// (profiles/r2_final_ncu_conv_tc_datapipe.txt): a `st.global.v8.b32` whose 32 lanes hit 32 different 128-byte lines costs ~49
+// wavefronts of the l1tex LSU data stage (l1tex__data_pipe_lsu_wavefronts, peak one per cycle); the MMAs' shared-memory
+// operands go through the TC side of the same stage (A: 32 + B: N/4 wavefronts per instruction, also one per cycle: the ~50
+// cycle floor of an N <= 64 MMA).  The two counters overlap only partly (their busy fractions add up to 96-135 % on the
+// thin layers), and the NHWC stores were 25-35 % of the LSU side in every conv kernel.  Staged through shared memory (4
+// conflict-free STS.128 wavefronts per 512 bytes) and written by the TMA unit they cost about a third of that, and the
 // tensor map's bounds clip the rows / channels that fall outside the tensor (no per-thread masks).
 __device__ __forceinline__ void tma_store_4d(uint32_t src, const CUtensorMap* tm, int c0, int c1, int c2, int c3) {
   asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
@@ -735,8 +737,8 @@ __device__ __forceinline__ void tma_store_4d(uint32_t src, const CUtensorMap* tm
 }
 
 // 16 bf16 channels of the shortcut / addend row.  32 lanes x 32 bytes in 32 different lines: like the stores, one 256-bit
-// request per lane costs about half the l1tex wavefronts of two 128-bit ones (3x3 32->32 @160^2 with a shortcut spends as
-// many data-pipe wavefronts on these loads as on its MMA operands).
+// request per lane costs about half the l1tex wavefronts of two 128-bit ones (ncu: the shortcut layers 3x3 64->64 @80^2
+// run 29.0 M LSU wavefronts against 16.7 M without the shortcut and 23.9 M for the MMA operands).
 __device__ __forceinline__ void ld_addend(const __nv_bfloat16* ptr, int wide, uint4& a0, uint4& a1) {
   if (wide) {
     asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
@@ -1315,10 +1317,11 @@ int32_t conv_tc_prepare(const ly_op& op, ConvTcState** out) {
   // (~1600 cycles per tile and warp), grows to ~3000 (two more TMEM round trips, 32 shuffles, the quarter-boundary
   // exchange + named barrier): 0.158 -> 0.185 ms, with a shortcut 0.166 -> 0.291 ms; 32->32 @160^2 0.311 -> 0.479 ms.
   // Round 2, second attempt (commit "fold with a tile-parallel shuffle epilogue", removed again): one exchange barrier per tile
-  // instead of one per chunk, rotating shuffles, all chunks of a row per warp: correct, 0.143 -> 0.170 ms.  ncu showed why no
-  // fold can win: the l1tex data pipe (one 128-byte wavefront per cycle) carries the MMAs' operand reads (A: 32 + B: N/4
-  // wavefronts per instruction: THAT is the ~50-cycle floor of an N <= 64 MMA) AND every shuffle / LDS / STS / global store of
-  // the epilogue; the fold removes 768 operand wavefronts per tile and adds 512 shuffles + ~300 exchange LDS/STS: 96 % busy.
+  // instead of one per chunk, rotating shuffles, all chunks of a row per warp: correct, 0.143 -> 0.170 ms.  ncu on that run: the
+  // l1tex data stage moves one 128-byte wavefront per cycle for the MMAs' operand reads (A: 32 + B: N/4 wavefronts per
+  // instruction: THAT is the ~50-cycle floor of an N <= 64 MMA) and one per cycle for the LSU side (shuffles, LDS / STS, global
+  // stores); the fold removes 768 operand wavefronts per tile and adds 512 shuffles + ~300 exchange LDS/STS on the other side:
+  // LSU 65.6 % + TC 30.4 % busy, tensor pipe 36 %, and the epilogue warps, not the issuer, set the pace.
   // tcgen05.shift (tools/tmem_probe.cu: one instruction shifts 8 columns by one lane inside each 32-lane quarter, ~24 cycles
   // each) would cost 24 shifts = as much tensor-pipe time as the fold saves, and cannot cross the quarter boundary either.
   static const int fold_env = env_int("LY_TC_FOLD", 0);
