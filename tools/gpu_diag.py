@@ -66,6 +66,16 @@ def registry():
     add("tc_1x1_up_128", G.check_conv, cin=128, cout=128, k=1, H=16, W=24, B=3, up=True)
     add("tc_1x1_up_256_noact", G.check_conv, cin=64, cout=256, k=1, H=20, W=20, act=False, up=True)
     add("tc_1x1_up_views", G.check_conv, cin=128, cout=64, k=1, H=8, W=8, up=True, src_off=256, dst_off=0, dst_extra=64)
+    # round 2: TMA-store epilogue (resident weights, flat / brick mappings): clipping at image edges and at the tail of the pixel
+    # range, channel-slice destinations (neighbouring channels must stay untouched), batch-spanning bricks; tile-parallel
+    # epilogue in pair mode with a directly loaded shortcut
+    add("tc_3x3_s2_k32_odd_views", G.check_conv, cin=32, cout=64, k=3, stride=2, H=26, W=38, B=3, dst_off=64, dst_extra=32)
+    add("tc_1x1_views_tail", G.check_conv, cin=64, cout=64, k=1, H=5, W=7, B=3, src_off=32, src_extra=32, dst_off=64, dst_extra=32)
+    add("tc_1x1_96_64", G.check_conv, cin=96, cout=64, k=1, H=12, W=20, B=3)
+    add("tc_1x1_res_128", G.check_conv, cin=64, cout=128, k=1, H=9, W=11, B=4, res=True)
+    add("tc_3x3_pair_res_views", G.check_conv, cin=128, cout=128, k=3, H=12, W=20, B=2, res=True, dst_off=128, dst_extra=64)
+    add("tc_3x3_tiny_maps_b40", G.check_conv, cin=64, cout=64, k=3, H=4, W=4, B=40)
+    add("tc_3x3_s2_tiny_b33", G.check_conv, cin=32, cout=32, k=3, stride=2, H=6, W=10, B=33)
     add("tc_3x3_big", G.check_conv, cin=64, cout=64, k=3, H=160, W=160, B=4)
     add("tc_1x1_big", G.check_conv, cin=256, cout=128, k=1, H=80, W=80, B=8)
     # fused conv chains (LY_OP_CHAIN): single stages first (bisecting), then the real blocks
