@@ -739,15 +739,20 @@ __device__ __forceinline__ void tma_store_4d(uint32_t src, const CUtensorMap* tm
 // 16 bf16 channels of the shortcut / addend row.  32 lanes x 32 bytes in 32 different lines: like the stores, one 256-bit
 // request per lane costs about half the l1tex wavefronts of two 128-bit ones (ncu: the shortcut layers 3x3 64->64 @80^2
 // run 29.0 M LSU wavefronts against 16.7 M without the shortcut and 23.9 M for the MMA operands).
+#define LY_LD8(qual)                                                                                                   \
+  asm volatile(qual " {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"                                                                \
+               : "=r"(a0.x), "=r"(a0.y), "=r"(a0.z), "=r"(a0.w), "=r"(a1.x), "=r"(a1.y), "=r"(a1.z), "=r"(a1.w) : "l"(ptr) : "memory")
 __device__ __forceinline__ void ld_addend(const __nv_bfloat16* ptr, int wide, uint4& a0, uint4& a1) {
-  if (wide) {
-    asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=r"(a0.x), "=r"(a0.y), "=r"(a0.z), "=r"(a0.w), "=r"(a1.x), "=r"(a1.y), "=r"(a1.z), "=r"(a1.w) : "l"(ptr) : "memory");
-  } else {
+  if (wide == 1) { LY_LD8("ld.global.v8.b32"); }
+  else if (wide == 2) { LY_LD8("ld.global.L2::64B.v8.b32"); }
+  else if (wide == 3) { LY_LD8("ld.global.L1::no_allocate.v8.b32"); }
+  else if (wide == 4) { LY_LD8("ld.global.L1::no_allocate.L2::64B.v8.b32"); }
+  else {
     a0 = *reinterpret_cast<const uint4*>(ptr);
     a1 = *reinterpret_cast<const uint4*>(ptr + 8);
   }
 }
+#undef LY_LD8
 
 template <int MAP, int ADD, bool NCHW>
 __device__ __forceinline__ void epilogue_tiles(const Params& p, uint32_t bar_base, uint32_t tmem_base, const float* s_bias) {
@@ -839,9 +844,11 @@ __device__ __forceinline__ void epilogue_tiles(const Params& p, uint32_t bar_bas
     } else if (valid) {
       drow = p.dst + (size_t)lin * (uint32_t)p.dCtot + p.dC0 + n0;
     }
-    // the addend of the first chunk is requested before the accumulator wait
-    uint4 a0 = make_uint4(0, 0, 0, 0), a1 = a0;
+    // the addend of the first TWO chunks is requested before the accumulator wait, later chunks two chunks ahead: one
+    // chunk of lead (~150 cycles of work) does not cover the DRAM latency of these scattered 32-byte reads
+    uint4 a0 = make_uint4(0, 0, 0, 0), a1 = a0, b0 = a0, b1 = a0;
     if ((kRes || kUp) && arow && cs < nchunks) ld_addend(arow + cs * 16, p.ld256, a0, a1);
+    if ((kRes || kUp) && arow && cs + CS < nchunks) ld_addend(arow + (cs + CS) * 16, p.ld256, b0, b1);
     const int bs = pair ? as >> 1 : as;          // barrier index of this accumulator
     { PROF_T0(); mbar_wait(bar_tfull(bar_base, bs), aphase); PROF_ADD(w_tfull); }
     tc_fence_after();
@@ -870,9 +877,10 @@ __device__ __forceinline__ void epilogue_tiles(const Params& p, uint32_t bar_bas
         ffma2(v[4 * j + 2], v[4 * j + 3], __uint_as_float(nxt[4 * j + 2]), __uint_as_float(nxt[4 * j + 3]), pre, pre, bb.z, bb.w);
       }
       const uint4 r0 = a0, r1 = a1;
+      if (kRes || kUp) { a0 = b0; a1 = b1; }
       if (ch + CS < nchunks) {
         tmem_ld16(taddr + c + 16 * CS, nxt);   // next chunk in flight during the activation / store of this one
-        if ((kRes || kUp) && arow) ld_addend(arow + c + 16 * CS, p.ld256, a0, a1);
+        if ((kRes || kUp) && arow && ch + 2 * CS < nchunks) ld_addend(arow + c + 32 * CS, p.ld256, b0, b1);
       } else {                                  // the last chunk of this warp sits in registers: release the stage
         tc_fence_before();
         __syncwarp();
@@ -1545,9 +1553,13 @@ int32_t conv_tc_prepare(const ly_op& op, ConvTcState** out) {
   p.st256 = st256_ok && op.dst.ptr && op.dst.ctot % 16 == 0 && op.dst.c0 % 16 == 0 && reinterpret_cast<uintptr_t>(op.dst.ptr) % 32 == 0;
   p.res = (const __nv_bfloat16*)op.res.ptr; p.rCtot = op.res.ctot; p.rC0 = op.res.c0;
   {
-    static const int ld256_ok = env_int("LY_LD256", 1);
+    static const int ld256_ok = env_int("LY_LD256", 5);
     const ly_view& av = op.res.ptr ? op.res : op.up;
-    p.ld256 = ld256_ok && av.ptr && av.ctot % 16 == 0 && av.c0 % 16 == 0 && reinterpret_cast<uintptr_t>(av.ptr) % 32 == 0;
+    // Variant (LY_LD256 = 1..4 forces one; default 5 = choose): the rows are read once, so they bypass L1 (no_allocate: 3x3 64->64
+    // @80^2 + shortcut 0.148 -> 0.140 ms); when a row slice is only 64 bytes of a wider pixel (the 32-channel C2f parts of a
+    // 96-channel concat buffer) the L2 fill is also capped at 64 bytes (0.396 -> 0.323 ms; with wider rows that cap costs 8 %).
+    const bool ok256 = ld256_ok && av.ptr && av.ctot % 16 == 0 && av.c0 % 16 == 0 && reinterpret_cast<uintptr_t>(av.ptr) % 32 == 0;
+    p.ld256 = !ok256 ? 0 : (ld256_ok >= 5 ? (bn <= 32 && av.ctot > bn ? 4 : 3) : ld256_ok);
   }
   p.up = (const __nv_bfloat16*)op.up.ptr; p.uCtot = op.up.ctot; p.uC0 = op.up.c0; p.uH = op.up.H; p.uW = op.up.W; p.Wreal = Wo;
   p.bias = op.bias;
