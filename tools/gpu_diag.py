@@ -173,6 +173,8 @@ def registry():
     add("model_s_bf16_nc7", M.check_model, name="yolov10s", precision="bf16", hw=64, B=2, nc=7)
     add("model_n_f32_nc90", M.check_model, name="yolov10n", precision="fp32", hw=64, B=1, nc=90)
     add("model_s_f32_nc7", M.check_model, name="yolov10s", precision="fp32", hw=(64, 96), B=1, nc=7)
+    add("model_s_352x608_b3", M.check_model, name="yolov10s", precision="bf16", hw=(352, 608), B=3)
+    add("model_s_640_b7_nc20", M.check_model, name="yolov10s", precision="bf16", hw=(640, 640), B=7, nc=20)
     add("model_s_golden", M.check_model_golden, name="yolov10s")
     add("model_s_golden_640_bf16", M.check_model_golden_640, precision="bf16")
     add("model_s_golden_640_f32", M.check_model_golden_640, precision="fp32")
