@@ -1427,6 +1427,10 @@ int32_t conv_tc_prepare(const ly_op& op, ConvTcState** out) {
   // to spare (1x1 256->128 @80^2 0.217 -> 0.201 ms, 3x3/s2 32->64 @320^2 0.469 -> 0.406 ms, the upsample-folded 1x1
   // 128->128 @80^2 0.230 -> 0.193 ms).  N tiles must be whole 32-channel groups (a partial group is clipped by the tensor
   // map only at the END of the channel range, not at an N-tile boundary).
+  // (Tried for the column-parallel role too -- N = 256, a warp owning four consecutive chunks = two 32-channel groups: bit-correct,
+  //  but slower on 7 of 10 wide 1x1 shapes (512->256 @40^2 0.118 -> 0.134 ms, 512->512 @20^2 0.060 -> 0.069, resident 128->256 @80^2
+  //  0.237 -> 0.243; only 256->512 @40^2 gained, 0.155 -> 0.142): those layers stream their weights and need the shared memory
+  //  for ring stages.  Not kept.)
   static const int ts_env = env_int("LY_TC_TMASTORE", 2);
   p.ts = (ts_env && p.epi_groups == 4 && p.halo != 2 && op.dst.ptr && !op.nchw && bn % 32 == 0 && (p.b_resident || ts_env >= 3))
              ? (ts_env == 1 ? 1 : 2) : 0;
