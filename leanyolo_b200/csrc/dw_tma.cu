@@ -452,7 +452,11 @@ int32_t launch_strip(const ly_op& op, cudaStream_t st) {
   p.total_tiles = (int)total;
   p.box_bytes = IWt * IHt * CB * 2;
   p.stage_bytes = (p.box_bytes + 127) / 128 * 128;
-  int stages = (72 * 1024) / p.stage_bytes;   // <= ~72 KB per CTA so that three CTAs share an SM
+  static const int dws_kb = getenv("LY_DWS_SMEM_KB") ? atoi(getenv("LY_DWS_SMEM_KB")) : 36;
+  static const int dws_ctas = getenv("LY_DWS_CTAS") ? atoi(getenv("LY_DWS_CTAS")) : 6;
+  // (round 2 sweep, KB per CTA / CTAs per SM: 72/3 0.404, 54/4 0.361, 40/5 0.446, 36/6 0.382, 100/2 0.464 ms on 640 ch @40^2; 36/6 is the
+  //  best or within 1 % of the best on all four shapes tried)
+  int stages = (dws_kb * 1024) / p.stage_bytes;
   if (stages > kMaxStagesV) stages = kMaxStagesV;
   if (stages < 2 && 2 * p.stage_bytes <= 200 * 1024) stages = 2;   // big 7x7 halo tiles: two CTAs per SM instead
   LY_CHECK_ARG(stages >= 2, "dw_tma: tile does not fit in shared memory");
@@ -479,8 +483,8 @@ int32_t launch_strip(const ly_op& op, cudaStream_t st) {
     LY_CUDA(cudaFuncSetAttribute(dw_strip_kernel<K, S, CBV, TW_T, TH_T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   }
   const int sms = sm_count();
-  // three CTAs per SM when they fit: more loads in flight, epilogue of one overlaps compute of the other
-  int grid = 3 * sms;
+  // several CTAs per SM: more loads in flight, the stores of one overlap the compute of the others
+  int grid = dws_ctas * sms;
   if (grid > p.total_tiles) grid = p.total_tiles;
   launch_k(dw_strip_kernel<K, S, CBV, TW_T, TH_T>, dim3(grid), dim3(kThreadsDw), smem, st, p);
   return post_launch("dwconv_tma");
