@@ -488,6 +488,7 @@ struct Layout {
 }  // namespace
 
 struct ChainState {
+  B2bState* b2b = nullptr;   // set: the chain is a 3x3 -> 1x1 tail handled by conv_b2b.cu (the fields below are unused)
   Params p;
   ly_chain chain;   // own copy (weights / bias pointers are device pointers that stay valid)
   int grid;
@@ -500,6 +501,15 @@ bool chain_tc_supported(const ly_op& op) {
 
 int32_t chain_tc_prepare(const ly_op& op, ChainState** out) {
   LY_CHECK_ARG(chain_tc_supported(op), "chain: needs a bf16 op with a chain description");
+  if (conv_b2b_supported(op)) {
+    B2bState* b = nullptr;
+    if (conv_b2b_prepare(op, &b) == LY_OK) {     // (does not fit in shared memory: fall through to the generic kernel)
+      ChainState* st = new ChainState();
+      st->b2b = b;
+      *out = st;
+      return LY_OK;
+    }
+  }
   const ly_chain& ch = *op.chain;
   LY_CHECK_ARG(ch.n_stages >= 1 && ch.n_stages <= kMaxSt && ch.n_regions >= 1 && ch.n_regions <= kMaxReg && ch.n_in >= 1 &&
                    ch.n_in <= ch.n_regions, "chain: bad stage / region counts");
@@ -813,6 +823,7 @@ int32_t chain_tc_prepare(const ly_op& op, ChainState** out) {
 }
 
 int32_t chain_tc_launch(const ChainState* st, float* nchw_override, cudaStream_t s) {
+  if (st->b2b) return conv_b2b_launch(st->b2b, nchw_override, s);
   if (nchw_override) {
     Params p = st->p;
     p.nchw = nchw_override;
@@ -823,6 +834,9 @@ int32_t chain_tc_launch(const ChainState* st, float* nchw_override, cudaStream_t
   return post_launch("chain_tc");
 }
 
-void chain_tc_free(ChainState* st) { delete st; }
+void chain_tc_free(ChainState* st) {
+  if (st && st->b2b) conv_b2b_free(st->b2b);
+  delete st;
+}
 
 }  // namespace ly

@@ -82,6 +82,12 @@ int32_t chain_tc_prepare(const ly_op& op, ChainState** out);
 int32_t chain_tc_launch(const ChainState* st, float* nchw_override, cudaStream_t s);
 void chain_tc_free(ChainState* st);
 bool chain_tc_supported(const ly_op& op);
+// 3x3 -> 1x1 tail of a regression stack as a back-to-back GEMM (conv_b2b.cu); chain_tc_prepare prefers it when it applies
+struct B2bState;
+bool conv_b2b_supported(const ly_op& op);
+int32_t conv_b2b_prepare(const ly_op& op, B2bState** out);
+int32_t conv_b2b_launch(const B2bState* st, float* nchw_override, cudaStream_t s);
+void conv_b2b_free(B2bState* st);
 
 int sm_count();
 // true exactly once per (flag, current device): per-device one-time setup such as cudaFuncSetAttribute (the

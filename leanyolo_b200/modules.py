@@ -396,7 +396,8 @@ class Detect(nn.Module):
             for (out_name, reg, cls), r in zip(branches, firsts):
                 fin = reg[i][2]
                 wf, bf = pb.param(fin.weight), pb.param(fin.bias)
-                if pb.chain_fusable() and r.c in (16, 32, 64) and r.c == c2 and (4 * self.reg_max) % 16 == 0:
+                if ((pb.tail_fusable() and r.c in (32, 64)) or (pb.chain_fusable() and r.c == 16)) and r.c == c2 and \
+                        (4 * self.reg_max) % 16 == 0 and 4 * self.reg_max <= 64:
                     # 3x3 -> 1x1 tail of the regression stack as one launch (the 3x3 result stays in shared memory)
                     wm, bm = reg[i][1].folded(pb)
                     pb.chain(r, [c2, c2], 1, [dict(k=3, act=True, w=wm, b=bm, src=[(0, 0, c2)], dst=(1, 0, c2)),

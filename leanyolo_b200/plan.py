@@ -413,6 +413,12 @@ class PlanBuilder:
         import os
         return self.tensor_core and os.environ.get("LEANYOLO_FUSE_CHAIN", "0") == "1"
 
+    def tail_fusable(self) -> bool:
+        """The 3x3 -> 1x1 tail of a regression stack as ONE back-to-back GEMM launch (csrc/conv_b2b.cu, reached through
+        LY_OP_CHAIN).  On by default on the bf16 tensor-core path; LEANYOLO_FUSE_TAIL=0 lowers the two convs separately."""
+        import os
+        return self.tensor_core and os.environ.get("LEANYOLO_FUSE_TAIL", "1") != "0"
+
     def chain(self, src: View, regions: Sequence[int], n_in: int, stages: Sequence[dict], *, dst: Optional[View] = None,
               nchw: Optional[Tuple[str, int, int, int, int]] = None) -> Optional[View]:
         """A chain of dense conv stages executed per spatial tile with every intermediate in shared memory

@@ -75,6 +75,23 @@ def spec_two_in(g):
 SPECS = {"c2f": spec_c2f, "tail": spec_tail, "single": spec_single, "two_in": spec_two_in}
 
 
+def build_tail_op(B, H, W, c, cout, seed=0):
+    """A ready-to-launch 3x3 -> 1x1 tail op with a public NCHW output on random data (timing tool: tools/bench_b2b.py)."""
+    g = torch.Generator().manual_seed(seed)
+    regions, n_in, stages = SPECS["tail"](g, c=c, cout=cout)
+    keep = []
+    ch = make_chain(regions, n_in, stages, keep)
+    x = torch.randn(B, H, W, c, device=DEV).to(torch.bfloat16)
+    out = torch.zeros(B, cout, H, W, device=DEV)
+    op = N.LyOp()
+    op.kind, op.dtype, op.B, op.k, op.stride, op.act, op.ext_slot = N.OP_CHAIN, N.LY_BF16, B, 1, 1, 0, -1
+    op.src = view(x, 0, c)
+    op.chain = C.pointer(ch)
+    op.nchw, op.nchw_ctot, op.nchw_c0, op.nchw_c = out.data_ptr(), cout, 0, cout
+    keep += [ch, x, out]
+    return op, keep
+
+
 def check_chain(kind="c2f", B=2, H=40, W=40, src_off=0, src_extra=0, dst_off=0, dst_extra=0, nchw=False, nchw_c=None,
                 seed=0, tol=2e-2, **kw):
     g = torch.Generator().manual_seed(seed)

@@ -230,10 +230,12 @@ def test_lowering_matches_oracle_fp32(name):
             assert float((outs[(br, i)] - ref[br][i]).abs().max() / ref[br][i].abs().max()) < 1e-4, (br, i)
 
 
-@pytest.mark.parametrize("chain", ["0", "1"])
-def test_lowering_bf16_storage_emulation_within_tolerance(chain, monkeypatch):
-    """chain=1: the C2f block and the regression tails lowered to LY_OP_CHAIN (opt-in fused chains)."""
+@pytest.mark.parametrize("chain,tail", [("0", "0"), ("0", "1"), ("1", "1")])
+def test_lowering_bf16_storage_emulation_within_tolerance(chain, tail, monkeypatch):
+    """tail=1 (default): the 3x3 -> 1x1 regression tails lowered to LY_OP_CHAIN (back-to-back GEMM kernel);
+    chain=1: also the C2f block (opt-in fused chains)."""
     monkeypatch.setenv("LEANYOLO_FUSE_CHAIN", chain)
+    monkeypatch.setenv("LEANYOLO_FUSE_TAIL", tail)
     m = get_model("yolov10s", weights=None, class_names=NAMES)
     sd = synth_state_dict(m.state_dict(), seed=1, gain=1.25)
     m.load_state_dict(sd)
@@ -241,7 +243,8 @@ def test_lowering_bf16_storage_emulation_within_tolerance(chain, monkeypatch):
     ref = O.forward(sd, x)
     pb = PlanBuilder(1, 128, 128, "bf16")
     m.emit(pb)
-    assert any(op.kind == "chain" for op in pb.ops) == (chain == "1")
+    n_chain = sum(op.kind == "chain" for op in pb.ops)
+    assert n_chain == (0 if tail == "0" and chain == "0" else (6 if chain == "0" else 7))   # 2 branches x 3 levels (+ the C2f block)
     outs = run_plan(pb, x, quant=lambda t: t.to(torch.bfloat16).float())
     for i in range(3):
         r = ref["one2one"][i]
@@ -277,7 +280,16 @@ def test_plan_is_pure_views_no_copy_ops_and_counts_flops():
     # head branches is one GEMM per level (-3) and 12 follow a depthwise conv in a fused dw->1x1
     # launch; RepVGGDW pairs merged: 24 dw -> 22, 12 of them inside the fused launches
     # the two upsample+concat+1x1 of the top-down neck are 2 convs each (half-resolution part + skip part), no upsample op
-    assert kinds == {"stem": 1, "conv": 73, "dw": 10, "dwpw": 12, "pool": 1, "attn": 1}
+    # round 2: the six 3x3 -> 1x1 regression tails (2 branches x 3 levels) are one back-to-back GEMM launch each (chain ops)
+    assert kinds == {"stem": 1, "conv": 61, "chain": 6, "dw": 10, "dwpw": 12, "pool": 1, "attn": 1}
+    os.environ["LEANYOLO_FUSE_TAIL"] = "0"
+    try:
+        pbt = PlanBuilder(1, 640, 640, "bf16")
+        m.emit(pbt)
+    finally:
+        del os.environ["LEANYOLO_FUSE_TAIL"]
+    assert sum(op.kind == "conv" for op in pbt.ops) == 73 and not any(op.kind == "chain" for op in pbt.ops)
+    assert abs(pbt.dense_flops() - pb.dense_flops()) < 1e-6 * pb.dense_flops()
     # opt-in fused chains (LY_OP_CHAIN): the 160x160 C2f block (4 convs) and the 3x3 -> 1x1 tails of the six regression stacks (2 each)
     os.environ["LEANYOLO_FUSE_CHAIN"] = "1"
     try:

@@ -85,6 +85,11 @@ def registry():
     add("chain_single_3x3_16_n48", CH.check_chain, kind="single", k=3, cin=16, cout=48, H=12, W=28, B=3)
     add("chain_tail_64_nchw", CH.check_chain, kind="tail", c=64, cout=64, H=20, W=20, nchw=True)
     add("chain_tail_64_80", CH.check_chain, kind="tail", c=64, cout=64, H=80, W=80, B=3, nchw=True, nchw_c=61)
+    # tails with a public NCHW output take the back-to-back GEMM kernel (conv_b2b.cu); odd sizes, channel padding, batch tails
+    add("chain_tail_64_odd_b5", CH.check_chain, kind="tail", c=64, cout=64, H=13, W=27, B=5, nchw=True)
+    add("chain_tail_32_48_nchw", CH.check_chain, kind="tail", c=32, cout=48, H=24, W=40, B=2, nchw=True, nchw_c=40)
+    add("chain_tail_64_160", CH.check_chain, kind="tail", c=64, cout=64, H=160, W=160, B=2, nchw=True)
+    add("chain_tail_64_act_last", CH.check_chain, kind="tail", c=64, cout=32, H=40, W=40, B=3, nchw=True, act_last=True)
     add("chain_tail_32_views", CH.check_chain, kind="tail", c=32, cout=48, H=24, W=40, act_last=True, src_off=32, src_extra=16, dst_off=16, dst_extra=32)
     add("chain_two_in", CH.check_chain, kind="two_in", H=20, W=36)
     add("chain_c2f_32", CH.check_chain, kind="c2f", c=32, H=40, W=40)
