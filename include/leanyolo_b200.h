@@ -106,7 +106,8 @@ typedef struct ly_chain_stage {
 typedef struct ly_chain {
   int32_t n_regions, n_in;
   int32_t region_c[LY_CHAIN_MAX_REGIONS];   /* channels per region: 16, 32 or 64 */
-  int32_t n_stages, reserved;
+  int32_t n_stages, reserved;               /* reserved == 2: stage 0 is a 3x3 with STRIDE 2 (two-stage chains of the back-to-back
+                                               kernel, conv_b2b.cu); 0: every stage has stride 1 */
   ly_chain_stage st[LY_CHAIN_MAX_STAGES];
 } ly_chain;
 

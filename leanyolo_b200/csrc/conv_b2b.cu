@@ -12,6 +12,13 @@
 // epilogues are tile-parallel (two tile groups of four quarter warps each, four accumulator stages per GEMM), so neither
 // waits for the other.  Layer by layer the pair costs a 64-channel bf16 round trip through HBM and a second launch.
 //
+// Stride-2 variant (backbone cv1 -> c2.cv1: 3x3/s2 32->64 then 1x1 64->64, the 64-channel 160x160 intermediate of yolov10s, 1.7 GB
+// of HBM traffic per step at batch 256, never exists): the band is loaded as FOUR parity planes (even / odd input rows x even /
+// odd input columns, TMA elementStrides = 2), each [plane row][P pixels] with the same pitch P as the accumulator rows
+// (m = oy*P + ox).  Tap (ky, kx) of output pixel m then reads row m + r_off*P + j_off of ONE plane: ky = 1 the even rows, ky =
+// 0 / 2 the odd rows at r_off 0 / 1; kx = 1 the even columns at j_off 1, kx = 0 / 2 the odd columns at j_off 0 / 1 (plane column j
+// holds input column 2j - 2 resp. 2j - 1, so column 0 is the left zero padding).  Same constant-offset descriptors as stride 1.
+//
 // Roles (one CTA per SM, persistent over (band, image) units):
 //   warp 0       TMA: both weight sets once (resident), the input band of every unit (2 stages)
 //   warp 1       tcgen05.mma issuer: GEMM 1 of tile i, then GEMM 2 of tile i-1 (its A2 tile is ready by then)
@@ -42,7 +49,12 @@ constexpr uint32_t kSmemMaxB = 227 * 1024;
 struct BParams {
   CUtensorMap tmA, tmW1, tmW2;
   int C, C1, C2;                 // input / middle / output channels (multiples of 16; C, C1 in {32, 64})
-  int H, W, B;
+  int H, W, B;                   // OUTPUT extent of the 3x3 (= input extent at stride 1, half of it at stride 2)
+  int s2;                        // the 3x3 has stride 2: the band is four parity planes (see the header comment)
+  int pw, npieces, piece1;       // stride 2: columns per TMA box, boxes per plane row, first column of the second box
+  uint32_t tap_off16[9];         // A-operand offset of every tap from the tile's first row, 16-byte units
+  uint32_t plane16[4];           // stride 2: offsets of the planes EE, EO, OE, OO inside a stage, 16-byte units
+  __nv_bfloat16* dst; int dCtot, dC0, st256;   // NHWC bf16 destination (instead of nchw)
   int band_r, band_w, band_mt, bands, total_units;
   uint32_t mg_bw, mg_bands;
   int a_stage, a_box;            // bytes
@@ -63,11 +75,11 @@ enum { kAFull = 0, kAEmpty = 2, kWFull = 4, kD1Full = 5, kD1Empty = 9, kA2Full =
 // rebuilt the descriptors from the parameter bank inside the loop: 65 cycles per iteration on the single issuing thread, more
 // than the MMA itself).
 template <int KS>
-__device__ __forceinline__ void b2b_gemm1(uint32_t d, uint32_t am, uint32_t w1lo, uint32_t slab16, uint32_t bw16, uint32_t row16,
+__device__ __forceinline__ void b2b_gemm1(uint32_t d, uint32_t am, uint32_t w1lo, uint32_t slab16, const uint32_t (&toff)[9],
                                           uint64_t hi, uint32_t idesc, bool skip) {
 #pragma unroll
   for (int tap = 0; tap < 9; ++tap) {
-    const uint32_t at = am + (uint32_t)(tap / 3) * bw16 + (uint32_t)(tap % 3) * row16;
+    const uint32_t at = am + toff[tap];
     const uint32_t bt = w1lo + (uint32_t)tap * slab16;
 #pragma unroll
     for (int kk = 0; kk < KS; ++kk)
@@ -139,7 +151,26 @@ __global__ void __launch_bounds__(kThreadsB, 1) conv_b2b_kernel(const __grid_con
         const int band = unit - (int)b * p.bands;
         mbar_wait(B(kAEmpty + sa), pa ^ 1u);
         mbar_expect_tx(B(kAFull + sa), (uint32_t)p.a_box);
-        tma_load_4d(a_base + (uint32_t)sa * p.a_stage, &p.tmA, B(kAFull + sa), 0, -1, band * p.band_r - 1, (int)b);
+        const uint32_t sb = a_base + (uint32_t)sa * p.a_stage;
+        if (!p.s2) {
+          tma_load_4d(sb, &p.tmA, B(kAFull + sa), 0, -1, band * p.band_r - 1, (int)b);
+        } else {
+          // four parity planes (even / odd input rows x even / odd input columns), every plane row loaded by 1-row boxes of
+          // pw columns (a box may traverse at most 256 input columns); rows and pieces start at multiples of 8 pixels
+          const uint32_t rowb = (uint32_t)(p.band_w * p.C * 2), colb = (uint32_t)(p.C * 2);
+          const int oy0 = band * p.band_r;
+          for (int pl = 0; pl < 4; ++pl) {
+            const int odd_r = pl >> 1, odd_c = pl & 1;
+            const int rows = p.band_r + odd_r;
+            for (int r = 0; r < rows; ++r)
+              for (int pc = 0; pc < p.npieces; ++pc) {
+                const int j0 = pc ? p.piece1 : 0;                      // plane column of the box's first pixel
+                tma_load_4d(sb + (p.plane16[pl] << 4) + (uint32_t)r * rowb + (uint32_t)j0 * colb, &p.tmA, B(kAFull + sa), 0,
+                            2 * j0 - 2 + odd_c,          // plane column j holds input column 2j - 2 (even planes) / 2j - 1 (odd planes)
+                            2 * (oy0 + r) - odd_r, (int)b);   // plane row r holds input row 2(oy0 + r) (even) / 2(oy0 + r) - 1 (odd)
+              }
+          }
+        }
         if (++sa == 2) { sa = 0; pa ^= 1u; }
       }
     }
@@ -147,7 +178,9 @@ __global__ void __launch_bounds__(kThreadsB, 1) conv_b2b_kernel(const __grid_con
     // ============================== MMA issuer ================================
     if (elect_one()) {
       const uint32_t row16 = (uint32_t)p.C >> 3;                         // one pixel row of the band, 16-byte units
-      const uint32_t bw16 = (uint32_t)p.band_w * row16;
+      uint32_t toff[9];
+#pragma unroll
+      for (int t = 0; t < 9; ++t) toff[t] = p.tap_off16[t];
       const int ks1 = p.C / 16, ks2 = p.C1 / 16;
       const uint64_t hi1 = (uint64_t)p.hi_a << 32, hi2 = (uint64_t)p.hi_a2 << 32;
       const uint32_t id1 = p.idesc1, id2 = p.idesc2, slab16 = (uint32_t)p.w1_slab >> 4, w1lo = (w1_base >> 4) | (1u << 16);
@@ -199,8 +232,8 @@ __global__ void __launch_bounds__(kThreadsB, 1) conv_b2b_kernel(const __grid_con
           IADD(w_d1e, m0, m1);
           const uint32_t d = tmem_base + (uint32_t)st * c1;
           const uint32_t am = a_lo0 + (uint32_t)sa * a_stage16 + (uint32_t)(mt * 128) * row16;
-          if (ks1 == 4) b2b_gemm1<4>(d, am, w1lo, slab16, bw16, row16, hi1, id1, BEXP(p, 1));
-          else b2b_gemm1<2>(d, am, w1lo, slab16, bw16, row16, hi1, id1, BEXP(p, 1));
+          if (ks1 == 4) b2b_gemm1<4>(d, am, w1lo, slab16, toff, hi1, id1, BEXP(p, 1));
+          else b2b_gemm1<2>(d, am, w1lo, slab16, toff, hi1, id1, BEXP(p, 1));
           umma_commit(B(kD1Full + st));
           IT(m2);
           IADD(t_i1, m1, m2);
@@ -306,7 +339,8 @@ __global__ void __launch_bounds__(kThreadsB, 1) conv_b2b_kernel(const __grid_con
       const uint32_t oy = __umulhi(m, p.mg_bw), ox = m - oy * (uint32_t)p.band_w;
       const uint32_t h = bd * (uint32_t)p.band_r + oy;
       const bool valid = ox < (uint32_t)p.W && oy < (uint32_t)p.band_r && h < (uint32_t)p.H;
-      float* nrow = valid ? p.nchw + (size_t)(b * (uint32_t)p.nCtot + (uint32_t)p.nC0) * hw + (h * (uint32_t)p.W + ox) : nullptr;
+      float* nrow = (valid && p.nchw) ? p.nchw + (size_t)(b * (uint32_t)p.nCtot + (uint32_t)p.nC0) * hw + (h * (uint32_t)p.W + ox) : nullptr;
+      __nv_bfloat16* drow = (valid && p.dst) ? p.dst + (size_t)((b * (uint32_t)p.H + h) * (uint32_t)p.W + ox) * (uint32_t)p.dCtot + p.dC0 : nullptr;
       const int st = (int)(j & (kAcc - 1));
       mbar_wait(B(kD2Full + st), (uint32_t)((j >> 2) & 1));
       tc_fence_after();
@@ -341,6 +375,14 @@ __global__ void __launch_bounds__(kThreadsB, 1) conv_b2b_kernel(const __grid_con
           for (int jj = 0; jj < 16; ++jj)
             if (c + jj < p.nC) np[(size_t)jj * hw] = v[jj];
         }
+        if (drow && !BEXP(p, 2)) {
+          if (p.st256) {
+            store_bf16x16(drow + c, v);
+          } else {
+            store_vec<__nv_bfloat16>(drow + c, v);
+            store_vec<__nv_bfloat16>(drow + c + 8, v + 8);
+          }
+        }
       }
       advance();
       advance();
@@ -363,13 +405,16 @@ struct B2bState {
   size_t smem;
 };
 
-// chain = [3x3 (SiLU) on the whole input region, 1x1 on its result], input and middle width 32 or 64, public NCHW output
+// chain = [3x3 (SiLU, stride 1 or 2) on the whole input region, 1x1 on its result], input and middle width 32 or 64; the result
+// goes to the public NCHW tensor or to an NHWC bf16 slice.  ly_chain.reserved == 2 marks a stride-2 first stage.
 bool conv_b2b_supported(const ly_op& op) {
-  if (op.kind != LY_OP_CHAIN || op.dtype != LY_BF16 || !op.chain || !op.nchw || op.dst.ptr) return false;
+  if (op.kind != LY_OP_CHAIN || op.dtype != LY_BF16 || !op.chain) return false;
+  if ((op.nchw != nullptr) == (op.dst.ptr != nullptr)) return false;
   static const int enabled = getenv("LY_B2B") ? atoi(getenv("LY_B2B")) : 1;
   if (!enabled) return false;
   const ly_chain& ch = *op.chain;
   if (ch.n_stages != 2 || ch.n_regions != 2 || ch.n_in != 1) return false;
+  const int stride = ch.reserved == 2 ? 2 : 1;
   const ly_chain_stage &s0 = ch.st[0], &s1 = ch.st[1];
   const int C = op.src.c, C1 = s0.cout, C2 = s1.cout;
   if (!(C == 32 || C == 64) || !(C1 == 32 || C1 == 64) || C2 % 16 || C2 < 16 || C2 > 64) return false;
@@ -378,7 +423,10 @@ bool conv_b2b_supported(const ly_op& op) {
   if (s0.dst.region != 1 || s0.dst.c0 != 0 || s0.dst.c != C1 || s0.res.region >= 0) return false;
   if (s1.k != 1 || s1.n_src != 1 || s1.src[0].region != 1 || s1.src[0].c0 != 0 || s1.src[0].c != C1) return false;
   if (s1.dst.region >= 0 || s1.res.region >= 0) return false;
-  if (op.src.c0 % 8 || op.src.ctot % 8 || op.src.W + 2 > 256) return false;
+  if (op.src.c0 % 8 || op.src.ctot % 8) return false;
+  if (stride == 1 && op.src.W + 2 > 256) return false;
+  if (stride == 2 && (op.src.H % 2 || op.src.W % 2 || op.src.W / 2 + 8 > 512)) return false;
+  if (op.dst.ptr && (op.dst.c != C2 || op.dst.c0 % 8 || op.dst.ctot % 8 || op.dst.H != op.src.H / stride || op.dst.W != op.src.W / stride)) return false;
   return true;
 }
 
@@ -390,29 +438,43 @@ int32_t conv_b2b_prepare(const ly_op& op, B2bState** out) {
   B2bState* st = new B2bState();
   BParams& p = st->p;
   memset(&p, 0, sizeof(p));
-  const int H = op.src.H, W = op.src.W;
+  const int stride = ch.reserved == 2 ? 2 : 1;
+  const int Hi = op.src.H, Wi = op.src.W, H = Hi / stride, W = Wi / stride;     // H, W: the OUTPUT extent
+  p.s2 = stride == 2;
   p.C = op.src.c; p.C1 = ch.st[0].cout; p.C2 = ch.st[1].cout;
   p.H = H; p.W = W; p.B = op.B;
   p.act2 = ch.st[1].act;
   p.exp = getenv("LY_TC_EXP") ? atoi(getenv("LY_TC_EXP")) : 0;
   p.b1 = ch.st[0].bias; p.b2 = ch.st[1].bias;
   p.nchw = op.nchw; p.nCtot = op.nchw_ctot; p.nC0 = op.nchw_c0; p.nC = op.nchw_c;
+  p.dst = (__nv_bfloat16*)op.dst.ptr; p.dCtot = op.dst.ctot; p.dC0 = op.dst.c0;
+  p.st256 = op.dst.ptr && op.dst.ctot % 16 == 0 && op.dst.c0 % 16 == 0 && reinterpret_cast<uintptr_t>(op.dst.ptr) % 32 == 0;
   p.w1_slab = (p.C1 * p.C * 2 + 1023) / 1024 * 1024;
   p.w2_bytes = (p.C2 * p.C1 * 2 + 1023) / 1024 * 1024;
   p.a2_stage = 128 * p.C1 * 2;
-  const int BW = W + 2;
+  // accumulator-row pitch: W + 2 padded columns (stride 1) or W + 1 rounded up to 8 pixels (stride 2: plane rows and the TMA
+  // pieces of a row then start on 512-byte boundaries whatever the swizzle width)
+  const int BW = p.s2 ? (W + 1 + 7) / 8 * 8 : W + 2;
+  const int rowb = p.C * 2;
   const long long fixed = 1024 + 9LL * p.w1_slab + p.w2_bytes + 2LL * p.a2_stage + (p.C1 + p.C2) * 4 + 8 * kBarSlots;
-  // band height: fewest MMA tiles per output row that fit two band stages (same model as conv_tc's band mode: the MMA issue
-  // and the TMA row rate are the two costs; with resident weights the former decides)
+  const int sms = sm_count();
+  auto stage_bytes = [&](int R, int mt) -> long long {
+    if (!p.s2) {
+      const int need_rows = mt * 128 + 2 * BW + 2;       // the tap windows of the last M tile reach 2*BW + 2 rows past its rows
+      return ((long long)std::max((R + 2) * BW, need_rows) * rowb + 1023) / 1024 * 1024;
+    }
+    const long long ev = ((long long)R * BW * rowb + 1023) / 1024 * 1024, od = ((long long)(R + 1) * BW * rowb + 1023) / 1024 * 1024;
+    return 2 * ev + 2 * od;     // (reads past the last plane land in the next stage / the weights: garbage rows, never stored)
+  };
+  // band height: the cheapest schedule that fits two band stages (MMA issue ~50 cycles per instruction, TMA ~5 cycles per row)
   int best_r = 0;
   double best_cost = 1e30;
-  const int sms = sm_count();
   for (int R = 1; R <= H && R + 2 <= 256; ++R) {
-    const long long stage = ((long long)(R + 2) * BW * p.C * 2 + 1023) / 1024 * 1024;
-    if (fixed + 2 * stage > (long long)kSmemMaxB) break;
     const int mt = ((R - 1) * BW + W + 127) / 128;
+    if (fixed + 2 * stage_bytes(R, mt) > (long long)kSmemMaxB) break;
     const long long units = (long long)((H + R - 1) / R) * op.B;
-    const double unit_cost = std::max((double)mt * (9 * (p.C / 16) * 50.0 + (p.C1 / 16) * 50.0), (double)(R + 2) * BW * 5.0);
+    const double rows_tma = p.s2 ? (double)(4 * R + 2) * BW : (double)(R + 2) * BW;
+    const double unit_cost = std::max((double)mt * (9 * (p.C / 16) * 50.0 + (p.C1 / 16) * 50.0), rows_tma * 5.0);
     const double cost = (double)((units + sms - 1) / sms) * unit_cost;
     if (cost < best_cost) { best_cost = cost; best_r = R; }
   }
@@ -425,10 +487,27 @@ int32_t conv_b2b_prepare(const ly_op& op, B2bState** out) {
   p.total_units = (int)units;
   p.mg_bw = (uint32_t)((1ull << 32) / (uint32_t)BW + 1);
   p.mg_bands = p.bands > 1 ? (uint32_t)((1ull << 32) / (uint32_t)p.bands + 1) : 0u;
-  p.a_box = (best_r + 2) * BW * p.C * 2;
-  // the tap windows of the last M tile reach 2*BW + 2 rows past the rows it outputs: the stage must cover them
-  const int need_rows = p.band_mt * 128 + 2 * BW + 2;
-  p.a_stage = (std::max((best_r + 2) * BW, need_rows) * p.C * 2 + 1023) / 1024 * 1024;
+  p.a_stage = (int)stage_bytes(best_r, p.band_mt);
+  const uint32_t row16 = (uint32_t)rowb >> 4;
+  if (!p.s2) {
+    p.a_box = (best_r + 2) * BW * rowb;
+    for (int t = 0; t < 9; ++t) p.tap_off16[t] = (uint32_t)((t / 3) * BW + (t % 3)) * row16;
+  } else {
+    const uint32_t ev = (uint32_t)(((long long)best_r * BW * rowb + 1023) / 1024 * 1024), od = (uint32_t)(((long long)(best_r + 1) * BW * rowb + 1023) / 1024 * 1024);
+    p.plane16[0] = 0; p.plane16[1] = ev >> 4; p.plane16[2] = (2 * ev) >> 4; p.plane16[3] = (2 * ev + od) >> 4;     // EE, EO, OE, OO
+    for (int t = 0; t < 9; ++t) {
+      const int ky = t / 3, kx = t % 3;
+      const int plane = (ky == 1 ? 0 : 2) + (kx == 1 ? 0 : 1);
+      const int r_off = ky == 2 ? 1 : 0, j_off = kx == 0 ? 0 : 1;
+      p.tap_off16[t] = p.plane16[plane] + (uint32_t)(r_off * BW + j_off) * row16;
+    }
+    // TMA pieces of a plane row: one box may traverse at most 256 input columns = 128 plane columns
+    p.npieces = BW <= 128 ? 1 : 2;
+    p.pw = p.npieces == 1 ? BW : (BW / 2 + 7) / 8 * 8;
+    p.piece1 = BW - p.pw;
+    if (p.pw > 128 || p.piece1 % 8) { delete st; set_error("conv_b2b: map too wide for the stride-2 band"); return LY_E_ARG; }
+    p.a_box = (2 * best_r + 2 * (best_r + 1)) * p.npieces * p.pw * rowb;
+  }
   st->smem = (size_t)fixed + 2 * (size_t)p.a_stage;
   if (st->smem > kSmemMaxB) { delete st; set_error("conv_b2b: tile does not fit in shared memory"); return LY_E_ARG; }
   if (st->smem < 120 * 1024) st->smem = 120 * 1024;     // one CTA per SM (all 512 TMEM columns)
@@ -445,10 +524,11 @@ int32_t conv_b2b_prepare(const ly_op& op, B2bState** out) {
   auto tswz = [](int kc) { return kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B; };
   {
     char* base = (char*)op.src.ptr + (size_t)op.src.c0 * 2;
-    cuuint64_t dims[4] = {(cuuint64_t)p.C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)op.B};
-    cuuint64_t strides[3] = {(cuuint64_t)op.src.ctot * 2, (cuuint64_t)op.src.ctot * 2 * W, (cuuint64_t)op.src.ctot * 2 * W * H};
+    cuuint64_t dims[4] = {(cuuint64_t)p.C, (cuuint64_t)Wi, (cuuint64_t)Hi, (cuuint64_t)op.B};
+    cuuint64_t strides[3] = {(cuuint64_t)op.src.ctot * 2, (cuuint64_t)op.src.ctot * 2 * Wi, (cuuint64_t)op.src.ctot * 2 * Wi * Hi};
     cuuint32_t box[4] = {(cuuint32_t)p.C, (cuuint32_t)BW, (cuuint32_t)(best_r + 2), 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
+    if (p.s2) { box[1] = 2 * p.pw; box[2] = 2; estr[1] = 2; estr[2] = 2; }      // one plane row piece: pw columns of one row
     CUresult r = encode(&p.tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, tswz(p.C),
                         p.C == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_64B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { delete st; set_error("conv_b2b: cuTensorMapEncodeTiled(A) failed with %d", (int)r); return LY_E_CUDA; }
@@ -479,8 +559,8 @@ int32_t conv_b2b_prepare(const ly_op& op, B2bState** out) {
   }
   static const int debug = getenv("LY_TC_DEBUG") ? atoi(getenv("LY_TC_DEBUG")) : 0;
   if (debug)
-    fprintf(stderr, "[conv_b2b] %dx%d C %d -> %d -> %d B %d: band R %d mt %d bands %d units %d a_stage %d smem %zu\n", H, W, p.C, p.C1, p.C2, op.B,
-            p.band_r, p.band_mt, p.bands, p.total_units, p.a_stage, st->smem);
+    fprintf(stderr, "[conv_b2b] s%d out %dx%d C %d -> %d -> %d B %d: band R %d pitch %d mt %d bands %d units %d a_stage %d pieces %d x %d smem %zu\n", stride,
+            H, W, p.C, p.C1, p.C2, op.B, p.band_r, BW, p.band_mt, p.bands, p.total_units, p.a_stage, p.npieces, p.pw, st->smem);
   *out = st;
   return LY_OK;
 }

@@ -151,6 +151,7 @@ class Engine:
         ex = op.extra
         ch = N.LyChain()
         ch.n_regions, ch.n_in, ch.n_stages = len(ex["regions"]), ex["n_in"], len(ex["stages"])
+        ch.reserved = 2 if ex.get("stride0", 1) == 2 else 0      # stride of the first stage (include/leanyolo_b200.h)
         for i, c in enumerate(ex["regions"]):
             ch.region_c[i] = c
         for i, st in enumerate(ex["stages"]):
@@ -249,9 +250,10 @@ class Engine:
                 for i, op in enumerate(comp.pb.ops):
                     flops = byts = 0
                     if op.kind == "chain":
-                        hw_ = op.src.H * op.src.W
+                        s0 = op.extra.get("stride0", 1)
+                        hw_ = (op.src.H // s0) * (op.src.W // s0)
                         flops = sum(2 * n * hw_ * st["cout"] * st["cin"] * st["k"] ** 2 for st in op.extra["stages"])
-                        byts = n * hw_ * (op.src.c * es + op.cout * (es if op.dst is not None else 4))
+                        byts = n * (op.src.H * op.src.W * op.src.c * es + hw_ * op.cout * (es if op.dst is not None else 4))
                     elif op.kind in ("conv", "dwpw"):
                         Ho, Wo = op.src.H // op.stride, op.src.W // op.stride
                         flops = 2 * n * Ho * Wo * op.cout * op.cin * op.k * op.k

@@ -125,14 +125,24 @@ class C2f(nn.Module):
         self.cv2 = ConvBN((2 + n) * c, cout, 1)
         self.m = nn.ModuleList([CIB(c, lk) if cib else Bottleneck(c, shortcut) for _ in range(n)])
 
-    def emit(self, pb, src, dst=None, upcat=None):
+    def emit(self, pb, src, dst=None, upcat=None, pre=None):
         """``upcat=(low, skip)``: the block's input is cat[upsample2x(low), skip] (top-down neck);
-        cv1 is then applied without materialising either (PlanBuilder.upcat_conv)."""
+        cv1 is then applied without materialising either (PlanBuilder.upcat_conv).
+        ``pre``: a stride-2 3x3 ``ConvBN`` whose output is this block's input: ``pre`` -> cv1 run as ONE back-to-back GEMM
+        launch on ``src`` (csrc/conv_b2b.cu), the tensor between them never exists (backbone.py: cv1 -> c2)."""
         c = self.c
-        if upcat is None and self._chain_ok(pb, src):
+        if upcat is None and pre is None and self._chain_ok(pb, src):
             return self._emit_chain(pb, src, dst)
-        cat = pb.buffer(src.H, src.W, (2 + self.n) * c)
-        if upcat is not None:
+        H, W = (src.H // 2, src.W // 2) if pre is not None else (src.H, src.W)
+        cat = pb.buffer(H, W, (2 + self.n) * c)
+        if pre is not None:
+            w0, b0 = pre.folded(pb)
+            w1, b1 = self.cv1.folded(pb)
+            cm = pre.conv.out_channels
+            pb.chain(src, [src.c, cm], 1, [dict(k=3, act=True, w=w0, b=b0, src=[(0, 0, src.c)], dst=(1, 0, cm)),
+                                           dict(k=1, act=self.cv1.act, w=w1, b=b1, src=[(1, 0, cm)])],
+                     dst=cat.view(0, 2 * c), stride0=2)
+        elif upcat is not None:
             w, b = self.cv1.folded(pb)
             pb.upcat_conv(upcat[0], upcat[1], w, b, act=self.cv1.act, dst=cat.view(0, 2 * c))
         else:
@@ -263,8 +273,13 @@ class Backbone(nn.Module):
         return out[("c3", 0)], out[("c4", 0)], out[("c5", 0)]
 
     def emit(self, pb, x, c3_dst=None, c4_dst=None, c5_dst=None):
-        y = self.cv1.emit(pb, x)
-        y = self.cv3.emit(pb, self.c2.emit(pb, y))
+        cv1, c2 = self.cv1, self.c2
+        if (pb.stem_pair_fusable() and cv1.k == 3 and cv1.s == 2 and cv1.g == 1 and cv1.act and x.c in (32, 64) and x.H % 2 == 0 and x.W % 2 == 0
+                and cv1.conv.out_channels in (32, 64) and c2.cv1.conv.out_channels in (32, 64) and c2.cv1.act and not pb.chain_fusable()):
+            y = c2.emit(pb, x, pre=cv1)       # cv1 (3x3 / s2) -> c2.cv1 (1x1) back to back: yolov10s 32 -> 64 -> 64
+        else:
+            y = c2.emit(pb, cv1.emit(pb, x))
+        y = self.cv3.emit(pb, y)
         c3 = self.c4.emit(pb, y, c3_dst)
         c4 = self.c6.emit(pb, self.sc5.emit(pb, c3), c4_dst)
         y = self.c8.emit(pb, self.sc7.emit(pb, c4))

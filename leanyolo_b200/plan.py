@@ -419,8 +419,15 @@ class PlanBuilder:
         import os
         return self.tensor_core and os.environ.get("LEANYOLO_FUSE_TAIL", "1") != "0"
 
+    def stem_pair_fusable(self) -> bool:
+        """Backbone cv1 (3x3 / s2) -> c2.cv1 (1x1) as one stride-2 back-to-back launch.  Opt-in (LEANYOLO_FUSE_S2=1): bit-correct, but on
+        yolov10s at batch 256 the fused launch takes 0.80 ms against 0.41 + 0.33 ms for the two layers: its band of one output row
+        (six parity-plane rows of 64-byte pixels, 12 TMA boxes) keeps only ~64 KB per SM in flight, see DESIGN.md."""
+        import os
+        return self.tail_fusable() and os.environ.get("LEANYOLO_FUSE_S2", "0") == "1"
+
     def chain(self, src: View, regions: Sequence[int], n_in: int, stages: Sequence[dict], *, dst: Optional[View] = None,
-              nchw: Optional[Tuple[str, int, int, int, int]] = None) -> Optional[View]:
+              nchw: Optional[Tuple[str, int, int, int, int]] = None, stride0: int = 1) -> Optional[View]:
         """A chain of dense conv stages executed per spatial tile with every intermediate in shared memory
         (``LY_OP_CHAIN``, include/leanyolo_b200.h).  ``regions``: channels of each shared-memory region (the first
         ``n_in`` are the 64-channel blocks of ``src``); ``stages``: dicts {k, act, w [cout,cin,k,k], b [cout],
@@ -436,15 +443,17 @@ class PlanBuilder:
                                w_off=self._add_w(w.numel() if self.dry else w.permute(0, 2, 3, 1).contiguous()),
                                b_off=self._add_b(b.numel() if self.dry else b)))
         cout = packed[-1]["cout"]
+        assert stride0 in (1, 2) and (stride0 == 1 or (stages[0]["k"] == 3 and src.H % 2 == 0 and src.W % 2 == 0))
+        Ho, Wo = src.H // stride0, src.W // stride0       # stride0 = 2: the FIRST stage is a stride-2 3x3 (back-to-back kernel only)
         if nchw is None:
             if dst is None:
-                dst = self.buffer(src.H, src.W, cout).view()
-            assert dst.c == cout and (dst.H, dst.W) == (src.H, src.W)
+                dst = self.buffer(Ho, Wo, cout).view()
+            assert dst.c == cout and (dst.H, dst.W) == (Ho, Wo)
         else:
             name, level, c0, c, ctot = nchw
-            self.outputs[(name, level)] = (ctot, src.H, src.W)
+            self.outputs[(name, level)] = (ctot, Ho, Wo)
         self.ops.append(Op("chain", src=src, dst=dst, k=1, stride=1, cin=src.c, cout=cout, nchw=nchw,
-                           extra=dict(regions=list(regions), n_in=n_in, stages=packed, cpad=cout)))
+                           extra=dict(regions=list(regions), n_in=n_in, stages=packed, cpad=cout, stride0=stride0)))
         return dst
 
     def sppf_pool(self, cat: Buf, c: int) -> None:
@@ -486,7 +495,8 @@ class PlanBuilder:
                 Ho, Wo = op.src.H // op.stride, op.src.W // op.stride
                 f += 2 * Ho * Wo * op.cout * op.cin * op.k * op.k
             elif op.kind == "chain":
-                f += sum(2 * op.src.H * op.src.W * st["cout"] * st["cin"] * st["k"] ** 2 for st in op.extra["stages"])
+                s0 = op.extra.get("stride0", 1)
+                f += sum(2 * (op.src.H // s0) * (op.src.W // s0) * st["cout"] * st["cin"] * st["k"] ** 2 for st in op.extra["stages"])
             elif op.kind == "stem":
                 f += 2 * op.dst.H * op.dst.W * op.cout * 27
         return f

@@ -16,10 +16,11 @@ def _bf16(t):
     return t.to(torch.bfloat16).float()
 
 
-def make_chain(regions, n_in, stages, keep):
+def make_chain(regions, n_in, stages, keep, stride0=1):
     """ctypes ly_chain from the python spec; device tensors are appended to ``keep``."""
     ch = N.LyChain()
     ch.n_regions, ch.n_in, ch.n_stages = len(regions), n_in, len(stages)
+    ch.reserved = 2 if stride0 == 2 else 0
     for i, c in enumerate(regions):
         ch.region_c[i] = c
     for i, st in enumerate(stages):
@@ -52,11 +53,13 @@ def spec_c2f(g, c, shortcut=True):
     ]
 
 
-def spec_tail(g, c, cout, act_last=False):
-    """3x3 c->c (+SiLU) -> 1x1 c->cout (+bias): the tail of a v10Detect regression stack (head.py:86-92)."""
-    return [c, c], 1, [
-        _stage(g, 3, c, c, True, [(0, 0, c)], dst=(1, 0, c)),
-        _stage(g, 1, c, cout, act_last, [(1, 0, c)]),
+def spec_tail(g, c, cout, act_last=False, cmid=None):
+    """3x3 c->cmid (+SiLU) -> 1x1 cmid->cout (+bias): the tail of a v10Detect regression stack (head.py:86-92); with
+    check_chain(stride0=2) and cmid != c the backbone's cv1 (3x3 / s2) -> c2.cv1 (1x1) pair."""
+    cm = cmid or c
+    return [c, cm], 1, [
+        _stage(g, 3, c, cm, True, [(0, 0, c)], dst=(1, 0, cm)),
+        _stage(g, 1, cm, cout, act_last, [(1, 0, cm)]),
     ]
 
 
@@ -93,16 +96,16 @@ def build_tail_op(B, H, W, c, cout, seed=0):
 
 
 def check_chain(kind="c2f", B=2, H=40, W=40, src_off=0, src_extra=0, dst_off=0, dst_extra=0, nchw=False, nchw_c=None,
-                seed=0, tol=2e-2, **kw):
+                seed=0, tol=2e-2, stride0=1, **kw):
     g = torch.Generator().manual_seed(seed)
     regions, n_in, stages = SPECS[kind](g, **kw)
     cin = sum(regions[:n_in])
     cout = stages[-1]["cout"]
     xs = _bf16(torch.randn(B, H, W, src_off + cin + src_extra, generator=g))
-    ref = run_chain(regions, n_in, stages, xs[..., src_off:src_off + cin], quant=_bf16)
-    d0 = _bf16(torch.randn(B, H, W, dst_off + cout + dst_extra, generator=g))
+    ref = run_chain(regions, n_in, stages, xs[..., src_off:src_off + cin], quant=_bf16, stride0=stride0)
+    d0 = _bf16(torch.randn(B, H // stride0, W // stride0, dst_off + cout + dst_extra, generator=g))
     keep = []
-    ch = make_chain(regions, n_in, stages, keep)
+    ch = make_chain(regions, n_in, stages, keep, stride0)
     x_d, d_d = xs.to(torch.bfloat16).to(DEV), d0.to(torch.bfloat16).to(DEV)
     op = N.LyOp()
     op.kind, op.dtype, op.B, op.k, op.stride, op.act, op.ext_slot = N.OP_CHAIN, N.LY_BF16, B, 1, 1, 0, -1
@@ -111,7 +114,7 @@ def check_chain(kind="c2f", B=2, H=40, W=40, src_off=0, src_extra=0, dst_off=0, 
     out_nchw = None
     if nchw:
         cr = nchw_c or cout
-        out_nchw = torch.zeros(B, cr + 3, H, W, device=DEV)
+        out_nchw = torch.zeros(B, cr + 3, H // stride0, W // stride0, device=DEV)
         op.nchw, op.nchw_ctot, op.nchw_c0, op.nchw_c = out_nchw.data_ptr(), cr + 3, 2, cr
     else:
         op.dst = view(d_d, dst_off, cout)

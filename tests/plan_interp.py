@@ -63,7 +63,7 @@ def run_plan(pb: PlanBuilder, x: torch.Tensor, quant=None):
                 stages.append(dict(k=st["k"], act=st["act"], cout=st["cout"], src=st["src"], dst=st["dst"], res=st["res"],
                                    w=w_blob[st["w_off"]:st["w_off"] + n].view(st["cout"], st["k"], st["k"], st["cin"]),
                                    b=b_blob[st["b_off"]:st["b_off"] + st["cout"]]))
-            y = run_chain(op.extra["regions"], op.extra["n_in"], stages, rd(op.src), quant=q)
+            y = run_chain(op.extra["regions"], op.extra["n_in"], stages, rd(op.src), quant=q, stride0=op.extra.get("stride0", 1))
             if op.dst is not None:
                 wr(op.dst, y)
             if op.nchw is not None:
@@ -128,7 +128,7 @@ def run_plan(pb: PlanBuilder, x: torch.Tensor, quant=None):
     return outs
 
 
-def run_chain(regions, n_in, stages, x, quant=None):
+def run_chain(regions, n_in, stages, x, quant=None, stride0=1):
     """Reference semantics of LY_OP_CHAIN (include/leanyolo_b200.h) on whole images.
 
     regions: channels per region; x: [B,H,W,sum(regions[:n_in])] NHWC fp32 (already in the storage
@@ -138,16 +138,17 @@ def run_chain(regions, n_in, stages, x, quant=None):
     [B,H,W,cout] fp32 result (not quantised)."""
     q = quant or (lambda t: t)
     B, H, W, _ = x.shape
-    reg = [torch.zeros(B, H, W, c) for c in regions]
+    Ho, Wo = H // stride0, W // stride0      # stride0 = 2: the first stage is a stride-2 3x3, everything after it is half size
+    reg = [torch.zeros(B, H, W, c) if i < n_in else torch.zeros(B, Ho, Wo, c) for i, c in enumerate(regions)]
     off = 0
     for i in range(n_in):
         reg[i] = x[..., off:off + regions[i]].clone()
         off += regions[i]
     y = None
-    for st in stages:
+    for si, st in enumerate(stages):
         xin = torch.cat([reg[r][..., c0:c0 + c] for r, c0, c in st["src"]], -1).permute(0, 3, 1, 2)
         w = st["w"].float().permute(0, 3, 1, 2)
-        y = F.conv2d(xin, w, st["b"].float(), 1, st["k"] // 2)
+        y = F.conv2d(xin, w, st["b"].float(), stride0 if si == 0 else 1, st["k"] // 2)
         if st["act"]:
             y = F.silu(y)
         y = y.permute(0, 2, 3, 1)

@@ -244,7 +244,25 @@ def test_lowering_bf16_storage_emulation_within_tolerance(chain, tail, monkeypat
     pb = PlanBuilder(1, 128, 128, "bf16")
     m.emit(pb)
     n_chain = sum(op.kind == "chain" for op in pb.ops)
-    assert n_chain == (0 if tail == "0" and chain == "0" else (6 if chain == "0" else 7))   # 2 branches x 3 levels (+ the C2f block)
+    # tails: 2 branches x 3 levels; + the whole C2f block with chain fusion
+    assert n_chain == (0 if tail == "0" and chain == "0" else (6 if chain == "0" else 7))
+    outs = run_plan(pb, x, quant=lambda t: t.to(torch.bfloat16).float())
+    for i in range(3):
+        r = ref["one2one"][i]
+        assert float((outs[("one2one", i)] - r).abs().max() / r.abs().max()) < 2e-2
+
+
+def test_lowering_stride2_pair_emulation_within_tolerance(monkeypatch):
+    """LEANYOLO_FUSE_S2=1: backbone cv1 (3x3 / s2) -> c2.cv1 (1x1) lowered to one stride-2 chain op."""
+    monkeypatch.setenv("LEANYOLO_FUSE_S2", "1")
+    m = get_model("yolov10s", weights=None, class_names=NAMES)
+    sd = synth_state_dict(m.state_dict(), seed=1, gain=1.25)
+    m.load_state_dict(sd)
+    x = synth_images(1, 128, 96, seed=2)
+    ref = O.forward(sd, x)
+    pb = PlanBuilder(1, 128, 96, "bf16")
+    m.emit(pb)
+    assert sum(op.kind == "chain" and op.extra.get("stride0") == 2 for op in pb.ops) == 1
     outs = run_plan(pb, x, quant=lambda t: t.to(torch.bfloat16).float())
     for i in range(3):
         r = ref["one2one"][i]
@@ -282,6 +300,15 @@ def test_plan_is_pure_views_no_copy_ops_and_counts_flops():
     # the two upsample+concat+1x1 of the top-down neck are 2 convs each (half-resolution part + skip part), no upsample op
     # round 2: the six 3x3 -> 1x1 regression tails (2 branches x 3 levels) are one back-to-back GEMM launch each (chain ops)
     assert kinds == {"stem": 1, "conv": 61, "chain": 6, "dw": 10, "dwpw": 12, "pool": 1, "attn": 1}
+    # opt-in: the backbone's cv1 (3x3 / s2) -> c2.cv1 (1x1) pair as one stride-2 back-to-back launch
+    os.environ["LEANYOLO_FUSE_S2"] = "1"
+    try:
+        pbs = PlanBuilder(1, 640, 640, "bf16")
+        m.emit(pbs)
+    finally:
+        del os.environ["LEANYOLO_FUSE_S2"]
+    assert sum(op.kind == "conv" for op in pbs.ops) == 59 and sum(op.kind == "chain" for op in pbs.ops) == 7
+    assert abs(pbs.dense_flops() - pb.dense_flops()) < 1e-6 * pb.dense_flops()
     os.environ["LEANYOLO_FUSE_TAIL"] = "0"
     try:
         pbt = PlanBuilder(1, 640, 640, "bf16")

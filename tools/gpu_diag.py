@@ -90,6 +90,12 @@ def registry():
     add("chain_tail_32_48_nchw", CH.check_chain, kind="tail", c=32, cout=48, H=24, W=40, B=2, nchw=True, nchw_c=40)
     add("chain_tail_64_160", CH.check_chain, kind="tail", c=64, cout=64, H=160, W=160, B=2, nchw=True)
     add("chain_tail_64_act_last", CH.check_chain, kind="tail", c=64, cout=32, H=40, W=40, B=3, nchw=True, act_last=True)
+    # stride-2 first stage (backbone cv1 -> c2.cv1): four parity planes, NHWC slice destination, odd plane sizes, two TMA pieces per row
+    add("chain_s2_32_64_64", CH.check_chain, kind="tail", c=32, cmid=64, cout=64, H=32, W=32, B=2, stride0=2, act_last=True)
+    add("chain_s2_views_odd", CH.check_chain, kind="tail", c=32, cmid=64, cout=64, H=26, W=38, B=3, stride0=2, act_last=True,
+        src_off=32, src_extra=32, dst_off=0, dst_extra=32)
+    add("chain_s2_wide_320", CH.check_chain, kind="tail", c=32, cmid=64, cout=64, H=16, W=320, B=2, stride0=2, act_last=True, dst_off=64, dst_extra=0)
+    add("chain_s2_64_64_32_nchw", CH.check_chain, kind="tail", c=64, cmid=64, cout=32, H=24, W=40, B=2, stride0=2, nchw=True)
     add("chain_tail_32_views", CH.check_chain, kind="tail", c=32, cout=48, H=24, W=40, act_last=True, src_off=32, src_extra=16, dst_off=16, dst_extra=32)
     add("chain_two_in", CH.check_chain, kind="two_in", H=20, W=36)
     add("chain_c2f_32", CH.check_chain, kind="c2f", c=32, H=40, W=40)
