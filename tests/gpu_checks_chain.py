@@ -78,19 +78,24 @@ def spec_two_in(g):
 SPECS = {"c2f": spec_c2f, "tail": spec_tail, "single": spec_single, "two_in": spec_two_in}
 
 
-def build_tail_op(B, H, W, c, cout, seed=0):
-    """A ready-to-launch 3x3 -> 1x1 tail op with a public NCHW output on random data (timing tool: tools/bench_b2b.py)."""
+def build_tail_op(B, H, W, c, cout, seed=0, cmid=None, stride0=1):
+    """A ready-to-launch 3x3 -> 1x1 op on random data (timing tool: tools/bench_b2b.py): stride 1 with a public NCHW output (a
+    regression tail) or stride 2 with an NHWC bf16 output (backbone cv1 -> c2.cv1)."""
     g = torch.Generator().manual_seed(seed)
-    regions, n_in, stages = SPECS["tail"](g, c=c, cout=cout)
+    regions, n_in, stages = SPECS["tail"](g, c=c, cout=cout, cmid=cmid, act_last=stride0 == 2)
     keep = []
-    ch = make_chain(regions, n_in, stages, keep)
+    ch = make_chain(regions, n_in, stages, keep, stride0)
     x = torch.randn(B, H, W, c, device=DEV).to(torch.bfloat16)
-    out = torch.zeros(B, cout, H, W, device=DEV)
     op = N.LyOp()
     op.kind, op.dtype, op.B, op.k, op.stride, op.act, op.ext_slot = N.OP_CHAIN, N.LY_BF16, B, 1, 1, 0, -1
     op.src = view(x, 0, c)
     op.chain = C.pointer(ch)
-    op.nchw, op.nchw_ctot, op.nchw_c0, op.nchw_c = out.data_ptr(), cout, 0, cout
+    if stride0 == 2:
+        out = torch.zeros(B, H // 2, W // 2, cout, device=DEV, dtype=torch.bfloat16)
+        op.dst = view(out, 0, cout)
+    else:
+        out = torch.zeros(B, cout, H, W, device=DEV)
+        op.nchw, op.nchw_ctot, op.nchw_c0, op.nchw_c = out.data_ptr(), cout, 0, cout
     keep += [ch, x, out]
     return op, keep
 

@@ -16,7 +16,7 @@ for src, dst in (("bench_default.json", "r2_final_bench_default.json"), ("bench_
 out = subprocess.run([sys.executable, os.path.join(R, "tools", "ncu_launch_summary.py"), os.path.join(O, "launches.csv"),
                       os.path.join(P, "r2_traffic.json")], capture_output=True, text=True).stdout
 open(os.path.join(P, "r2_final_ncu_launch_summary.txt"), "w").write(out)
-hdr = ("# ncu --set full --clock-control none --import-source on -k regex:conv_tc -s 219 -c 24  (python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-other-configs)\n"
+hdr = ("# ncu --set full --clock-control none --import-source on -k regex:conv_tc -s 183 -c 24  (python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-other-configs)\n"
        "# the first 24 conv_tc launches of one step of yolov10s 640x640 batch 256 (backbone cv1 .. c6), round-2 final build: tile-parallel epilogue, 8 TMEM stages,\n"
        "# TMA-store epilogue on resident-weight layers.  The .ncu-rep (358 MB for a whole step) is summarised on the GPU box and not kept.\n")
 open(os.path.join(P, "r2_final_ncu_conv_tc_full_24_launches.txt"), "w").write(hdr + open(os.path.join(O, "ncu_conv_tc_table.txt")).read())
@@ -35,7 +35,7 @@ for n, r in enumerate(rows[2:]):
         n, float(r[idx["gpu__time_duration.sum"]]), cyc, tc, ls, lsu_pct / 100 * cyc * 148, tc / (cyc * 148) * 100, lsu_pct,
         float(r[idx["sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed"]])))
 open(os.path.join(P, "r2_final_ncu_conv_tc_datapipe.txt"), "w").writelines(lines)
-hdr2 = ("# ncu --set full --clock-control none -k 'regex:^(dwpw_mma|stem_mma|dw7|attn_mma|best|topk)_kernel' -s 60 -c 12 "
+hdr2 = ("# ncu --set full --clock-control none -k 'regex:^(conv_b2b|dwpw_mma|stem_mma|dw7|attn_mma|best|topk)_kernel' -s 72 -c 18 "
         "(python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-other-configs), round-2 final build\n")
 open(os.path.join(P, "r2_final_ncu_other_kernels.txt"), "w").write(hdr2 + open(os.path.join(O, "ncu_other_table.txt")).read())
 rows = list(csv.reader(open(os.path.join(O, "clocks.csv"))))[1:]
