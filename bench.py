@@ -327,6 +327,51 @@ def main():
                          "same detections up to fp32 summation order); per-GPU detections left on the device, no gather"}
         model(x)      # restore both cached branches for the decode timing below
 
+    # ---- BASELINE config 4 (yolov10x, 2048 images sharded by image over 8 GPUs, detections gathered over NCCL): a short run
+    # appended to the default 8-GPU invocation (every rank takes part: same API, same timing rules, 3 timed steps)
+    config4 = None
+    if (world == int(os.environ.get("LY_BENCH_CONFIG4_WORLD", "8")) and world > 1 and not a.no_other_configs and a.model == "yolov10s" and a.decode == "topk" and a.imgsz == 640 and a.batch == 256
+            and a.sub_batch == 0):
+        mx = get_model("yolov10x", weights=None, class_names=names)
+        mx.load_state_dict(synth_state_dict(mx.state_dict(), seed=0, gain=1.0), strict=True)
+        mx = mx.to(dev).eval()
+        shx = ShardedDetector(mx, max_det=300, depth=2)
+        tkx = []
+
+        def stepx():
+            tkx.append(shx.submit_detections(mx.detect(x)))
+            if len(tkx) > 1:
+                shx.collect(tkx.pop(0))
+
+        def drainx():
+            while tkx:
+                shx.collect(tkx.pop(0))
+
+        allg = shx.collect(shx.submit_detections(mx.detect(x))).clone()
+        okx = bool(torch.equal(allg[rank * B:(rank + 1) * B], mx.detect(x)))
+        flag = torch.tensor([1 if okx else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        del allg
+        for _ in range(3):
+            stepx()
+        drainx()
+        torch.cuda.synchronize()
+        dist.barrier()
+        c4_steps = 3
+        e0.record()
+        for _ in range(c4_steps):
+            stepx()
+        drainx()
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        config4 = {"value": round(world * B * c4_steps / (float(t.item()) / 1e3), 1), "unit": "images/s",
+                   "ms_per_step": round(float(t.item()) / c4_steps, 3), "steps": c4_steps, "warmup": 3, "global_batch": world * B,
+                   "gather_check": "own slice bit-equal" if int(flag.item()) == 1 else "MISMATCH",
+                   "whole_step_tensor_frac": round(DENSE_GFLOP.get("yolov10x", 0) * B * c4_steps / (float(t.item()) / 1e3) / 1e3 / load_peaks()["tf_sust"], 4)}
+        del mx, shx
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -424,6 +469,10 @@ def main():
                               "nms_gbs": ((rf.get("by_kind") or {}).get("nms") or {}).get("gbs"), "clocks": d.get("clocks")}
             except Exception as e:   # never let a side run break the headline line
                 other[key] = {"error": f"{type(e).__name__}: {e}"[:300]}
+
+    if config4 is not None:
+        other = dict(other or {})
+        other[f"config4: yolov10x 640x640 batch {world * B} sharded by image over {world} GPUs, top-k decode, detections gathered over NCCL"] = config4
 
     out = {
         "metric": "images/sec (fwd+decode)", "value": round(value, 1), "unit": "images/s", "n_gpus": world,

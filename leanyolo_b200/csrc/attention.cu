@@ -131,12 +131,12 @@ attn_kernel(const T* __restrict__ qkv, int N, int sCtot, int sC0, int nh, T* __r
 // tcgen05/TMEM pipeline to amortise, so each warp owns 16 query rows and runs
 // mma.sync.m16n8k16 (bf16 x bf16 -> fp32) for both S = Q K^T and O = P V, with the online
 // softmax kept in registers between them (S accumulator fragments are re-packed in place as
-// the A operand of the second MMA).  K/V blocks of 64 keys are double-buffered in shared
-// memory with cp.async (zero-filled past N and in the padded key columns); V^T fragments
-// come from ldmatrix.trans.  5 warps per CTA = 80 queries: N = 400 tiles with no waste.
+// the A operand of the second MMA).  K/V blocks of 80 keys are double-buffered in shared
+// memory with cp.async (zero-filled past N and in the padded key columns); K fragments come
+// from ldmatrix, V^T fragments from ldmatrix.trans.  5 warps per CTA = 80 queries: N = 400 tiles with no waste.
 // ---------------------------------------------------------------------------------------
 constexpr int AT_WARPS = 5;
-constexpr int AT_KB = 64;    // keys per shared-memory block
+constexpr int AT_KB = 80;    // keys per shared-memory block (400 = 5 x 80 and 1600 = 20 x 80 tokens: no masked tail at 640^2 / 1280^2)
 
 __device__ __forceinline__ void mma_bf16_16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
   asm volatile(
@@ -226,31 +226,49 @@ attn_mma_kernel(const __nv_bfloat16* __restrict__ qkv, int N, int sCtot, int sC0
       asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     __syncthreads();
-    const uint8_t* ks_p = sm + (blk & 1) * STAGE;
     const uint32_t vs_u = sm_u + (blk & 1) * STAGE + AT_KB * KPITCH;
 
     float s[AT_KB / 8][4];
+    {
+      // K fragments through ldmatrix: matrix i of an x4 = rows j*8 .. j*8+7, bytes 16*i .. 16*i+15 of the key rows
+      // (= b0 / b1 of k-step i/2); the padded pitch keeps the eight 16-byte rows of a matrix on distinct banks
+      const uint32_t krow = sm_u + (uint32_t)((blk & 1) * STAGE) + (uint32_t)(lane & 7) * KPITCH;
 #pragma unroll
-    for (int j = 0; j < AT_KB / 8; ++j) {
-      s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
-      const uint8_t* kr = ks_p + (j * 8 + g) * KPITCH + 4 * t;
+      for (int j = 0; j < AT_KB / 8; ++j) {
+        s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+        const uint32_t kj = krow + (uint32_t)(j * 8) * KPITCH;
 #pragma unroll
-      for (int ks = 0; ks < KS; ++ks) {
-        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(kr + ks * 32);
-        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(kr + ks * 32 + 16);
-        mma_bf16_16816(s[j], qa[ks], b0, b1);
+        for (int ks = 0; ks + 1 < KS; ks += 2) {
+          uint32_t b0, b1, b2, b3;
+          asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                       : "=r"(b0), "=r"(b1), "=r"(b2), "=r"(b3)
+                       : "r"(kj + (uint32_t)(ks * 32 + (lane >> 3) * 16)));
+          mma_bf16_16816(s[j], qa[ks], b0, b1);
+          mma_bf16_16816(s[j], qa[ks + 1], b2, b3);
+        }
+        if (KS & 1) {
+          uint32_t b0, b1;
+          asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];"
+                       : "=r"(b0), "=r"(b1)
+                       : "r"(kj + (uint32_t)((KS - 1) * 32 + ((lane >> 3) & 1) * 16)));
+          mma_bf16_16816(s[j], qa[KS - 1], b0, b1);
+        }
       }
     }
-    // scale into the log2 domain, mask keys past N, block row max
-    const int kbase = blk * AT_KB + 2 * t;
+    // mask keys past N (last block only), block row max of the RAW scores (scale > 0), then one FFMA per score into
+    // the log2 domain: p = 2^(s * scale - max * scale)
+    if ((blk + 1) * AT_KB > N) {
+      const int kbase = blk * AT_KB + 2 * t;
+#pragma unroll
+      for (int j = 0; j < AT_KB / 8; ++j) {
+        const int key = kbase + j * 8;
+        if (key >= N) { s[j][0] = -INFINITY; s[j][2] = -INFINITY; }
+        if (key + 1 >= N) { s[j][1] = -INFINITY; s[j][3] = -INFINITY; }
+      }
+    }
     float bm0 = -INFINITY, bm1 = -INFINITY;
 #pragma unroll
     for (int j = 0; j < AT_KB / 8; ++j) {
-      const int key = kbase + j * 8;
-      s[j][0] = key < N ? s[j][0] * scale_log2e : -INFINITY;
-      s[j][1] = key + 1 < N ? s[j][1] * scale_log2e : -INFINITY;
-      s[j][2] = key < N ? s[j][2] * scale_log2e : -INFINITY;
-      s[j][3] = key + 1 < N ? s[j][3] * scale_log2e : -INFINITY;
       bm0 = fmaxf(bm0, fmaxf(s[j][0], s[j][1]));
       bm1 = fmaxf(bm1, fmaxf(s[j][2], s[j][3]));
     }
@@ -258,16 +276,18 @@ attn_mma_kernel(const __nv_bfloat16* __restrict__ qkv, int N, int sCtot, int sC0
     bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 2));
     bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 1));
     bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 2));
-    const float nm0 = fmaxf(m0r, bm0), nm1 = fmaxf(m1r, bm1);   // finite: every block holds >= 1 valid key
-    const float c0 = ex2(m0r - nm0), c1 = ex2(m1r - nm1);        // first block: ex2(-inf) = 0
-    m0r = nm0; m1r = nm1;
-    l0 *= c0; l1 *= c1;
+    const float nm0 = fmaxf(m0r, bm0 * scale_log2e), nm1 = fmaxf(m1r, bm1 * scale_log2e);   // finite: every block holds >= 1 valid key
+    if (__any_sync(0xffffffffu, nm0 != m0r || nm1 != m1r)) {     // the running max moved for some row of this warp: rescale
+      const float c0 = ex2(m0r - nm0), c1 = ex2(m1r - nm1);      // first block: ex2(-inf) = 0
+      l0 *= c0; l1 *= c1;
 #pragma unroll
-    for (int i = 0; i < NT; ++i) { o[i][0] *= c0; o[i][1] *= c0; o[i][2] *= c1; o[i][3] *= c1; }
+      for (int i = 0; i < NT; ++i) { o[i][0] *= c0; o[i][1] *= c0; o[i][2] *= c1; o[i][3] *= c1; }
+      m0r = nm0; m1r = nm1;
+    }
 #pragma unroll
     for (int j = 0; j < AT_KB / 8; ++j) {
-      s[j][0] = ex2(s[j][0] - nm0); s[j][1] = ex2(s[j][1] - nm0);
-      s[j][2] = ex2(s[j][2] - nm1); s[j][3] = ex2(s[j][3] - nm1);
+      s[j][0] = ex2(fmaf(s[j][0], scale_log2e, -nm0)); s[j][1] = ex2(fmaf(s[j][1], scale_log2e, -nm0));
+      s[j][2] = ex2(fmaf(s[j][2], scale_log2e, -nm1)); s[j][3] = ex2(fmaf(s[j][3], scale_log2e, -nm1));
       l0 += s[j][0] + s[j][1];
       l1 += s[j][2] + s[j][3];
     }
