@@ -159,7 +159,7 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool p
 }
 
 template <int KDP, int HD>
-__global__ void __launch_bounds__(AT_WARPS * 32)
+__global__ void __launch_bounds__(AT_WARPS * 32, 3)
 attn_mma_kernel(const __nv_bfloat16* __restrict__ qkv, int N, int sCtot, int sC0, int nh, __nv_bfloat16* __restrict__ out,
                 int dCtot, int dC0, float scale_log2e) {
   constexpr int KD16 = (KDP + 15) / 16 * 16;
@@ -181,15 +181,41 @@ attn_mma_kernel(const __nv_bfloat16* __restrict__ qkv, int N, int sCtot, int sC0
   const int qoff = h * KDP, koff = nh * KDP + h * KDP, voff = 2 * nh * KDP + h * HD;
   const uint32_t sm_u = smem_u32(sm);
 
+  // Loader mapping, fixed for the kernel's life: thread -> (row lr0 of a pass, 16-byte chunk lc of the K | V row); one pass
+  // covers RP key rows, so a block costs PASSES cp.async + pointer bumps per thread.  (ncu on the round-1 loop, which
+  // re-derived (row, chunk) from a flat index: 65 instructions per chunk = 40 % of the kernel's instruction stream.)
+  constexpr int TOT = KCH + VCH, RP = (AT_WARPS * 32) / TOT, PASSES = (AT_KB + RP - 1) / RP;
+  const int lc = threadIdx.x % TOT, lr0 = threadIdx.x / TOT;
+  const bool l_on = lr0 < RP;
+  const bool l_isk = lc < KCH;
+  const bool l_zero = l_isk && lc * 8 >= KDP;                       // padded key columns: zero fill
+  const __nv_bfloat16* l_row0 = base + (l_isk ? koff + (l_zero ? 0 : lc * 8) : voff + (lc - KCH) * 8);
+  const uint32_t l_dst0 = l_isk ? (uint32_t)(lr0 * KPITCH + lc * 16) : (uint32_t)(AT_KB * KPITCH + lr0 * VPITCH + (lc - KCH) * 16);
+  const uint32_t l_dstep = (uint32_t)RP * (l_isk ? (uint32_t)KPITCH : (uint32_t)VPITCH);
+  const long long l_sstep = (long long)RP * sCtot;
+
   auto load_block = [&](int blk, int stage) {
     const int m0 = blk * AT_KB;
-    const uint32_t ks = sm_u + stage * STAGE, vs = ks + AT_KB * KPITCH;
-    for (int i = threadIdx.x; i < AT_KB * (KCH + VCH); i += AT_WARPS * 32) {
-      const int r = i / (KCH + VCH), c = i - r * (KCH + VCH);
-      const bool rok = m0 + r < N;
-      const __nv_bfloat16* row = base + (long long)(rok ? m0 + r : 0) * sCtot;
-      if (c < KCH) cp_async16(ks + r * KPITCH + c * 16, row + koff + (c * 8 < KDP ? c * 8 : 0), rok && c * 8 < KDP);
-      else cp_async16(vs + r * VPITCH + (c - KCH) * 16, row + voff + (c - KCH) * 8, rok);
+    if (l_on) {
+      const __nv_bfloat16* src = l_row0 + (long long)(m0 + lr0) * sCtot;
+      uint32_t dst = sm_u + (uint32_t)(stage * STAGE) + l_dst0;
+      if (m0 + AT_KB <= N) {            // full block: no row checks
+#pragma unroll
+        for (int u = 0; u < PASSES; ++u) {
+          if ((u + 1) * RP <= AT_KB || lr0 + u * RP < AT_KB) cp_async16(dst, src, !l_zero);
+          src += l_sstep; dst += l_dstep;
+        }
+      } else {                          // last block of a map whose token count is not a multiple of AT_KB: rows past N are zeros
+#pragma unroll
+        for (int u = 0; u < PASSES; ++u) {
+          const int r = lr0 + u * RP;
+          if ((u + 1) * RP <= AT_KB || r < AT_KB) {
+            const bool rok = m0 + r < N;
+            cp_async16(dst, rok ? src : l_row0, rok && !l_zero);
+          }
+          src += l_sstep; dst += l_dstep;
+        }
+      }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
