@@ -536,6 +536,63 @@ pool_kernel(T* buf, int H, int W, int Ctot, int C0, int C, int cbv) {
   }
 }
 
+// Same op for maps whose row of channel vectors (W * cbv) fits the CTA: a thread keeps ONE (x, channel vector) column
+// and walks the rows y = y0, y0 + rpp, ...: the (pixel, vector) split and the four x-border tests are computed once,
+// every pass is shifts, adds and compares.  (ncu on the flat-index kernel above at 20x20x256, batch 256: 63 M
+// warp-instructions of which 9 M were the maxima; i / cbv, p % W and p / W are runtime divisions on every item of all
+// seven passes; the plane load stalled on one global load per loop iteration.)
+template <typename T>
+__global__ void __launch_bounds__(256)
+pool_rows_kernel(T* buf, int H, int W, int Ctot, int C0, int C, int cbv_log2) {
+  constexpr int V = Elem<T>::kVec;
+  pdl_trigger();
+  pdl_wait();
+  extern __shared__ __align__(16) uint4 psm[];   // [2][H*W][cbv]
+  const int cbv = 1 << cbv_log2;
+  const int cols = W << cbv_log2, items = H * cols;
+  const int rpp = 256 / cols;                    // rows per pass (host: cols <= 256)
+  const int y0 = threadIdx.x / cols, within = threadIdx.x - y0 * cols;
+  const int Hn = y0 < rpp ? H : 0;               // idle tail threads (256 - rpp * cols) own no rows, but take part in the barriers
+  uint4* cur = psm;
+  uint4* tmp = psm + items;
+  const int x = within >> cbv_log2, v = within & (cbv - 1);
+  const int ol1 = x >= 1 ? -cbv : 0, ol2 = x >= 2 ? -2 * cbv : 0, or1 = x + 1 < W ? cbv : 0, or2 = x + 2 < W ? 2 * cbv : 0;
+  T* gcol = buf + (long long)blockIdx.y * H * W * Ctot + C0 + blockIdx.x * cbv * V + (long long)x * Ctot + v * V;
+  const long long grow = (long long)W * Ctot;    // elements between rows of the map
+  const int step = rpp * cols;
+  {
+    int y = y0;
+    for (; y + 3 * rpp < Hn; y += 4 * rpp) {      // four loads in flight per thread
+      const T* g = gcol + (long long)y * grow;
+      const uint4 a = *reinterpret_cast<const uint4*>(g);
+      const uint4 b = *reinterpret_cast<const uint4*>(g + (long long)rpp * grow);
+      const uint4 c = *reinterpret_cast<const uint4*>(g + 2LL * rpp * grow);
+      const uint4 d = *reinterpret_cast<const uint4*>(g + 3LL * rpp * grow);
+      const int i = y * cols + within;
+      cur[i] = a; cur[i + step] = b; cur[i + 2 * step] = c; cur[i + 3 * step] = d;
+    }
+    for (; y < Hn; y += rpp) cur[y * cols + within] = *reinterpret_cast<const uint4*>(gcol + (long long)y * grow);
+  }
+  __syncthreads();
+  for (int stage = 1; stage <= 3; ++stage) {
+    for (int y = y0, i = y0 * cols + within; y < Hn; y += rpp, i += step) {   // row max -> tmp
+      // a border tap re-reads the centre (max with itself): five independent loads, no branches
+      const uint4 c0 = cur[i], l1 = cur[i + ol1], l2 = cur[i + ol2], r1 = cur[i + or1], r2 = cur[i + or2];
+      tmp[i] = vmax<T>(vmax<T>(vmax<T>(l2, l1), vmax<T>(r1, r2)), c0);
+    }
+    __syncthreads();
+    T* gout = gcol + stage * C;
+    for (int y = y0, i = y0 * cols + within; y < Hn; y += rpp, i += step) {   // column max -> cur (and out)
+      const uint4 c0 = tmp[i], u1 = tmp[y >= 1 ? i - cols : i], u2 = tmp[y >= 2 ? i - 2 * cols : i];
+      const uint4 d1 = tmp[y + 1 < H ? i + cols : i], d2 = tmp[y + 2 < H ? i + 2 * cols : i];
+      const uint4 m = vmax<T>(vmax<T>(vmax<T>(u2, u1), vmax<T>(d1, d2)), c0);
+      *reinterpret_cast<uint4*>(gout + (long long)y * grow) = m;
+      cur[i] = m;   // cur is only read by the row pass, which finished before the barrier above
+    }
+    __syncthreads();
+  }
+}
+
 // nearest x2: dst(b, y, x, :) = src(b, y/2, x/2, :)   (layers.py:240)
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -704,6 +761,17 @@ static int32_t run_pool(const ly_op& op, cudaStream_t s) {
     LY_CUDA(cudaFuncSetAttribute(pool_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   }
   dim3 grid(nvec / cbv, op.B);
+  static const int pool_rows = getenv("LY_POOL_ROWS") ? atoi(getenv("LY_POOL_ROWS")) : 1;
+  if (pool_rows && op.src.W * cbv <= 256) {
+    int lg = 0;
+    while ((1 << lg) < cbv) ++lg;
+    static std::atomic<unsigned long long> attr_devs_r{0};
+    if (first_on_device(attr_devs_r)) {
+      LY_CUDA(cudaFuncSetAttribute(pool_rows_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    }
+    launch_k(pool_rows_kernel<T>, grid, dim3(256), smem, s, (T*)op.src.ptr, op.src.H, op.src.W, op.src.ctot, op.src.c0, op.src.c, lg);
+    return post_launch("sppf_pool");
+  }
   launch_k(pool_kernel<T>, grid, dim3(256), smem, s, (T*)op.src.ptr, op.src.H, op.src.W, op.src.ctot, op.src.c0, op.src.c, cbv);
   return post_launch("sppf_pool");
 }
