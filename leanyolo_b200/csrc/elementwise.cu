@@ -179,7 +179,7 @@ __device__ __forceinline__ int stem_slot_w(int k) {
   return ((j % 3) * 3 + kx) * 3 + (j / 3);
 }
 
-template <typename TIn, int NT>
+template <typename TIn, int NT, int LDR = 0>
 __global__ void __launch_bounds__(SM_THREADS, 4)
 stem_mma_kernel(const TIn* __restrict__ x, int H, int W, __nv_bfloat16* __restrict__ dst, int dCtot, int dC0,
                 const float* __restrict__ w, const float* __restrict__ bias,
@@ -257,6 +257,62 @@ stem_mma_kernel(const TIn* __restrict__ x, int H, int W, __nv_bfloat16* __restri
       tile[(1 * SM_IH + r) * SM_IWP + col + 3] = __float2bfloat16_rn(f1);
       tile[(2 * SM_IH + r) * SM_IWP + col + 3] = __float2bfloat16_rn(f2);
     }
+  } else
+  if constexpr (LDR == 1) {
+    // Same staging as the loader below with the index arithmetic taken out of the per-vector path (ncu, source level: 469 M
+    // warp-instructions per launch for 13 M MMAs, ~100 per staged vector: two divisions by constants, the bounds tests and
+    // the 64-bit address, all done twice): item i + SM_THREADS is (line + DL, vector + DV) with one carry, the image-border
+    // tests exist only in the tiles that touch the border (22 % of them at 640 x 640), validity is kept as a bit per vector.
+    constexpr int VPL = SM_TW * 2 / 4 + 1, NL = 3 * SM_IH, NV = NL * VPL, PER = (NV + SM_THREADS - 1) / SM_THREADS;
+    constexpr int DL = SM_THREADS / VPL, DV = SM_THREADS - DL * VPL;
+    static_assert((PER - 1) * SM_THREADS <= NV, "only the last pass may run past the tile");
+    using Vec = typename std::conditional<sizeof(TIn) == 1, uchar4, float4>::type;
+    Vec v[PER];
+    const int hi0 = 2 * ho0 - 1, wi0 = 2 * wo0 - 4;
+    const TIn* xb = x + (long long)b * 3 * H * W;
+    const bool interior = hi0 >= 0 && hi0 + SM_IH <= H && wi0 >= 0 && wi0 + 4 * VPL <= W;
+    const int line0 = tid / VPL, vi0 = tid - line0 * VPL;
+    unsigned okmask = 0;
+    auto stage = [&](auto border_tag) {
+      constexpr bool BORDER = decltype(border_tag)::value;
+      {
+        int line = line0, vi = vi0;
+#pragma unroll
+        for (int it = 0; it < PER; ++it) {
+          const int c = (line >= SM_IH ? 1 : 0) + (line >= 2 * SM_IH ? 1 : 0);
+          const int hi = hi0 + line - c * SM_IH, wi = wi0 + 4 * vi;
+          bool ok = it < PER - 1 || line < NL;
+          if (BORDER) ok = ok && (unsigned)hi < (unsigned)H && (unsigned)wi < (unsigned)W;
+          if (ok) {
+            v[it] = __ldg(reinterpret_cast<const Vec*>(xb + (long long)((c * H + hi) * W + wi)));
+            okmask |= 1u << it;
+          } else {
+            v[it] = Vec{0, 0, 0, 0};
+          }
+          vi += DV; line += DL;
+          if (vi >= VPL) { vi -= VPL; ++line; }
+        }
+      }
+      {
+        int line = line0, vi = vi0;
+#pragma unroll
+        for (int it = 0; it < PER; ++it) {
+          if (it < PER - 1 || line < NL) {
+            const int c = (line >= SM_IH ? 1 : 0) + (line >= 2 * SM_IH ? 1 : 0);
+            const float sc = c == 0 ? s0 : (c == 1 ? s1 : s2), rc = c == 0 ? r0 : (c == 1 ? r1 : r2);
+            const bool ok = !BORDER || ((okmask >> it) & 1u) != 0;
+            const float f0 = ok ? ((float)v[it].x - sc) * rc : 0.f, f1 = ok ? ((float)v[it].y - sc) * rc : 0.f;
+            const float f2 = ok ? ((float)v[it].z - sc) * rc : 0.f, f3 = ok ? ((float)v[it].w - sc) * rc : 0.f;
+            const __nv_bfloat162 lo2 = __floats2bfloat162_rn(f0, f1), hi2 = __floats2bfloat162_rn(f2, f3);
+            *reinterpret_cast<uint2*>(tile + line * SM_IWP + 4 * vi) =
+                make_uint2(*reinterpret_cast<const uint32_t*>(&lo2), *reinterpret_cast<const uint32_t*>(&hi2));
+          }
+          vi += DV; line += DL;
+          if (vi >= VPL) { vi -= VPL; ++line; }
+        }
+      }
+    };
+    if (interior) stage(std::false_type{}); else stage(std::true_type{});
   } else
   {
     // aligned 4-element vectors: vector v of a line covers input columns 2*wo0 - 4 + 4v .. +3;
@@ -685,13 +741,17 @@ int32_t launch_stem(const ly_op& op, cudaStream_t s) {
     LY_CHECK_ARG(stem_tiles <= 0x7FFFFFFF, "stem: too many tiles");
     static const int stem_persist = getenv("LY_STEM_PERSIST") ? atoi(getenv("LY_STEM_PERSIST")) : 1;
     dim3 g2((unsigned)(stem_persist ? std::min<long long>(stem_tiles, 4LL * sm_count()) : stem_tiles), 1, 1);
-#define LY_STEM_MMA(TIN, NT)                                                                                          \
-  launch_k(stem_mma_kernel<TIN, NT>, g2, dim3(SM_THREADS), 0, s, (const TIN*)op.nchw, H, W, (__nv_bfloat16*)op.dst.ptr, op.dst.ctot, \
+    static const int stem_ldr = getenv("LY_STEM_LOADER") ? atoi(getenv("LY_STEM_LOADER")) : 1;
+#define LY_STEM_MMA(TIN, NT) LY_STEM_MMA_L(TIN, NT, 0)
+#define LY_STEM_MMA_L(TIN, NT, LDR)                                                                                   \
+  launch_k(stem_mma_kernel<TIN, NT, LDR>, g2, dim3(SM_THREADS), 0, s, (const TIN*)op.nchw, H, W, (__nv_bfloat16*)op.dst.ptr, op.dst.ctot, \
                                                      op.dst.c0, (const float*)op.w, op.bias, op.sub[0], op.sub[1],    \
                                                      op.sub[2], op.div[0], op.div[1], op.div[2], op.nh, op.kdp, op.hd, op.B)
 #define LY_STEM_NT(NT)                                                 \
   case NT:                                                             \
-    if (lb) LY_STEM_MMA(ly_lb_desc, NT); else if (u8) LY_STEM_MMA(uint8_t, NT); else LY_STEM_MMA(float, NT);     \
+    if (lb) LY_STEM_MMA(ly_lb_desc, NT);                                                                        \
+    else if (stem_ldr) { if (u8) LY_STEM_MMA_L(uint8_t, NT, 1); else LY_STEM_MMA_L(float, NT, 1); }                 \
+    else { if (u8) LY_STEM_MMA(uint8_t, NT); else LY_STEM_MMA(float, NT); }                                           \
     return post_launch("stem_mma");
     switch (Cpad / 8) {
       LY_STEM_NT(2) LY_STEM_NT(4) LY_STEM_NT(6) LY_STEM_NT(8) LY_STEM_NT(10)
@@ -699,6 +759,7 @@ int32_t launch_stem(const ly_op& op, cudaStream_t s) {
     }
 #undef LY_STEM_NT
 #undef LY_STEM_MMA
+#undef LY_STEM_MMA_L
   }
   LY_CHECK_ARG(!lb, "stem: the fused letterbox loader needs the bf16 tensor-core stem (Cout_pad in {16,32,48,64,80}, W %% 4 == 0)");
   if (op.dtype == LY_F32) {
