@@ -179,6 +179,14 @@ __device__ __forceinline__ int stem_slot_w(int k) {
   return ((j % 3) * 3 + kx) * 3 + (j / 3);
 }
 
+// one raw staging vector (16 bytes of fp32 or 4 bytes of uint8 pixels) global -> shared; `ok` false = zero fill, no read
+template <int BYTES>
+__device__ __forceinline__ void stem_cp_async(uint32_t dst, const void* src, bool ok) {
+  const int sz = ok ? BYTES : 0;
+  if (BYTES == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+  else asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+
 template <typename TIn, int NT, int LDR = 0>
 __global__ void __launch_bounds__(SM_THREADS, 4)
 stem_mma_kernel(const TIn* __restrict__ x, int H, int W, __nv_bfloat16* __restrict__ dst, int dCtot, int dC0,
@@ -205,6 +213,36 @@ stem_mma_kernel(const TIn* __restrict__ x, int H, int W, __nv_bfloat16* __restri
   __syncthreads();
 
   const unsigned short* tl = reinterpret_cast<const unsigned short*>(tile);
+
+  // LDR == 2: the raw pixels of tile n+1 travel global -> shared (cp.async) while tile n is multiplied; a thread converts
+  // exactly the vectors it requested itself, so the raw buffer needs no barrier of its own.
+  constexpr int P_VPL = SM_TW * 2 / 4 + 1, P_NL = 3 * SM_IH, P_NV = P_NL * P_VPL, P_PER = (P_NV + SM_THREADS - 1) / SM_THREADS;
+  constexpr int P_DL = SM_THREADS / P_VPL, P_DV = SM_THREADS - P_DL * P_VPL;
+  constexpr int P_VB = sizeof(TIn) == 1 ? 4 : 16;
+  __shared__ __align__(16) uint8_t raw[LDR == 2 ? P_PER * SM_THREADS * P_VB : 16];
+  const int p_line0 = tid / P_VPL, p_vi0 = tid - p_line0 * P_VPL;
+  auto issue_raw = [&](int tq) {
+    if constexpr (LDR == 2 && !std::is_same<TIn, ly_lb_desc>::value) {
+      const int bq = tq / (ntx * nty), rq = tq - bq * (ntx * nty);
+      const int hi0 = 2 * ((rq / ntx) * SM_TH) - 1, wi0 = 2 * ((rq % ntx) * SM_TW) - 4;
+      const TIn* xb = x + (long long)bq * 3 * H * W;
+      const bool border = !(hi0 >= 0 && hi0 + SM_IH <= H && wi0 >= 0 && wi0 + 4 * P_VPL <= W);
+      const uint32_t rdst = (uint32_t)__cvta_generic_to_shared(raw) + (uint32_t)tid * P_VB;
+      int line = p_line0, vi = p_vi0;
+#pragma unroll
+      for (int it = 0; it < P_PER; ++it) {
+        const int c = (line >= SM_IH ? 1 : 0) + (line >= 2 * SM_IH ? 1 : 0);
+        const int hi = hi0 + line - c * SM_IH, wi = wi0 + 4 * vi;
+        bool ok = it < P_PER - 1 || line < P_NL;
+        if (border) ok = ok && (unsigned)hi < (unsigned)H && (unsigned)wi < (unsigned)W;
+        stem_cp_async<P_VB>(rdst + (uint32_t)(it * SM_THREADS * P_VB), ok ? xb + (long long)((c * H + hi) * W + wi) : xb, ok);
+        vi += P_DV; line += P_DL;
+        if (vi >= P_VPL) { vi -= P_VPL; ++line; }
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  if (LDR == 2 && (int)blockIdx.x < total_tiles) issue_raw(blockIdx.x);
 
   for (int tix = blockIdx.x; tix < total_tiles; tix += gridDim.x) {
   const int b = tix / (ntx * nty), trem = tix - b * (ntx * nty);
@@ -257,6 +295,36 @@ stem_mma_kernel(const TIn* __restrict__ x, int H, int W, __nv_bfloat16* __restri
       tile[(1 * SM_IH + r) * SM_IWP + col + 3] = __float2bfloat16_rn(f1);
       tile[(2 * SM_IH + r) * SM_IWP + col + 3] = __float2bfloat16_rn(f2);
     }
+  } else
+  if constexpr (LDR == 2) {
+    using Vec = typename std::conditional<sizeof(TIn) == 1, uchar4, float4>::type;
+    const int hi0 = 2 * ho0 - 1, wi0 = 2 * wo0 - 4;
+    const bool border = !(hi0 >= 0 && hi0 + SM_IH <= H && wi0 >= 0 && wi0 + 4 * P_VPL <= W);
+    asm volatile("cp.async.wait_group 0;" ::: "memory");      // this thread's vectors of THIS tile have landed
+    const Vec* rsrc = reinterpret_cast<const Vec*>(raw) + tid;
+    int line = p_line0, vi = p_vi0;
+#pragma unroll
+    for (int it = 0; it < P_PER; ++it) {
+      if (it < P_PER - 1 || line < P_NL) {
+        const int c = (line >= SM_IH ? 1 : 0) + (line >= 2 * SM_IH ? 1 : 0);
+        const float sc = c == 0 ? s0 : (c == 1 ? s1 : s2), rc = c == 0 ? r0 : (c == 1 ? r1 : r2);
+        bool ok = true;
+        if (border) {
+          const int hi = hi0 + line - c * SM_IH, wi = wi0 + 4 * vi;
+          ok = (unsigned)hi < (unsigned)H && (unsigned)wi < (unsigned)W;
+        }
+        const Vec q = rsrc[it * SM_THREADS];
+        const float f0 = ok ? ((float)q.x - sc) * rc : 0.f, f1 = ok ? ((float)q.y - sc) * rc : 0.f;
+        const float f2 = ok ? ((float)q.z - sc) * rc : 0.f, f3 = ok ? ((float)q.w - sc) * rc : 0.f;
+        const __nv_bfloat162 lo2 = __floats2bfloat162_rn(f0, f1), hi2 = __floats2bfloat162_rn(f2, f3);
+        *reinterpret_cast<uint2*>(tile + line * SM_IWP + 4 * vi) =
+            make_uint2(*reinterpret_cast<const uint32_t*>(&lo2), *reinterpret_cast<const uint32_t*>(&hi2));
+      }
+      vi += P_DV; line += P_DL;
+      if (vi >= P_VPL) { vi -= P_VPL; ++line; }
+    }
+    // the raw slots of this thread are free again: request the next tile now, it lands while this one is multiplied
+    if (tix + (int)gridDim.x < total_tiles) issue_raw(tix + gridDim.x);
   } else
   if constexpr (LDR == 1) {
     // Same staging as the loader below with the index arithmetic taken out of the per-vector path (ncu, source level: 469 M
@@ -750,6 +818,7 @@ int32_t launch_stem(const ly_op& op, cudaStream_t s) {
 #define LY_STEM_NT(NT)                                                 \
   case NT:                                                             \
     if (lb) LY_STEM_MMA(ly_lb_desc, NT);                                                                        \
+    else if (stem_ldr == 2) { if (u8) LY_STEM_MMA_L(uint8_t, NT, 2); else LY_STEM_MMA_L(float, NT, 2); }            \
     else if (stem_ldr) { if (u8) LY_STEM_MMA_L(uint8_t, NT, 1); else LY_STEM_MMA_L(float, NT, 1); }                 \
     else { if (u8) LY_STEM_MMA(uint8_t, NT); else LY_STEM_MMA(float, NT); }                                           \
     return post_launch("stem_mma");
