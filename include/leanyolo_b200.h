@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define LY_ABI_VERSION 4
+#define LY_ABI_VERSION 5
 
 #if defined(LY_BUILD) && defined(__GNUC__)
 #define LY_API __attribute__((visibility("default")))
@@ -160,6 +160,11 @@ LY_API int32_t ly_launch(const ly_op* op, void* stream);
  * offsets them by whole images so one plan built for a sub-batch can sweep a
  * larger batch.                                                              */
 typedef struct ly_plan ly_plan;
+/* Shape validation of one op description on the HOST (no device needed; ly_plan_create runs it on every op first): known
+ * kind and dtype, B >= 1, every present view a channel slice [c0, c0+c) of its buffer, kind-specific required fields.
+ * Returns LY_E_ARG with ly_last_error() set.  The reference validates the same things implicitly when nn.Conv2d /
+ * torch.cat raise on mismatched shapes (layers.py:51-88, 157-173). */
+LY_API int32_t ly_op_validate(const ly_op* op);
 LY_API int32_t ly_plan_create(const ly_op* ops, int32_t n_ops, ly_plan** out);
 LY_API int32_t ly_plan_run(ly_plan* plan, float* const* ext, int32_t n_ext, int32_t img0, void* stream);
 /* Same as ly_plan_run, with a CUDA event between consecutive launches: fills

@@ -13,7 +13,7 @@ import os
 # LEANYOLO_B200_LIB: load an experimental build (LY_BUILD_DIR=... python -m leanyolo_b200.build) instead of the in-tree one
 LIB_PATH = Path(os.environ.get("LEANYOLO_B200_LIB") or Path(__file__).resolve().parent / "_lib" / "libleanyolo_b200.so")
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 LY_BF16, LY_F32 = 0, 1
 OP_STEM, OP_CONV, OP_DW, OP_POOL, OP_UP, OP_ATTN, OP_EXPORT, OP_IMPORT, OP_DWPW, OP_CHAIN = 1, 2, 3, 4, 5, 6, 7, 8, 9, 10
 CHAIN_MAX_STAGES, CHAIN_MAX_BLOCKS, CHAIN_MAX_REGIONS = 6, 4, 8
@@ -74,6 +74,7 @@ PROTOTYPES = {
     "ly_device_check": (C.c_int32, [C.POINTER(C.c_int32)]),
     "ly_launch_count": (C.c_int64, []),
     "ly_launch": (C.c_int32, [C.POINTER(LyOp), C.c_void_p]),
+    "ly_op_validate": (C.c_int32, [C.POINTER(LyOp)]),
     "ly_plan_create": (C.c_int32, [C.POINTER(LyOp), C.c_int32, C.POINTER(C.c_void_p)]),
     "ly_plan_run": (C.c_int32, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_void_p]),
     "ly_plan_profile": (C.c_int32, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_void_p,

@@ -148,10 +148,70 @@ int32_t ly_launch(const ly_op* op, void* stream) {
   return dispatch(*op, (cudaStream_t)stream);
 }
 
+static int32_t validate_view(const char* what, const ly_view& v) {
+  if (!v.ptr) return LY_OK;
+  LY_CHECK_ARG(v.H > 0 && v.W > 0 && v.c > 0 && v.ctot > 0 && v.c0 >= 0 && (long long)v.c0 + v.c <= v.ctot,
+               "%s view [H %d, W %d, channels %d..%d of %d] is not a channel slice of an NHWC buffer", what, v.H, v.W, v.c0,
+               v.c0 + v.c, v.ctot);
+  return LY_OK;
+}
+
+/* Host-side shape validation of one op description (no device needed): what every kernel family assumes before it
+ * looks at an op.  The per-kernel limits (alignment, channel multiples, shared-memory fit) stay with the kernels. */
+int32_t ly_op_validate(const ly_op* op) {
+  LY_CHECK_ARG(op != nullptr, "null op");
+  LY_CHECK_ARG(op->kind >= LY_OP_STEM && op->kind <= LY_OP_CHAIN, "unknown op kind %d", op->kind);
+  LY_CHECK_ARG(op->dtype == LY_BF16 || op->dtype == LY_F32, "unknown dtype %d", op->dtype);
+  LY_CHECK_ARG(op->B >= 1, "batch %d", op->B);
+  int32_t rc;
+  if ((rc = validate_view("src", op->src)) != LY_OK) return rc;
+  if ((rc = validate_view("dst", op->dst)) != LY_OK) return rc;
+  if ((rc = validate_view("res", op->res)) != LY_OK) return rc;
+  if ((rc = validate_view("up", op->up)) != LY_OK) return rc;
+  if (op->nchw_ctot > 0)
+    LY_CHECK_ARG(op->nchw_c0 >= 0 && op->nchw_c >= 0 && (long long)op->nchw_c0 + op->nchw_c <= op->nchw_ctot,
+                 "NCHW channels %d..%d of %d", op->nchw_c0, op->nchw_c0 + op->nchw_c, op->nchw_ctot);
+  switch (op->kind) {
+    case LY_OP_CONV:
+    case LY_OP_DW:
+      LY_CHECK_ARG(op->k >= 1 && (op->k & 1) && (op->stride == 1 || op->stride == 2), "k %d stride %d", op->k, op->stride);
+      LY_CHECK_ARG(op->src.ptr != nullptr, "conv: no source");
+      LY_CHECK_ARG(op->dst.ptr != nullptr || op->nchw != nullptr || op->ext_slot >= 0, "conv: no destination");
+      if (op->res.ptr && op->dst.ptr)
+        LY_CHECK_ARG(op->res.H == op->dst.H && op->res.W == op->dst.W, "shortcut %dx%d vs output %dx%d", op->res.H, op->res.W, op->dst.H, op->dst.W);
+      break;
+    case LY_OP_DWPW:
+      LY_CHECK_ARG(op->pre_k == 3 && op->pre_w && op->pre_bias && op->src.ptr, "dwpw: depthwise stage missing or not 3x3");
+      break;
+    case LY_OP_ATTN:
+      LY_CHECK_ARG(op->nh >= 1 && op->kdp >= 1 && op->hd >= 1 && op->src.ptr && op->dst.ptr, "attention: heads %d key dim %d head dim %d", op->nh, op->kdp, op->hd);
+      break;
+    case LY_OP_CHAIN:
+      LY_CHECK_ARG(op->chain != nullptr, "chain: no description");
+      LY_CHECK_ARG(op->chain->n_stages >= 1 && op->chain->n_stages <= LY_CHAIN_MAX_STAGES && op->chain->n_regions >= 1 &&
+                   op->chain->n_regions <= LY_CHAIN_MAX_REGIONS, "chain: %d stages, %d regions", op->chain->n_stages, op->chain->n_regions);
+      break;
+    case LY_OP_POOL:
+    case LY_OP_UP:
+      LY_CHECK_ARG(op->src.ptr && op->dst.ptr, "pool / upsample: null view");
+      break;
+    default: break;
+  }
+  return LY_OK;
+}
+
 int32_t ly_plan_create(const ly_op* ops, int32_t n_ops, ly_plan** out) {
   LY_CHECK_ARG(ops && n_ops > 0 && out, "ly_plan_create: bad arguments");
   int32_t rc = check_arch();
   if (rc != LY_OK) return rc;
+  for (int i = 0; i < n_ops; ++i) {
+    if (ly_op_validate(&ops[i]) != LY_OK) {
+      char msg[400];
+      snprintf(msg, sizeof(msg), "%.380s", g_err);
+      set_error("plan op %d: %s", i, msg);
+      return LY_E_ARG;
+    }
+  }
   ly_plan* pl = new ly_plan();
   pl->ops.assign(ops, ops + n_ops);
   pl->tc.assign(n_ops, nullptr);

@@ -38,6 +38,54 @@ class Compiled:
     in_keys: List[Tuple[str, int]] = None
 
 
+def serialise_ops(pb: PlanBuilder, B: int, dtype: str, impl: int, base: int, wbase: int, bbase: int, in_u8=False):
+    """The C-ABI description (``ly_op[]``) of a lowered plan: views become (buffer base + offset, H, W, pitch, c0, c),
+    parameters become addresses inside the packed weight / bias blobs.  External pointer table of a run:
+    [image | named NCHW inputs ... | NCHW outputs ...].  Returns (array, chain structs that must outlive
+    ``ly_plan_create``, input keys, output keys).  Pure host code: the CPU tests feed it to ``ly_op_validate``."""
+    in_keys = list(pb.inputs.keys())
+    out_keys = sorted(pb.outputs.keys())
+    in_slots = {k: i + 1 for i, k in enumerate(in_keys)}
+    slots = {k: i + 1 + len(in_keys) for i, k in enumerate(out_keys)}
+    arr = (N.LyOp * len(pb.ops))()
+    esz = pb.esize
+    dt = N.LY_BF16 if dtype == "bf16" else N.LY_F32
+    chains = []     # ctypes ly_chain structs: must outlive ly_plan_create (which copies them)
+    for i, op in enumerate(pb.ops):
+        o = arr[i]
+        o.kind, o.dtype, o.B = _KIND[op.kind], dt, B
+        o.k, o.stride, o.act, o.impl = op.k, op.stride, int(op.act), impl
+        o.src, o.dst, o.res = _view(op.src, base), _view(op.dst, base), _view(op.res, base)
+        o.ext_slot = -1
+        if op.kind == "stem":
+            o.w, o.bias = bbase + 4 * op.w_off, bbase + 4 * op.b_off
+            for j in range(3):
+                o.sub[j], o.div[j] = op.extra["sub"][j], op.extra["div"][j]
+            o.ext_slot = 0
+            if in_u8 == "lb":     # fused letterbox: ext[0] is the device array of ly_lb_desc, border colour in nh/kdp/hd
+                o.impl = N.STEM_IN_LB
+                o.nh, o.kdp, o.hd = 114, 114, 114
+            elif in_u8:
+                o.impl = N.STEM_IN_U8
+        elif op.w_off >= 0:
+            o.w, o.bias = wbase + esz * op.w_off, bbase + 4 * op.b_off
+        if op.extra.get("up") is not None:
+            o.up = _view(op.extra["up"], base)
+        if op.kind == "dwpw":
+            o.pre_w, o.pre_bias = wbase + esz * op.extra["pre_w_off"], bbase + 4 * op.extra["pre_b_off"]
+            o.pre_k, o.pre_act = 3, int(op.extra["pre_act"])
+        if op.attn is not None:
+            o.nh, o.kdp, o.hd, o.scale = op.attn
+        if op.nchw is not None:
+            name, level, c0, c, ctot = op.nchw
+            o.nchw_ctot, o.nchw_c0, o.nchw_c = ctot, c0, c
+            o.ext_slot = in_slots[(name, level)] if op.kind == "import" else slots[(name, level)]
+        if op.kind == "chain":
+            chains.append(Engine._chain_struct(op, wbase, bbase, esz))
+            o.chain = C.pointer(chains[-1])
+    return arr, chains, in_keys, out_keys
+
+
 class Engine:
     """One per (model, dtype).  ``emit`` fills a PlanBuilder for a batch of ``B`` images."""
 
@@ -97,48 +145,8 @@ class Engine:
         if ws is None or ws.numel() < pb.ws_bytes:
             ws = torch.empty(max(pb.ws_bytes, 1024), dtype=torch.uint8, device=self.device)
             self._workspaces[(B, H, W)] = ws
-        # external pointer table of a run: [image | named NCHW inputs ... | NCHW outputs ...]
-        in_keys = list(pb.inputs.keys())
-        out_keys = sorted(pb.outputs.keys())
-        in_slots = {k: i + 1 for i, k in enumerate(in_keys)}
-        slots = {k: i + 1 + len(in_keys) for i, k in enumerate(out_keys)}
-        arr = (N.LyOp * len(pb.ops))()
         base, wbase, bbase = ws.data_ptr(), self._w.data_ptr(), self._b.data_ptr()
-        esz = pb.esize
-        dt = N.LY_BF16 if self.dtype == "bf16" else N.LY_F32
-        chains = []     # ctypes ly_chain structs: must outlive ly_plan_create (which copies them)
-        for i, op in enumerate(pb.ops):
-            o = arr[i]
-            o.kind, o.dtype, o.B = _KIND[op.kind], dt, B
-            o.k, o.stride, o.act, o.impl = op.k, op.stride, int(op.act), self.impl
-            o.src, o.dst, o.res = _view(op.src, base), _view(op.dst, base), _view(op.res, base)
-            o.ext_slot = -1
-            if op.kind == "stem":
-                o.w, o.bias = bbase + 4 * op.w_off, bbase + 4 * op.b_off
-                for j in range(3):
-                    o.sub[j], o.div[j] = op.extra["sub"][j], op.extra["div"][j]
-                o.ext_slot = 0
-                if in_u8 == "lb":     # fused letterbox: ext[0] is the device array of ly_lb_desc, border colour in nh/kdp/hd
-                    o.impl = N.STEM_IN_LB
-                    o.nh, o.kdp, o.hd = 114, 114, 114
-                elif in_u8:
-                    o.impl = N.STEM_IN_U8
-            elif op.w_off >= 0:
-                o.w, o.bias = wbase + esz * op.w_off, bbase + 4 * op.b_off
-            if op.extra.get("up") is not None:
-                o.up = _view(op.extra["up"], base)
-            if op.kind == "dwpw":
-                o.pre_w, o.pre_bias = wbase + esz * op.extra["pre_w_off"], bbase + 4 * op.extra["pre_b_off"]
-                o.pre_k, o.pre_act = 3, int(op.extra["pre_act"])
-            if op.attn is not None:
-                o.nh, o.kdp, o.hd, o.scale = op.attn
-            if op.nchw is not None:
-                name, level, c0, c, ctot = op.nchw
-                o.nchw_ctot, o.nchw_c0, o.nchw_c = ctot, c0, c
-                o.ext_slot = in_slots[(name, level)] if op.kind == "import" else slots[(name, level)]
-            if op.kind == "chain":
-                chains.append(self._chain_struct(op, wbase, bbase, esz))
-                o.chain = C.pointer(chains[-1])
+        arr, chains, in_keys, out_keys = serialise_ops(pb, B, self.dtype, self.impl, base, wbase, bbase, in_u8)
         handle = C.c_void_p()
         with torch.cuda.device(self.device):
             N.check(self.lib.ly_plan_create(arr, len(pb.ops), C.byref(handle)), "ly_plan_create")

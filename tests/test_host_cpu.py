@@ -441,3 +441,76 @@ def test_coco_bbox_map_known_answers():
          {"image_id": 1, "category_id": 3, "bbox": [10, 10, 100, 100], "score": 0.5}]
     assert coco_bbox_map(gtc, d)["mAP50-95"] == 1.0
     assert coco_bbox_map(one, [])["mAP50-95"] == 0.0
+
+
+# ---------------------------------------------------------------------------------------------
+# C-side shape validation (ly_op_validate, run by ly_plan_create on every op): host-only code, so it is exercised
+# here on the REAL op lists of every variant (nothing the lowering emits may be rejected) and on corrupted ops.
+def _all_plans():
+    from leanyolo_b200.engine import serialise_ops
+    cases = [(n, 2, 64, 64, "bf16", {}) for n in list_models()]
+    cases += [("yolov10s", 1, 352, 608, "bf16", {}), ("yolov10s", 2, 64, 64, "f32", {}), ("yolov10m", 1, 64, 96, "f32", {}),
+              ("yolov10s", 1, 640, 640, "bf16", {"LEANYOLO_FUSE_CHAIN": "1"}), ("yolov10s", 1, 640, 640, "bf16", {"LEANYOLO_FUSE_S2": "1"}),
+              ("yolov10s", 1, 640, 640, "bf16", {"LEANYOLO_FUSE_TAIL": "0"})]
+    for name, B, H, W, dt, env in cases:
+        m = get_model(name, weights=None, class_names=NAMES)
+        emits = [("full", lambda pb, m=m: m.emit(pb)), ("taps", lambda pb, m=m: m.emit(pb, True)),
+                 ("one2one", lambda pb, m=m: m.emit(pb, False, "one2one"))]
+        if not env:
+            emits += [(p, lambda pb, m=m, p=p: m._emit_part(pb, p)) for p in ("backbone", "neck", "head")]
+        for tag, emit in emits:
+            os.environ.update(env)
+            try:
+                pb = PlanBuilder(B, H, W, dt, dry=True)
+                emit(pb)
+            finally:
+                for k in env:
+                    del os.environ[k]
+            pb.assign_offsets()
+            for in_u8 in (False, True, "lb") if tag == "full" and dt == "bf16" else (False,):
+                arr, chains, _, _ = serialise_ops(pb, B, dt, N.IMPL_AUTO, 0x7f0000000000, 0x7e0000000000, 0x7d0000000000, in_u8)
+                yield f"{name} {B}x{H}x{W} {dt} {tag} {env} u8={in_u8}", pb, arr, chains
+
+
+def test_op_validate_accepts_every_op_the_lowering_emits():
+    lib = N.lib()
+    n = 0
+    for tag, pb, arr, chains in _all_plans():
+        for i in range(len(pb.ops)):
+            rc = lib.ly_op_validate(ctypes.byref(arr[i]))
+            assert rc == 0, f"{tag}: op {i} ({pb.ops[i].kind}) rejected: {lib.ly_last_error().decode()}"
+            n += 1
+    assert n > 3000
+
+
+def test_op_validate_rejects_bad_shapes_with_a_message():
+    from leanyolo_b200.engine import serialise_ops
+    lib = N.lib()
+    m = get_model("yolov10n", weights=None, class_names=NAMES)
+    pb = PlanBuilder(1, 64, 64, "bf16", dry=True)
+    m.emit(pb)
+    pb.assign_offsets()
+
+    def fresh():
+        return serialise_ops(pb, 1, "bf16", N.IMPL_AUTO, 0x7f0000000000, 0x7e0000000000, 0x7d0000000000)
+
+    conv = next(i for i, op in enumerate(pb.ops) if op.kind == "conv")
+    attn = next(i for i, op in enumerate(pb.ops) if op.kind == "attn")
+    dwpw = next(i for i, op in enumerate(pb.ops) if op.kind == "dwpw")
+
+    def bad(i, mutate, needle):
+        arr, chains, _, _ = fresh()
+        mutate(arr[i])
+        assert lib.ly_op_validate(ctypes.byref(arr[i])) == -1        # LY_E_ARG
+        assert needle in lib.ly_last_error().decode()
+
+    bad(conv, lambda o: setattr(o, "kind", 99), "unknown op kind 99")
+    bad(conv, lambda o: setattr(o, "dtype", 7), "unknown dtype 7")
+    bad(conv, lambda o: setattr(o, "B", 0), "batch 0")
+    bad(conv, lambda o: setattr(o.src, "c", o.src.ctot + 16), "src view")
+    bad(conv, lambda o: setattr(o.dst, "H", 0), "dst view")
+    bad(conv, lambda o: setattr(o, "stride", 3), "stride 3")
+    bad(conv, lambda o: setattr(o, "k", 2), "k 2")
+    bad(attn, lambda o: setattr(o, "nh", 0), "attention")
+    bad(dwpw, lambda o: setattr(o, "pre_k", 5), "dwpw")
+    assert lib.ly_op_validate(None) == -1
