@@ -514,3 +514,27 @@ def test_op_validate_rejects_bad_shapes_with_a_message():
     bad(attn, lambda o: setattr(o, "nh", 0), "attention")
     bad(dwpw, lambda o: setattr(o, "pre_k", 5), "dwpw")
     assert lib.ly_op_validate(None) == -1
+
+
+# ---------------------------------------------------------------------------------------------
+# bench.py --impl reference (the reference's algorithm on the host cores): JSON contract of the line the driver parses
+def test_bench_reference_arm_contract_and_rank_gating():
+    import json
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--model", "yolov10n", "--imgsz", "64",
+           "--steps", "1", "--warmup", "1", "--gpus", "2"]
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0, r.stderr[-500:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1                                     # exactly ONE JSON line on stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "images/sec (fwd+decode)" and d["unit"] == "images/s"
+    assert d["higher_is_better"] is True and d["n_gpus"] == 2 and d["value"] > 0 and d["vs_baseline"] is None
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "yolov10n 64x64" in d["config"]["workload"] and "model" not in d["config"]
+    # under torchrun only rank 0 runs the CPU arm; the other ranks exit 0 without work or output
+    r1 = subprocess.run(cmd, capture_output=True, text=True, timeout=60, env=dict(env, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1"))
+    assert r1.returncode == 0 and r1.stdout.strip() == ""
